@@ -1,0 +1,179 @@
+"""CPU tests of the oracle itself: independent cross-checks (torch CPU ops, brute-force CTC, direct loops).
+These pin the restatement's *mathematics*; they cannot pin TF1/librosa quirks (parity unpinned, see oracle header)."""
+import math
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import speecht_oracle as O
+
+
+def test_same_padding_matches_tf_rule():
+  assert O.same_padding(1001, 48, 2) == (501, 23, 24)
+  assert O.same_padding(1000, 48, 2) == (500, 23, 23)
+  assert O.same_padding(501, 7, 1) == (501, 3, 3)
+  assert O.same_padding(501, 32, 1) == (501, 15, 16)
+  assert O.same_padding(501, 1, 1) == (501, 0, 0)
+  assert O.same_padding(5, 48, 2) == (3, 23, 24)
+
+
+@pytest.mark.parametrize('k,s,cin,cout,t', [(48, 2, 16, 10, 101), (48, 2, 16, 10, 100), (7, 1, 10, 10, 51),
+                                             (32, 1, 10, 24, 51), (1, 1, 24, 29, 51), (32, 1, 6, 8, 5)])
+def test_conv_forward_backward_vs_torch(k, s, cin, cout, t):
+  rng = np.random.default_rng(1)
+  x = rng.standard_normal((3, t, cin))
+  w = rng.standard_normal((k, cin, cout)) * 0.1
+  b = rng.standard_normal((cout,))
+  y = O.conv1d_same(x, w, b, s, relu=False)
+  out, left, right = O.same_padding(t, k, s)
+  xt = torch.tensor(x, requires_grad=True)
+  wt = torch.tensor(w, requires_grad=True)
+  bt = torch.tensor(b, requires_grad=True)
+  xp = F.pad(xt.permute(0, 2, 1), (left, right))
+  yt = F.conv1d(xp, wt.permute(2, 1, 0), bt, stride=s).permute(0, 2, 1)
+  assert yt.shape[1] == out
+  np.testing.assert_allclose(y, yt.detach().numpy(), rtol=1e-10, atol=1e-10)
+  dy = rng.standard_normal(y.shape)
+  yt.backward(torch.tensor(dy))
+  dx, dw, db = O.conv1d_same_backward(x, w, s, dy)
+  np.testing.assert_allclose(dx, xt.grad.numpy(), rtol=1e-9, atol=1e-9)
+  np.testing.assert_allclose(dw, wt.grad.numpy(), rtol=1e-9, atol=1e-9)
+  np.testing.assert_allclose(db, bt.grad.numpy(), rtol=1e-9, atol=1e-9)
+
+
+def test_ctc_vs_brute_force_enumeration():
+  rng = np.random.default_rng(2)
+  C = 4
+  for label in ([0], [1, 1], [0, 1, 2], [2, 2, 1], []):
+    T = 5
+    logits = rng.standard_normal((T, 1, C))
+    loss, _ = O.ctc_loss_and_grad(logits, [label], [T])
+    bf = O.ctc_brute_force_loss(logits[:, 0, :], label)
+    assert abs(loss[0] - bf) < 1e-10, (label, loss, bf)
+
+
+def test_ctc_vs_torch_loss_and_grad():
+  rng = np.random.default_rng(3)
+  T, B, C = 40, 5, 29
+  logits = rng.standard_normal((T, B, C)) * 2
+  seq = [40, 33, 40, 25, 12]
+  labels = [O.synthetic_labels(rng, n, s) for n, s in zip([10, 7, 15, 1, 5], seq)]
+  labels[3] = np.array([], dtype=np.int32)          # empty transcript
+  loss, grad = O.ctc_loss_and_grad(logits, labels, seq)
+  lt = torch.tensor(logits, requires_grad=True)
+  lsm = F.log_softmax(lt, dim=2)
+  tl = F.ctc_loss(lsm, torch.tensor(np.concatenate(labels).astype(np.int64)), torch.tensor(seq),
+                  torch.tensor([len(l) for l in labels]), blank=C - 1, reduction='none')
+  np.testing.assert_allclose(loss, tl.detach().numpy(), rtol=1e-9, atol=1e-9)
+  tl.sum().backward()
+  np.testing.assert_allclose(grad, lt.grad.numpy(), rtol=1e-7, atol=1e-9)
+  # frames beyond seq_len carry no gradient; in-range rows sum to ~0 over classes
+  assert np.all(grad[33:, 1] == 0)
+  assert np.abs(grad.sum(axis=2)).max() < 1e-9
+
+
+def test_ctc_rejects_infeasible_and_bad_labels():
+  logits = np.zeros((4, 1, 5))
+  with pytest.raises(O.CTCLabelError):
+    O.ctc_loss_and_grad(logits, [[1, 1, 1]], [4])        # needs 5 frames
+  with pytest.raises(O.CTCLabelError):
+    O.ctc_loss_and_grad(logits, [[4]], [4])              # blank id as label
+  O.ctc_loss_and_grad(logits, [[1, 1]], [3])             # exactly enough
+
+
+def test_greedy_decoder_rules():
+  C = 4
+  def onehot(seq):
+    x = np.full((len(seq), 1, C), -1.0, dtype=np.float32)
+    for t, c in enumerate(seq):
+      x[t, 0, c] = 1.0
+    return x
+  (idx, val, shape), neg = O.ctc_greedy_decoder(onehot([0, 0, 3, 0, 1, 1, 3, 3, 2]), [9])
+  assert val.tolist() == [0, 0, 1, 2] and shape.tolist() == [1, 4]
+  assert idx.tolist() == [[0, 0], [0, 1], [0, 2], [0, 3]]
+  assert neg[0, 0] == -9.0
+  (idx, val, shape), _ = O.ctc_greedy_decoder(onehot([0, 0, 3, 0, 1, 1, 3, 3, 2]), [9], merge_repeated=False)
+  assert val.tolist() == [0, 0, 0, 1, 1, 2]
+  # ties: first maximum wins; only frames < seq_len count
+  x = np.zeros((3, 1, C), dtype=np.float32)
+  (idx, val, shape), _ = O.ctc_greedy_decoder(x, [2])
+  assert val.tolist() == [0]
+  # all-blank utterance produces no entries and a zero-width dense shape
+  (idx, val, shape), _ = O.ctc_greedy_decoder(onehot([3, 3]), [2])
+  assert idx.shape == (0, 2) and shape.tolist() == [1, 0]
+
+
+def test_extract_decoded_ids_quirk():
+  idx = np.array([[0, 0], [0, 1], [2, 0]])
+  val = np.array([5, 6, 7])
+  assert O.extract_decoded_ids(idx, val) == [[5, 6], [7]]    # utterance 1 (empty) leaves no entry
+
+
+def test_adam_tf1_matches_closed_form_and_differs_from_torch():
+  p = np.array([1.0, -2.0], dtype=np.float64); g = np.array([0.5, 0.25])
+  m = np.zeros(2); v = np.zeros(2)
+  O.adam_tf1([p], [g], [m], [v], lr=0.1, step=1)
+  lr_t = 0.1 * math.sqrt(1 - 0.999) / (1 - 0.9)
+  exp = np.array([1.0, -2.0]) - lr_t * (0.1 * g) / (np.sqrt(0.001 * g * g) + 1e-3)
+  np.testing.assert_allclose(p, exp, rtol=1e-12)
+
+
+def test_clip_by_global_norm():
+  g = [np.full((3,), 4.0), np.full((4,), 3.0)]
+  out, norm = O.clip_by_global_norm(g, 5.0)
+  assert abs(norm - math.sqrt(48 + 36)) < 1e-12
+  np.testing.assert_allclose(out[0], g[0] * 5.0 / norm)
+  out, norm = O.clip_by_global_norm([np.array([0.3])], 5.0)
+  np.testing.assert_allclose(out[0], [0.3])
+
+
+def test_mel_filterbank_and_spectrogram_properties():
+  fb = O.mel_filterbank(16000, 512, 128)
+  assert fb.shape == (128, 257) and np.all(fb >= 0)
+  # Slaney area normalisation: each triangle integrates to ~1 over Hz -> sum * bin_width ~ 1
+  area = fb.sum(axis=1) * (8000 / 256)
+  assert np.all(np.abs(area[10:] - 1.0) < 0.35)
+  rng = np.random.default_rng(4)
+  wav = (0.1 * rng.standard_normal(16000)).astype(np.float32)
+  feat = O.calc_power_spectrogram(wav, 16000)
+  assert feat.shape == (101, 128)
+  assert abs(feat.mean()) < 1e-9 and abs(feat.std() - 1) < 1e-9
+  # STFT against scipy's own short-time FFT of the same reflect-padded frames
+  import scipy.signal
+  S = O.stft_power(wav, 512, 160)
+  f, t, Z = scipy.signal.stft(np.pad(wav.astype(np.float64), 256, mode='reflect'), window='hann', nperseg=512,
+                              noverlap=512 - 160, boundary=None, padded=False)
+  ref = np.abs(Z * 256.0) ** 2     # scipy scales by 1/sum(window) = 1/256
+  np.testing.assert_allclose(S, ref, rtol=1e-8, atol=1e-12)
+
+
+def test_train_step_gradients_vs_torch_autograd_tiny_net():
+  """Whole step (forward, CTC, backward) on a scaled-down layer table vs torch autograd."""
+  rng = np.random.default_rng(5)
+  layers = [(6, 2, 8, 12, True), (3, 1, 12, 12, True), (4, 1, 12, 16, True), (1, 1, 16, 6, False)]
+  weights = O.xavier_weights(rng, layers=layers, dtype=np.float64)
+  weights = [(w, rng.standard_normal(b.shape) * 0.1) for w, b in weights]
+  x = rng.standard_normal((3, 21, 8))
+  lengths = np.array([21, 17, 21])
+  labels = [[0, 1, 1], [2], [4, 3, 2, 1]]
+  logits, acts = O.wav2letter_forward(x, weights, layers=layers, keep_activations=True)
+  loss, dlog = O.ctc_loss_and_grad(logits, labels, lengths // 2)
+  grads = O.wav2letter_backward(acts, weights, dlog / 3, layers=layers)
+  tw = [(torch.tensor(w, requires_grad=True), torch.tensor(b, requires_grad=True)) for w, b in weights]
+  h = torch.tensor(x)
+  for (k, s, cin, cout, relu), (w, b) in zip(layers, tw):
+    out, left, right = O.same_padding(h.shape[1], k, s)
+    h = F.conv1d(F.pad(h.permute(0, 2, 1), (left, right)), w.permute(2, 1, 0), b, stride=s).permute(0, 2, 1)
+    if relu:
+      h = torch.relu(h)
+  lt = h.permute(1, 0, 2)
+  np.testing.assert_allclose(logits, lt.detach().numpy(), rtol=1e-9, atol=1e-9)
+  tl = F.ctc_loss(F.log_softmax(lt, 2), torch.tensor(sum(labels, [])), torch.tensor(lengths // 2),
+                  torch.tensor([len(l) for l in labels]), blank=5, reduction='none')
+  np.testing.assert_allclose(loss, tl.detach().numpy(), rtol=1e-9)
+  tl.mean().backward()
+  for (dw, db), (w, b) in zip(grads, tw):
+    np.testing.assert_allclose(dw, w.grad.numpy(), rtol=1e-7, atol=1e-10)
+    np.testing.assert_allclose(db, b.grad.numpy(), rtol=1e-7, atol=1e-10)

@@ -1,0 +1,354 @@
+// a8/a9 -- CTC loss forward + gradient (replaces tf.nn.ctc_loss and the gradient TF registers for it,
+// reference speech_model.py:74-75,78).  TF1 defaults: ctc_merge_repeated=True, blank = num_classes-1,
+// softmax applied internally, frames t >= seq_len get zero gradient.
+//
+// Three kernels:
+//   1. ctc_log_softmax : one warp per (b,t) row, warp-shuffle max / sum over the 29 classes.
+//   2. ctc_alpha_beta  : grid (B,2): CTA (b,0) runs the alpha recursion, CTA (b,1) the beta recursion, both
+//                        500-1500 strictly serial steps with one __syncthreads per step.  The running values are
+//                        kept in double (magnitudes reach -1e3..-1e4, where an fp32 ulp is 1e-4..1e-3) while every
+//                        transcendental runs in fp32 on differences <= 0 -- error per step ~1e-7 instead of ~1e-4.
+//   3. ctc_grad        : one warp per (b,t) row: occupancy per class from alpha+beta-logp, grad = softmax - occ.
+// Algorithmic bytes = read logits + write grad = 2*T*B*C*4; the alpha/beta lattices (T*S doubles each) are
+// workspace traffic on top.  The recursion is latency-bound by construction.
+#include "st_common.cuh"
+#include <math.h>
+#include <vector>
+
+namespace {
+
+constexpr int kABThreads = 256;
+
+__global__ void __launch_bounds__(256)
+ctc_log_softmax_kernel(const float* __restrict__ logits, int64_t stride_t, int64_t stride_b, int T, int B, int C,
+                       const int32_t* __restrict__ seq_len, float* __restrict__ lsm) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= B * T) return;
+  const int b = row / T, t = row - b * T;
+  if (t >= seq_len[b]) return;
+  const float* src = logits + (int64_t)t * stride_t + (int64_t)b * stride_b;
+  float mx = -INFINITY;
+  for (int c = lane; c < C; c += 32) mx = fmaxf(mx, src[c]);
+  mx = warp_max(mx);
+  float sum = 0.f;
+  for (int c = lane; c < C; c += 32) sum += expf(src[c] - mx);
+  sum = warp_sum(sum);
+  const float lse = mx + logf(sum);
+  float* dst = lsm + (int64_t)row * C;
+  for (int c = lane; c < C; c += 32) dst[c] = src[c] - lse;
+}
+
+__device__ __forceinline__ double lse3(double a0, double a1, double a2) {
+  const double m = fmax(a0, fmax(a1, a2));
+  if (m == -INFINITY) return -INFINITY;
+  const float s = __expf((float)(a0 - m)) + __expf((float)(a1 - m)) + __expf((float)(a2 - m));
+  return m + (double)__logf(s);
+}
+
+// dynamic smem: double buf[2][S + 4]; int ext[S]; unsigned char skip[S + 2]
+__global__ void __launch_bounds__(kABThreads)
+ctc_alpha_beta_kernel(const float* __restrict__ lsm, int T, int C, const int32_t* __restrict__ labels,
+                      const int32_t* __restrict__ label_offsets, const int32_t* __restrict__ seq_len, int blank,
+                      int s_pad, double* __restrict__ alpha, double* __restrict__ beta,
+                      double* __restrict__ logp, float* __restrict__ loss, int32_t* __restrict__ status) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int b = blockIdx.x;
+  const bool is_beta = blockIdx.y == 1;
+  const int l0 = label_offsets[b];
+  const int L = label_offsets[b + 1] - l0;
+  const int S = 2 * L + 1;
+  int len = seq_len[b];
+  len = len > T ? T : len;
+  double* buf = reinterpret_cast<double*>(smem_raw);                    // [2][s_pad + 4]
+  const int bstride = s_pad + 4;
+  int* ext = reinterpret_cast<int*>(buf + 2 * bstride);                 // [s_pad]
+  unsigned char* skip = reinterpret_cast<unsigned char*>(ext + s_pad);  // [s_pad + 2]
+  __shared__ int s_bad;
+  if (threadIdx.x == 0) s_bad = 0;
+  __syncthreads();
+
+  // extended label sequence + feasibility (device-side mirror of st_ctc_validate_labels_host)
+  int repeats = 0, bad = 0;
+  for (int s = threadIdx.x; s < S + 2 && S <= s_pad; s += kABThreads) {
+    int e = blank;
+    if (s < S && (s & 1)) {
+      e = labels[l0 + (s >> 1)];
+      if (e < 0 || e >= C || e == blank) { bad = 1; e = blank; }
+      if (s >= 3 && e == labels[l0 + (s >> 1) - 1]) repeats++;
+    }
+    if (s < S) ext[s] = e;
+  }
+  if (bad) atomicOr(&s_bad, 1);
+  if (repeats) atomicAdd(&s_bad, repeats << 1);
+  __syncthreads();
+  const int n_rep = s_bad >> 1;
+  const bool infeasible = (s_bad & 1) || (L + n_rep > len) || len < 0 || S > s_pad;
+  for (int s = threadIdx.x; s < S + 2 && S <= s_pad; s += kABThreads) {
+    // skip[s]: transition s-2 -> s allowed
+    skip[s] = (s >= 2 && s < S && ext[s] != blank && ext[s] != ext[s - 2]) ? 1 : 0;
+  }
+  for (int i = threadIdx.x; i < 2 * bstride; i += kABThreads) buf[i] = -INFINITY;
+  __syncthreads();
+
+  if (infeasible || len <= 0) {
+    if (!is_beta && threadIdx.x == 0) {
+      status[b] = infeasible ? 1 : 0;
+      loss[b] = infeasible ? INFINITY : 0.f;
+      logp[b] = infeasible ? -INFINITY : 0.0;
+    }
+    return;
+  }
+  if (!is_beta && threadIdx.x == 0) status[b] = 0;
+
+  const float* lrow = lsm + (int64_t)b * T * C;
+  double* lat = (is_beta ? beta : alpha) + (int64_t)b * T * s_pad;
+  constexpr int NS_MAX = 8;                                             // S <= 8*256 = 2048 (label len <= 1023)
+  int my_ext[NS_MAX];
+  unsigned char my_skip[NS_MAX];
+  float lp_next[NS_MAX];
+  const int ns = (S + kABThreads - 1) / kABThreads;
+#pragma unroll
+  for (int j = 0; j < NS_MAX; ++j) {
+    const int s = threadIdx.x + j * kABThreads;
+    my_ext[j] = (j < ns && s < S) ? ext[s] : blank;
+    my_skip[j] = 0;
+  }
+
+  if (!is_beta) {
+    // alpha_0
+#pragma unroll
+    for (int j = 0; j < NS_MAX; ++j) {
+      const int s = threadIdx.x + j * kABThreads;
+      if (j < ns && s < S) {
+        my_skip[j] = skip[s];
+        double v = (s < 2) ? (double)lrow[my_ext[j]] : -INFINITY;
+        buf[2 + s] = v;                                                 // slot 0, +2 pad so s-1, s-2 read -inf
+        lat[s] = v;
+        lp_next[j] = (len > 1) ? lrow[(int64_t)C + my_ext[j]] : 0.f;
+      }
+    }
+    __syncthreads();
+    for (int t = 1; t < len; ++t) {
+      const double* prev = buf + ((t - 1) & 1) * bstride;
+      double* cur = buf + (t & 1) * bstride;
+#pragma unroll
+      for (int j = 0; j < NS_MAX; ++j) {
+        const int s = threadIdx.x + j * kABThreads;
+        if (j < ns && s < S) {
+          const float lp = lp_next[j];
+          if (t + 1 < len) lp_next[j] = lrow[(int64_t)(t + 1) * C + my_ext[j]];
+          const double a0 = prev[2 + s], a1 = prev[1 + s];
+          const double a2 = my_skip[j] ? prev[s] : -INFINITY;
+          const double v = lse3(a0, a1, a2) + (double)lp;
+          cur[2 + s] = v;
+          lat[(int64_t)t * s_pad + s] = v;
+        }
+      }
+      __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+      const double* fin = buf + ((len - 1) & 1) * bstride;
+      const double lpz = lse3(fin[2 + S - 1], S > 1 ? fin[2 + S - 2] : -INFINITY, -INFINITY);
+      logp[b] = lpz;
+      loss[b] = (float)(-lpz);
+      if (lpz == -INFINITY) status[b] = 1;
+    }
+  } else {
+    // beta_{len-1}; smem holds g_t(s) = beta_t(s) + lp_t(s) for the step below to consume
+    const float* last = lrow + (int64_t)(len - 1) * C;
+#pragma unroll
+    for (int j = 0; j < NS_MAX; ++j) {
+      const int s = threadIdx.x + j * kABThreads;
+      if (j < ns && s < S) {
+        my_skip[j] = skip[s + 2];                                       // transition s -> s+2
+        const double v = (s >= S - 2) ? 0.0 : -INFINITY;
+        lat[(int64_t)(len - 1) * s_pad + s] = v;
+        buf[((len - 1) & 1) * bstride + s] = v + (double)last[my_ext[j]];
+        lp_next[j] = (len > 1) ? lrow[(int64_t)(len - 2) * C + my_ext[j]] : 0.f;
+      }
+    }
+    __syncthreads();
+    for (int t = len - 2; t >= 0; --t) {
+      const double* nxt = buf + ((t + 1) & 1) * bstride;               // entries S..S+3 stay -inf
+      double* cur = buf + (t & 1) * bstride;
+#pragma unroll
+      for (int j = 0; j < NS_MAX; ++j) {
+        const int s = threadIdx.x + j * kABThreads;
+        if (j < ns && s < S) {
+          const float lp = lp_next[j];
+          if (t > 0) lp_next[j] = lrow[(int64_t)(t - 1) * C + my_ext[j]];
+          const double b0 = nxt[s], b1 = nxt[s + 1];
+          const double b2 = my_skip[j] ? nxt[s + 2] : -INFINITY;
+          const double v = lse3(b0, b1, b2);
+          lat[(int64_t)t * s_pad + s] = v;
+          cur[s] = v + (double)lp;
+        }
+      }
+      __syncthreads();
+    }
+  }
+}
+
+// One warp per (b,t) row.  grad row = grad_scale * (softmax - occupancy); zero for t >= seq_len[b].
+__global__ void __launch_bounds__(256)
+ctc_grad_kernel(const float* __restrict__ lsm, const double* __restrict__ alpha, const double* __restrict__ beta,
+                const double* __restrict__ logp, const int32_t* __restrict__ labels,
+                const int32_t* __restrict__ label_offsets, const int32_t* __restrict__ seq_len,
+                const int32_t* __restrict__ status, int T, int B, int C, int blank, int s_pad,
+                float grad_scale, float* __restrict__ grad, int64_t stride_t, int64_t stride_b,
+                __nv_bfloat16* __restrict__ planes, int n_planes, int c_pad) {
+  __shared__ float bins[8][64];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row = blockIdx.x * 8 + warp;
+  if (row >= B * T) return;
+  const int b = row / T, t = row - b * T;
+  const int len = min(seq_len[b], T);
+  const bool live = t < len && status[b] == 0;
+  float g0 = 0.f, g1 = 0.f;                     // classes lane and lane+32 (C <= 64)
+  if (live) {
+    bins[warp][lane] = 0.f;
+    bins[warp][lane + 32] = 0.f;
+    __syncwarp();
+    const int l0 = label_offsets[b];
+    const int S = 2 * (label_offsets[b + 1] - l0) + 1;
+    const double lz = logp[b];
+    const double* a = alpha + ((int64_t)b * T + t) * s_pad;
+    const double* be = beta + ((int64_t)b * T + t) * s_pad;
+    float blank_sum = 0.f;
+    for (int s = lane; s < S; s += 32) {
+      const double v = a[s] + be[s] - lz;
+      const float e = (v > -100.0) ? __expf((float)v) : 0.f;
+      if (s & 1) {
+        atomicAdd(&bins[warp][labels[l0 + (s >> 1)]], e);
+      } else {
+        blank_sum += e;
+      }
+    }
+    blank_sum = warp_sum(blank_sum);
+    __syncwarp();
+    const float* lr = lsm + (int64_t)row * C;
+    if (lane < C) {
+      float occ = bins[warp][lane] + (lane == blank ? blank_sum : 0.f);
+      g0 = grad_scale * (__expf(lr[lane]) - occ);
+    }
+    if (lane + 32 < C) {
+      float occ = bins[warp][lane + 32] + (lane + 32 == blank ? blank_sum : 0.f);
+      g1 = grad_scale * (__expf(lr[lane + 32]) - occ);
+    }
+  }
+  if (grad) {
+    float* dst = grad + (int64_t)t * stride_t + (int64_t)b * stride_b;
+    if (lane < C) dst[lane] = g0;
+    if (lane + 32 < C) dst[lane + 32] = g1;
+  }
+  if (planes) {
+    // planes[p][b][t][c_pad]: value = sum_p plane_p; columns >= C are zero
+    const int64_t plane_stride = (int64_t)B * T * c_pad;
+    for (int c = lane; c < c_pad; c += 32) {
+      const float v = (c >= C) ? 0.f : (c < 32 ? g0 : g1);
+      float rem = v;
+      for (int p = 0; p < n_planes; ++p) {
+        const __nv_bfloat16 h = __float2bfloat16_rn(rem);
+        planes[p * plane_stride + ((int64_t)b * T + t) * c_pad + c] = h;
+        rem -= __bfloat162float(h);
+      }
+    }
+  }
+}
+
+inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
+
+}  // namespace
+
+ST_API int st_ctc_validate_labels_host(const int32_t* labels_host, const int32_t* label_offsets_host,
+                                       const int32_t* seq_len_host, int B, int T, int blank) {
+  ST_CHECK_ARG(label_offsets_host && seq_len_host, "st_ctc_validate_labels_host: null pointer");
+  for (int b = 0; b < B; ++b) {
+    const int l0 = label_offsets_host[b], l1 = label_offsets_host[b + 1];
+    ST_CHECK_ARG(l1 >= l0, "st_ctc_validate_labels_host: label_offsets not monotone at batch %d", b);
+    if (seq_len_host[b] > T || seq_len_host[b] < 0) {
+      st_set_error("sequence_length(%d) = %d outside [0, max_time=%d]", b, seq_len_host[b], T);
+      return ST_ERR_CTC_LABELS;
+    }
+    int repeats = 0;
+    for (int i = l0; i < l1; ++i) {
+      if (labels_host[i] < 0 || labels_host[i] >= blank) {
+        st_set_error("label id %d outside [0, num_classes-1=%d) in batch %d", labels_host[i], blank, b);
+        return ST_ERR_CTC_LABELS;
+      }
+      if (i > l0 && labels_host[i] == labels_host[i - 1]) repeats++;
+    }
+    if ((l1 - l0) + repeats > seq_len_host[b]) {
+      st_set_error("Not enough time for target transition sequence (required: %d, available: %d) in batch %d",
+                   (l1 - l0) + repeats, seq_len_host[b], b);
+      return ST_ERR_CTC_LABELS;
+    }
+  }
+  return ST_OK;
+}
+
+static size_t ctc_offsets(int T, int B, int C, int max_label_len, size_t* off_alpha, size_t* off_beta,
+                          size_t* off_logp, int* s_pad_out) {
+  const int s_pad = round_up(2 * max_label_len + 1, 4);
+  size_t off = 0;
+  off += (size_t)B * T * C * sizeof(float);
+  off = (off + 255) / 256 * 256;
+  *off_alpha = off;
+  off += (size_t)B * T * s_pad * sizeof(double);
+  *off_beta = off;
+  off += (size_t)B * T * s_pad * sizeof(double);
+  *off_logp = off;
+  off += (size_t)B * sizeof(double);
+  *s_pad_out = s_pad;
+  return (off + 255) / 256 * 256;
+}
+
+ST_API size_t st_ctc_workspace_bytes(int T, int B, int C, int max_label_len) {
+  size_t a, b, l;
+  int sp;
+  return ctc_offsets(T, B, C, max_label_len, &a, &b, &l, &sp);
+}
+
+ST_API int st_ctc_loss(const float* logits, int64_t stride_t, int64_t stride_b, int T, int B, int C,
+                       const int32_t* labels, const int32_t* label_offsets, int max_label_len,
+                       const int32_t* seq_len, int blank, float* loss, float* grad, float grad_scale,
+                       void* grad_planes, int n_planes, int c_pad, int32_t* status, void* workspace,
+                       size_t workspace_bytes, st_stream_t stream) {
+  ST_CHECK_ARG(logits && label_offsets && seq_len && loss && status && workspace, "st_ctc_loss: null pointer");
+  ST_CHECK_ARG(T > 0 && B > 0 && C > 1 && C <= 64, "st_ctc_loss: need T,B > 0 and 1 < C <= 64 (C=%d)", C);
+  ST_CHECK_ARG(blank >= 0 && blank < C, "st_ctc_loss: blank outside [0,C)");
+  ST_CHECK_ARG(!grad_planes || (n_planes >= 1 && n_planes <= 3 && c_pad >= C && c_pad <= 64),
+               "st_ctc_loss: bad plane arguments");
+  ST_CHECK_ARG(max_label_len >= 0 && max_label_len <= 1023, "st_ctc_loss: max_label_len %d outside [0,1023]",
+               max_label_len);
+  size_t off_a, off_b, off_l;
+  int s_pad = 0;
+  const size_t need = ctc_offsets(T, B, C, max_label_len, &off_a, &off_b, &off_l, &s_pad);
+  ST_CHECK_ARG(workspace_bytes >= need, "st_ctc_loss: workspace %zu < required %zu bytes", workspace_bytes, need);
+  char* ws = static_cast<char*>(workspace);
+  float* lsm = reinterpret_cast<float*>(ws);
+  double* alpha = reinterpret_cast<double*>(ws + off_a);
+  double* beta = reinterpret_cast<double*>(ws + off_b);
+  double* logp = reinterpret_cast<double*>(ws + off_l);
+  cudaStream_t s = st_cu(stream);
+
+  const int rows = B * T;
+  ctc_log_softmax_kernel<<<(rows + 7) / 8, 256, 0, s>>>(logits, stride_t, stride_b, T, B, C, seq_len, lsm);
+  ST_CUDA_LAUNCH_CHECK("ctc_log_softmax_kernel");
+
+  const size_t smem = (size_t)2 * (s_pad + 4) * sizeof(double) + (size_t)s_pad * sizeof(int) + (size_t)(s_pad + 2) + 16;
+  if (smem > 48 * 1024) {
+    ST_CUDA_CALL(cudaFuncSetAttribute(ctc_alpha_beta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  }
+  ctc_alpha_beta_kernel<<<dim3(B, 2), kABThreads, smem, s>>>(lsm, T, C, labels, label_offsets, seq_len, blank,
+                                                            s_pad, alpha, beta, logp, loss, status);
+  ST_CUDA_LAUNCH_CHECK("ctc_alpha_beta_kernel");
+  if (grad || grad_planes) {
+    ctc_grad_kernel<<<(rows + 7) / 8, 256, 0, s>>>(lsm, alpha, beta, logp, labels, label_offsets, seq_len, status,
+                                                   T, B, C, blank, s_pad, grad_scale, grad, stride_t, stride_b,
+                                                   static_cast<__nv_bfloat16*>(grad_planes), n_planes, c_pad);
+    ST_CUDA_LAUNCH_CHECK("ctc_grad_kernel");
+  }
+  return ST_OK;
+}

@@ -1,0 +1,248 @@
+"""W2LEngine -- device-side state and step sequencing of the Wav2Letter hot path.
+
+What the reference does in one `sess.run` (speech_model.py:235) -- forward through 11 conv layers
+(speech_model.py:275-295), CTC loss (:74-75), gradients (:78), clip_by_global_norm (:80), Adam (:77,:81), greedy
+decode (:113) -- is sequenced here as calls into libspeecht_b200.so.  The engine owns:
+
+  * ONE flat fp32 buffer each for parameters, gradients, Adam m and Adam v (the 22 tensors of the model at
+    256-byte aligned offsets), so clip/Adam/allreduce are single streaming passes;
+  * per-shape activation buffers [B,T,C] (NWC, the reference layout);
+  * for the tensor-core precisions, a native plan object (csrc/w2l_plan.cu) that holds the bf16 operand planes and
+    enqueues the whole forward/backward.
+
+precision:
+  'fp32'   -- exact fp32 on the CUDA cores (FFMA).  Strict-accuracy path.
+  'bf16x3' -- tcgen05 tensor cores, every fp32 operand split into hi+lo bf16 planes, 3 products, fp32 accumulate in
+              TMEM.  Meets the 1e-4 activation / loss parity gates (measured in tests/test_gpu_parity.py).
+  'bf16'   -- tcgen05, single bf16 plane, fp32 accumulate (BASELINE configs 3-4).  Does NOT meet the 1e-4 gate.
+"""
+import math
+
+import numpy as np
+import torch
+
+from . import ops
+from ._lib import check, lib, ptr, stream_ptr
+
+PRECISIONS = ('fp32', 'bf16x3', 'bf16')
+
+
+def layer_table(input_size=128, num_classes=29):
+  """(filter_width, stride, cin, cout, relu) per layer -- reference speech_model.py:275-292."""
+  layers = [(48, 2, input_size, 250, True)]
+  layers += [(7, 1, 250, 250, True)] * 7
+  layers += [(32, 1, 250, 2000, True), (1, 1, 2000, 2000, True), (1, 1, 2000, num_classes, False)]
+  return layers
+
+
+class ParamLayout:
+  """Offsets (in floats) of filters / bias of every layer inside the flat buffers; 64-float (256 B) aligned."""
+
+  ALIGN = 64
+
+  def __init__(self, layers):
+    self.layers = layers
+    self.w_off, self.b_off = [], []
+    off = 0
+    for (k, _s, cin, cout, _r) in layers:
+      self.w_off.append(off)
+      off = self._up(off + k * cin * cout)
+      self.b_off.append(off)
+      off = self._up(off + cout)
+    self.total = off
+    self.n_params = sum(k * cin * cout + cout for (k, _s, cin, cout, _r) in layers)
+
+  def _up(self, x):
+    return (x + self.ALIGN - 1) // self.ALIGN * self.ALIGN
+
+  def views(self, flat):
+    out = []
+    for i, (k, _s, cin, cout, _r) in enumerate(self.layers):
+      w = flat[self.w_off[i]:self.w_off[i] + k * cin * cout].view(k, cin, cout)
+      b = flat[self.b_off[i]:self.b_off[i] + cout]
+      out.append((w, b))
+    return out
+
+
+class W2LEngine:
+
+  def __init__(self, input_size=128, num_classes=29, device=None, precision='fp32', process_group=None):
+    if not torch.cuda.is_available():
+      raise RuntimeError('speecht_b200 needs a CUDA device: there is no CPU fallback')
+    if precision not in PRECISIONS:
+      raise ValueError('precision must be one of %s' % (PRECISIONS,))
+    lib()                                                     # fail loudly if the native library is missing
+    self.device = torch.device(device if device is not None else 'cuda:%d' % torch.cuda.current_device())
+    self.input_size, self.num_classes = input_size, num_classes
+    self.precision = precision
+    self.layers = layer_table(input_size, num_classes)
+    self.layout = ParamLayout(self.layers)
+    n = self.layout.total
+    self.params = torch.zeros((n,), dtype=torch.float32, device=self.device)
+    self.grads = torch.zeros((n,), dtype=torch.float32, device=self.device)
+    self.adam_m = torch.zeros((n,), dtype=torch.float32, device=self.device)
+    self.adam_v = torch.zeros((n,), dtype=torch.float32, device=self.device)
+    self.weights = self.layout.views(self.params)
+    self.weight_grads = self.layout.views(self.grads)
+    self.global_step = 0
+    self.process_group = process_group
+    self.world_size = 1
+    if process_group is not None:
+      import torch.distributed as dist
+      self.world_size = dist.get_world_size(process_group)
+    self._normsq = torch.zeros((1,), dtype=torch.float64, device=self.device)
+    self._bufs = {}
+    self._plan = None
+    self._weights_version = 0
+    self.launches = 0                                         # native kernel launches issued (bench gpu_launches)
+
+  # ---------------------------------------------------------------- parameters
+  def init_xavier(self, seed=0):
+    """tf.contrib.layers.xavier_initializer on [K,Cin,Cout] + zero bias (speech_model.py:150-152)."""
+    rng = np.random.default_rng(seed)
+    for (k, _s, cin, cout, _r), (w, b) in zip(self.layers, self.weights):
+      limit = math.sqrt(6.0 / (k * cin + k * cout))
+      w.copy_(torch.from_numpy(rng.uniform(-limit, limit, size=(k, cin, cout)).astype(np.float32)))
+      b.zero_()
+    self.mark_weights_changed()
+
+  def load_weights(self, weights):
+    """weights: list of (filters [K,Cin,Cout], bias [Cout]) numpy arrays in the `export` .npy layout."""
+    if len(weights) != len(self.layers):
+      raise ValueError('expected %d layers, got %d' % (len(self.layers), len(weights)))
+    for (w, b), (wn, bn) in zip(self.weights, weights):
+      if tuple(wn.shape) != tuple(w.shape) or tuple(bn.shape) != tuple(b.shape):
+        raise ValueError('weight shape mismatch: %s vs %s' % (wn.shape, tuple(w.shape)))
+      w.copy_(torch.from_numpy(np.ascontiguousarray(wn, dtype=np.float32)))
+      b.copy_(torch.from_numpy(np.ascontiguousarray(bn, dtype=np.float32)))
+    self.mark_weights_changed()
+
+  def export_weights(self):
+    return [(w.cpu().numpy().copy(), b.cpu().numpy().copy()) for w, b in self.weights]
+
+  def mark_weights_changed(self):
+    self._weights_version += 1
+
+  def reset_optimizer(self):
+    self.adam_m.zero_()
+    self.adam_v.zero_()
+    self.global_step = 0
+
+  # ---------------------------------------------------------------- buffers
+  def _buf(self, name, shape, dtype=torch.float32):
+    key = (name, tuple(shape), dtype)
+    t = self._bufs.get(key)
+    if t is None:
+      # drop same-name buffers of other shapes so ragged batches do not accumulate memory
+      for k in [k for k in self._bufs if k[0] == name]:
+        del self._bufs[k]
+      t = torch.empty(shape, dtype=dtype, device=self.device)
+      self._bufs[key] = t
+    return t
+
+  def _out_lengths(self, T):
+    outs = []
+    t = T
+    for (k, s, _ci, _co, _r) in self.layers:
+      t = -(-t // s)
+      outs.append(t)
+    return outs
+
+  # ---------------------------------------------------------------- forward
+  def forward(self, inputs, keep_activations=False):
+    """inputs [B,T,input_size] f32 CUDA -> logits [T',B,num_classes] (time-major VIEW, speech_model.py:295)."""
+    if inputs.dim() != 3 or inputs.shape[2] != self.input_size:
+      raise ValueError('inputs must be [batch, time, %d]' % self.input_size)
+    inputs = inputs.contiguous()
+    if self.precision != 'fp32':
+      return self._tc().forward(inputs, keep_activations)
+    B, T, _ = inputs.shape
+    acts = [inputs]
+    x = inputs
+    for li, ((k, s, cin, cout, relu), (w, b)) in enumerate(zip(self.layers, self.weights)):
+      to = -(-x.shape[1] // s)
+      y = self._buf('act%d' % (li + 1), (B, to, cout))
+      ops.conv1d(x, w, b, stride=s, relu=relu, out=y)
+      self.launches += 1
+      x = y
+      if keep_activations:
+        acts.append(y)
+    self._acts = acts if keep_activations else None
+    self._logits_bm = x                                       # [B,T',C] batch-major storage
+    return x.transpose(0, 1)
+
+  # ---------------------------------------------------------------- backward (fp32 path)
+  def _backward_fp32(self, dlogits_bm):
+    acts = self._acts
+    dy = dlogits_bm
+    for li in reversed(range(len(self.layers))):
+      (k, s, cin, cout, relu) = self.layers[li]
+      dw, db = self.weight_grads[li]
+      y_act = acts[li + 1] if relu else None
+      ops.conv1d_backprop_filter(acts[li], dy, k, stride=s, y_act=y_act, dw=dw, db=db)
+      self.launches += 4
+      if li > 0:
+        dx = self._buf('dx%d' % (li & 1), tuple(acts[li].shape))
+        ops.conv1d_backprop_input(dy, self.weights[li][0], tuple(acts[li].shape), stride=s, y_act=y_act, out=dx)
+        self.launches += 1
+        dy = dx
+
+  # ---------------------------------------------------------------- steps
+  def _tc(self):
+    if self._plan is None:
+      from .tc_plan import TCPlan
+      self._plan = TCPlan(self)
+    return self._plan
+
+  def evaluate_step(self, inputs, sequence_lengths, labels=None, decode=True):
+    """model.step(update=False, decode=True): returns dict(loss [B] tensor|None, avg_loss, decoded, logits)."""
+    logits = self.forward(inputs, keep_activations=False)
+    ctc_len = np.asarray(sequence_lengths, dtype=np.int32) // 2      # speech_model.py:74,114
+    out = {'logits': logits, 'loss': None, 'avg_loss': None, 'decoded': None}
+    if labels is not None:
+      loss, _ = ops.ctc_loss(labels, logits, ctc_len, want_grad=False)
+      self.launches += 2
+      out['loss'] = loss
+      out['avg_loss'] = loss.mean()
+    if decode:
+      out['decoded'], out['neg_sum_logits'] = ops.ctc_greedy_decoder(logits, ctc_len)
+      self.launches += 1
+    return out
+
+  def train_step(self, inputs, sequence_lengths, labels, learning_rate, max_gradient_norm=5.0, decode=False):
+    """model.step(update=True): forward, CTC, backward, [allreduce], clip_by_global_norm, Adam.
+    Returns dict(avg_loss device scalar (LOCAL batch mean), loss [B], decoded|None)."""
+    if self.precision != 'fp32':
+      return self._tc().train_step(inputs, sequence_lengths, labels, learning_rate, max_gradient_norm, decode)
+    B = inputs.shape[0]
+    logits = self.forward(inputs, keep_activations=True)
+    ctc_len = np.asarray(sequence_lengths, dtype=np.int32) // 2
+    scale = 1.0 / (B * self.world_size)                                # tf.reduce_mean folded into the gradient
+    loss, dlogits = ops.ctc_loss(labels, logits, ctc_len, want_grad=True, grad_scale=scale)
+    self.launches += 3
+    out = {'loss': loss, 'avg_loss': loss.mean(), 'decoded': None, 'logits': logits}
+    if decode:
+      out['decoded'], out['neg_sum_logits'] = ops.ctc_greedy_decoder(logits, ctc_len)
+      self.launches += 1
+    self._backward_fp32(dlogits.transpose(0, 1))                        # batch-major storage, contiguous
+    self.apply_gradients(learning_rate, max_gradient_norm)
+    return out
+
+  def allreduce_gradients(self):
+    if self.world_size > 1:
+      import torch.distributed as dist
+      dist.all_reduce(self.grads, op=dist.ReduceOp.SUM, group=self.process_group)
+
+  def apply_gradients(self, learning_rate, max_gradient_norm=5.0):
+    """[allreduce] + tf.clip_by_global_norm + Adam(eps=1e-3) on the flat buffers (speech_model.py:77-82)."""
+    self.allreduce_gradients()
+    self.global_step += 1
+    self._normsq.zero_()
+    ops.global_norm_sq(self.grads, self._normsq)
+    ops.clip_adam(self.params, self.grads, self.adam_m, self.adam_v, self.global_step, learning_rate,
+                  max_norm=max_gradient_norm, normsq=self._normsq)
+    self.launches += 2
+    self.mark_weights_changed()
+
+  def grad_norm(self):
+    return float(torch.sqrt(ops.global_norm_sq(self.grads)).item())

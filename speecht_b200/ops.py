@@ -1,0 +1,268 @@
+"""Operator-level host mirror: one function per TensorFlow-1 / librosa call on the reference's hot path.
+
+Each function takes CUDA torch tensors (torch is only the allocator / stream owner), calls the C ABI in
+libspeecht_b200.so through ctypes and returns torch tensors.  Names and argument meaning follow the reference's
+call sites (file:line in the docstrings); errors are raised as Python exceptions like the reference's ops do.
+There is no CPU implementation here: without the CUDA library or a GPU these raise.
+"""
+from collections import namedtuple
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import check, lib, ptr, stream_ptr
+
+SparseTensorValue = namedtuple('SparseTensorValue', ['indices', 'values', 'dense_shape'])
+
+
+def _require_cuda(*tensors):
+  for t in tensors:
+    if t is not None and not t.is_cuda:
+      raise ValueError('speecht_b200 ops need CUDA tensors (no CPU fallback)')
+
+
+def same_padding(t_in, k, stride):
+  """TF 'SAME' geometry: (out, pad_left, pad_right)."""
+  out = -(-t_in // stride)
+  total = max((out - 1) * stride + k - t_in, 0)
+  return out, total // 2, total - total // 2
+
+
+# ------------------------------------------------------------------------------------------------
+# conv (exact fp32 path)
+# ------------------------------------------------------------------------------------------------
+def conv1d(value, filters, bias=None, stride=1, relu=False, out=None):
+  """tf.nn.conv1d(value, filters, stride, 'SAME') + tf.nn.bias_add + tf.nn.relu (speech_model.py:155,173,177).
+  value [B,T,Cin] f32, filters [K,Cin,Cout] f32 -> [B,ceil(T/stride),Cout]."""
+  _require_cuda(value, filters, bias)
+  value, filters = value.contiguous(), filters.contiguous()
+  B, T, Cin = value.shape
+  K, Cin2, Cout = filters.shape
+  if Cin2 != Cin:
+    raise ValueError('filter input channels %d != value channels %d' % (Cin2, Cin))
+  To = -(-T // stride)
+  if out is None:
+    out = torch.empty((B, To, Cout), device=value.device, dtype=torch.float32)
+  check(lib().st_conv1d_fwd_f32(ptr(value), ptr(filters), ptr(bias), ptr(out), B, T, Cin, Cout, K, stride,
+                                int(bool(relu)), stream_ptr()))
+  return out
+
+
+def conv1d_backprop_input(dy, filters, input_shape, stride=1, y_act=None, out=None):
+  """Gradient of conv1d wrt its input; y_act (the layer's post-ReLU output) fuses the ReLU backward mask."""
+  _require_cuda(dy, filters, y_act)
+  dy, filters = dy.contiguous(), filters.contiguous()
+  B, T, Cin = input_shape
+  K, _, Cout = filters.shape
+  if out is None:
+    out = torch.empty((B, T, Cin), device=dy.device, dtype=torch.float32)
+  check(lib().st_conv1d_bwd_data_f32(ptr(dy), ptr(y_act), ptr(filters), ptr(out), B, T, Cin, Cout, K, stride,
+                                     stream_ptr()))
+  return out
+
+
+def conv1d_backprop_filter(value, dy, filter_width, stride=1, y_act=None, dw=None, db=None):
+  """Gradient of conv1d+bias wrt filters [K,Cin,Cout] and bias [Cout]."""
+  _require_cuda(value, dy, y_act)
+  value, dy = value.contiguous(), dy.contiguous()
+  B, T, Cin = value.shape
+  Cout = dy.shape[2]
+  if dw is None:
+    dw = torch.empty((filter_width, Cin, Cout), device=value.device, dtype=torch.float32)
+  if db is None:
+    db = torch.empty((Cout,), device=value.device, dtype=torch.float32)
+  check(lib().st_conv1d_bwd_filter_f32(ptr(value), ptr(dy), ptr(y_act), ptr(dw), ptr(db), B, T, Cin, Cout,
+                                       filter_width, stride, stream_ptr()))
+  return dw, db
+
+
+# ------------------------------------------------------------------------------------------------
+# CTC
+# ------------------------------------------------------------------------------------------------
+def flatten_labels(labels):
+  """list of int sequences (or a SparseTensorValue as speech_input.py:48-69 builds) -> (flat int32, offsets int32)."""
+  if isinstance(labels, SparseTensorValue) or (hasattr(labels, 'indices') and hasattr(labels, 'dense_shape')):
+    B = int(labels.dense_shape[0])
+    rows = [[] for _ in range(B)]
+    for (b, _j), v in zip(np.asarray(labels.indices), np.asarray(labels.values)):
+      rows[int(b)].append(int(v))
+    labels = rows
+  lens = [len(l) for l in labels]
+  offsets = np.zeros((len(labels) + 1,), dtype=np.int32)
+  offsets[1:] = np.cumsum(lens)
+  flat = np.concatenate([np.asarray(l, dtype=np.int32).reshape(-1) for l in labels]) if sum(lens) else \
+    np.zeros((0,), dtype=np.int32)
+  return np.ascontiguousarray(flat, dtype=np.int32), offsets
+
+
+_ctc_ws_cache = {}
+
+
+def _workspace(key, nbytes, device):
+  buf = _ctc_ws_cache.get(key)
+  if buf is None or buf.numel() < nbytes or buf.device != device:
+    buf = torch.empty((max(int(nbytes), 256),), dtype=torch.uint8, device=device)
+    _ctc_ws_cache[key] = buf
+  return buf
+
+
+def ctc_loss(labels, logits, sequence_length, want_grad=True, grad_scale=1.0, grad_planes=None, time_major=True,
+             validate=True):
+  """tf.nn.ctc_loss(labels, logits, sequence_length) (speech_model.py:74) and its gradient.
+
+  logits: [T,B,C] (time_major, may be a transposed VIEW of a [B,T,C] buffer -- strides are honoured, no copy).
+  labels: list of int lists, or the sparse triple of speech_input.py:48-69.  Blank = C-1.
+  Returns (loss [B], grad like logits or None).  Raises CTCLabelError like TF's InvalidArgumentError when a label
+  does not fit its sequence."""
+  _require_cuda(logits)
+  if not time_major:
+    logits = logits.transpose(0, 1)
+  T, B, C = logits.shape
+  if logits.stride(2) != 1 or logits.dtype != torch.float32:
+    raise ValueError('logits must be float32 with unit class stride')
+  flat, offsets = flatten_labels(labels)
+  seq_host = np.ascontiguousarray(np.asarray(sequence_length.cpu() if torch.is_tensor(sequence_length)
+                                             else sequence_length, dtype=np.int32))
+  if validate:
+    check(lib().st_ctc_validate_labels_host(flat.ctypes.data, offsets.ctypes.data, seq_host.ctypes.data, B, T, C - 1))
+  dev = logits.device
+  max_len = int(np.max(np.diff(offsets))) if B else 0
+  d_flat = torch.from_numpy(flat if flat.size else np.zeros((1,), np.int32)).to(dev)
+  d_off = torch.from_numpy(offsets).to(dev)
+  d_seq = torch.from_numpy(seq_host).to(dev)
+  loss = torch.empty((B,), dtype=torch.float32, device=dev)
+  status = torch.empty((B,), dtype=torch.int32, device=dev)
+  grad = None
+  if want_grad:
+    grad = torch.empty_strided(logits.shape, logits.stride(), dtype=torch.float32, device=dev)
+  nbytes = lib().st_ctc_workspace_bytes(T, B, C, max_len)
+  ws = _workspace(('ctc', dev), nbytes, dev)
+  n_planes, c_pad = (0, 0) if grad_planes is None else (grad_planes.shape[0], grad_planes.shape[-1])
+  check(lib().st_ctc_loss(ptr(logits), logits.stride(0), logits.stride(1), T, B, C, ptr(d_flat), ptr(d_off), max_len,
+                          ptr(d_seq), C - 1, ptr(loss), ptr(grad), float(grad_scale), ptr(grad_planes), n_planes,
+                          c_pad, ptr(status), ptr(ws), ws.numel(), stream_ptr()))
+  return loss, grad
+
+
+def ctc_greedy_decoder(logits, sequence_length, merge_repeated=True):
+  """tf.nn.ctc_greedy_decoder(logits [T,B,C], sequence_length, merge_repeated) (speech_model.py:113-115).
+  Returns ([SparseTensorValue(indices int64 [N,2], values int64 [N], dense_shape int64 [2])], neg_sum_logits [B,1])
+  as numpy, like sess.run would hand it to evaluation.py:144,161-171."""
+  _require_cuda(logits)
+  T, B, C = logits.shape
+  if logits.stride(2) != 1 or logits.dtype != torch.float32:
+    raise ValueError('logits must be float32 with unit class stride')
+  dev = logits.device
+  if torch.is_tensor(sequence_length):
+    d_seq = sequence_length.to(device=dev, dtype=torch.int32)
+  else:
+    d_seq = torch.from_numpy(np.ascontiguousarray(np.asarray(sequence_length, dtype=np.int32))).to(dev)
+  values = torch.empty((B, max(T, 1)), dtype=torch.int32, device=dev)
+  counts = torch.empty((B,), dtype=torch.int32, device=dev)
+  neg = torch.empty((B,), dtype=torch.float32, device=dev)
+  check(lib().st_ctc_greedy_decode(ptr(logits), logits.stride(0), logits.stride(1), T, B, C, ptr(d_seq), C - 1,
+                                   int(bool(merge_repeated)), ptr(values), ptr(counts), ptr(neg), stream_ptr()))
+  return [sparse_from_rows(values, counts)], neg.cpu().numpy().reshape(B, 1)
+
+
+def sparse_from_rows(values, counts):
+  """[B,T] int32 rows + counts -> the SparseTensor triple TF returns (row-major order)."""
+  counts_h = counts.cpu().numpy().astype(np.int64)
+  values_h = values.cpu().numpy()
+  B = counts_h.shape[0]
+  n = int(counts_h.sum())
+  indices = np.zeros((n, 2), dtype=np.int64)
+  vals = np.zeros((n,), dtype=np.int64)
+  pos = 0
+  for b in range(B):
+    c = int(counts_h[b])
+    indices[pos:pos + c, 0] = b
+    indices[pos:pos + c, 1] = np.arange(c)
+    vals[pos:pos + c] = values_h[b, :c]
+    pos += c
+  shape = np.array([B, int(counts_h.max()) if B else 0], dtype=np.int64)
+  return SparseTensorValue(indices, vals, shape)
+
+
+# ------------------------------------------------------------------------------------------------
+# optimiser
+# ------------------------------------------------------------------------------------------------
+def global_norm_sq(flat_grads, accum=None):
+  """sum(g^2) over the flat gradient buffer (first half of tf.clip_by_global_norm, speech_model.py:80)."""
+  _require_cuda(flat_grads)
+  if accum is None:
+    accum = torch.zeros((1,), dtype=torch.float64, device=flat_grads.device)
+  check(lib().st_sumsq(ptr(flat_grads), flat_grads.numel(), ptr(accum), stream_ptr()))
+  return accum
+
+
+def clip_adam(params, grads, m, v, step, lr, max_norm=5.0, beta1=0.9, beta2=0.999, eps=1e-3, normsq=None,
+              grad_prescale=1.0):
+  """tf.clip_by_global_norm(grads, max_norm) + AdamOptimizer(lr, epsilon=1e-3).apply_gradients
+  (speech_model.py:77-82) on flat buffers, in place.  `normsq` = device double from global_norm_sq (None: no clip)."""
+  _require_cuda(params, grads, m, v)
+  check(lib().st_clip_adam(ptr(params), ptr(grads), ptr(m), ptr(v), params.numel(), float(lr), float(beta1),
+                           float(beta2), float(eps), int(step), float(max_norm), ptr(normsq), float(grad_prescale),
+                           stream_ptr()))
+
+
+# ------------------------------------------------------------------------------------------------
+# features
+# ------------------------------------------------------------------------------------------------
+def _hz_to_mel(f):
+  f = np.asarray(f, dtype=np.float64)
+  f_sp = 200.0 / 3
+  min_log_hz = 1000.0
+  logstep = np.log(6.4) / 27.0
+  return np.where(f >= min_log_hz, min_log_hz / f_sp + np.log(np.maximum(f, 1e-300) / min_log_hz) / logstep, f / f_sp)
+
+
+def _mel_to_hz(m):
+  m = np.asarray(m, dtype=np.float64)
+  f_sp = 200.0 / 3
+  min_log_hz = 1000.0
+  min_log_mel = min_log_hz / f_sp
+  logstep = np.log(6.4) / 27.0
+  return np.where(m >= min_log_mel, min_log_hz * np.exp(logstep * (m - min_log_mel)), f_sp * m)
+
+
+def mel_filterbank(sr, n_fft=512, n_mels=128):
+  """librosa.filters.mel(sr, n_fft, n_mels) defaults: Slaney scale, fmin 0, fmax sr/2, area-normalised."""
+  n_bins = 1 + n_fft // 2
+  fft_f = np.linspace(0.0, sr / 2.0, n_bins)
+  mel_f = _mel_to_hz(np.linspace(_hz_to_mel(0.0), _hz_to_mel(sr / 2.0), n_mels + 2))
+  fdiff = np.diff(mel_f)
+  ramps = mel_f[:, None] - fft_f[None, :]
+  w = np.maximum(0.0, np.minimum(-ramps[:-2] / fdiff[:-1, None], ramps[2:] / fdiff[1:, None]))
+  w *= (2.0 / (mel_f[2:] - mel_f[:-2]))[:, None]
+  return w.astype(np.float32)
+
+
+_mel_cache = {}
+
+
+def power_spectrogram(wav, n_samples, samplerate, n_mels=128, n_fft=512, hop_length=160):
+  """Batched calc_power_spectrogram (preprocessing.py:36-58) on the GPU.
+  wav [B, max_samples] f32 CUDA (rows zero-padded), n_samples int list -> (features [B,T_max,n_mels], frames [B])."""
+  _require_cuda(wav)
+  wav = wav.contiguous()
+  B, max_samples = wav.shape
+  n_host = np.ascontiguousarray(np.asarray(n_samples, dtype=np.int32))
+  if n_host.min() <= n_fft // 2:
+    raise ValueError('audio shorter than n_fft/2 cannot be reflect-padded')
+  dev = wav.device
+  key = (float(samplerate), n_fft, n_mels, dev)
+  basis = _mel_cache.get(key)
+  if basis is None:
+    basis = torch.from_numpy(mel_filterbank(samplerate, n_fft, n_mels)).to(dev)
+    _mel_cache[key] = basis
+  T_max = 1 + int(n_host.max()) // hop_length
+  out = torch.empty((B, T_max, n_mels), dtype=torch.float32, device=dev)
+  frames = torch.empty((B,), dtype=torch.int32, device=dev)
+  d_n = torch.from_numpy(n_host).to(dev)
+  nbytes = lib().st_melspec_workspace_bytes(B, max_samples, n_fft, hop_length, n_mels)
+  ws = _workspace(('mel', dev), nbytes, dev)
+  check(lib().st_melspec(ptr(wav), wav.stride(0), ptr(d_n), B, int(n_host.max()), ptr(basis), n_fft, hop_length,
+                         n_mels, ptr(out), T_max, ptr(frames), ptr(ws), ws.numel(), stream_ptr()))
+  return out, frames

@@ -1,0 +1,192 @@
+"""Input loaders (mirror of reference speecht/speech_input.py).
+
+Same class and method names -- BaseInputLoader._get_inputs_feed_item / _get_labels_feed_item, get_inputs,
+get_feed_dict, SingleInputLoader.set_input, InputBatchLoader.start_threads -- but the TF1 FIFOQueue(100) fed by
+enqueue ops (speech_input.py:147-156,181-207) is a plain bounded queue.Queue of ready host batches; model.step
+dequeues from it.  The feed layout is the reference's: inputs zero-padded to the batch max length with NO masking
+downstream (speech_input.py:38-43), labels as the COO triple with dense_shape [B, max input time]
+(speech_input.py:59-69).
+"""
+import queue
+import threading
+from abc import abstractmethod
+
+import numpy as np
+
+from .errors import OutOfRangeError
+from .ops import SparseTensorValue
+
+
+class Placeholder:
+  """Stands in for the tf.placeholder handles callers use as feed_dict keys."""
+
+  def __init__(self, name):
+    self.name = name
+
+  def __repr__(self):
+    return '<Placeholder %s>' % self.name
+
+
+class Coordinator:
+  """Minimal tf.train.Coordinator: should_stop / request_stop / register_thread / join."""
+
+  def __init__(self):
+    self._stop = threading.Event()
+    self._threads = []
+
+  def should_stop(self):
+    return self._stop.is_set()
+
+  def request_stop(self):
+    self._stop.set()
+
+  def register_thread(self, t):
+    self._threads.append(t)
+
+  def join(self, timeout=5.0):
+    for t in self._threads:
+      t.join(timeout)
+
+
+class BaseInputLoader:
+
+  def __init__(self, input_size):
+    self.input_size = input_size
+
+  def _get_inputs_feed_item(self, input_list):
+    """speech_input.py:27-45 -> (input_tensor [B,max_time,input_size] f32, sequence_lengths, max_time).
+    (The reference builds float64 and lets the f32 placeholder cast; building f32 directly is value-identical.)"""
+    sequence_lengths = np.array([inp.shape[0] for inp in input_list], dtype=np.int32)
+    max_time = int(sequence_lengths.max())
+    input_tensor = np.zeros((len(input_list), max_time, self.input_size), dtype=np.float32)
+    for idx, inp in enumerate(input_list):
+      input_tensor[idx, :inp.shape[0], :] = inp
+    return input_tensor, sequence_lengths, max_time
+
+  @staticmethod
+  def _get_labels_feed_item(label_list, max_time):
+    """speech_input.py:48-69 -> SparseTensorValue(indices [N,2], values [N], dense_shape [B, max_time])."""
+    label_shape = np.array([len(label_list), max_time], dtype=np.int64)
+    label_indices = []
+    label_values = []
+    for label_idx, label in enumerate(label_list):
+      for id_idx, identifier in enumerate(label):
+        label_indices.append([label_idx, id_idx])
+        label_values.append(identifier)
+    label_indices = np.array(label_indices, dtype=np.int64).reshape(-1, 2)
+    label_values = np.array(label_values, dtype=np.int64)
+    return SparseTensorValue(label_indices, label_values, label_shape)
+
+  @abstractmethod
+  def get_inputs(self):
+    raise NotImplementedError()
+
+  def get_feed_dict(self):
+    return None
+
+  def dequeue(self):
+    """Next ready batch (inputs, sequence_lengths, labels) or None when the loader feeds through get_feed_dict."""
+    return None
+
+
+class SingleInputLoader(BaseInputLoader):
+  """Feeds single inputs through the feed dict (speech_input.py:79-127)."""
+
+  def __init__(self, input_size):
+    super().__init__(input_size)
+    self.speech_input = None
+    self.inputs = Placeholder('inputs')
+    self.sequence_lengths = Placeholder('sequence_lengths')
+
+  def get_inputs(self):
+    return self.inputs, self.sequence_lengths, None
+
+  def get_feed_dict(self):
+    if self.speech_input is None:
+      raise ValueError('Speech input must be provided using `set_input` first!')
+    input_tensor, sequence_lengths, _max_time = self._get_inputs_feed_item([self.speech_input])
+    self.speech_input = None
+    return {self.inputs: input_tensor, self.sequence_lengths: sequence_lengths}
+
+  def set_input(self, speech_input):
+    self.speech_input = speech_input
+
+
+class InputBatchLoader(BaseInputLoader):
+  """Background threads assemble batches into a bounded queue (speech_input.py:130-218)."""
+
+  _END = object()
+
+  def __init__(self, input_size, batch_size, data_generator_creator, max_steps=None, capacity=100):
+    super().__init__(input_size)
+    self.batch_size = batch_size
+    self.data_generator_creator = data_generator_creator
+    self.steps_left = max_steps
+    self.inputs = Placeholder('inputs')
+    self.sequence_lengths = Placeholder('sequence_lengths')
+    self.labels = Placeholder('labels')
+    self.queue = queue.Queue(maxsize=capacity)
+    self._lock = threading.Lock()
+    self._live_threads = 0
+    self._closed = False
+
+  def get_inputs(self):
+    return self.inputs, self.sequence_lengths, self.labels
+
+  def _batch(self, iterable):
+    args = [iter(iterable)] * self.batch_size
+    return zip(*args)
+
+  def _put(self, item, coord):
+    while True:
+      try:
+        self.queue.put(item, timeout=0.1)
+        return True
+      except queue.Full:
+        if coord is not None and coord.should_stop():
+          return False
+
+  def _enqueue(self, sess, coord):
+    try:
+      data_generator = self.data_generator_creator()
+      for sample_batch in self._batch(data_generator):
+        input_list, label_list = zip(*sample_batch)
+        input_tensor, sequence_lengths, max_time = self._get_inputs_feed_item(input_list)
+        labels = self._get_labels_feed_item(label_list, max_time)
+        if not self._put((input_tensor, sequence_lengths, labels), coord):
+          break
+        # the reference decrements steps_left unsynchronised across feeder threads (speech_input.py:199-202);
+        # here the counter is locked so exactly max_steps batches are produced
+        with self._lock:
+          if self.steps_left is not None:
+            self.steps_left -= 1
+            if self.steps_left <= 0:
+              break
+        if coord is not None and coord.should_stop():
+          break
+    finally:
+      with self._lock:
+        self._live_threads -= 1
+        last = self._live_threads == 0
+      if last:
+        self._closed = True
+        self._put(self._END, None)
+
+  def start_threads(self, sess, coord, n_threads=1):
+    threads = []
+    with self._lock:
+      self._live_threads += n_threads
+    for _ in range(n_threads):
+      t = threading.Thread(target=self._enqueue, args=(sess, coord))
+      t.daemon = True
+      t.start()
+      coord.register_thread(t)
+      threads.append(t)
+    return threads
+
+  def dequeue(self):
+    item = self.queue.get()
+    if item is self._END:
+      self.queue.put(self._END)          # stay closed for any later step
+      raise OutOfRangeError('input queue is closed and has insufficient elements')
+    return item

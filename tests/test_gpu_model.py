@@ -1,0 +1,129 @@
+"""GPU parity tests, model level: the engine / SpeechModel.step against the oracle and the committed fixtures."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import speecht_oracle as O
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
+sys.path.insert(0, GOLDEN)
+
+
+def rel(a, b):
+  a = np.asarray(a, np.float64); b = np.asarray(b, np.float64)
+  return float(np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-30))
+
+
+def _engine(precision, weights):
+  from speecht_b200.engine import W2LEngine
+  eng = W2LEngine(precision=precision)
+  eng.load_weights(weights)
+  return eng
+
+
+# tolerance of the parity gate (BASELINE.json): 1e-4 relative for fp32-class arithmetic; bf16 is reported, not gated
+GATE = {'fp32': 1e-4, 'bf16x3': 1e-4, 'bf16': 5e-2}
+
+
+@pytest.mark.parametrize('precision', ['fp32', 'bf16x3', 'bf16'])
+def test_config1_evaluate_parity(precision):
+  """BASELINE configs[0]: evaluate --step-count 1 on 4 synthetic 1 s utterances: loss + greedy labels."""
+  import make_golden as G
+  g = np.load(os.path.join(GOLDEN, 'config1_eval.npz'))
+  inputs, lengths, labels = O.synthetic_batch(seed=0, batch=4, seconds=1)
+  weights = O.xavier_weights(np.random.default_rng(1234), dtype=np.float32)
+  eng = _engine(precision, weights)
+  res = eng.evaluate_step(torch.from_numpy(inputs).cuda(), lengths, labels)
+  logits = res['logits'].cpu().numpy()
+  assert logits.shape == g['logits'].shape == (51, 4, 29)
+  assert rel(logits, g['logits']) < GATE[precision], rel(logits, g['logits'])
+  assert rel(res['loss'].cpu().numpy(), g['loss']) < GATE[precision]
+  if precision != 'bf16':
+    np.testing.assert_array_equal(res['decoded'][0].values, g['decoded_values'])
+    np.testing.assert_array_equal(res['decoded'][0].indices, g['decoded_indices'])
+    np.testing.assert_array_equal(res['decoded'][0].dense_shape, g['decoded_shape'])
+
+
+@pytest.mark.parametrize('precision', ['fp32', 'bf16x3'])
+def test_ragged_batch_parity_padding_not_masked(precision):
+  g = np.load(os.path.join(GOLDEN, 'ragged_eval.npz'))
+  inputs, lengths, labels = O.synthetic_batch(seed=7, batch=4, seconds=[1, 2, 1, 3])
+  weights = O.xavier_weights(np.random.default_rng(1234), dtype=np.float32)
+  eng = _engine(precision, weights)
+  res = eng.evaluate_step(torch.from_numpy(inputs).cuda(), lengths, labels)
+  assert rel(res['logits'].cpu().numpy(), g['logits']) < 1e-4
+  assert rel(res['loss'].cpu().numpy(), g['loss']) < 1e-4
+  np.testing.assert_array_equal(res['decoded'][0].values, g['decoded_values'])
+  np.testing.assert_array_equal(res['decoded'][0].indices, g['decoded_indices'])
+
+
+@pytest.mark.parametrize('precision', ['fp32', 'bf16x3'])
+def test_train_step_parity(precision):
+  """One full model.step(update=True) on B=3 x 1 s: activations, gradients, global norm, Adam update vs oracle."""
+  inputs, lengths, labels = O.synthetic_batch(seed=3, batch=3, seconds=1)
+  weights = O.xavier_weights(np.random.default_rng(99), dtype=np.float32)
+  weights = [(w, (0.01 * np.random.default_rng(i).standard_normal(b.shape)).astype(np.float32))
+             for i, (w, b) in enumerate(weights)]
+  eng = _engine(precision, weights)
+  w64 = [(w.astype(np.float64), b.astype(np.float64)) for w, b in weights]
+  m = [(np.zeros_like(w), np.zeros_like(b)) for w, b in w64]
+  v = [(np.zeros_like(w), np.zeros_like(b)) for w, b in w64]
+  ref = O.train_step(inputs, lengths, labels, w64, m, v, step=1, lr=1e-4, dtype=np.float64)
+  res = eng.train_step(torch.from_numpy(inputs).cuda(), lengths, labels, 1e-4)
+  assert rel(res['loss'].cpu().numpy(), ref['loss']) < 1e-4
+  assert abs(res['avg_loss'].item() - ref['avg_loss']) < 1e-4 * abs(ref['avg_loss'])
+  assert abs(eng.grad_norm() - ref['grad_norm']) < 1e-4 * ref['grad_norm']
+  for li, ((dw, db), (rdw, rdb)) in enumerate(zip(eng.weight_grads, ref['grads'])):
+    assert rel(dw.cpu().numpy(), rdw) < 1e-4, (li, rel(dw.cpu().numpy(), rdw))
+    assert rel(db.cpu().numpy(), rdb) < 1e-4, (li, rel(db.cpu().numpy(), rdb))
+  for li, ((w, b), (rw, rb)) in enumerate(zip(eng.export_weights(), w64)):
+    assert rel(w, rw) < 1e-5 and np.max(np.abs(b - rb)) < 1e-5, li
+  assert eng.global_step == 1
+  # second step exercises Adam's bias correction with non-zero moments
+  ref2 = O.train_step(inputs, lengths, labels, w64, m, v, step=2, lr=1e-4, dtype=np.float64)
+  res2 = eng.train_step(torch.from_numpy(inputs).cuda(), lengths, labels, 1e-4)
+  assert abs(res2['avg_loss'].item() - ref2['avg_loss']) < 1e-4 * abs(ref2['avg_loss'])
+  for (w, b), (rw, rb) in zip(eng.export_weights(), w64):
+    assert rel(w, rw) < 1e-5
+
+
+def test_speech_model_step_surface():
+  """The reference-facing call: create_default_model + model.step in the orders training.py:63 and
+  evaluation.py:132-137 use, fed by an InputBatchLoader thread, ending with OutOfRangeError."""
+  import types
+  from speecht_b200 import speech_model, speech_input
+  from speecht_b200.errors import OutOfRangeError
+  inputs, lengths, labels = O.synthetic_batch(seed=0, batch=4, seconds=1)
+  samples = [(inputs[i, :lengths[i]], labels[i]) for i in range(4)]
+  loader = speech_input.InputBatchLoader(128, 2, lambda: iter(samples * 2), max_steps=3)
+  flags = types.SimpleNamespace(command='train', learning_rate=1e-4, learning_rate_decay_factor=0.5,
+                                max_gradient_norm=5.0, momentum=0.9, log_dir='/tmp/log', run_name='t',
+                                run_type='train', precision='fp32')
+  model = speech_model.create_default_model(flags, 128, loader)
+  with speech_model.Session() as sess:
+    model.restore_or_create(sess, '/tmp/speecht_b200_no_such_dir')
+    coord = speech_input.Coordinator()
+    loader.start_threads(sess, coord, n_threads=1)
+    out = model.step(sess)                                             # training.py:63
+    assert len(out) == 2 and np.isfinite(out[0]) and out[1] is None
+    assert model.global_step.eval() == 1
+    avg_loss, decoded, label = model.step(sess, update=False, decode=True, return_label=True)   # evaluation.py:136
+    assert decoded[0].indices.shape[1] == 2 and label.dense_shape.tolist() == [2, 101]
+    assert model.global_step.eval() == 1
+    model.step(sess)
+    with pytest.raises(OutOfRangeError):
+      model.step(sess)
+    lr0 = model.learning_rate.eval()
+    sess.run(model.learning_rate_decay_op)
+    assert abs(model.learning_rate.eval() - 0.5 * lr0) < 1e-12
+    path = model.saver.save(sess, '/tmp/speecht_b200_ckpt/speechT.ckpt', global_step=model.global_step) \
+      if os.makedirs('/tmp/speecht_b200_ckpt', exist_ok=True) is None else None
+    before = model.engine.params.clone()
+    model.engine.params.zero_()
+    model.restore(sess, '/tmp/speecht_b200_ckpt')
+    assert torch.equal(before, model.engine.params) and model.global_step.eval() == 2
+    coord.request_stop(); coord.join()

@@ -176,21 +176,17 @@ def same_padding(t_in: int, k: int, stride: int) -> Tuple[int, int, int]:
   return out, total // 2, total - total // 2
 
 
-def _im2col(x: np.ndarray, k: int, stride: int):
-  b, t, c = x.shape
-  out, left, right = same_padding(t, k, stride)
-  xp = np.pad(x, ((0, 0), (left, right), (0, 0)))
-  win = np.lib.stride_tricks.sliding_window_view(xp, k, axis=1)      # [B, Tp-K+1, C, K]
-  win = win[:, ::stride][:, :out]                                    # [B, out, C, K]
-  return win, out
-
-
 def conv1d_same(x: np.ndarray, w: np.ndarray, bias: np.ndarray, stride: int, relu: bool):
   """tf.nn.conv1d(value[B,T,Cin], filters[K,Cin,Cout], stride, 'SAME') (cross-correlation) + bias_add
-  + optional relu (speech_model.py:155,173,177)."""
-  k = w.shape[0]
-  win, out = _im2col(x, k, stride)
-  y = np.tensordot(win, w, axes=([3, 2], [0, 1]))                    # [B, out, Cout]
+  + optional relu (speech_model.py:155,173,177).  One BLAS GEMM per filter tap."""
+  k, cin, cout = w.shape
+  b, t, _ = x.shape
+  out, left, right = same_padding(t, k, stride)
+  xp = np.pad(x, ((0, 0), (left, right), (0, 0)))
+  y = np.zeros((b, out, cout), dtype=x.dtype)
+  span = (out - 1) * stride + 1
+  for j in range(k):
+    y += np.matmul(xp[:, j:j + span:stride], w[j])
   y = y + bias
   return np.maximum(y, 0) if relu else y
 
@@ -199,14 +195,16 @@ def conv1d_same_backward(x, w, stride, dy):
   """Gradients of y = conv1d_same(x, w) (pre-activation) wrt x, w, bias."""
   k, cin, cout = w.shape
   b, t, _ = x.shape
-  win, out = _im2col(x, k, stride)
-  dw = np.tensordot(win, dy, axes=([0, 1], [0, 1])).transpose(1, 0, 2)   # [C,K,Cout] -> [K,C,Cout]
-  db = dy.sum(axis=(0, 1))
-  _, left, right = same_padding(t, k, stride)
+  out, left, right = same_padding(t, k, stride)
+  xp = np.pad(x, ((0, 0), (left, right), (0, 0)))
+  span = (out - 1) * stride + 1
+  dy2 = dy.reshape(-1, cout)
+  dw = np.empty_like(w, dtype=dy.dtype)
   dxp = np.zeros((b, t + left + right, cin), dtype=dy.dtype)
   for j in range(k):
-    contrib = dy @ w[j].T                                               # [B,out,Cin]
-    dxp[:, j:j + out * stride:stride][:, :out] += contrib
+    dw[j] = np.ascontiguousarray(xp[:, j:j + span:stride]).reshape(-1, cin).T @ dy2
+    dxp[:, j:j + span:stride] += np.matmul(dy, w[j].T)
+  db = dy.sum(axis=(0, 1))
   dx = dxp[:, left:left + t]
   return dx, dw, db
 

@@ -95,6 +95,8 @@ class W2LEngine:
     self._plan = None
     self._weights_version = 0
     self.launches = 0                                         # native kernel launches issued (bench gpu_launches)
+    self.record_kernel_times = False                          # bench.py: CUDA events around the conv kernels
+    self.kernel_times = []                                    # (kernel name, algorithmic flops, start, stop)
 
   # ---------------------------------------------------------------- parameters
   def init_xavier(self, seed=0):
@@ -127,6 +129,59 @@ class W2LEngine:
     self.adam_m.zero_()
     self.adam_v.zero_()
     self.global_step = 0
+
+  # ---------------------------------------------------------------- per-kernel timing (bench.py roofline)
+  class _Timed:
+    def __init__(self, eng, name, flops):
+      self.eng, self.name, self.flops = eng, name, flops
+
+    def __enter__(self):
+      if self.eng.record_kernel_times:
+        self.e0 = torch.cuda.Event(enable_timing=True)
+        self.e1 = torch.cuda.Event(enable_timing=True)
+        self.e0.record()
+
+    def __exit__(self, *exc):
+      if self.eng.record_kernel_times:
+        self.e1.record()
+        self.eng.kernel_times.append((self.name, self.flops, self.e0, self.e1))
+      return False
+
+  def _timed(self, name, flops):
+    return W2LEngine._Timed(self, name, flops)
+
+  def roofline_report(self, peaks_path=None):
+    """Roofline of the dominant kernel from the events recorded inside the timed steps: achieved = algorithmic
+    FLOPs of its launches / their summed CUDA-event duration; peak = MEASURED_PEAKS.json (sustained bf16 figure,
+    the kernel is timed inside a long step) or the B200_PROFILING.md fallback."""
+    import json
+    import os
+    torch.cuda.synchronize(self.device)
+    by = {}
+    for name, flops, e0, e1 in self.kernel_times:
+      ms = e0.elapsed_time(e1)
+      acc = by.setdefault(name, [0.0, 0.0, 0])
+      acc[0] += flops; acc[1] += ms; acc[2] += 1
+    if not by:
+      return None
+    peak, src = 1590.0, 'fallback 1.59 PFLOP/s (B200_PROFILING.md)'
+    if peaks_path and os.path.exists(peaks_path):
+      pk = json.load(open(peaks_path))
+      peak, src = float(pk.get('bf16_tflops_sustained', pk.get('bf16_tflops'))), 'MEASURED_PEAKS.json bf16_tflops_sustained'
+    name = max(by, key=lambda k: by[k][1])
+    flops, ms, n = by[name]
+    achieved = flops / (ms * 1e-3) / 1e12
+    passes = {'fp32': None, 'bf16x3': 3, 'bf16': 1}[self.precision]
+    rep = {'kernel': name, 'bound': 'tensor', 'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s',
+           'frac': achieved / peak, 'traffic': None, 'launches': n, 'avg_launch_ms': ms / n, 'peak_source': src,
+           'kernels': {k: {'tflops': v[0] / (v[1] * 1e-3) / 1e12, 'ms_total': v[1], 'launches': v[2]}
+                       for k, v in by.items()}}
+    if passes:
+      rep['mma_passes'] = passes
+      rep['tensor_pipe_frac'] = passes * achieved / peak
+    else:
+      rep['note'] = 'fp32 FFMA path: compared with the bf16 tensor peak only for reference'
+    return rep
 
   # ---------------------------------------------------------------- buffers
   def _buf(self, name, shape, dtype=torch.float32):
@@ -162,7 +217,8 @@ class W2LEngine:
     for li, ((k, s, cin, cout, relu), (w, b)) in enumerate(zip(self.layers, self.weights)):
       to = -(-x.shape[1] // s)
       y = self._buf('act%d' % (li + 1), (B, to, cout))
-      ops.conv1d(x, w, b, stride=s, relu=relu, out=y)
+      with self._timed('conv_gemm_f32_kernel', 2.0 * k * cin * cout * to * B):
+        ops.conv1d(x, w, b, stride=s, relu=relu, out=y)
       self.launches += 1
       x = y
       if keep_activations:
@@ -179,11 +235,14 @@ class W2LEngine:
       (k, s, cin, cout, relu) = self.layers[li]
       dw, db = self.weight_grads[li]
       y_act = acts[li + 1] if relu else None
-      ops.conv1d_backprop_filter(acts[li], dy, k, stride=s, y_act=y_act, dw=dw, db=db)
-      self.launches += 4
+      flops = 2.0 * k * cin * cout * dy.shape[0] * dy.shape[1]
+      with self._timed('conv_gemm_f32_kernel', flops):
+        ops.conv1d_backprop_filter(acts[li], dy, k, stride=s, y_act=y_act, dw=dw, db=db)
+      self.launches += 2
       if li > 0:
         dx = self._buf('dx%d' % (li & 1), tuple(acts[li].shape))
-        ops.conv1d_backprop_input(dy, self.weights[li][0], tuple(acts[li].shape), stride=s, y_act=y_act, out=dx)
+        with self._timed('conv_gemm_f32_kernel', flops):
+          ops.conv1d_backprop_input(dy, self.weights[li][0], tuple(acts[li].shape), stride=s, y_act=y_act, out=dx)
         self.launches += 1
         dy = dx
 

@@ -157,7 +157,7 @@ def save_exported_weights(directory, weights):
 class SpeechModel:
 
   def __init__(self, input_loader: BaseInputLoader, input_size: int, num_classes: int, precision: str = 'bf16x3',
-               process_group=None, device=None):
+               process_group=None, device=None, engine=None):
     """
     Args:
       input_loader: the object that provides input batches
@@ -169,7 +169,8 @@ class SpeechModel:
     self.input_size = input_size
     self.convolution_count = 0
     self.inputs, self.sequence_lengths, self.labels = input_loader.get_inputs()
-    self.engine = self._create_network(num_classes, precision, process_group, device)
+    self.engine = engine if engine is not None else self._create_network(num_classes, precision, process_group,
+                                                                         device)
     self.global_step = _GlobalStep(self.engine)
     self._training = False
     self._decoding = False
@@ -295,7 +296,8 @@ def create_default_model(flags, input_size: int, speech_input: BaseInputLoader) 
   """speech_model.py:298-324: same flag names; `flags.precision` (optional) selects the conv arithmetic."""
   model = Wav2LetterModel(input_loader=speech_input, input_size=input_size, num_classes=vocabulary.SIZE + 1,
                           precision=getattr(flags, 'precision', 'bf16x3'),
-                          process_group=getattr(flags, 'process_group', None))
+                          process_group=getattr(flags, 'process_group', None),
+                          engine=getattr(flags, 'engine', None))
   if flags.command == 'train':
     model.add_training_ops(learning_rate=flags.learning_rate,
                            learning_rate_decay_factor=flags.learning_rate_decay_factor,

@@ -104,7 +104,11 @@ class ClockSampler:
     for line in self.proc.stdout:
       self.lines.append(line.strip())
 
-  def stop(self):
+  def mark(self):
+    return len(self.lines)
+
+  def stop(self, first=0, last=None):
+    self.lines = self.lines[first:last]
     if self.proc is None:
       return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
     self.proc.terminate()
@@ -229,16 +233,17 @@ def run_ours(args, rank, local_rank, world):
     h = host_sets[i % n_sets]
     eng.train_step(dev_inputs[i % n_sets], h[1], h[2], lr)
 
+  sampler = ClockSampler(local_rank)
+  if rank == 0:
+    sampler.start()                                          # nvidia-smi needs ~1 s before its first sample
   for i in range(args.warmup):
     step_resident(i)
   eng.kernel_times = []                                      # (name, flops, event pair) recorded inside the steps
   eng.record_kernel_times = True
   launches0 = eng.launches
-  sampler = ClockSampler(local_rank)
-  if rank == 0:
-    sampler.start()
+  mark0 = sampler.mark()
   ms_total = timed(step_resident, args.steps)
-  clocks = sampler.stop() if rank == 0 else None
+  mark1 = sampler.mark()
   launches = eng.launches - launches0
   eng.record_kernel_times = False
   ms_step = ms_total / args.steps
@@ -277,6 +282,12 @@ def run_ours(args, rank, local_rank, world):
     model.step(sess)
   e2e_ms = timed(lambda i: model.step(sess), args.steps) / args.steps
   e2e_value = world * B / (e2e_ms * 1e-3)
+  clocks = None
+  if rank == 0:
+    mark2 = sampler.mark()
+    # samples taken during the device-resident timed region; if it was shorter than the 100 ms sampling period,
+    # fall back to everything up to the end of the e2e region (same kernels, same load)
+    clocks = sampler.stop(mark0, mark1 if mark1 > mark0 else mark2)
 
   if world > 1:
     dist.destroy_process_group()

@@ -1,0 +1,65 @@
+// Internal interface between the tcgen05 conv kernels (conv_tc.cu) and the step plan (w2l_plan.cu).
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace tc {
+
+constexpr int kTileM = 128;      // output rows (time steps of one utterance) per tile
+constexpr int kChunkK = 64;      // bf16 elements per 128-byte swizzled shared-memory row
+
+// ---- forward / data-gradient kernel: D[b,t,n] = sum_{tap j, chunk c} A[b, t+shift_j, acol_j + c] * Bm[n + j*brow, j*bcol + c]
+struct ConvParams {
+  // contraction
+  int taps, chunks_per_tap, pad_left, a_sign, a_stride, a_cin;
+  int b_row_step, b_col_step, b_plane_rows;
+  // output tiling
+  int B, To, N, m_tiles_per_utt, n_tiles;
+  // epilogue
+  const float* bias;
+  int relu;
+  __nv_bfloat16* out_planes;
+  int64_t out_plane_stride;      // elements between planes
+  int ld_out;
+  float* out_f32;
+  int ld_f32;
+  const __nv_bfloat16* mask_hi;  // same [B,To,ld_mask] indexing as the output; value > 0 passes
+  int ld_mask;
+};
+
+// ---- filter-gradient kernel: dW[j, ci, co] += sum_{b,t} X[b, t+shift_j, acol_j + ci] * dZ[b, t, co]
+struct WgradParams {
+  int B, To, t_chunks;
+  int taps, pad_left, a_stride, a_cin;
+  int m_tiles, n_tiles, split;
+  int Cin, Cout;
+  float* dW;
+  int use_atomic;
+};
+
+int make_map_3d(CUtensorMap* map, const void* base, int C, int T, int Bn, int64_t ld, int64_t batch_stride,
+                int box_c, int box_t);
+int make_map_2d(CUtensorMap* map, const void* base, int cols, int rows, int64_t ld, int box_c, int box_r);
+
+// block_n: 32 or 256 (conv) / 64 or 256 (wgrad); n_planes: 1 or 2.
+int launch_conv(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvParams& p, int block_n, int n_planes,
+                cudaStream_t stream);
+int launch_wgrad(const CUtensorMap& tmX, const CUtensorMap& tmDZ, const WgradParams& p, int block_n, int n_planes,
+                 cudaStream_t stream);
+
+// fp32 [B][T][F] -> planes [n_planes][B][Tpad][F] (rows t >= T zero)
+int launch_split_input(const float* x, __nv_bfloat16* planes, int B, int T, int Tpad, int F, int n_planes,
+                       cudaStream_t stream);
+// W [K][Cin][Cout] fp32 -> forward layout planes [n][Cout][K*cin_p] (K-major), backward layout planes [n][K*Cin][ld_co]
+int launch_pack_filter(const float* w, int K, int Cin, int Cout, __nv_bfloat16* fwd, int cin_p, __nv_bfloat16* bwd,
+                       int ld_co, int n_planes, cudaStream_t stream);
+// db[n] = sum over rows and planes of dz planes [n_planes][rows][ld]
+int launch_bias_grad(const __nv_bfloat16* dz, int64_t rows, int N, int ld, int n_planes, float* db,
+                     cudaStream_t stream);
+// planes [n][rows][ld] -> fp32 [rows][cols] (debug / tests)
+int launch_merge_planes(const __nv_bfloat16* planes, int64_t rows, int cols, int ld, int n_planes, float* dst,
+                        int64_t ld_dst, cudaStream_t stream);
+
+}  // namespace tc

@@ -102,6 +102,33 @@ int st_melspec(const float* wav, int64_t wav_stride, const int32_t* n_samples, i
                float* out, int T_max, int32_t* out_frames, void* workspace, size_t workspace_bytes,
                st_stream_t stream);
 
+/* ---- a6 on the tensor cores + a13: the whole step as a plan                     speech_model.py:235,275-295 ----
+ * For a fixed (batch B, time T) shape the 11-layer stack is a fixed launch sequence of tcgen05/TMEM/TMA
+ * implicit-GEMM kernels (csrc/conv_tc.cu) over bf16 operand planes (n_planes = ST_PREC_BF16 or ST_PREC_BF16X3).
+ * The plan owns no device memory: the caller provides one arena (st_plan_arena_bytes, 1024-byte aligned) and the
+ * flat fp32 parameter / gradient buffers (layout: per layer filters [K,Cin,Cout] then bias [Cout], each start
+ * rounded up to 64 floats; st_plan_param_floats gives the total).
+ *   st_plan_pack_weights : fp32 parameters -> bf16 operand planes (call after every parameter change)
+ *   st_plan_forward      : inputs [B,T,input_size] fp32 -> logits fp32 [B,T',32] at st_plan_logits (classes 0..C-1
+ *                          valid; view it time-major with stride_t=32, stride_b=T'*32, T' = st_plan_logit_frames)
+ *   st_plan_backward     : consumes d(loss)/d(logits) from the bf16 planes [n_planes][B][T'][64] at
+ *                          st_plan_dlogits_planes (st_ctc_loss writes them with c_pad=64) -> flat gradient buffer
+ *   st_plan_get_activation: output of layer 0..9 merged back to fp32 [B,T',Cout] (parity tests); -1 = input planes */
+typedef struct st_plan st_plan;
+int st_plan_create(st_plan** out, int B, int T, int input_size, int num_classes, int n_planes);
+int st_plan_destroy(st_plan* plan);
+size_t st_plan_arena_bytes(const st_plan* plan);
+int64_t st_plan_param_floats(const st_plan* plan);
+int st_plan_logit_frames(const st_plan* plan);
+int st_plan_bind(st_plan* plan, void* arena, size_t arena_bytes, float* params, float* grads);
+int st_plan_pack_weights(st_plan* plan, st_stream_t stream);
+int st_plan_forward(st_plan* plan, const float* inputs, st_stream_t stream);
+int st_plan_backward(st_plan* plan, st_stream_t stream);
+float* st_plan_logits(st_plan* plan);
+void* st_plan_dlogits_planes(st_plan* plan);
+int st_plan_get_activation(st_plan* plan, int layer, float* dst, st_stream_t stream);
+int st_plan_launches(const st_plan* plan);
+
 #ifdef __cplusplus
 }
 #endif

@@ -48,6 +48,19 @@ _SIGNATURES = {
   'st_clip_adam': (c_int, [P, P, P, P, c_int64, c_float, c_float, c_float, c_float, c_int64, c_float, P, c_float, P]),
   'st_melspec_workspace_bytes': (c_size_t, [c_int, c_int, c_int, c_int, c_int]),
   'st_melspec': (c_int, [P, c_int64, P, c_int, c_int, P, c_int, c_int, c_int, P, c_int, P, P, c_size_t, P]),
+  'st_plan_create': (c_int, [ctypes.POINTER(c_void_p), c_int, c_int, c_int, c_int, c_int]),
+  'st_plan_destroy': (c_int, [P]),
+  'st_plan_arena_bytes': (c_size_t, [P]),
+  'st_plan_param_floats': (c_int64, [P]),
+  'st_plan_logit_frames': (c_int, [P]),
+  'st_plan_bind': (c_int, [P, P, c_size_t, P, P]),
+  'st_plan_pack_weights': (c_int, [P, P]),
+  'st_plan_forward': (c_int, [P, P, P]),
+  'st_plan_backward': (c_int, [P, P]),
+  'st_plan_logits': (c_void_p, [P]),
+  'st_plan_dlogits_planes': (c_void_p, [P]),
+  'st_plan_get_activation': (c_int, [P, c_int, P, P]),
+  'st_plan_launches': (c_int, [P]),
 }
 
 _lib = None

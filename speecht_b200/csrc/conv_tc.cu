@@ -1,0 +1,752 @@
+// a6 on the 5th-generation tensor cores: conv1d 'SAME' + bias + ReLU, its data gradient and its filter gradient
+// as TMA-fed tcgen05 implicit GEMMs with fp32 accumulators in TMEM.  Replaces tf.nn.conv1d / bias_add / relu
+// (reference speech_model.py:155,173,177) and the gradients TF autodiff derives (speech_model.py:78).
+//
+// Operand format: every fp32 tensor is held as `NPL` bf16 planes whose sum is the value (NPL=1: plain bf16;
+// NPL=2: hi + lo split, x = hi + lo + O(2^-17 |x|)).  A product of two split operands is accumulated as
+// hi*hi + hi*lo + lo*hi (3 MMAs, the lo*lo term is below 2^-16 relative) in ONE fp32 TMEM accumulator.
+//
+// Layout (NWC, the reference's): activations [plane][batch][time][channels], channels contiguous, so a tile of 128
+// time steps x 64 channels is one 3-D TMA box {64, 128, 1}; a filter tap k just shifts the time coordinate by
+// (k - pad_left) and TMA's out-of-bounds zero fill IS the 'SAME' zero padding (no halo buffers, no im2col).
+// Stride 2 (layer 0) is expressed on the pair view [B, T/2, 2*Cin] of the same memory.
+//
+// tc_conv_kernel (forward and data gradient): persistent, one CTA per SM, 192 threads:
+//   warp 0   : TMA producer  (A planes + B planes of one 64-wide K chunk per pipeline stage)
+//   warp 1   : TMEM allocator + single-thread tcgen05.mma issuer (128 x BLOCK_N x 16 per instruction)
+//   warps 2-5: epilogue: tcgen05.ld 32 lanes x 32 columns, +bias, ReLU / ReLU-mask, split to planes, 16-byte stores
+// Two accumulator stages in TMEM (2 x BLOCK_N columns) overlap the epilogue of tile i with the MMAs of tile i+1.
+// tc_wgrad_kernel (filter gradient): same roles; both operands are MN-major (the contraction runs over time, the
+// slow axis), expressed through the MN-major SWIZZLE_128B shared-memory descriptors; split-K over (batch, time).
+//
+// Roofline: tensor-pipe bound.  Algorithmic FLOPs per launch = 2*K*Cin*Cout*T'*B (unpadded); the tensor pipe
+// executes NPL==2 ? 3x : 1x that (plus <= 2.4 % channel / 2.2 % time padding).
+#include "st_common.cuh"
+#include "conv_tc.h"
+#include "tc_ptx.cuh"
+
+namespace tc {
+
+namespace {
+
+constexpr int kThreads = 192;
+constexpr int kSmemBudget = 227 * 1024;
+
+template <int BLOCK_N, int NPL>
+struct ConvCfg {
+  static constexpr int A_BYTES = kTileM * kChunkK * 2;           // 16 KB: 128 rows x 128 B
+  static constexpr int B_BYTES = BLOCK_N * kChunkK * 2;
+  static constexpr int STAGE_BYTES = NPL * (A_BYTES + B_BYTES);
+  static constexpr int STAGES_RAW = (kSmemBudget - 2048) / STAGE_BYTES;
+  static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 2048;  // 1024 alignment slack + barriers
+  static constexpr int TMEM_COLS = 2 * BLOCK_N < 32 ? 32 : 2 * BLOCK_N;
+  static_assert(STAGES >= 2, "pipeline needs at least two stages");
+  static_assert(TMEM_COLS == 64 || TMEM_COLS == 128 || TMEM_COLS == 256 || TMEM_COLS == 512, "TMEM columns");
+};
+
+__device__ __forceinline__ int floordiv(int a, int b) {
+  int q = a / b;
+  return (a % b != 0 && ((a < 0) != (b < 0))) ? q - 1 : q;
+}
+
+__device__ __forceinline__ uint32_t pack_bf16x2(__nv_bfloat16 lo, __nv_bfloat16 hi) {
+  return (uint32_t)__bfloat16_as_ushort(lo) | ((uint32_t)__bfloat16_as_ushort(hi) << 16);
+}
+
+// Splits 8 fp32 values into NPL planes and stores each plane's 8 bf16 as one 16-byte vector.
+template <int NPL>
+__device__ __forceinline__ void store_planes8(__nv_bfloat16* dst, int64_t plane_stride, const float* v) {
+  float rem[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) rem[i] = v[i];
+#pragma unroll
+  for (int p = 0; p < NPL; ++p) {
+    __nv_bfloat16 h[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      h[i] = __float2bfloat16_rn(rem[i]);
+      rem[i] -= __bfloat162float(h[i]);
+    }
+    uint4 pk;
+    pk.x = pack_bf16x2(h[0], h[1]);
+    pk.y = pack_bf16x2(h[2], h[3]);
+    pk.z = pack_bf16x2(h[4], h[5]);
+    pk.w = pack_bf16x2(h[6], h[7]);
+    *reinterpret_cast<uint4*>(dst + p * plane_stride) = pk;
+  }
+}
+
+template <int BLOCK_N, int NPL>
+__global__ void __launch_bounds__(kThreads, 1)
+tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const ConvParams p) {
+  using Cfg = ConvCfg<BLOCK_N, NPL>;
+  constexpr int STAGES = Cfg::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  // SWIZZLE_128B tiles need 1024-byte alignment in the shared window
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full = empty_bar + STAGES;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int num_tiles = p.B * p.m_tiles_per_utt * p.n_tiles;
+  const int m_tiles = p.B * p.m_tiles_per_utt;
+  const int nk = p.taps * p.chunks_per_tap;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmA);
+    prefetch_tmap(&tmB);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full_bar + s, 1);
+      mbar_init(empty_bar + s, 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tmem_full + a, 1);
+      mbar_init(tmem_empty + a, 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================================================== TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int mt = tile % m_tiles, nt = tile / m_tiles;          // m fastest: a wave shares one filter slab
+        const int b = mt / p.m_tiles_per_utt;
+        const int t0 = (mt - b * p.m_tiles_per_utt) * kTileM;
+        const int n0 = nt * BLOCK_N;
+        for (int it = 0; it < nk; ++it) {
+          const int j = it / p.chunks_per_tap, cc = it - j * p.chunks_per_tap;
+          const int m = p.a_sign * (j - p.pad_left);
+          const int shift = p.a_stride == 1 ? m : floordiv(m, p.a_stride);
+          const int a_col = (m - shift * p.a_stride) * p.a_cin + cc * kChunkK;
+          mbar_wait(empty_bar + stage, phase ^ 1);
+          mbar_expect_tx(full_bar + stage, Cfg::STAGE_BYTES);
+          uint8_t* st = smem + stage * Cfg::STAGE_BYTES;
+#pragma unroll
+          for (int pl = 0; pl < NPL; ++pl)
+            tma_load_3d(&tmA, full_bar + stage, st + pl * Cfg::A_BYTES, a_col, t0 + shift, pl * p.B + b);
+#pragma unroll
+          for (int pl = 0; pl < NPL; ++pl)
+            tma_load_2d(&tmB, full_bar + stage, st + NPL * Cfg::A_BYTES + pl * Cfg::B_BYTES,
+                        j * p.b_col_step + cc * kChunkK, pl * p.b_plane_rows + n0 + j * p.b_row_step);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ===================================================== MMA issuer (one thread)
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(kTileM, BLOCK_N, 0, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      int local = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
+        const int acc = local & 1;
+        const uint32_t acc_phase = (local >> 1) & 1;
+        mbar_wait(tmem_empty + acc, acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+        for (int it = 0; it < nk; ++it) {
+          mbar_wait(full_bar + stage, phase);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+          const uint32_t b_addr = a_addr + NPL * Cfg::A_BYTES;
+          uint32_t accumulate = it > 0 ? 1u : 0u;
+          // products, smallest first: lo*hi, hi*lo, hi*hi (NPL==2) / hi*hi (NPL==1)
+#pragma unroll
+          for (int pr = 0; pr < (NPL == 2 ? 3 : 1); ++pr) {
+            const int pa = (NPL == 2) ? (pr == 0 ? 1 : 0) : 0;
+            const int pb = (NPL == 2) ? (pr == 1 ? 1 : 0) : 0;
+            const uint64_t da = make_smem_desc_sw128(a_addr + pa * Cfg::A_BYTES, 16, 1024);
+            const uint64_t db = make_smem_desc_sw128(b_addr + pb * Cfg::B_BYTES, 16, 1024);
+#pragma unroll
+            for (int kk = 0; kk < kChunkK / 16; ++kk) {
+              // advancing 16 bf16 along K = 32 bytes inside the 128-byte swizzled row = +2 in the address field
+              umma_bf16(d_tmem, da + (uint64_t)(kk * 2), db + (uint64_t)(kk * 2), idesc, accumulate);
+              accumulate = 1u;
+            }
+          }
+          umma_commit(empty_bar + stage);                 // smem slot reusable once these MMAs have read it
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(tmem_full + acc);                     // accumulator complete -> epilogue
+      }
+    }
+    __syncwarp();
+  } else {
+    // ===================================================== epilogue warps 2..5
+    const int quarter = warp & 3;                         // TMEM lane quarter this warp may read
+    const int row = quarter * 32 + lane;
+    int local = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
+      const int acc = local & 1;
+      const uint32_t acc_phase = (local >> 1) & 1;
+      const int mt = tile % m_tiles, nt = tile / m_tiles;
+      const int b = mt / p.m_tiles_per_utt;
+      const int t = (mt - b * p.m_tiles_per_utt) * kTileM + row;
+      const int n0 = nt * BLOCK_N;
+      const bool row_ok = t < p.To;
+      const int64_t out_row = (int64_t)b * p.To + t;
+      mbar_wait(tmem_full + acc, acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BLOCK_N;
+#pragma unroll 1
+      for (int c = 0; c < BLOCK_N / 32; ++c) {
+        uint32_t r[32];
+        tmem_ld32(taddr + c * 32, r);
+        tmem_ld_wait();
+        const int nc = n0 + c * 32;
+        float v[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const int n = nc + i;
+          float x = __uint_as_float(r[i]);
+          if (n < p.N) {
+            if (p.bias) x += __ldg(p.bias + n);
+            if (p.relu) x = fmaxf(x, 0.f);
+          } else {
+            x = 0.f;
+          }
+          v[i] = x;
+        }
+        if (row_ok) {
+          if (p.mask_hi) {
+            const __nv_bfloat16* mrow = p.mask_hi + out_row * p.ld_mask + nc;
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              if (nc + g * 8 < p.ld_mask) {
+                const uint4 mk = *reinterpret_cast<const uint4*>(mrow + g * 8);
+                const uint32_t w[4] = {mk.x, mk.y, mk.z, mk.w};
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  // bf16 > 0  <=>  sign bit clear and magnitude non-zero
+                  const uint32_t lo16 = w[i] & 0xffffu, hi16 = w[i] >> 16;
+                  if (!(lo16 != 0 && lo16 < 0x8000u)) v[g * 8 + 2 * i] = 0.f;
+                  if (!(hi16 != 0 && hi16 < 0x8000u)) v[g * 8 + 2 * i + 1] = 0.f;
+                }
+              }
+            }
+          }
+          if (p.out_planes) {
+            __nv_bfloat16* orow = p.out_planes + out_row * p.ld_out + nc;
+#pragma unroll
+            for (int g = 0; g < 4; ++g)
+              if (nc + g * 8 < p.ld_out) store_planes8<NPL>(orow + g * 8, p.out_plane_stride, v + g * 8);
+          }
+          if (p.out_f32) {
+            float* frow = p.out_f32 + out_row * p.ld_f32 + nc;
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (nc + i < p.ld_f32) frow[i] = v[i];
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tmem_empty + acc);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ filter gradient
+template <int BLOCK_N, int NPL>
+struct WgradCfg {
+  static constexpr int A_BYTES = kTileM * kChunkK * 2;           // 2 boxes of [64 rows][64 ch]
+  static constexpr int B_BYTES = BLOCK_N * kChunkK * 2;          // BLOCK_N/64 boxes
+  static constexpr int STAGE_BYTES = NPL * (A_BYTES + B_BYTES);
+  static constexpr int STAGES_RAW = (kSmemBudget - 2048) / STAGE_BYTES;
+  static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 2048;
+  static constexpr int TMEM_COLS = 2 * BLOCK_N < 32 ? 32 : 2 * BLOCK_N;
+  static constexpr int BOX_BYTES = 64 * 128;                     // one {64 ch, 64 rows} box
+};
+
+template <int BLOCK_N, int NPL>
+__global__ void __launch_bounds__(kThreads, 1)
+tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmDZ,
+                const WgradParams p) {
+  using Cfg = WgradCfg<BLOCK_N, NPL>;
+  constexpr int STAGES = Cfg::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full = empty_bar + STAGES;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tiles_mn = p.m_tiles * p.n_tiles;
+  const int num_items = p.taps * tiles_mn * p.split;
+  const int total_iters = p.B * p.t_chunks;
+  const int iters_per_split = (total_iters + p.split - 1) / p.split;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmX);
+    prefetch_tmap(&tmDZ);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full_bar + s, 1);
+      mbar_init(empty_bar + s, 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tmem_full + a, 1);
+      mbar_init(tmem_empty + a, 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // item -> (split, tap, m tile, n tile); split slowest so that concurrently running CTAs hit different dW tiles
+  auto decode = [&](int item, int& sp, int& j, int& mt, int& nt) {
+    sp = item / (p.taps * tiles_mn);
+    int rem = item - sp * (p.taps * tiles_mn);
+    j = rem / tiles_mn;
+    rem -= j * tiles_mn;
+    nt = rem / p.m_tiles;
+    mt = rem - nt * p.m_tiles;
+  };
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+        int sp, j, mt, nt;
+        decode(item, sp, j, mt, nt);
+        const int m = j - p.pad_left;
+        const int shift = p.a_stride == 1 ? m : floordiv(m, p.a_stride);
+        const int a_col = (m - shift * p.a_stride) * p.a_cin + mt * kTileM;
+        const int n0 = nt * BLOCK_N;
+        const int q0 = sp * iters_per_split;
+        const int q1 = min(total_iters, q0 + iters_per_split);
+        for (int q = q0; q < q1; ++q) {
+          const int b = q / p.t_chunks;
+          const int t0 = (q - b * p.t_chunks) * kChunkK;
+          mbar_wait(empty_bar + stage, phase ^ 1);
+          mbar_expect_tx(full_bar + stage, Cfg::STAGE_BYTES);
+          uint8_t* st = smem + stage * Cfg::STAGE_BYTES;
+#pragma unroll
+          for (int pl = 0; pl < NPL; ++pl)
+#pragma unroll
+            for (int h = 0; h < kTileM / 64; ++h)
+              tma_load_3d(&tmX, full_bar + stage, st + pl * Cfg::A_BYTES + h * Cfg::BOX_BYTES, a_col + h * 64,
+                          t0 + shift, pl * p.B + b);
+#pragma unroll
+          for (int pl = 0; pl < NPL; ++pl)
+#pragma unroll
+            for (int h = 0; h < BLOCK_N / 64; ++h)
+              tma_load_3d(&tmDZ, full_bar + stage, st + NPL * Cfg::A_BYTES + pl * Cfg::B_BYTES + h * Cfg::BOX_BYTES,
+                          n0 + h * 64, t0, pl * p.B + b);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(kTileM, BLOCK_N, 1, 1);      // both operands MN-major
+      int stage = 0;
+      uint32_t phase = 0;
+      int local = 0;
+      for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++local) {
+        int sp, j, mt, nt;
+        decode(item, sp, j, mt, nt);
+        const int q0 = sp * iters_per_split;
+        const int q1 = min(total_iters, q0 + iters_per_split);
+        const int acc = local & 1;
+        const uint32_t acc_phase = (local >> 1) & 1;
+        mbar_wait(tmem_empty + acc, acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+        uint32_t accumulate = 0u;
+        for (int q = q0; q < q1; ++q) {
+          mbar_wait(full_bar + stage, phase);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+          const uint32_t b_addr = a_addr + NPL * Cfg::A_BYTES;
+#pragma unroll
+          for (int pr = 0; pr < (NPL == 2 ? 3 : 1); ++pr) {
+            const int pa = (NPL == 2) ? (pr == 0 ? 1 : 0) : 0;
+            const int pb = (NPL == 2) ? (pr == 1 ? 1 : 0) : 0;
+#pragma unroll
+            for (int kk = 0; kk < kChunkK / 16; ++kk) {
+              // MN-major SW128: a K step of 16 rows = 2 swizzle atoms of 8 rows x 128 B = 2048 bytes;
+              // LBO = distance between 64-wide MN blocks (one TMA box), SBO = 1024 (next 8 K rows)
+              const uint64_t da = make_smem_desc_sw128(a_addr + pa * Cfg::A_BYTES + kk * 2048, Cfg::BOX_BYTES, 1024);
+              const uint64_t db = make_smem_desc_sw128(b_addr + pb * Cfg::B_BYTES + kk * 2048, Cfg::BOX_BYTES, 1024);
+              umma_bf16(d_tmem, da, db, idesc, accumulate);
+              accumulate = 1u;
+            }
+          }
+          umma_commit(empty_bar + stage);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(tmem_full + acc);
+      }
+    }
+    __syncwarp();
+  } else {
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;
+    int local = 0;
+    for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++local) {
+      int sp, j, mt, nt;
+      decode(item, sp, j, mt, nt);
+      const int q0 = sp * iters_per_split;
+      const bool has_work = q0 < total_iters;
+      const int acc = local & 1;
+      const uint32_t acc_phase = (local >> 1) & 1;
+      const int ci = mt * kTileM + row;
+      const int n0 = nt * BLOCK_N;
+      mbar_wait(tmem_full + acc, acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BLOCK_N;
+      float* wrow = p.dW + ((int64_t)j * p.Cin + ci) * p.Cout;
+#pragma unroll 1
+      for (int c = 0; c < BLOCK_N / 32; ++c) {
+        uint32_t r[32];
+        tmem_ld32(taddr + c * 32, r);
+        tmem_ld_wait();
+        if (has_work && ci < p.Cin) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const int co = n0 + c * 32 + i;
+            if (co < p.Cout) {
+              const float x = __uint_as_float(r[i]);
+              if (p.use_atomic) atomicAdd(wrow + co, x);
+              else wrow[co] = x;
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tmem_empty + acc);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ small kernels
+template <int NPL>
+__global__ void __launch_bounds__(256)
+split_input_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ planes, int B, int T, int Tpad, int F) {
+  // one thread per 8 consecutive features
+  const int64_t groups = (int64_t)B * Tpad * (F / 8);
+  const int64_t plane_stride = (int64_t)B * Tpad * F;
+  for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < groups; g += (int64_t)gridDim.x * blockDim.x) {
+    const int f8 = (int)(g % (F / 8));
+    const int64_t bt = g / (F / 8);
+    const int t = (int)(bt % Tpad);
+    const int b = (int)(bt / Tpad);
+    float v[8];
+    if (t < T) {
+      const float4* src = reinterpret_cast<const float4*>(x + ((int64_t)b * T + t) * F + f8 * 8);
+      const float4 a = __ldg(src), c = __ldg(src + 1);
+      v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = c.x; v[5] = c.y; v[6] = c.z; v[7] = c.w;
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] = 0.f;
+    }
+    store_planes8<NPL>(planes + ((int64_t)b * Tpad + t) * F + f8 * 8, plane_stride, v);
+  }
+}
+
+// W [K][Cin][Cout] -> fwd[pl][co][k*cin_p + ci] via a 32x32 shared-memory transpose; block (32, 8)
+template <int NPL>
+__global__ void pack_filter_fwd_kernel(const float* __restrict__ w, int K, int Cin, int Cout,
+                                       __nv_bfloat16* __restrict__ fwd, int cin_p) {
+  __shared__ float tile[32][33];
+  const int k = blockIdx.z;
+  const int ci0 = blockIdx.y * 32, co0 = blockIdx.x * 32;
+  for (int i = threadIdx.y; i < 32; i += 8) {
+    const int ci = ci0 + i, co = co0 + threadIdx.x;
+    tile[i][threadIdx.x] = (ci < Cin && co < Cout) ? w[((int64_t)k * Cin + ci) * Cout + co] : 0.f;
+  }
+  __syncthreads();
+  const int64_t ld = (int64_t)K * cin_p;
+  const int64_t plane_stride = (int64_t)Cout * ld;
+  for (int i = threadIdx.y; i < 32; i += 8) {
+    const int co = co0 + i, ci = ci0 + threadIdx.x;
+    if (co < Cout && ci < cin_p) {
+      float rem = tile[threadIdx.x][i];
+#pragma unroll
+      for (int pl = 0; pl < NPL; ++pl) {
+        const __nv_bfloat16 h = __float2bfloat16_rn(rem);
+        fwd[pl * plane_stride + (int64_t)co * ld + (int64_t)k * cin_p + ci] = h;
+        rem -= __bfloat162float(h);
+      }
+    }
+  }
+}
+
+// W [K*Cin][Cout] -> bwd[pl][row][ld_co] (columns >= Cout zero)
+template <int NPL>
+__global__ void __launch_bounds__(256)
+pack_filter_bwd_kernel(const float* __restrict__ w, int64_t rows, int Cout, __nv_bfloat16* __restrict__ bwd, int ld_co) {
+  const int64_t total = rows * ld_co;
+  const int64_t plane_stride = total;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int co = (int)(i % ld_co);
+    const int64_t r = i / ld_co;
+    float rem = co < Cout ? __ldg(w + r * Cout + co) : 0.f;
+#pragma unroll
+    for (int pl = 0; pl < NPL; ++pl) {
+      const __nv_bfloat16 h = __float2bfloat16_rn(rem);
+      bwd[pl * plane_stride + i] = h;
+      rem -= __bfloat162float(h);
+    }
+  }
+}
+
+// db[n] += sum_rows sum_planes dz[pl][row][n]; block (32 column pairs, 8 row lanes); grid (ceil(ld/64), chunks)
+__global__ void bias_grad_planes_kernel(const __nv_bfloat16* __restrict__ dz, int64_t rows, int N, int ld,
+                                        int n_planes, float* __restrict__ db, int rows_per_block) {
+  __shared__ float part[8][66];
+  const int c2 = blockIdx.x * 32 + threadIdx.x;            // column pair index
+  const int64_t r0 = (int64_t)blockIdx.y * rows_per_block;
+  const int64_t r1 = min(rows, r0 + rows_per_block);
+  const int64_t plane_stride = rows * ld;
+  float a0 = 0.f, a1 = 0.f;
+  if (c2 * 2 < ld) {
+    for (int pl = 0; pl < n_planes; ++pl) {
+      const __nv_bfloat162* src = reinterpret_cast<const __nv_bfloat162*>(dz + pl * plane_stride);
+      for (int64_t r = r0 + threadIdx.y; r < r1; r += 8) {
+        const float2 f = __bfloat1622float2(src[(r * ld) / 2 + c2]);
+        a0 += f.x;
+        a1 += f.y;
+      }
+    }
+  }
+  part[threadIdx.y][threadIdx.x * 2] = a0;
+  part[threadIdx.y][threadIdx.x * 2 + 1] = a1;
+  __syncthreads();
+  if (threadIdx.y == 0) {
+    float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { s0 += part[i][threadIdx.x * 2]; s1 += part[i][threadIdx.x * 2 + 1]; }
+    if (c2 * 2 < N) atomicAdd(db + c2 * 2, s0);
+    if (c2 * 2 + 1 < N) atomicAdd(db + c2 * 2 + 1, s1);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+merge_planes_kernel(const __nv_bfloat16* __restrict__ planes, int64_t rows, int cols, int ld, int n_planes,
+                    float* __restrict__ dst, int64_t ld_dst) {
+  const int64_t total = rows * cols;
+  const int64_t plane_stride = rows * ld;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % cols);
+    const int64_t r = i / cols;
+    float acc = 0.f;
+    for (int pl = n_planes - 1; pl >= 0; --pl) acc += __bfloat162float(planes[pl * plane_stride + r * ld + c]);
+    dst[r * ld_dst + c] = acc;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* sym = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess) {
+      fn = reinterpret_cast<EncodeTiledFn>(sym);
+    }
+  }
+  return fn;
+}
+
+int grid_for(int work_items) {
+  const int sms = st_num_sms();
+  return work_items < sms ? work_items : sms;
+}
+
+template <int BLOCK_N, int NPL>
+int launch_conv_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvParams& p, cudaStream_t stream) {
+  using Cfg = ConvCfg<BLOCK_N, NPL>;
+  static bool configured = false;
+  if (!configured) {
+    ST_CUDA_CALL(cudaFuncSetAttribute(tc_conv_kernel<BLOCK_N, NPL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      Cfg::SMEM_BYTES));
+    configured = true;
+  }
+  const int tiles = p.B * p.m_tiles_per_utt * p.n_tiles;
+  tc_conv_kernel<BLOCK_N, NPL><<<grid_for(tiles), kThreads, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, p);
+  ST_CUDA_LAUNCH_CHECK("tc_conv_kernel");
+  return ST_OK;
+}
+
+template <int BLOCK_N, int NPL>
+int launch_wgrad_t(const CUtensorMap& tmX, const CUtensorMap& tmDZ, const WgradParams& p, cudaStream_t stream) {
+  using Cfg = WgradCfg<BLOCK_N, NPL>;
+  static bool configured = false;
+  if (!configured) {
+    ST_CUDA_CALL(cudaFuncSetAttribute(tc_wgrad_kernel<BLOCK_N, NPL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      Cfg::SMEM_BYTES));
+    configured = true;
+  }
+  const int items = p.taps * p.m_tiles * p.n_tiles * p.split;
+  tc_wgrad_kernel<BLOCK_N, NPL><<<grid_for(items), kThreads, Cfg::SMEM_BYTES, stream>>>(tmX, tmDZ, p);
+  ST_CUDA_LAUNCH_CHECK("tc_wgrad_kernel");
+  return ST_OK;
+}
+
+}  // namespace
+
+int make_map_3d(CUtensorMap* map, const void* base, int C, int T, int Bn, int64_t ld, int64_t batch_stride,
+                int box_c, int box_t) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) {
+    st_set_error("cuTensorMapEncodeTiled is not available from the CUDA driver");
+    return ST_ERR_CUDA;
+  }
+  const cuuint64_t dims[3] = {(cuuint64_t)C, (cuuint64_t)T, (cuuint64_t)Bn};
+  const cuuint64_t strides[2] = {(cuuint64_t)ld * 2, (cuuint64_t)batch_stride * 2};
+  const cuuint32_t box[3] = {(cuuint32_t)box_c, (cuuint32_t)box_t, 1};
+  const cuuint32_t estr[3] = {1, 1, 1};
+  const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    st_set_error("cuTensorMapEncodeTiled(3d: C=%d T=%d B=%d ld=%lld) failed with CUresult %d", C, T, Bn,
+                 (long long)ld, (int)r);
+    return ST_ERR_CUDA;
+  }
+  return ST_OK;
+}
+
+int make_map_2d(CUtensorMap* map, const void* base, int cols, int rows, int64_t ld, int box_c, int box_r) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) {
+    st_set_error("cuTensorMapEncodeTiled is not available from the CUDA driver");
+    return ST_ERR_CUDA;
+  }
+  const cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  const cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  const cuuint32_t box[2] = {(cuuint32_t)box_c, (cuuint32_t)box_r};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    st_set_error("cuTensorMapEncodeTiled(2d: cols=%d rows=%d ld=%lld) failed with CUresult %d", cols, rows,
+                 (long long)ld, (int)r);
+    return ST_ERR_CUDA;
+  }
+  return ST_OK;
+}
+
+int launch_conv(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvParams& p, int block_n, int n_planes,
+                cudaStream_t stream) {
+  if (block_n == 256 && n_planes == 2) return launch_conv_t<256, 2>(tmA, tmB, p, stream);
+  if (block_n == 256 && n_planes == 1) return launch_conv_t<256, 1>(tmA, tmB, p, stream);
+  if (block_n == 32 && n_planes == 2) return launch_conv_t<32, 2>(tmA, tmB, p, stream);
+  if (block_n == 32 && n_planes == 1) return launch_conv_t<32, 1>(tmA, tmB, p, stream);
+  st_set_error("launch_conv: unsupported (block_n=%d, n_planes=%d)", block_n, n_planes);
+  return ST_ERR_UNSUPPORTED;
+}
+
+int launch_wgrad(const CUtensorMap& tmX, const CUtensorMap& tmDZ, const WgradParams& p, int block_n, int n_planes,
+                 cudaStream_t stream) {
+  if (block_n == 256 && n_planes == 2) return launch_wgrad_t<256, 2>(tmX, tmDZ, p, stream);
+  if (block_n == 256 && n_planes == 1) return launch_wgrad_t<256, 1>(tmX, tmDZ, p, stream);
+  if (block_n == 64 && n_planes == 2) return launch_wgrad_t<64, 2>(tmX, tmDZ, p, stream);
+  if (block_n == 64 && n_planes == 1) return launch_wgrad_t<64, 1>(tmX, tmDZ, p, stream);
+  st_set_error("launch_wgrad: unsupported (block_n=%d, n_planes=%d)", block_n, n_planes);
+  return ST_ERR_UNSUPPORTED;
+}
+
+int launch_split_input(const float* x, __nv_bfloat16* planes, int B, int T, int Tpad, int F, int n_planes,
+                       cudaStream_t stream) {
+  ST_CHECK_ARG(F % 8 == 0, "launch_split_input: feature count must be a multiple of 8");
+  const int64_t groups = (int64_t)B * Tpad * (F / 8);
+  int blocks = (int)((groups + 255) / 256);
+  const int cap = 16 * st_num_sms();
+  blocks = blocks > cap ? cap : blocks;
+  if (n_planes == 2) split_input_kernel<2><<<blocks, 256, 0, stream>>>(x, planes, B, T, Tpad, F);
+  else split_input_kernel<1><<<blocks, 256, 0, stream>>>(x, planes, B, T, Tpad, F);
+  ST_CUDA_LAUNCH_CHECK("split_input_kernel");
+  return ST_OK;
+}
+
+int launch_pack_filter(const float* w, int K, int Cin, int Cout, __nv_bfloat16* fwd, int cin_p, __nv_bfloat16* bwd,
+                       int ld_co, int n_planes, cudaStream_t stream) {
+  if (fwd) {
+    dim3 grid((Cout + 31) / 32, (cin_p + 31) / 32, K);
+    if (n_planes == 2) pack_filter_fwd_kernel<2><<<grid, dim3(32, 8), 0, stream>>>(w, K, Cin, Cout, fwd, cin_p);
+    else pack_filter_fwd_kernel<1><<<grid, dim3(32, 8), 0, stream>>>(w, K, Cin, Cout, fwd, cin_p);
+    ST_CUDA_LAUNCH_CHECK("pack_filter_fwd_kernel");
+  }
+  if (bwd) {
+    const int64_t rows = (int64_t)K * Cin;
+    int blocks = (int)((rows * ld_co + 255) / 256);
+    const int cap = 16 * st_num_sms();
+    blocks = blocks > cap ? cap : blocks;
+    if (n_planes == 2) pack_filter_bwd_kernel<2><<<blocks, 256, 0, stream>>>(w, rows, Cout, bwd, ld_co);
+    else pack_filter_bwd_kernel<1><<<blocks, 256, 0, stream>>>(w, rows, Cout, bwd, ld_co);
+    ST_CUDA_LAUNCH_CHECK("pack_filter_bwd_kernel");
+  }
+  return ST_OK;
+}
+
+int launch_bias_grad(const __nv_bfloat16* dz, int64_t rows, int N, int ld, int n_planes, float* db,
+                     cudaStream_t stream) {
+  ST_CUDA_CALL(cudaMemsetAsync(db, 0, (size_t)N * sizeof(float), stream));
+  int chunks = (int)((rows + 127) / 128);
+  const int cap = 2 * st_num_sms();
+  chunks = chunks > cap ? cap : (chunks < 1 ? 1 : chunks);
+  const int rows_per_block = (int)((rows + chunks - 1) / chunks);
+  dim3 grid((ld + 63) / 64, chunks);
+  bias_grad_planes_kernel<<<grid, dim3(32, 8), 0, stream>>>(dz, rows, N, ld, n_planes, db, rows_per_block);
+  ST_CUDA_LAUNCH_CHECK("bias_grad_planes_kernel");
+  return ST_OK;
+}
+
+int launch_merge_planes(const __nv_bfloat16* planes, int64_t rows, int cols, int ld, int n_planes, float* dst,
+                        int64_t ld_dst, cudaStream_t stream) {
+  int blocks = (int)((rows * cols + 255) / 256);
+  const int cap = 16 * st_num_sms();
+  blocks = blocks > cap ? cap : (blocks < 1 ? 1 : blocks);
+  merge_planes_kernel<<<blocks, 256, 0, stream>>>(planes, rows, cols, ld, n_planes, dst, ld_dst);
+  ST_CUDA_LAUNCH_CHECK("merge_planes_kernel");
+  return ST_OK;
+}
+
+}  // namespace tc

@@ -1,0 +1,323 @@
+// Step plan of the tensor-core path: what the reference runs as ONE sess.run over its TF1 graph
+// (speech_model.py:235; network speech_model.py:275-295) is, for a fixed (batch, time) shape, a fixed sequence of
+// kernel launches over buffers carved from one caller-owned arena.  The plan owns no device memory: it records
+// offsets, TMA tensor maps and launch parameters, and enqueues
+//   forward : split input -> 11 x tc_conv_kernel (bias+ReLU fused; the last layer writes fp32 logits)
+//   backward: per layer bias-grad, tc_wgrad_kernel (filter grad into the flat fp32 gradient buffer) and
+//             tc_conv_kernel in data-gradient mode with the ReLU mask fused into its epilogue.
+// CTC (ctc.cu) sits between the two and writes d(loss)/d(logits) straight into the plan's bf16 planes.
+#include "st_common.cuh"
+#include "conv_tc.h"
+#include <vector>
+
+namespace {
+
+struct Layer {
+  int K, stride, Cin, Cout, relu;
+  int Ti, To, pad_left;
+  int ld_in, ld_out;          // channel stride of the input / output activation planes
+  int cin_p;                  // Cin rounded up to 64 (forward filter layout)
+  int ld_co;                  // Cout rounded up (backward filter layout)
+  size_t off_wfwd, off_wbwd;  // arena offsets (bytes)
+  size_t off_out;             // arena offset of this layer's OUTPUT activation planes (layers 0..9)
+  int64_t w_off, b_off;       // float offsets into the flat parameter / gradient buffers
+  CUtensorMap tm_fwd_a, tm_fwd_b;     // forward
+  CUtensorMap tm_dg_a[2], tm_dg_b;    // data gradient (A = dz ping or pong)
+  CUtensorMap tm_wg_x, tm_wg_dz[2];   // filter gradient
+  int wg_split;
+};
+
+int round_up(int x, int m) { return (x + m - 1) / m * m; }
+
+}  // namespace
+
+struct st_plan {
+  int B, T, Tpad, F, C, npl;
+  int To;                      // logit frames
+  std::vector<Layer> layers;
+  size_t off_in, off_logits, off_dlogits, off_dz[2], arena_bytes;
+  size_t dz_elems;             // elements per plane of a dz buffer
+  char* arena;
+  float* params;
+  float* grads;
+  int launches;
+  bool bound;
+};
+
+namespace {
+
+int choose_split(int base_items, int total_iters) {
+  const int sms = st_num_sms();
+  static const int cands[] = {1, 2, 3, 4, 6, 8, 12, 16, 24, 32, 48, 64, 96, 128};
+  int best = 1;
+  double best_eff = 0.0;
+  for (int s : cands) {
+    if (s > 1 && total_iters / s < 4) break;
+    const int items = base_items * s;
+    const double eff = (double)items / (double)(((items + sms - 1) / sms) * sms);
+    if (eff >= 0.92) return s;
+    if (eff > best_eff + 1e-9) { best_eff = eff; best = s; }
+  }
+  return best;
+}
+
+__nv_bfloat16* bf(st_plan* p, size_t off) { return reinterpret_cast<__nv_bfloat16*>(p->arena + off); }
+
+const __nv_bfloat16* act_in(st_plan* p, int l) { return l == 0 ? bf(p, p->off_in) : bf(p, p->layers[l - 1].off_out); }
+
+}  // namespace
+
+ST_API int st_plan_create(st_plan** out, int B, int T, int input_size, int num_classes, int n_planes) {
+  ST_CHECK_ARG(out && B > 0 && T > 1, "st_plan_create: bad shape");
+  ST_CHECK_ARG(n_planes == 1 || n_planes == 2, "st_plan_create: n_planes must be 1 (bf16) or 2 (bf16x3)");
+  ST_CHECK_ARG(input_size % 64 == 0, "st_plan_create: input_size must be a multiple of 64 (got %d)", input_size);
+  ST_CHECK_ARG(num_classes >= 2 && num_classes <= 32, "st_plan_create: num_classes must be in [2,32]");
+  st_plan* p = new st_plan();
+  p->B = B; p->T = T; p->Tpad = round_up(T, 2); p->F = input_size; p->C = num_classes; p->npl = n_planes;
+  p->arena = nullptr; p->params = nullptr; p->grads = nullptr; p->launches = 0; p->bound = false;
+  // reference speech_model.py:275-292
+  const int table[11][5] = {{48, 2, input_size, 250, 1}, {7, 1, 250, 250, 1}, {7, 1, 250, 250, 1}, {7, 1, 250, 250, 1},
+                            {7, 1, 250, 250, 1},         {7, 1, 250, 250, 1}, {7, 1, 250, 250, 1}, {7, 1, 250, 250, 1},
+                            {32, 1, 250, 2000, 1},       {1, 1, 2000, 2000, 1}, {1, 1, 2000, num_classes, 0}};
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off = (off + bytes + 1023) / 1024 * 1024; return o; };
+  p->off_in = take((size_t)n_planes * B * p->Tpad * input_size * 2);
+  int t = T, ld_prev = input_size;
+  int64_t poff = 0;
+  for (int l = 0; l < 11; ++l) {
+    Layer L{};
+    L.K = table[l][0]; L.stride = table[l][1]; L.Cin = table[l][2]; L.Cout = table[l][3]; L.relu = table[l][4];
+    L.Ti = t;
+    L.To = (t + L.stride - 1) / L.stride;
+    int pad_total = (L.To - 1) * L.stride + L.K - L.Ti;
+    if (pad_total < 0) pad_total = 0;
+    L.pad_left = pad_total / 2;
+    L.ld_in = ld_prev;
+    L.ld_out = l == 10 ? 32 : round_up(L.Cout, 8);
+    if (L.Cout == 250) L.ld_out = 256;
+    L.cin_p = round_up(L.Cin, 64);
+    L.ld_co = l == 10 ? 64 : round_up(L.Cout, 8);
+    if (L.Cout == 250) L.ld_co = 256;
+    L.off_wfwd = take((size_t)n_planes * L.Cout * L.K * L.cin_p * 2);
+    L.off_wbwd = l > 0 ? take((size_t)n_planes * L.K * L.Cin * L.ld_co * 2) : 0;
+    L.off_out = l < 10 ? take((size_t)n_planes * B * L.To * L.ld_out * 2) : 0;
+    // flat parameter layout: must match engine.ParamLayout (64-float alignment)
+    L.w_off = poff;
+    poff = (poff + (int64_t)L.K * L.Cin * L.Cout + 63) / 64 * 64;
+    L.b_off = poff;
+    poff = (poff + L.Cout + 63) / 64 * 64;
+    t = L.To;
+    ld_prev = L.ld_out;
+    p->layers.push_back(L);
+  }
+  p->To = t;
+  p->off_logits = take((size_t)B * p->To * 32 * sizeof(float));
+  p->off_dlogits = take((size_t)n_planes * B * p->To * 64 * 2);
+  p->dz_elems = (size_t)B * p->To * 2000;
+  p->off_dz[0] = take((size_t)n_planes * p->dz_elems * 2);
+  p->off_dz[1] = take((size_t)n_planes * p->dz_elems * 2);
+  p->arena_bytes = off;
+  *out = p;
+  return ST_OK;
+}
+
+ST_API int st_plan_destroy(st_plan* p) {
+  delete p;
+  return ST_OK;
+}
+
+ST_API size_t st_plan_arena_bytes(const st_plan* p) { return p ? p->arena_bytes : 0; }
+ST_API int64_t st_plan_param_floats(const st_plan* p) {
+  if (!p) return 0;
+  const Layer& L = p->layers.back();
+  return (L.b_off + L.Cout + 63) / 64 * 64;
+}
+ST_API int st_plan_logit_frames(const st_plan* p) { return p ? p->To : 0; }
+ST_API float* st_plan_logits(st_plan* p) { return p && p->arena ? reinterpret_cast<float*>(p->arena + p->off_logits) : nullptr; }
+ST_API void* st_plan_dlogits_planes(st_plan* p) { return p && p->arena ? p->arena + p->off_dlogits : nullptr; }
+ST_API int st_plan_launches(const st_plan* p) { return p ? p->launches : 0; }
+
+ST_API int st_plan_bind(st_plan* p, void* arena, size_t arena_bytes, float* params, float* grads) {
+  ST_CHECK_ARG(p && arena && params && grads, "st_plan_bind: null pointer");
+  ST_CHECK_ARG(arena_bytes >= p->arena_bytes, "st_plan_bind: arena %zu < required %zu bytes", arena_bytes, p->arena_bytes);
+  ST_CHECK_ARG((reinterpret_cast<uintptr_t>(arena) & 1023) == 0, "st_plan_bind: arena must be 1024-byte aligned");
+  p->arena = static_cast<char*>(arena);
+  p->params = params;
+  p->grads = grads;
+  const int B = p->B, npl = p->npl;
+  int rc;
+  for (int l = 0; l < 11; ++l) {
+    Layer& L = p->layers[l];
+    const __nv_bfloat16* xin = act_in(p, l);
+    const int block_n = l == 10 ? 32 : 256;
+    // ---- forward: A = input activation planes, B = forward filter planes [Cout rows][K*cin_p]
+    if (L.stride == 1) {
+      rc = tc::make_map_3d(&L.tm_fwd_a, xin, L.Cin, L.Ti, npl * B, L.ld_in, (int64_t)L.Ti * L.ld_in, 64, 128);
+    } else {
+      // pair view [B, Tpad/2, 2*Cin] of the (even-padded) input planes
+      rc = tc::make_map_3d(&L.tm_fwd_a, xin, 2 * L.Cin, p->Tpad / 2, npl * B, 2 * L.ld_in, (int64_t)p->Tpad * L.ld_in,
+                           64, 128);
+    }
+    if (rc) return rc;
+    rc = tc::make_map_2d(&L.tm_fwd_b, bf(p, L.off_wfwd), L.K * L.cin_p, npl * L.Cout, (int64_t)L.K * L.cin_p, 64,
+                         block_n);
+    if (rc) return rc;
+    // ---- filter gradient: X = input activation planes (boxes of 64 rows), dZ = gradient wrt this layer's output
+    if (L.stride == 1) {
+      rc = tc::make_map_3d(&L.tm_wg_x, xin, L.Cin, L.Ti, npl * B, L.ld_in, (int64_t)L.Ti * L.ld_in, 64, 64);
+    } else {
+      rc = tc::make_map_3d(&L.tm_wg_x, xin, 2 * L.Cin, p->Tpad / 2, npl * B, 2 * L.ld_in, (int64_t)p->Tpad * L.ld_in,
+                           64, 64);
+    }
+    if (rc) return rc;
+    for (int s = 0; s < 2; ++s) {
+      const __nv_bfloat16* dz = l == 10 ? bf(p, p->off_dlogits) : bf(p, p->off_dz[s]);
+      const int ld_dz = l == 10 ? 64 : L.ld_out;
+      const int64_t plane_rows = (int64_t)L.To * ld_dz;
+      // NOTE: planes of a dz buffer are p->dz_elems apart only for the shared ping/pong buffers; expressing the
+      // plane index as an extra "batch" needs a uniform stride, so dz planes are laid out [npl][B][To][ld] densely
+      // inside their buffer (plane stride = B*To*ld) -- see dz_plane_stride().
+      rc = tc::make_map_3d(&L.tm_wg_dz[s], dz, l == 10 ? 64 : L.Cout, L.To, npl * B, ld_dz, plane_rows, 64, 64);
+      if (rc) return rc;
+      // ---- data gradient (layers 1..10): A = dz of this layer, B = backward filter planes [K*Cin rows][ld_co]
+      if (l > 0) {
+        rc = tc::make_map_3d(&L.tm_dg_a[s], dz, l == 10 ? 64 : L.Cout, L.To, npl * B, ld_dz, plane_rows, 64, 128);
+        if (rc) return rc;
+      }
+    }
+    if (l > 0) {
+      rc = tc::make_map_2d(&L.tm_dg_b, bf(p, L.off_wbwd), l == 10 ? 64 : L.Cout, npl * L.K * L.Cin, L.ld_co, 64, 256);
+      if (rc) return rc;
+    }
+    const int m_tiles = (L.Cin + 127) / 128;
+    const int n_tiles = l == 10 ? 1 : (L.Cout + 255) / 256;
+    L.wg_split = choose_split(L.K * m_tiles * n_tiles, B * ((L.To + 63) / 64));
+  }
+  p->bound = true;
+  return ST_OK;
+}
+
+// fp32 parameters -> bf16 operand planes (forward K-major layout for every layer, backward layout for layers 1..10)
+ST_API int st_plan_pack_weights(st_plan* p, st_stream_t stream) {
+  ST_CHECK_ARG(p && p->bound, "st_plan_pack_weights: plan is not bound");
+  cudaStream_t s = st_cu(stream);
+  for (int l = 0; l < 11; ++l) {
+    Layer& L = p->layers[l];
+    int rc = tc::launch_pack_filter(p->params + L.w_off, L.K, L.Cin, L.Cout, bf(p, L.off_wfwd), L.cin_p,
+                                    l > 0 ? bf(p, L.off_wbwd) : nullptr, L.ld_co, p->npl, s);
+    if (rc) return rc;
+    p->launches += l > 0 ? 2 : 1;
+  }
+  return ST_OK;
+}
+
+ST_API int st_plan_forward(st_plan* p, const float* inputs, st_stream_t stream) {
+  ST_CHECK_ARG(p && p->bound && inputs, "st_plan_forward: plan is not bound / null input");
+  cudaStream_t s = st_cu(stream);
+  int rc = tc::launch_split_input(inputs, bf(p, p->off_in), p->B, p->T, p->Tpad, p->F, p->npl, s);
+  if (rc) return rc;
+  p->launches++;
+  for (int l = 0; l < 11; ++l) {
+    Layer& L = p->layers[l];
+    const int block_n = l == 10 ? 32 : 256;
+    tc::ConvParams c{};
+    c.taps = L.K;
+    c.chunks_per_tap = L.cin_p / 64;
+    c.pad_left = L.pad_left;
+    c.a_sign = 1;
+    c.a_stride = L.stride;
+    c.a_cin = L.Cin;
+    c.b_row_step = 0;
+    c.b_col_step = L.cin_p;
+    c.b_plane_rows = L.Cout;
+    c.B = p->B; c.To = L.To; c.N = L.Cout;
+    c.m_tiles_per_utt = (L.To + tc::kTileM - 1) / tc::kTileM;
+    c.n_tiles = (L.Cout + block_n - 1) / block_n;
+    c.bias = p->params + L.b_off;
+    c.relu = L.relu;
+    if (l < 10) {
+      c.out_planes = bf(p, L.off_out);
+      c.out_plane_stride = (int64_t)p->B * L.To * L.ld_out;
+      c.ld_out = L.ld_out;
+    } else {
+      c.out_f32 = reinterpret_cast<float*>(p->arena + p->off_logits);
+      c.ld_f32 = 32;
+    }
+    rc = tc::launch_conv(L.tm_fwd_a, L.tm_fwd_b, c, block_n, p->npl, s);
+    if (rc) return rc;
+    p->launches++;
+  }
+  return ST_OK;
+}
+
+// Consumes d(loss)/d(logits) from the dlogits planes (written by st_ctc_loss) and fills the flat gradient buffer.
+ST_API int st_plan_backward(st_plan* p, st_stream_t stream) {
+  ST_CHECK_ARG(p && p->bound, "st_plan_backward: plan is not bound");
+  cudaStream_t s = st_cu(stream);
+  int cur = 0;                                  // dz buffer holding the gradient wrt layer l's output (l < 10)
+  for (int l = 10; l >= 0; --l) {
+    Layer& L = p->layers[l];
+    const __nv_bfloat16* dz = l == 10 ? bf(p, p->off_dlogits) : bf(p, p->off_dz[cur]);
+    const int ld_dz = l == 10 ? 64 : L.ld_out;
+    const int64_t rows = (int64_t)p->B * L.To;
+    int rc = tc::launch_bias_grad(dz, rows, L.Cout, ld_dz, p->npl, p->grads + L.b_off, s);
+    if (rc) return rc;
+    p->launches++;
+    // ---- filter gradient
+    tc::WgradParams w{};
+    w.B = p->B; w.To = L.To; w.t_chunks = (L.To + 63) / 64;
+    w.taps = L.K; w.pad_left = L.pad_left; w.a_stride = L.stride; w.a_cin = L.Cin;
+    w.m_tiles = (L.Cin + 127) / 128;
+    w.n_tiles = l == 10 ? 1 : (L.Cout + 255) / 256;
+    w.split = L.wg_split;
+    w.Cin = L.Cin; w.Cout = L.Cout;
+    w.dW = p->grads + L.w_off;
+    w.use_atomic = w.split > 1;
+    if (w.use_atomic) ST_CUDA_CALL(cudaMemsetAsync(w.dW, 0, (size_t)L.K * L.Cin * L.Cout * sizeof(float), s));
+    rc = tc::launch_wgrad(L.tm_wg_x, L.tm_wg_dz[l == 10 ? 0 : cur], w, l == 10 ? 64 : 256, p->npl, s);
+    if (rc) return rc;
+    p->launches++;
+    // ---- data gradient, ReLU mask of the layer below fused
+    if (l > 0) {
+      Layer& Lb = p->layers[l - 1];
+      const int nxt = l == 10 ? 0 : cur ^ 1;
+      tc::ConvParams c{};
+      c.taps = L.K;
+      c.chunks_per_tap = l == 10 ? 1 : (L.Cout + 63) / 64;
+      c.pad_left = L.pad_left;
+      c.a_sign = -1;
+      c.a_stride = 1;
+      c.a_cin = 0;
+      c.b_row_step = L.Cin;
+      c.b_col_step = 0;
+      c.b_plane_rows = L.K * L.Cin;
+      c.B = p->B; c.To = L.Ti; c.N = L.Cin;
+      c.m_tiles_per_utt = (L.Ti + tc::kTileM - 1) / tc::kTileM;
+      c.n_tiles = (L.Cin + 255) / 256;
+      c.bias = nullptr;
+      c.relu = 0;
+      c.out_planes = bf(p, p->off_dz[nxt]);
+      c.out_plane_stride = (int64_t)p->B * Lb.To * Lb.ld_out;
+      c.ld_out = Lb.ld_out;
+      c.mask_hi = bf(p, Lb.off_out);
+      c.ld_mask = Lb.ld_out;
+      rc = tc::launch_conv(L.tm_dg_a[l == 10 ? 0 : cur], L.tm_dg_b, c, 256, p->npl, s);
+      if (rc) return rc;
+      p->launches++;
+      cur = nxt;
+    }
+  }
+  return ST_OK;
+}
+
+// Debug / test access: activation planes of layer `layer` output (0..9) merged to fp32 [B][To][Cout];
+// layer = -1 gives the split input [B][Tpad][F].
+ST_API int st_plan_get_activation(st_plan* p, int layer, float* dst, st_stream_t stream) {
+  ST_CHECK_ARG(p && p->bound && dst && layer >= -1 && layer < 10, "st_plan_get_activation: bad argument");
+  if (layer < 0)
+    return tc::launch_merge_planes(bf(p, p->off_in), (int64_t)p->B * p->Tpad, p->F, p->F, p->npl, dst, p->F,
+                                   st_cu(stream));
+  Layer& L = p->layers[layer];
+  return tc::launch_merge_planes(bf(p, L.off_out), (int64_t)p->B * L.To, L.Cout, L.ld_out, p->npl, dst, L.Cout,
+                                 st_cu(stream));
+}

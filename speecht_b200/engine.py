@@ -195,6 +195,14 @@ class W2LEngine:
       self._bufs[key] = t
     return t
 
+  def conv_flops_forward(self, B, T):
+    """Algorithmic forward FLOPs of the stack: sum_l 2*K*Cin*Cout*T_out*B with the true (unpadded) channel counts."""
+    total, t = 0.0, T
+    for (k, s, cin, cout, _r) in self.layers:
+      t = -(-t // s)
+      total += 2.0 * k * cin * cout * t * B
+    return total
+
   def _out_lengths(self, T):
     outs = []
     t = T

@@ -1,0 +1,124 @@
+"""TCPlan -- host side of the tensor-core step plan (csrc/w2l_plan.cu) for the 'bf16x3' and 'bf16' precisions.
+
+One native plan per (batch, time) shape, each bound to an arena allocated through torch and to the engine's flat
+parameter / gradient buffers.  The sequence per train step is
+  pack_weights (fp32 -> bf16 planes)  ->  plan.forward  ->  st_ctc_loss (writes d loss/d logits planes)
+  ->  plan.backward  ->  [NCCL allreduce]  ->  clip_by_global_norm + Adam on the flat fp32 buffers.
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import ops
+from ._lib import check, lib, ptr, stream_ptr
+
+N_PLANES = {'bf16': 1, 'bf16x3': 2}
+MAX_CACHED_SHAPES = 4
+
+
+class _Shape:
+  def __init__(self, engine, B, T):
+    self.B, self.T = B, T
+    self.handle = ctypes.c_void_p()
+    check(lib().st_plan_create(ctypes.byref(self.handle), B, T, engine.input_size, engine.num_classes,
+                               N_PLANES[engine.precision]))
+    n = lib().st_plan_param_floats(self.handle)
+    if n != engine.params.numel():
+      raise RuntimeError('native parameter layout (%d floats) != engine layout (%d)' % (n, engine.params.numel()))
+    nbytes = lib().st_plan_arena_bytes(self.handle)
+    self.arena = torch.zeros((nbytes + 1024,), dtype=torch.uint8, device=engine.device)
+    base = self.arena.data_ptr()
+    self.arena_ptr = (base + 1023) // 1024 * 1024
+    check(lib().st_plan_bind(self.handle, ctypes.c_void_p(self.arena_ptr), nbytes, ptr(engine.params),
+                             ptr(engine.grads)))
+    self.To = lib().st_plan_logit_frames(self.handle)
+    # fp32 logits [B, To, 32] inside the arena, exposed as the reference's time-major [T', B, C] view
+    off = lib().st_plan_logits(self.handle) - base
+    flat = self.arena[off:off + B * self.To * 32 * 4].view(torch.float32).view(B, self.To, 32)
+    self.logits_bm = flat[:, :, :engine.num_classes]
+    self.logits_tm = self.logits_bm.transpose(0, 1)
+    off = lib().st_plan_dlogits_planes(self.handle) - base
+    npl = N_PLANES[engine.precision]
+    self.dlogits_planes = self.arena[off:off + npl * B * self.To * 64 * 2].view(torch.bfloat16).view(npl, B, self.To, 64)
+    self.weights_version = -1
+
+  def close(self):
+    if self.handle:
+      lib().st_plan_destroy(self.handle)
+      self.handle = None
+
+  def __del__(self):
+    try:
+      self.close()
+    except Exception:
+      pass
+
+
+class TCPlan:
+
+  def __init__(self, engine):
+    self.engine = engine
+    self.shapes = {}
+
+  def _shape(self, B, T):
+    key = (B, T)
+    sh = self.shapes.get(key)
+    if sh is None:
+      if len(self.shapes) >= MAX_CACHED_SHAPES:
+        old = next(iter(self.shapes))
+        self.shapes.pop(old).close()
+      sh = _Shape(self.engine, B, T)
+      self.shapes[key] = sh
+    return sh
+
+  def _launch_count(self, sh, before):
+    self.engine.launches += lib().st_plan_launches(sh.handle) - before
+
+  def _pack(self, sh):
+    if sh.weights_version != self.engine._weights_version:
+      before = lib().st_plan_launches(sh.handle)
+      with self.engine._timed('pack_filter_kernels', 0.0):
+        check(lib().st_plan_pack_weights(sh.handle, stream_ptr()))
+      sh.weights_version = self.engine._weights_version
+      self._launch_count(sh, before)
+
+  def forward(self, inputs, keep_activations=False):
+    eng = self.engine
+    B, T, _ = inputs.shape
+    sh = self._shape(B, T)
+    self._pack(sh)
+    before = lib().st_plan_launches(sh.handle)
+    with eng._timed('tc_conv_kernel(fwd)', eng.conv_flops_forward(B, T)):
+      check(lib().st_plan_forward(sh.handle, ptr(inputs), stream_ptr()))
+    self._launch_count(sh, before)
+    self._last = sh
+    return sh.logits_tm
+
+  def activation(self, layer):
+    """fp32 copy of layer `layer`'s output [B,T',Cout] from the last forward (tests)."""
+    sh = self._last
+    k, s, cin, cout, relu = self.engine.layers[layer]
+    out = torch.empty((sh.B, sh.To, cout), dtype=torch.float32, device=self.engine.device)
+    check(lib().st_plan_get_activation(sh.handle, layer, ptr(out), stream_ptr()))
+    return out
+
+  def train_step(self, inputs, sequence_lengths, labels, learning_rate, max_gradient_norm=5.0, decode=False):
+    eng = self.engine
+    B, T, _ = inputs.shape
+    logits = self.forward(inputs.contiguous(), keep_activations=True)
+    sh = self._last
+    ctc_len = np.asarray(sequence_lengths, dtype=np.int32) // 2
+    scale = 1.0 / (B * eng.world_size)
+    loss, _ = ops.ctc_loss(labels, logits, ctc_len, want_grad=False, grad_scale=scale, grad_planes=sh.dlogits_planes)
+    eng.launches += 3
+    out = {'loss': loss, 'avg_loss': loss.mean(), 'decoded': None, 'logits': logits}
+    if decode:
+      out['decoded'], out['neg_sum_logits'] = ops.ctc_greedy_decoder(logits, ctc_len)
+      eng.launches += 1
+    before = lib().st_plan_launches(sh.handle)
+    with eng._timed('tc_conv_kernel+tc_wgrad_kernel(bwd)', 2.0 * eng.conv_flops_forward(B, T)):
+      check(lib().st_plan_backward(sh.handle, stream_ptr()))
+    self._launch_count(sh, before)
+    eng.apply_gradients(learning_rate, max_gradient_norm)
+    return out

@@ -124,6 +124,7 @@ int st_plan_bind(st_plan* plan, void* arena, size_t arena_bytes, float* params, 
 int st_plan_pack_weights(st_plan* plan, st_stream_t stream);
 int st_plan_forward(st_plan* plan, const float* inputs, st_stream_t stream);
 int st_plan_backward(st_plan* plan, st_stream_t stream);
+int st_plan_backward_range(st_plan* plan, int layer_hi, int layer_lo, st_stream_t stream);  /* 10 first, downwards */
 float* st_plan_logits(st_plan* plan);
 void* st_plan_dlogits_planes(st_plan* plan);
 int st_plan_get_activation(st_plan* plan, int layer, float* dst, st_stream_t stream);

@@ -42,6 +42,7 @@ struct st_plan {
   float* grads;
   int launches;
   bool bound;
+  int cur_dz;                  // ping/pong buffer holding the gradient wrt the next layer to process
 };
 
 namespace {
@@ -74,7 +75,7 @@ ST_API int st_plan_create(st_plan** out, int B, int T, int input_size, int num_c
   ST_CHECK_ARG(num_classes >= 2 && num_classes <= 32, "st_plan_create: num_classes must be in [2,32]");
   st_plan* p = new st_plan();
   p->B = B; p->T = T; p->Tpad = round_up(T, 2); p->F = input_size; p->C = num_classes; p->npl = n_planes;
-  p->arena = nullptr; p->params = nullptr; p->grads = nullptr; p->launches = 0; p->bound = false;
+  p->arena = nullptr; p->params = nullptr; p->grads = nullptr; p->launches = 0; p->bound = false; p->cur_dz = 0;
   // reference speech_model.py:275-292
   const int table[11][5] = {{48, 2, input_size, 250, 1}, {7, 1, 250, 250, 1}, {7, 1, 250, 250, 1}, {7, 1, 250, 250, 1},
                             {7, 1, 250, 250, 1},         {7, 1, 250, 250, 1}, {7, 1, 250, 250, 1}, {7, 1, 250, 250, 1},
@@ -251,11 +252,15 @@ ST_API int st_plan_forward(st_plan* p, const float* inputs, st_stream_t stream) 
 }
 
 // Consumes d(loss)/d(logits) from the dlogits planes (written by st_ctc_loss) and fills the flat gradient buffer.
-ST_API int st_plan_backward(st_plan* p, st_stream_t stream) {
+// st_plan_backward_range runs layers hi..lo (hi >= lo); call with hi=10 first, then continue downwards -- the caller
+// may launch the gradient allreduce of the finished layers in between (speecht_b200/tc_plan.py).
+ST_API int st_plan_backward_range(st_plan* p, int hi, int lo, st_stream_t stream) {
   ST_CHECK_ARG(p && p->bound, "st_plan_backward: plan is not bound");
+  ST_CHECK_ARG(hi <= 10 && lo >= 0 && hi >= lo, "st_plan_backward_range: need 10 >= hi >= lo >= 0");
   cudaStream_t s = st_cu(stream);
-  int cur = 0;                                  // dz buffer holding the gradient wrt layer l's output (l < 10)
-  for (int l = 10; l >= 0; --l) {
+  if (hi == 10) p->cur_dz = 0;
+  int cur = p->cur_dz;                          // dz buffer holding the gradient wrt layer l's output (l < 10)
+  for (int l = hi; l >= lo; --l) {
     Layer& L = p->layers[l];
     const __nv_bfloat16* dz = l == 10 ? bf(p, p->off_dlogits) : bf(p, p->off_dz[cur]);
     const int ld_dz = l == 10 ? 64 : L.ld_out;
@@ -307,8 +312,11 @@ ST_API int st_plan_backward(st_plan* p, st_stream_t stream) {
       cur = nxt;
     }
   }
+  p->cur_dz = cur;
   return ST_OK;
 }
+
+ST_API int st_plan_backward(st_plan* p, st_stream_t stream) { return st_plan_backward_range(p, 10, 0, stream); }
 
 // Debug / test access: activation planes of layer `layer` output (0..9) merged to fp32 [B][To][Cout];
 // layer = -1 gives the split input [B][Tpad][F].

@@ -295,14 +295,23 @@ class W2LEngine:
     self.apply_gradients(learning_rate, max_gradient_norm)
     return out
 
-  def allreduce_gradients(self):
-    if self.world_size > 1:
-      import torch.distributed as dist
-      dist.all_reduce(self.grads, op=dist.ReduceOp.SUM, group=self.process_group)
+  def allreduce_gradients(self, async_ranges=None):
+    """NCCL sum-allreduce of the flat gradient buffer (the only collective on the path).
+    async_ranges: list of (start, stop) float ranges -> returns work handles instead of blocking."""
+    from . import parallel
+    if self.world_size == 1:
+      return []
+    handles = parallel.allreduce_flat(self.grads, self.process_group, async_ranges)
+    if async_ranges is None:
+      for h in handles:
+        h.wait()
+      return []
+    return handles
 
-  def apply_gradients(self, learning_rate, max_gradient_norm=5.0):
+  def apply_gradients(self, learning_rate, max_gradient_norm=5.0, reduced=False):
     """[allreduce] + tf.clip_by_global_norm + Adam(eps=1e-3) on the flat buffers (speech_model.py:77-82)."""
-    self.allreduce_gradients()
+    if not reduced:
+      self.allreduce_gradients()
     self.global_step += 1
     self._normsq.zero_()
     ops.global_norm_sq(self.grads, self._normsq)

@@ -1,0 +1,80 @@
+"""Data parallelism over the utterance batch -- new work, the reference is single-process.
+
+One process per GPU.  Every op on the path is independent per utterance except tf.reduce_mean (speech_model.py:75),
+the global-norm clip (:80) and the weight update (:81), so the ONLY collective is a sum-allreduce of the flat
+gradient buffer (24.66 M floats, 98.7 MB) over NCCL/NVLink; the 1/(B_local*world) factor is folded into the CTC
+gradient, the global norm is computed on the reduced gradient (identical on all ranks -> no second collective) and
+every rank applies the identical Adam update.  These helpers are device-agnostic so the host logic is tested with
+gloo on CPU (tests/test_parallel_gloo.py).
+"""
+import os
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+
+def init_from_env(backend=None):
+  """torchrun contract: RANK / LOCAL_RANK / WORLD_SIZE / MASTER_ADDR / MASTER_PORT.  Returns (rank, local, world)."""
+  rank = int(os.environ.get('RANK', '0'))
+  local = int(os.environ.get('LOCAL_RANK', '0'))
+  world = int(os.environ.get('WORLD_SIZE', '1'))
+  if world > 1 and not dist.is_initialized():
+    if backend is None:
+      backend = 'nccl' if torch.cuda.is_available() else 'gloo'
+    if backend == 'nccl':
+      torch.cuda.set_device(local)
+      dist.init_process_group(backend, device_id=torch.device('cuda', local))
+    else:
+      dist.init_process_group(backend)
+  return rank, local, world
+
+
+def shard_batch(n_items, rank, world):
+  """Contiguous shard [start, stop) of a global batch of n_items utterances; sizes differ by at most one."""
+  base, extra = divmod(n_items, world)
+  start = rank * base + min(rank, extra)
+  return start, start + base + (1 if rank < extra else 0)
+
+
+def gradient_scale(local_batch, world):
+  """Factor folded into d(loss)/d(logits): mean over the GLOBAL batch when every rank holds local_batch items."""
+  return 1.0 / (local_batch * world)
+
+
+def allreduce_flat(flat, group=None, buckets=None):
+  """Sum-allreduce of the flat gradient buffer.  `buckets` = list of (start, stop) float ranges launched as
+  separate collectives (async) so that early-finished layers overlap with the rest of backward; None = one call."""
+  if not dist.is_initialized() or dist.get_world_size(group) == 1:
+    return []
+  if not buckets:
+    return [dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group, async_op=True)]
+  return [dist.all_reduce(flat[a:b], op=dist.ReduceOp.SUM, group=group, async_op=True) for a, b in buckets]
+
+
+def mean_scalar(value, group=None):
+  """Average of a per-rank scalar tensor (the reported avg_loss of the global batch)."""
+  if not dist.is_initialized() or dist.get_world_size(group) == 1:
+    return value
+  out = value.clone()
+  dist.all_reduce(out, op=dist.ReduceOp.SUM, group=group)
+  return out / dist.get_world_size(group)
+
+
+def max_scalar(x, device=None, group=None):
+  """Max over ranks of a python float (bench timing: the slowest rank defines the step time)."""
+  if not dist.is_initialized() or dist.get_world_size(group) == 1:
+    return float(x)
+  t = torch.tensor([float(x)], dtype=torch.float64, device=device)
+  dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
+  return float(t.item())
+
+
+def gather_decoded(decoded_rows, group=None):
+  """Decode (config 5) is embarrassingly parallel: only the compacted label lists travel.  decoded_rows is this
+  rank's list of int lists; returns the concatenation in rank order on every rank."""
+  if not dist.is_initialized() or dist.get_world_size(group) == 1:
+    return list(decoded_rows)
+  gathered = [None] * dist.get_world_size(group)
+  dist.all_gather_object(gathered, [list(map(int, r)) for r in decoded_rows], group=group)
+  return [row for part in gathered for row in part]

@@ -94,7 +94,6 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_tiles = p.B * p.m_tiles_per_utt * p.n_tiles;
-  const int m_tiles = p.B * p.m_tiles_per_utt;
   const int nk = p.taps * p.chunks_per_tap;
 
   if (warp == 0 && lane == 0) {
@@ -122,7 +121,8 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int mt = tile % m_tiles, nt = tile / m_tiles;          // m fastest: a wave shares one filter slab
+        const int nt = tile % p.n_tiles, mt = tile / p.n_tiles;      // n fastest: the A rows of a tile are read from
+                                                                     // HBM once and shared through L2 by its n tiles
         const int b = mt / p.m_tiles_per_utt;
         const int t0 = (mt - b * p.m_tiles_per_utt) * kTileM;
         const int n0 = nt * BLOCK_N;
@@ -194,7 +194,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
       const int acc = local & 1;
       const uint32_t acc_phase = (local >> 1) & 1;
-      const int mt = tile % m_tiles, nt = tile / m_tiles;
+      const int nt = tile % p.n_tiles, mt = tile / p.n_tiles;
       const int b = mt / p.m_tiles_per_utt;
       const int t = (mt - b * p.m_tiles_per_utt) * kTileM + row;
       const int n0 = nt * BLOCK_N;
@@ -297,10 +297,15 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // stream-K: the (tile, k-iteration) space is cut into gridDim.x equal contiguous ranges, so every SM gets the same
+  // number of MMAs whatever the tile count; a tile covered by a single CTA is stored, a shared one accumulated
+  // with fp32 atomics into the (pre-zeroed) gradient buffer.
   const int tiles_mn = p.m_tiles * p.n_tiles;
-  const int num_items = p.taps * tiles_mn * p.split;
+  const int num_tiles = p.taps * tiles_mn;
   const int total_iters = p.B * p.t_chunks;
-  const int iters_per_split = (total_iters + p.split - 1) / p.split;
+  const int64_t space = (int64_t)num_tiles * total_iters;
+  const int64_t range_begin = space * blockIdx.x / gridDim.x;
+  const int64_t range_end = space * (blockIdx.x + 1) / gridDim.x;
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmX);
@@ -321,12 +326,10 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  // item -> (split, tap, m tile, n tile); split slowest so that concurrently running CTAs hit different dW tiles
-  auto decode = [&](int item, int& sp, int& j, int& mt, int& nt) {
-    sp = item / (p.taps * tiles_mn);
-    int rem = item - sp * (p.taps * tiles_mn);
-    j = rem / tiles_mn;
-    rem -= j * tiles_mn;
+  // tile -> (tap, n tile, m tile)
+  auto decode = [&](int tile, int& j, int& mt, int& nt) {
+    j = tile / tiles_mn;
+    const int rem = tile - j * tiles_mn;
     nt = rem / p.m_tiles;
     mt = rem - nt * p.m_tiles;
   };
@@ -335,15 +338,17 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
-        int sp, j, mt, nt;
-        decode(item, sp, j, mt, nt);
+      for (int64_t pos = range_begin; pos < range_end;) {
+        const int tile = (int)(pos / total_iters);
+        const int q0 = (int)(pos - (int64_t)tile * total_iters);
+        const int q1 = (int)min((int64_t)total_iters, q0 + (range_end - pos));
+        pos += q1 - q0;
+        int j, mt, nt;
+        decode(tile, j, mt, nt);
         const int m = j - p.pad_left;
         const int shift = p.a_stride == 1 ? m : floordiv(m, p.a_stride);
         const int a_col = (m - shift * p.a_stride) * p.a_cin + mt * kTileM;
         const int n0 = nt * BLOCK_N;
-        const int q0 = sp * iters_per_split;
-        const int q1 = min(total_iters, q0 + iters_per_split);
         for (int q = q0; q < q1; ++q) {
           const int b = q / p.t_chunks;
           const int t0 = (q - b * p.t_chunks) * kChunkK;
@@ -373,11 +378,11 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
       int stage = 0;
       uint32_t phase = 0;
       int local = 0;
-      for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++local) {
-        int sp, j, mt, nt;
-        decode(item, sp, j, mt, nt);
-        const int q0 = sp * iters_per_split;
-        const int q1 = min(total_iters, q0 + iters_per_split);
+      for (int64_t pos = range_begin; pos < range_end; ++local) {
+        const int tile = (int)(pos / total_iters);
+        const int q0 = (int)(pos - (int64_t)tile * total_iters);
+        const int q1 = (int)min((int64_t)total_iters, q0 + (range_end - pos));
+        pos += q1 - q0;
         const int acc = local & 1;
         const uint32_t acc_phase = (local >> 1) & 1;
         mbar_wait(tmem_empty + acc, acc_phase ^ 1);
@@ -414,11 +419,14 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
     const int quarter = warp & 3;
     const int row = quarter * 32 + lane;
     int local = 0;
-    for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++local) {
-      int sp, j, mt, nt;
-      decode(item, sp, j, mt, nt);
-      const int q0 = sp * iters_per_split;
-      const bool has_work = q0 < total_iters;
+    for (int64_t pos = range_begin; pos < range_end; ++local) {
+      const int tile = (int)(pos / total_iters);
+      const int q0 = (int)(pos - (int64_t)tile * total_iters);
+      const int q1 = (int)min((int64_t)total_iters, q0 + (range_end - pos));
+      pos += q1 - q0;
+      int j, mt, nt;
+      decode(tile, j, mt, nt);
+      const bool whole_tile = q0 == 0 && q1 == total_iters;
       const int acc = local & 1;
       const uint32_t acc_phase = (local >> 1) & 1;
       const int ci = mt * kTileM + row;
@@ -432,14 +440,14 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
         uint32_t r[32];
         tmem_ld32(taddr + c * 32, r);
         tmem_ld_wait();
-        if (has_work && ci < p.Cin) {
+        if (ci < p.Cin) {
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
             const int co = n0 + c * 32 + i;
             if (co < p.Cout) {
               const float x = __uint_as_float(r[i]);
-              if (p.use_atomic) atomicAdd(wrow + co, x);
-              else wrow[co] = x;
+              if (whole_tile) wrow[co] = x;
+              else atomicAdd(wrow + co, x);
             }
           }
         }
@@ -622,8 +630,10 @@ int launch_wgrad_t(const CUtensorMap& tmX, const CUtensorMap& tmDZ, const WgradP
                                       Cfg::SMEM_BYTES));
     configured = true;
   }
-  const int items = p.taps * p.m_tiles * p.n_tiles * p.split;
-  tc_wgrad_kernel<BLOCK_N, NPL><<<grid_for(items), kThreads, Cfg::SMEM_BYTES, stream>>>(tmX, tmDZ, p);
+  // at least 4 k-iterations per CTA, at most one CTA per SM
+  const int64_t space = (int64_t)p.taps * p.m_tiles * p.n_tiles * p.B * p.t_chunks;
+  const int ctas = (int)(space / 4 < 1 ? 1 : (space / 4 > st_num_sms() ? st_num_sms() : space / 4));
+  tc_wgrad_kernel<BLOCK_N, NPL><<<ctas, kThreads, Cfg::SMEM_BYTES, stream>>>(tmX, tmDZ, p);
   ST_CUDA_LAUNCH_CHECK("tc_wgrad_kernel");
   return ST_OK;
 }

@@ -33,10 +33,9 @@ struct ConvParams {
 struct WgradParams {
   int B, To, t_chunks;
   int taps, pad_left, a_stride, a_cin;
-  int m_tiles, n_tiles, split;
+  int m_tiles, n_tiles;
   int Cin, Cout;
-  float* dW;
-  int use_atomic;
+  float* dW;                     // must be zero on entry (stream-K accumulates shared tiles with atomics)
 };
 
 int make_map_3d(CUtensorMap* map, const void* base, int C, int T, int Bn, int64_t ld, int64_t batch_stride,

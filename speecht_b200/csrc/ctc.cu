@@ -46,7 +46,10 @@ __device__ __forceinline__ double lse3(double a0, double a1, double a2) {
   return m + (double)__logf(s);
 }
 
-// dynamic smem: double buf[2][S + 4]; int ext[S]; unsigned char skip[S + 2]
+// dynamic smem: double buf[2][s_pad + 4]; int ext[s_pad]; unsigned char skip[s_pad + 2]; [float lsm_s[len*C]]
+// NS = extended-label positions per thread (S <= NS*256).  LSM_SMEM: the utterance's log-softmax rows are staged in
+// shared memory up front (one coalesced pass) so that the serial recursion never waits on an L2 round trip.
+template <int NS, bool LSM_SMEM>
 __global__ void __launch_bounds__(kABThreads)
 ctc_alpha_beta_kernel(const float* __restrict__ lsm, int T, int C, const int32_t* __restrict__ labels,
                       const int32_t* __restrict__ label_offsets, const int32_t* __restrict__ seq_len, int blank,
@@ -64,6 +67,7 @@ ctc_alpha_beta_kernel(const float* __restrict__ lsm, int T, int C, const int32_t
   const int bstride = s_pad + 4;
   int* ext = reinterpret_cast<int*>(buf + 2 * bstride);                 // [s_pad]
   unsigned char* skip = reinterpret_cast<unsigned char*>(ext + s_pad);  // [s_pad + 2]
+  float* lsm_s = reinterpret_cast<float*>(smem_raw + (((size_t)2 * bstride * 8 + (size_t)s_pad * 4 + s_pad + 2 + 15) & ~(size_t)15));
   __shared__ int s_bad;
   if (threadIdx.x == 0) s_bad = 0;
   __syncthreads();
@@ -83,12 +87,17 @@ ctc_alpha_beta_kernel(const float* __restrict__ lsm, int T, int C, const int32_t
   if (repeats) atomicAdd(&s_bad, repeats << 1);
   __syncthreads();
   const int n_rep = s_bad >> 1;
-  const bool infeasible = (s_bad & 1) || (L + n_rep > len) || len < 0 || S > s_pad;
+  const bool infeasible = (s_bad & 1) || (L + n_rep > len) || len < 0 || S > s_pad || S > NS * kABThreads;
   for (int s = threadIdx.x; s < S + 2 && S <= s_pad; s += kABThreads) {
     // skip[s]: transition s-2 -> s allowed
     skip[s] = (s >= 2 && s < S && ext[s] != blank && ext[s] != ext[s - 2]) ? 1 : 0;
   }
   for (int i = threadIdx.x; i < 2 * bstride; i += kABThreads) buf[i] = -INFINITY;
+  const float* lrow = lsm + (int64_t)b * T * C;
+  if (LSM_SMEM && !infeasible && len > 0) {
+    for (int i = threadIdx.x; i < len * C; i += kABThreads) lsm_s[i] = lrow[i];
+    lrow = lsm_s;
+  }
   __syncthreads();
 
   if (infeasible || len <= 0) {
@@ -101,48 +110,55 @@ ctc_alpha_beta_kernel(const float* __restrict__ lsm, int T, int C, const int32_t
   }
   if (!is_beta && threadIdx.x == 0) status[b] = 0;
 
-  const float* lrow = lsm + (int64_t)b * T * C;
   double* lat = (is_beta ? beta : alpha) + (int64_t)b * T * s_pad;
-  constexpr int NS_MAX = 8;                                             // S <= 8*256 = 2048 (label len <= 1023)
-  int my_ext[NS_MAX];
-  unsigned char my_skip[NS_MAX];
-  float lp_next[NS_MAX];
-  const int ns = (S + kABThreads - 1) / kABThreads;
+  int my_ext[NS];
+  bool my_skip[NS], live[NS];
 #pragma unroll
-  for (int j = 0; j < NS_MAX; ++j) {
+  for (int j = 0; j < NS; ++j) {
     const int s = threadIdx.x + j * kABThreads;
-    my_ext[j] = (j < ns && s < S) ? ext[s] : blank;
-    my_skip[j] = 0;
+    live[j] = s < S;
+    my_ext[j] = live[j] ? ext[s] : blank;
+    my_skip[j] = false;
   }
 
   if (!is_beta) {
     // alpha_0
 #pragma unroll
-    for (int j = 0; j < NS_MAX; ++j) {
+    for (int j = 0; j < NS; ++j) {
       const int s = threadIdx.x + j * kABThreads;
-      if (j < ns && s < S) {
-        my_skip[j] = skip[s];
-        double v = (s < 2) ? (double)lrow[my_ext[j]] : -INFINITY;
+      if (live[j]) {
+        my_skip[j] = skip[s] != 0;
+        const double v = (s < 2) ? (double)lrow[my_ext[j]] : -INFINITY;
         buf[2 + s] = v;                                                 // slot 0, +2 pad so s-1, s-2 read -inf
         lat[s] = v;
-        lp_next[j] = (len > 1) ? lrow[(int64_t)C + my_ext[j]] : 0.f;
       }
     }
     __syncthreads();
     for (int t = 1; t < len; ++t) {
       const double* prev = buf + ((t - 1) & 1) * bstride;
       double* cur = buf + (t & 1) * bstride;
+      const float* lp_row = lrow + (int64_t)t * C;
+      double a0[NS], a1[NS], a2[NS], v[NS];
+      float lp[NS];
 #pragma unroll
-      for (int j = 0; j < NS_MAX; ++j) {
+      for (int j = 0; j < NS; ++j) {
         const int s = threadIdx.x + j * kABThreads;
-        if (j < ns && s < S) {
-          const float lp = lp_next[j];
-          if (t + 1 < len) lp_next[j] = lrow[(int64_t)(t + 1) * C + my_ext[j]];
-          const double a0 = prev[2 + s], a1 = prev[1 + s];
-          const double a2 = my_skip[j] ? prev[s] : -INFINITY;
-          const double v = lse3(a0, a1, a2) + (double)lp;
-          cur[2 + s] = v;
-          lat[(int64_t)t * s_pad + s] = v;
+        if (live[j]) {
+          a0[j] = prev[2 + s];
+          a1[j] = prev[1 + s];
+          a2[j] = my_skip[j] ? prev[s] : -INFINITY;
+          lp[j] = lp_row[my_ext[j]];
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < NS; ++j)
+        if (live[j]) v[j] = lse3(a0[j], a1[j], a2[j]) + (double)lp[j];
+#pragma unroll
+      for (int j = 0; j < NS; ++j) {
+        const int s = threadIdx.x + j * kABThreads;
+        if (live[j]) {
+          cur[2 + s] = v[j];
+          lat[(int64_t)t * s_pad + s] = v[j];
         }
       }
       __syncthreads();
@@ -158,31 +174,41 @@ ctc_alpha_beta_kernel(const float* __restrict__ lsm, int T, int C, const int32_t
     // beta_{len-1}; smem holds g_t(s) = beta_t(s) + lp_t(s) for the step below to consume
     const float* last = lrow + (int64_t)(len - 1) * C;
 #pragma unroll
-    for (int j = 0; j < NS_MAX; ++j) {
+    for (int j = 0; j < NS; ++j) {
       const int s = threadIdx.x + j * kABThreads;
-      if (j < ns && s < S) {
-        my_skip[j] = skip[s + 2];                                       // transition s -> s+2
+      if (live[j]) {
+        my_skip[j] = skip[s + 2] != 0;                                  // transition s -> s+2
         const double v = (s >= S - 2) ? 0.0 : -INFINITY;
         lat[(int64_t)(len - 1) * s_pad + s] = v;
         buf[((len - 1) & 1) * bstride + s] = v + (double)last[my_ext[j]];
-        lp_next[j] = (len > 1) ? lrow[(int64_t)(len - 2) * C + my_ext[j]] : 0.f;
       }
     }
     __syncthreads();
     for (int t = len - 2; t >= 0; --t) {
       const double* nxt = buf + ((t + 1) & 1) * bstride;               // entries S..S+3 stay -inf
       double* cur = buf + (t & 1) * bstride;
+      const float* lp_row = lrow + (int64_t)t * C;
+      double b0[NS], b1[NS], b2[NS], v[NS];
+      float lp[NS];
 #pragma unroll
-      for (int j = 0; j < NS_MAX; ++j) {
+      for (int j = 0; j < NS; ++j) {
         const int s = threadIdx.x + j * kABThreads;
-        if (j < ns && s < S) {
-          const float lp = lp_next[j];
-          if (t > 0) lp_next[j] = lrow[(int64_t)(t - 1) * C + my_ext[j]];
-          const double b0 = nxt[s], b1 = nxt[s + 1];
-          const double b2 = my_skip[j] ? nxt[s + 2] : -INFINITY;
-          const double v = lse3(b0, b1, b2);
-          lat[(int64_t)t * s_pad + s] = v;
-          cur[s] = v + (double)lp;
+        if (live[j]) {
+          b0[j] = nxt[s];
+          b1[j] = nxt[s + 1];
+          b2[j] = my_skip[j] ? nxt[s + 2] : -INFINITY;
+          lp[j] = lp_row[my_ext[j]];
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < NS; ++j)
+        if (live[j]) v[j] = lse3(b0[j], b1[j], b2[j]);
+#pragma unroll
+      for (int j = 0; j < NS; ++j) {
+        const int s = threadIdx.x + j * kABThreads;
+        if (live[j]) {
+          lat[(int64_t)t * s_pad + s] = v[j];
+          cur[s] = v[j] + (double)lp[j];
         }
       }
       __syncthreads();
@@ -337,12 +363,29 @@ ST_API int st_ctc_loss(const float* logits, int64_t stride_t, int64_t stride_b, 
   ctc_log_softmax_kernel<<<(rows + 7) / 8, 256, 0, s>>>(logits, stride_t, stride_b, T, B, C, seq_len, lsm);
   ST_CUDA_LAUNCH_CHECK("ctc_log_softmax_kernel");
 
-  const size_t smem = (size_t)2 * (s_pad + 4) * sizeof(double) + (size_t)s_pad * sizeof(int) + (size_t)(s_pad + 2) + 16;
-  if (smem > 48 * 1024) {
-    ST_CUDA_CALL(cudaFuncSetAttribute(ctc_alpha_beta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const size_t smem_base = (((size_t)2 * (s_pad + 4) * sizeof(double) + (size_t)s_pad * sizeof(int) + (size_t)(s_pad + 2) + 15) &
+                            ~(size_t)15);
+  const size_t smem_lsm = (size_t)T * C * sizeof(float);
+  const bool lsm_in_smem = smem_base + smem_lsm + 64 <= 200 * 1024;
+  const size_t smem = smem_base + (lsm_in_smem ? smem_lsm : 0) + 64;
+  const int S_max = 2 * max_label_len + 1;
+  const int ns = S_max <= kABThreads ? 1 : (S_max <= 2 * kABThreads ? 2 : (S_max <= 4 * kABThreads ? 4 : 8));
+#define ST_CTC_LAUNCH(NS_, SM_)                                                                                      \
+  do {                                                                                                               \
+    if (smem > 48 * 1024)                                                                                            \
+      ST_CUDA_CALL(cudaFuncSetAttribute(ctc_alpha_beta_kernel<NS_, SM_>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                        (int)smem));                                                                 \
+    ctc_alpha_beta_kernel<NS_, SM_><<<dim3(B, 2), kABThreads, smem, s>>>(lsm, T, C, labels, label_offsets, seq_len,  \
+                                                                       blank, s_pad, alpha, beta, logp, loss, status); \
+  } while (0)
+  if (lsm_in_smem) {
+    if (ns == 1) ST_CTC_LAUNCH(1, true); else if (ns == 2) ST_CTC_LAUNCH(2, true);
+    else if (ns == 4) ST_CTC_LAUNCH(4, true); else ST_CTC_LAUNCH(8, true);
+  } else {
+    if (ns == 1) ST_CTC_LAUNCH(1, false); else if (ns == 2) ST_CTC_LAUNCH(2, false);
+    else if (ns == 4) ST_CTC_LAUNCH(4, false); else ST_CTC_LAUNCH(8, false);
   }
-  ctc_alpha_beta_kernel<<<dim3(B, 2), kABThreads, smem, s>>>(lsm, T, C, labels, label_offsets, seq_len, blank,
-                                                            s_pad, alpha, beta, logp, loss, status);
+#undef ST_CTC_LAUNCH
   ST_CUDA_LAUNCH_CHECK("ctc_alpha_beta_kernel");
   if (grad || grad_planes) {
     ctc_grad_kernel<<<(rows + 7) / 8, 256, 0, s>>>(lsm, alpha, beta, logp, labels, label_offsets, seq_len, status,

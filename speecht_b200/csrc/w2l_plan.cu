@@ -24,7 +24,6 @@ struct Layer {
   CUtensorMap tm_fwd_a, tm_fwd_b;     // forward
   CUtensorMap tm_dg_a[2], tm_dg_b;    // data gradient (A = dz ping or pong)
   CUtensorMap tm_wg_x, tm_wg_dz[2];   // filter gradient
-  int wg_split;
 };
 
 int round_up(int x, int m) { return (x + m - 1) / m * m; }
@@ -46,21 +45,6 @@ struct st_plan {
 };
 
 namespace {
-
-int choose_split(int base_items, int total_iters) {
-  const int sms = st_num_sms();
-  static const int cands[] = {1, 2, 3, 4, 6, 8, 12, 16, 24, 32, 48, 64, 96, 128};
-  int best = 1;
-  double best_eff = 0.0;
-  for (int s : cands) {
-    if (s > 1 && total_iters / s < 4) break;
-    const int items = base_items * s;
-    const double eff = (double)items / (double)(((items + sms - 1) / sms) * sms);
-    if (eff >= 0.92) return s;
-    if (eff > best_eff + 1e-9) { best_eff = eff; best = s; }
-  }
-  return best;
-}
 
 __nv_bfloat16* bf(st_plan* p, size_t off) { return reinterpret_cast<__nv_bfloat16*>(p->arena + off); }
 
@@ -190,9 +174,6 @@ ST_API int st_plan_bind(st_plan* p, void* arena, size_t arena_bytes, float* para
       rc = tc::make_map_2d(&L.tm_dg_b, bf(p, L.off_wbwd), l == 10 ? 64 : L.Cout, npl * L.K * L.Cin, L.ld_co, 64, 256);
       if (rc) return rc;
     }
-    const int m_tiles = (L.Cin + 127) / 128;
-    const int n_tiles = l == 10 ? 1 : (L.Cout + 255) / 256;
-    L.wg_split = choose_split(L.K * m_tiles * n_tiles, B * ((L.To + 63) / 64));
   }
   p->bound = true;
   return ST_OK;
@@ -274,11 +255,9 @@ ST_API int st_plan_backward_range(st_plan* p, int hi, int lo, st_stream_t stream
     w.taps = L.K; w.pad_left = L.pad_left; w.a_stride = L.stride; w.a_cin = L.Cin;
     w.m_tiles = (L.Cin + 127) / 128;
     w.n_tiles = l == 10 ? 1 : (L.Cout + 255) / 256;
-    w.split = L.wg_split;
     w.Cin = L.Cin; w.Cout = L.Cout;
     w.dW = p->grads + L.w_off;
-    w.use_atomic = w.split > 1;
-    if (w.use_atomic) ST_CUDA_CALL(cudaMemsetAsync(w.dW, 0, (size_t)L.K * L.Cin * L.Cout * sizeof(float), s));
+    ST_CUDA_CALL(cudaMemsetAsync(w.dW, 0, (size_t)L.K * L.Cin * L.Cout * sizeof(float), s));
     rc = tc::launch_wgrad(L.tm_wg_x, L.tm_wg_dz[l == 10 ? 0 : cur], w, l == 10 ? 64 : 256, p->npl, s);
     if (rc) return rc;
     p->launches++;

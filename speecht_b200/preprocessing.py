@@ -1,0 +1,183 @@
+"""Feature extraction + the preprocessed-sample store (mirror of reference speecht/preprocessing.py).
+
+`calc_power_spectrogram(audio_data, samplerate, n_mels=128, n_fft=512, hop_length=160)` keeps the reference
+signature (preprocessing.py:36) and runs on the GPU (csrc/melspec.cu).  `SpeechCorpusReader` keeps the on-disk
+contract between `preprocess` and `train/evaluate`: `<data>/preprocessed-power/<split>/<audio_id>.npz` with keys
+`audio_fragments [T, n_mels]` and `transcript [L]` (preprocessing.py:178,199-206,243-279).
+
+Decoding FLAC needs an audio decoder the image does not have (no soundfile / audioread / ffmpeg): audio loading is
+delegated to an injectable `load_audio(path) -> (samples, samplerate)`; WAV files are read with the stdlib.
+The MFCC feature type (preprocessing.py:61-84) is out of scope (not the default, not on the hot path).
+"""
+import fnmatch
+import logging
+import os
+import random
+import wave
+
+import numpy as np
+
+from . import vocabulary
+
+
+def normalize(values):
+  """(x - mean) / std over the whole array (preprocessing.py:29-33)."""
+  return (values - np.mean(values)) / np.std(values)
+
+
+def calc_power_spectrogram(audio_data, samplerate, n_mels=128, n_fft=512, hop_length=160):
+  """preprocessing.py:36-58 on the GPU.  audio_data: 1-D float array -> ndarray [time, n_mels] float32."""
+  import torch
+  from . import ops
+  wav = torch.from_numpy(np.ascontiguousarray(audio_data, dtype=np.float32)).cuda()[None]
+  feat, frames = ops.power_spectrogram(wav, [wav.shape[1]], samplerate, n_mels=n_mels, n_fft=n_fft,
+                                       hop_length=hop_length)
+  return feat[0, :int(frames[0].item())].cpu().numpy()
+
+
+def calc_power_spectrogram_batch(audio_list, samplerate, n_mels=128, n_fft=512, hop_length=160):
+  """Batched variant: list of 1-D arrays -> list of [time_i, n_mels] arrays, one kernel sequence for all."""
+  import torch
+  from . import ops
+  lens = [len(a) for a in audio_list]
+  host = np.zeros((len(audio_list), max(lens)), dtype=np.float32)
+  for i, a in enumerate(audio_list):
+    host[i, :lens[i]] = a
+  feat, frames = ops.power_spectrogram(torch.from_numpy(host).cuda(), lens, samplerate, n_mels=n_mels, n_fft=n_fft,
+                                       hop_length=hop_length)
+  feat, frames = feat.cpu().numpy(), frames.cpu().numpy()
+  return [feat[i, :frames[i]].copy() for i in range(len(audio_list))]
+
+
+def load_wav(path):
+  """Minimal PCM16 WAV reader (the reference uses librosa.load, preprocessing.py:169, which resamples to 22050 Hz;
+  no resampler is available here, so the native rate is returned)."""
+  with wave.open(path, 'rb') as f:
+    if f.getsampwidth() != 2:
+      raise ValueError('only 16-bit PCM WAV is supported')
+    data = np.frombuffer(f.readframes(f.getnframes()), dtype=np.int16).astype(np.float32) / 32768.0
+    if f.getnchannels() > 1:
+      data = data.reshape(-1, f.getnchannels()).mean(axis=1)
+    return data, f.getframerate()
+
+
+def iglob_recursive(directory, file_pattern):
+  for root, _dirs, file_names in os.walk(directory):
+    for filename in fnmatch.filter(file_names, file_pattern):
+      yield os.path.join(root, filename)
+
+
+class SpeechCorpusReader:
+  """Reads / writes the preprocessed corpus (preprocessing.py:103-279)."""
+
+  AUDIO_PATTERNS = ('*.flac', '*.wav')
+
+  def __init__(self, data_directory, load_audio=None):
+    self._data_directory = data_directory
+    self._transcript_dict_cache = None
+    self._load_audio = load_audio or load_wav
+
+  @property
+  def _transcript_dict(self):
+    if not self._transcript_dict_cache:
+      self._transcript_dict_cache = self._build_transcript()
+    return self._transcript_dict_cache
+
+  @staticmethod
+  def _get_transcript_entries(transcript_directory):
+    """Yields [audio_id, sentence] from every *.trans.txt (lines `ID WORD1 WORD2 ...`)."""
+    for transcript_file in iglob_recursive(transcript_directory, '*.trans.txt'):
+      with open(transcript_file, 'r') as f:
+        for line in f:
+          yield line.rstrip('\n').split(' ', 1)
+
+  def _build_transcript(self):
+    return {entry[0]: vocabulary.sentence_to_ids(entry[1])
+            for entry in self._get_transcript_entries(self._data_directory)}
+
+  @classmethod
+  def _extract_audio_id(cls, audio_file):
+    return os.path.splitext(os.path.basename(audio_file))[0]
+
+  def _audio_files(self, directory):
+    files = []
+    for pattern in self.AUDIO_PATTERNS:
+      files.extend(iglob_recursive(self._data_directory + '/' + directory, pattern))
+    return files
+
+  def _get_directory(self, feature_type, sub_directory):
+    preprocess_directory = 'preprocessed'
+    if feature_type == calc_power_spectrogram or feature_type == 'power':
+      preprocess_directory += '-power'
+    return self._data_directory + '/' + preprocess_directory + '/' + sub_directory
+
+  def generate_samples(self, directory, preprocess_fnc):
+    """(audio_id, audio_fragments, transcript) for every audio file below `directory`."""
+    transcript_dict = self._transcript_dict
+    for audio_file in self._audio_files(directory):
+      audio_data, samplerate = self._load_audio(audio_file)
+      audio_id = self._extract_audio_id(audio_file)
+      yield audio_id, preprocess_fnc(audio_data, samplerate), transcript_dict[audio_id]
+
+  def store_samples(self, directory, preprocess_fnc, batch_size=32):
+    """Preprocess every audio file of `directory` into <preprocessed[-power]>/<directory>/<audio_id>.npz.
+    The reference fans out over a multiprocessing Pool (preprocessing.py:229); here utterances are batched onto
+    the GPU instead when the feature function is the power spectrogram."""
+    out_directory = self._get_directory(preprocess_fnc, directory)
+    os.makedirs(out_directory, exist_ok=True)
+    transcript_dict = self._transcript_dict
+    files = self._audio_files(directory)
+    for i in range(0, len(files), batch_size):
+      chunk = files[i:i + batch_size]
+      loaded = [self._load_audio(f) for f in chunk]
+      rates = {sr for _a, sr in loaded}
+      if preprocess_fnc == calc_power_spectrogram and len(rates) == 1:
+        feats = calc_power_spectrogram_batch([a for a, _sr in loaded], rates.pop())
+      else:
+        feats = [preprocess_fnc(a, sr) for a, sr in loaded]
+      for audio_file, fragments in zip(chunk, feats):
+        audio_id = self._extract_audio_id(audio_file)
+        np.savez(out_directory + '/' + audio_id, audio_fragments=fragments, transcript=transcript_dict[audio_id])
+
+  def load_samples(self, directory, max_size=False, loop_infinitely=False, limit_count=0, feature_type='mfcc'):
+    """Iterator of (audio_fragments, transcript) over the stored .npz files, shuffled; preprocessing.py:243-279."""
+    load_directory = self._get_directory(feature_type, directory)
+    if not os.path.exists(load_directory):
+      raise ValueError('Directory {} does not exist'.format(load_directory))
+    files = list(iglob_recursive(load_directory, '*.npz'))
+    random.shuffle(files)
+    if limit_count:
+      files = files[:limit_count]
+    while True:
+      for file in files:
+        with np.load(file) as data:
+          audio_length = data['audio_fragments'].shape[0]
+          if not max_size or audio_length <= max_size:
+            yield data['audio_fragments'], data['transcript']
+          else:
+            logging.warning('Audio snippet too long: {}'.format(audio_length))
+      if not loop_infinitely:
+        break
+      random.shuffle(files)
+
+
+class Preprocessing:
+  """`speecht-cli preprocess` (preprocessing.py:282-311) without the corpus download (no network here)."""
+
+  def __init__(self, flags):
+    self.flags = flags
+
+  def run(self):
+    corpus_reader = SpeechCorpusReader(self.flags.data_dir)
+    if self.flags.feature_type == 'power':
+      preprocess_fnc = calc_power_spectrogram
+    elif self.flags.feature_type == 'mfcc':
+      raise ValueError('mfcc features are out of scope of speecht_b200; use --power')
+    else:
+      raise ValueError('Feature type must be mfcc or power.')
+    preprocess_all = not (self.flags.train_only or self.flags.test_only or self.flags.dev_only)
+    for enabled, split, title in ((self.flags.train_only, 'train', 'training'), (self.flags.test_only, 'test', 'test'),
+                                  (self.flags.dev_only, 'dev', 'development')):
+      if enabled or preprocess_all:
+        print('Preprocessing {} data'.format(title))
+        corpus_reader.store_samples(split, preprocess_fnc)

@@ -172,3 +172,62 @@ def test_speech_model_step_surface():
     model.restore(sess, '/tmp/speecht_b200_ckpt')
     assert torch.equal(before, model.engine.params) and model.global_step.eval() == 2
     coord.request_stop(); coord.join()
+
+
+def test_cli_evaluate_step_count_1_is_the_config1_parity_gate(tmp_path, capsys):
+  """BASELINE configs[0] through the reference-facing executors: `evaluate --step-count 1` on 4 synthetic 1 s
+  utterances stored in the .npz layout, weights restored from the `export` .npy layout, greedy decode."""
+  import importlib.machinery
+  import importlib.util
+  from speecht_b200 import speech_model, vocabulary
+  from speecht_b200.evaluation import Evaluation
+  g = np.load(os.path.join(GOLDEN, 'config1_eval.npz'))
+  inputs, lengths, labels = O.synthetic_batch(seed=0, batch=4, seconds=1)
+  weights = O.xavier_weights(np.random.default_rng(1234), dtype=np.float32)
+  data = tmp_path / 'data' / 'preprocessed-power' / 'test'
+  data.mkdir(parents=True)
+  for i in range(4):
+    np.savez(data / ('utt%d' % i), audio_fragments=inputs[i, :lengths[i]], transcript=labels[i])
+  run_dir = tmp_path / 'train' / 'gate'
+  speech_model.save_exported_weights(str(run_dir), weights)
+  loader = importlib.machinery.SourceFileLoader('cli', os.path.join(os.path.dirname(GOLDEN), '..', 'speecht-cli-b200'))
+  spec = importlib.util.spec_from_loader('cli', loader)
+  cli = importlib.util.module_from_spec(spec)
+  loader.exec_module(cli)
+  flags = cli.parse(['evaluate', '--step-count', '1', '--batch-size', '4', '--run-name', 'gate', '--no-save',
+                     '--data-dir', str(tmp_path / 'data'), '--train-dir', str(tmp_path / 'train'),
+                     '--log-dir', str(tmp_path / 'log')])
+  stats = Evaluation(flags).run()
+  out = capsys.readouterr().out
+  assert 'validation average loss %.2f' % float(np.mean(g['loss'])) in out
+  # decoded label sequences (order of the shuffled batch does not matter) are bit-exact with the golden decode
+  want = sorted(O.extract_decoded_ids(g['decoded_indices'], g['decoded_values']))
+  got = sorted([vocabulary.letter_to_id(c) for c in line[len('decoded: '):]] for line in out.splitlines()
+               if line.startswith('decoded: '))
+  assert got == want
+  assert stats.decodings_counter == 4
+
+
+def test_cli_train_checkpoints_and_resumes(tmp_path):
+  import importlib.machinery
+  import importlib.util
+  from speecht_b200.training import Training
+  from speecht_b200.speech_model import latest_checkpoint
+  inputs, lengths, labels = O.synthetic_batch(seed=2, batch=6, seconds=1)
+  data = tmp_path / 'data' / 'preprocessed-power' / 'train'
+  data.mkdir(parents=True)
+  for i in range(6):
+    np.savez(data / ('utt%d' % i), audio_fragments=inputs[i, :lengths[i]], transcript=labels[i])
+  loader = importlib.machinery.SourceFileLoader('cli', os.path.join(os.path.dirname(GOLDEN), '..', 'speecht-cli-b200'))
+  spec = importlib.util.spec_from_loader('cli', loader)
+  cli = importlib.util.module_from_spec(spec)
+  loader.exec_module(cli)
+  argv = ['train', '--batch-size', '2', '--steps-per-checkpoint', '2', '--run-name', 'r', '--learning-rate', '1e-3',
+          '--data-dir', str(tmp_path / 'data'), '--train-dir', str(tmp_path / 'train'), '--log-dir', str(tmp_path / 'log')]
+  flags = cli.parse(argv)
+  os.makedirs(flags.run_train_dir, exist_ok=True)
+  model = Training(flags).run(max_steps=4)
+  assert model.global_step.eval() == 4
+  assert latest_checkpoint(flags.run_train_dir).endswith('speechT.ckpt-4')
+  model2 = Training(cli.parse(argv)).run(max_steps=2)          # resumes from step 4
+  assert model2.global_step.eval() == 6

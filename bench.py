@@ -238,22 +238,26 @@ def run_ours(args, rank, local_rank, world):
     sampler.start()                                          # nvidia-smi needs ~1 s before its first sample
   for i in range(args.warmup):
     step_resident(i)
-  eng.kernel_times = []                                      # (name, flops, event pair) recorded inside the steps
-  eng.record_kernel_times = True
+  eng.start_kernel_timing()                                  # CUDA-event pairs around the conv kernels, in-stream
   launches0 = eng.launches
   mark0 = sampler.mark()
   ms_total = timed(step_resident, args.steps)
   mark1 = sampler.mark()
   launches = eng.launches - launches0
-  eng.record_kernel_times = False
+  timings = eng.stop_kernel_timing()
   ms_step = ms_total / args.steps
   value = world * B / (ms_step * 1e-3)
 
   # ---- roofline of the dominant kernel, from events recorded inside the timed region
   roofline = None
   if rank == 0:
-    roofline = eng.roofline_report(os.path.join(ROOT, 'MEASURED_PEAKS.json')) if hasattr(eng, 'roofline_report') \
-      else None
+    roofline = eng.roofline_report(timings, args.steps, os.path.join(ROOT, 'MEASURED_PEAKS.json'))
+    if roofline is not None and os.path.exists(os.path.join(ROOT, 'profiles', 'traffic.json')):
+      # dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed
+      # `ncu --set full` capture (profiles/), keyed by precision
+      tr = json.load(open(os.path.join(ROOT, 'profiles', 'traffic.json'))).get(args.precision, {})
+      roofline['traffic'] = tr.get('bytes_per_launch')
+      roofline['traffic_source'] = tr.get('source')
 
   # ---- end-to-end through SpeechModel.step with host batches (`e2e`)
   class HostFeed(speech_input.BaseInputLoader):

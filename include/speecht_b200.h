@@ -129,6 +129,10 @@ float* st_plan_logits(st_plan* plan);
 void* st_plan_dlogits_planes(st_plan* plan);
 int st_plan_get_activation(st_plan* plan, int layer, float* dst, st_stream_t stream);
 int st_plan_launches(const st_plan* plan);
+/* bench support: CUDA-event pair around every tensor-core launch (kind 0 = forward conv, 1 = data gradient,
+ * 2 = filter gradient); st_plan_read_timings is host-synchronous and returns the number of records written. */
+int st_plan_set_timing(st_plan* plan, int enable);
+int st_plan_read_timings(st_plan* plan, int* kind, int* layer, double* flops, float* ms, int max_records);
 
 #ifdef __cplusplus
 }

@@ -62,6 +62,8 @@ _SIGNATURES = {
   'st_plan_dlogits_planes': (c_void_p, [P]),
   'st_plan_get_activation': (c_int, [P, c_int, P, P]),
   'st_plan_launches': (c_int, [P]),
+  'st_plan_set_timing': (c_int, [P, c_int]),
+  'st_plan_read_timings': (c_int, [P, P, P, P, P, c_int]),
 }
 
 _lib = None

@@ -538,35 +538,43 @@ pack_filter_bwd_kernel(const float* __restrict__ w, int64_t rows, int Cout, __nv
   }
 }
 
-// db[n] += sum_rows sum_planes dz[pl][row][n]; block (32 column pairs, 8 row lanes); grid (ceil(ld/64), chunks)
-__global__ void bias_grad_planes_kernel(const __nv_bfloat16* __restrict__ dz, int64_t rows, int N, int ld,
-                                        int n_planes, float* __restrict__ db, int rows_per_block) {
-  __shared__ float part[8][66];
-  const int c2 = blockIdx.x * 32 + threadIdx.x;            // column pair index
+// db[n] += sum_rows sum_planes dz[pl][row][n]; block (32 column octets, 8 row lanes): each thread streams 16-byte
+// vectors (8 bf16 columns) down its rows; grid (ceil(ld/256), row chunks)
+__global__ void __launch_bounds__(256)
+bias_grad_planes_kernel(const __nv_bfloat16* __restrict__ dz, int64_t rows, int N, int ld, int n_planes,
+                        float* __restrict__ db, int rows_per_block) {
+  __shared__ float part[8][32 * 8 + 1];
+  const int c8 = blockIdx.x * 32 + threadIdx.x;            // column octet index
   const int64_t r0 = (int64_t)blockIdx.y * rows_per_block;
   const int64_t r1 = min(rows, r0 + rows_per_block);
   const int64_t plane_stride = rows * ld;
-  float a0 = 0.f, a1 = 0.f;
-  if (c2 * 2 < ld) {
+  float acc[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+  if (c8 * 8 < ld) {
     for (int pl = 0; pl < n_planes; ++pl) {
-      const __nv_bfloat162* src = reinterpret_cast<const __nv_bfloat162*>(dz + pl * plane_stride);
+      const __nv_bfloat16* src = dz + pl * plane_stride + c8 * 8;
+#pragma unroll 4
       for (int64_t r = r0 + threadIdx.y; r < r1; r += 8) {
-        const float2 f = __bfloat1622float2(src[(r * ld) / 2 + c2]);
-        a0 += f.x;
-        a1 += f.y;
+        const uint4 v = *reinterpret_cast<const uint4*>(src + r * ld);
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          acc[2 * i] += __uint_as_float(w[i] << 16);
+          acc[2 * i + 1] += __uint_as_float(w[i] & 0xffff0000u);
+        }
       }
     }
   }
-  part[threadIdx.y][threadIdx.x * 2] = a0;
-  part[threadIdx.y][threadIdx.x * 2 + 1] = a1;
-  __syncthreads();
-  if (threadIdx.y == 0) {
-    float s0 = 0.f, s1 = 0.f;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) { s0 += part[i][threadIdx.x * 2]; s1 += part[i][threadIdx.x * 2 + 1]; }
-    if (c2 * 2 < N) atomicAdd(db + c2 * 2, s0);
-    if (c2 * 2 + 1 < N) atomicAdd(db + c2 * 2 + 1, s1);
-  }
+  for (int i = 0; i < 8; ++i) part[threadIdx.y][threadIdx.x * 8 + i] = acc[i];
+  __syncthreads();
+  const int tid = threadIdx.y * 32 + threadIdx.x;          // 256 threads <-> 256 columns of this block
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s += part[i][tid];
+  const int n = blockIdx.x * 256 + tid;
+  if (n < N) atomicAdd(db + n, s);
 }
 
 __global__ void __launch_bounds__(256)
@@ -739,11 +747,11 @@ int launch_pack_filter(const float* w, int K, int Cin, int Cout, __nv_bfloat16* 
 int launch_bias_grad(const __nv_bfloat16* dz, int64_t rows, int N, int ld, int n_planes, float* db,
                      cudaStream_t stream) {
   ST_CUDA_CALL(cudaMemsetAsync(db, 0, (size_t)N * sizeof(float), stream));
-  int chunks = (int)((rows + 127) / 128);
-  const int cap = 2 * st_num_sms();
+  int chunks = (int)((rows + 63) / 64);
+  const int cap = 8 * st_num_sms() / ((ld + 255) / 256);
   chunks = chunks > cap ? cap : (chunks < 1 ? 1 : chunks);
   const int rows_per_block = (int)((rows + chunks - 1) / chunks);
-  dim3 grid((ld + 63) / 64, chunks);
+  dim3 grid((ld + 255) / 256, chunks);
   bias_grad_planes_kernel<<<grid, dim3(32, 8), 0, stream>>>(dz, rows, N, ld, n_planes, db, rows_per_block);
   ST_CUDA_LAUNCH_CHECK("bias_grad_planes_kernel");
   return ST_OK;

@@ -41,10 +41,35 @@ struct st_plan {
   float* grads;
   int launches;
   bool bound;
+  // optional per-launch CUDA-event timing of the tensor-core kernels (bench.py roofline)
+  bool timing;
+  std::vector<cudaEvent_t> ev_pool;
+  struct Rec { int kind, layer; double flops; int e0, e1; };   // kind 0 = conv fwd, 1 = data grad, 2 = filter grad
+  std::vector<Rec> recs;
+  int ev_used;
   int cur_dz;                  // ping/pong buffer holding the gradient wrt the next layer to process
 };
 
 namespace {
+
+int timed_begin(st_plan* p, cudaStream_t s) {
+  if (!p->timing) return -1;
+  while ((int)p->ev_pool.size() < p->ev_used + 2) {
+    cudaEvent_t e;
+    if (cudaEventCreate(&e) != cudaSuccess) return -1;
+    p->ev_pool.push_back(e);
+  }
+  const int i = p->ev_used;
+  p->ev_used += 2;
+  cudaEventRecord(p->ev_pool[i], s);
+  return i;
+}
+
+void timed_end(st_plan* p, int i, int kind, int layer, double flops, cudaStream_t s) {
+  if (i < 0) return;
+  cudaEventRecord(p->ev_pool[i + 1], s);
+  p->recs.push_back({kind, layer, flops, i, i + 1});
+}
 
 __nv_bfloat16* bf(st_plan* p, size_t off) { return reinterpret_cast<__nv_bfloat16*>(p->arena + off); }
 
@@ -59,7 +84,7 @@ ST_API int st_plan_create(st_plan** out, int B, int T, int input_size, int num_c
   ST_CHECK_ARG(num_classes >= 2 && num_classes <= 32, "st_plan_create: num_classes must be in [2,32]");
   st_plan* p = new st_plan();
   p->B = B; p->T = T; p->Tpad = round_up(T, 2); p->F = input_size; p->C = num_classes; p->npl = n_planes;
-  p->arena = nullptr; p->params = nullptr; p->grads = nullptr; p->launches = 0; p->bound = false; p->cur_dz = 0;
+  p->arena = nullptr; p->params = nullptr; p->grads = nullptr; p->launches = 0; p->bound = false; p->cur_dz = 0; p->timing = false; p->ev_used = 0;
   // reference speech_model.py:275-292
   const int table[11][5] = {{48, 2, input_size, 250, 1}, {7, 1, 250, 250, 1}, {7, 1, 250, 250, 1}, {7, 1, 250, 250, 1},
                             {7, 1, 250, 250, 1},         {7, 1, 250, 250, 1}, {7, 1, 250, 250, 1}, {7, 1, 250, 250, 1},
@@ -107,6 +132,7 @@ ST_API int st_plan_create(st_plan** out, int B, int T, int input_size, int num_c
 }
 
 ST_API int st_plan_destroy(st_plan* p) {
+  if (p) for (cudaEvent_t e : p->ev_pool) cudaEventDestroy(e);
   delete p;
   return ST_OK;
 }
@@ -225,8 +251,10 @@ ST_API int st_plan_forward(st_plan* p, const float* inputs, st_stream_t stream) 
       c.out_f32 = reinterpret_cast<float*>(p->arena + p->off_logits);
       c.ld_f32 = 32;
     }
+    const int ti = timed_begin(p, s);
     rc = tc::launch_conv(L.tm_fwd_a, L.tm_fwd_b, c, block_n, p->npl, s);
     if (rc) return rc;
+    timed_end(p, ti, 0, l, 2.0 * L.K * L.Cin * L.Cout * (double)L.To * p->B, s);
     p->launches++;
   }
   return ST_OK;
@@ -258,8 +286,10 @@ ST_API int st_plan_backward_range(st_plan* p, int hi, int lo, st_stream_t stream
     w.Cin = L.Cin; w.Cout = L.Cout;
     w.dW = p->grads + L.w_off;
     ST_CUDA_CALL(cudaMemsetAsync(w.dW, 0, (size_t)L.K * L.Cin * L.Cout * sizeof(float), s));
+    int ti = timed_begin(p, s);
     rc = tc::launch_wgrad(L.tm_wg_x, L.tm_wg_dz[l == 10 ? 0 : cur], w, l == 10 ? 64 : 256, p->npl, s);
     if (rc) return rc;
+    timed_end(p, ti, 2, l, 2.0 * L.K * L.Cin * L.Cout * (double)L.To * p->B, s);
     p->launches++;
     // ---- data gradient, ReLU mask of the layer below fused
     if (l > 0) {
@@ -285,8 +315,10 @@ ST_API int st_plan_backward_range(st_plan* p, int hi, int lo, st_stream_t stream
       c.ld_out = Lb.ld_out;
       c.mask_hi = bf(p, Lb.off_out);
       c.ld_mask = Lb.ld_out;
+      ti = timed_begin(p, s);
       rc = tc::launch_conv(L.tm_dg_a[l == 10 ? 0 : cur], L.tm_dg_b, c, 256, p->npl, s);
       if (rc) return rc;
+      timed_end(p, ti, 1, l, 2.0 * L.K * L.Cin * L.Cout * (double)L.To * p->B, s);
       p->launches++;
       cur = nxt;
     }
@@ -307,4 +339,31 @@ ST_API int st_plan_get_activation(st_plan* p, int layer, float* dst, st_stream_t
   Layer& L = p->layers[layer];
   return tc::launch_merge_planes(bf(p, L.off_out), (int64_t)p->B * L.To, L.Cout, L.ld_out, p->npl, dst, L.Cout,
                                  st_cu(stream));
+}
+
+// Per-launch timing of the tensor-core kernels.  st_plan_set_timing(plan, 1) starts recording a CUDA event pair
+// around every tc_conv / tc_wgrad launch on the launch stream; st_plan_read_timings synchronises the events and
+// returns up to `max` records as (kind, layer, flops, milliseconds), clearing the log.  Host-synchronous.
+ST_API int st_plan_set_timing(st_plan* p, int enable) {
+  ST_CHECK_ARG(p, "st_plan_set_timing: null plan");
+  p->timing = enable != 0;
+  p->recs.clear();
+  p->ev_used = 0;
+  return ST_OK;
+}
+
+ST_API int st_plan_read_timings(st_plan* p, int* kind, int* layer, double* flops, float* ms, int max) {
+  ST_CHECK_ARG(p && kind && layer && flops && ms, "st_plan_read_timings: null pointer");
+  int n = 0;
+  for (const st_plan::Rec& r : p->recs) {
+    if (n >= max) break;
+    ST_CUDA_CALL(cudaEventSynchronize(p->ev_pool[r.e1]));
+    float t = 0.f;
+    ST_CUDA_CALL(cudaEventElapsedTime(&t, p->ev_pool[r.e0], p->ev_pool[r.e1]));
+    kind[n] = r.kind; layer[n] = r.layer; flops[n] = r.flops; ms[n] = t;
+    ++n;
+  }
+  p->recs.clear();
+  p->ev_used = 0;
+  return n;
 }

@@ -150,37 +150,61 @@ class W2LEngine:
   def _timed(self, name, flops):
     return W2LEngine._Timed(self, name, flops)
 
-  def roofline_report(self, peaks_path=None):
-    """Roofline of the dominant kernel from the events recorded inside the timed steps: achieved = algorithmic
-    FLOPs of its launches / their summed CUDA-event duration; peak = MEASURED_PEAKS.json (sustained bf16 figure,
-    the kernel is timed inside a long step) or the B200_PROFILING.md fallback."""
+  def start_kernel_timing(self):
+    self.kernel_times = []
+    self.record_kernel_times = True
+    if self.precision != 'fp32':
+      self._tc().set_timing(True)
+
+  def stop_kernel_timing(self):
+    """-> list of (kernel, tag, layer, flops, ms) for every timed launch since start_kernel_timing."""
+    self.record_kernel_times = False
+    torch.cuda.synchronize(self.device)
+    out = [(name, 'conv', -1, flops, e0.elapsed_time(e1)) for name, flops, e0, e1 in self.kernel_times]
+    if self.precision != 'fp32':
+      out += self._tc().read_timings()
+      self._tc().set_timing(False)
+    self.kernel_times = []
+    return out
+
+  def roofline_report(self, timings, steps, peaks_path=None):
+    """Roofline of the dominant kernel from CUDA events recorded around its launches INSIDE the timed steps:
+    achieved = algorithmic FLOPs of those launches / their summed duration; peak = MEASURED_PEAKS.json
+    (bf16_tflops_sustained: the kernel is timed inside a long step) or the B200_PROFILING.md fallback."""
     import json
     import os
-    torch.cuda.synchronize(self.device)
-    by = {}
-    for name, flops, e0, e1 in self.kernel_times:
-      ms = e0.elapsed_time(e1)
+    by, per_layer = {}, {}
+    for name, tag, layer, flops, ms in timings:
       acc = by.setdefault(name, [0.0, 0.0, 0])
       acc[0] += flops; acc[1] += ms; acc[2] += 1
+      if layer >= 0:
+        pl = per_layer.setdefault('L%d.%s' % (layer, tag), [0.0, 0.0])
+        pl[0] += flops; pl[1] += ms
     if not by:
       return None
     peak, src = 1590.0, 'fallback 1.59 PFLOP/s (B200_PROFILING.md)'
     if peaks_path and os.path.exists(peaks_path):
       pk = json.load(open(peaks_path))
-      peak, src = float(pk.get('bf16_tflops_sustained', pk.get('bf16_tflops'))), 'MEASURED_PEAKS.json bf16_tflops_sustained'
+      peak, src = float(pk.get('bf16_tflops_sustained', pk.get('bf16_tflops'))), \
+        'MEASURED_PEAKS.json bf16_tflops_sustained (cuBLAS bf16, back-to-back)'
     name = max(by, key=lambda k: by[k][1])
     flops, ms, n = by[name]
     achieved = flops / (ms * 1e-3) / 1e12
     passes = {'fp32': None, 'bf16x3': 3, 'bf16': 1}[self.precision]
     rep = {'kernel': name, 'bound': 'tensor', 'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s',
-           'frac': achieved / peak, 'traffic': None, 'launches': n, 'avg_launch_ms': ms / n, 'peak_source': src,
-           'kernels': {k: {'tflops': v[0] / (v[1] * 1e-3) / 1e12, 'ms_total': v[1], 'launches': v[2]}
-                       for k, v in by.items()}}
+           'frac': achieved / peak, 'traffic': None, 'launches_per_step': n / steps, 'avg_launch_ms': ms / n,
+           'ms_per_step': ms / steps, 'peak_source': src,
+           'kernels': {k: {'tflops': v[0] / (v[1] * 1e-3) / 1e12, 'ms_per_step': v[1] / steps,
+                           'launches_per_step': v[2] / steps} for k, v in by.items()},
+           'layers_ms_per_step': {k: round(v[1] / steps, 4) for k, v in sorted(per_layer.items())}}
     if passes:
       rep['mma_passes'] = passes
       rep['tensor_pipe_frac'] = passes * achieved / peak
+      rep['note'] = ('achieved = algorithmic FLOPs (unpadded, 1 pass) / event time; in bf16x3 mode the tensor pipe '
+                     'executes 3 MMAs per algorithmic MAC, tensor_pipe_frac = 3*frac') if passes == 3 else \
+                    'plain bf16: one MMA pass'
     else:
-      rep['note'] = 'fp32 FFMA path: compared with the bf16 tensor peak only for reference'
+      rep['note'] = 'exact-fp32 FFMA path: compared with the bf16 tensor peak for reference only'
     return rep
 
   # ---------------------------------------------------------------- buffers

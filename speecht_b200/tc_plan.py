@@ -70,7 +70,30 @@ class TCPlan:
         self.shapes.pop(old).close()
       sh = _Shape(self.engine, B, T)
       self.shapes[key] = sh
+      if getattr(self, 'timing', False):
+        check(lib().st_plan_set_timing(sh.handle, 1))
     return sh
+
+  def set_timing(self, enable):
+    """CUDA-event pairs around every tensor-core launch (recorded on the launch stream, inside the steps)."""
+    self.timing = bool(enable)
+    for sh in self.shapes.values():
+      check(lib().st_plan_set_timing(sh.handle, int(self.timing)))
+
+  def read_timings(self):
+    """-> list of (kernel name, layer, algorithmic flops, ms); host-synchronous, clears the native log."""
+    out = []
+    names = {0: 'tc_conv_kernel', 1: 'tc_conv_kernel', 2: 'tc_wgrad_kernel'}
+    tags = {0: 'fwd', 1: 'dgrad', 2: 'wgrad'}
+    for sh in self.shapes.values():
+      cap = 8192
+      kind = (ctypes.c_int * cap)(); layer = (ctypes.c_int * cap)()
+      flops = (ctypes.c_double * cap)(); ms = (ctypes.c_float * cap)()
+      n = lib().st_plan_read_timings(sh.handle, kind, layer, flops, ms, cap)
+      if n < 0:
+        check(n)
+      out += [(names[kind[i]], tags[kind[i]], layer[i], flops[i], ms[i]) for i in range(n)]
+    return out
 
   def _launch_count(self, sh, before):
     self.engine.launches += lib().st_plan_launches(sh.handle) - before
@@ -78,8 +101,7 @@ class TCPlan:
   def _pack(self, sh):
     if sh.weights_version != self.engine._weights_version:
       before = lib().st_plan_launches(sh.handle)
-      with self.engine._timed('pack_filter_kernels', 0.0):
-        check(lib().st_plan_pack_weights(sh.handle, stream_ptr()))
+      check(lib().st_plan_pack_weights(sh.handle, stream_ptr()))
       sh.weights_version = self.engine._weights_version
       self._launch_count(sh, before)
 
@@ -89,8 +111,7 @@ class TCPlan:
     sh = self._shape(B, T)
     self._pack(sh)
     before = lib().st_plan_launches(sh.handle)
-    with eng._timed('tc_conv_kernel(fwd)', eng.conv_flops_forward(B, T)):
-      check(lib().st_plan_forward(sh.handle, ptr(inputs), stream_ptr()))
+    check(lib().st_plan_forward(sh.handle, ptr(inputs), stream_ptr()))
     self._launch_count(sh, before)
     self._last = sh
     return sh.logits_tm
@@ -117,7 +138,7 @@ class TCPlan:
       out['decoded'], out['neg_sum_logits'] = ops.ctc_greedy_decoder(logits, ctc_len)
       eng.launches += 1
     before = lib().st_plan_launches(sh.handle)
-    with eng._timed('tc_conv_kernel+tc_wgrad_kernel(bwd)', 2.0 * eng.conv_flops_forward(B, T)):
+    if True:
       if eng.world_size > 1:
         # layers 10..8 hold 82 % of the gradient bytes and finish first: their allreduce overlaps layers 7..0
         split = eng.layout.w_off[8]

@@ -94,6 +94,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_tiles = p.B * p.m_tiles_per_utt * p.n_tiles;
+  const int m_tiles = p.B * p.m_tiles_per_utt;
   const int nk = p.taps * p.chunks_per_tap;
 
   if (warp == 0 && lane == 0) {
@@ -121,13 +122,17 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int nt = tile % p.n_tiles, mt = tile / p.n_tiles;      // n fastest: the A rows of a tile are read from
-                                                                     // HBM once and shared through L2 by its n tiles
+        // n fastest (A rows read from HBM once, shared through L2 by their n tiles) when A is too big for L2;
+        // m fastest (one filter slab hot in L2 for the whole wave) otherwise
+        const int nt = p.n_fastest ? tile % p.n_tiles : tile / m_tiles;
+        const int mt = p.n_fastest ? tile / p.n_tiles : tile % m_tiles;
         const int b = mt / p.m_tiles_per_utt;
         const int t0 = (mt - b * p.m_tiles_per_utt) * kTileM;
         const int n0 = nt * BLOCK_N;
         for (int it = 0; it < nk; ++it) {
-          const int j = it / p.chunks_per_tap, cc = it - j * p.chunks_per_tap;
+          // channel chunk outer, filter tap inner: the taps of one chunk re-read (shifted) the same A rows, which
+          // stay in L2, instead of sweeping the whole channel range once per tap
+          const int cc = it / p.taps, j = it - cc * p.taps;
           const int m = p.a_sign * (j - p.pad_left);
           const int shift = p.a_stride == 1 ? m : floordiv(m, p.a_stride);
           const int a_col = (m - shift * p.a_stride) * p.a_cin + cc * kChunkK;
@@ -194,7 +199,8 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
       const int acc = local & 1;
       const uint32_t acc_phase = (local >> 1) & 1;
-      const int nt = tile % p.n_tiles, mt = tile / p.n_tiles;
+      const int nt = p.n_fastest ? tile % p.n_tiles : tile / m_tiles;
+      const int mt = p.n_fastest ? tile / p.n_tiles : tile % m_tiles;
       const int b = mt / p.m_tiles_per_utt;
       const int t = (mt - b * p.m_tiles_per_utt) * kTileM + row;
       const int n0 = nt * BLOCK_N;
@@ -203,10 +209,26 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       mbar_wait(tmem_full + acc, acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BLOCK_N;
+      // ReLU-mask vectors (data gradient only) are fetched one 32-column chunk ahead of their use
+      uint4 mk[4];
+      auto load_mask = [&](int c) {
+        const int nc = n0 + c * 32;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          mk[g] = make_uint4(0x3f803f80u, 0x3f803f80u, 0x3f803f80u, 0x3f803f80u);      // bf16 1.0 pairs: pass
+          if (p.mask_hi && row_ok && nc + g * 8 < p.ld_mask)
+            mk[g] = *reinterpret_cast<const uint4*>(p.mask_hi + out_row * p.ld_mask + nc + g * 8);
+        }
+      };
+      load_mask(0);
 #pragma unroll 1
       for (int c = 0; c < BLOCK_N / 32; ++c) {
         uint32_t r[32];
         tmem_ld32(taddr + c * 32, r);
+        uint4 mcur[4];
+#pragma unroll
+        for (int g = 0; g < 4; ++g) mcur[g] = mk[g];
+        if (c + 1 < BLOCK_N / 32) load_mask(c + 1);
         tmem_ld_wait();
         const int nc = n0 + c * 32;
         float v[32];
@@ -224,19 +246,15 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         if (row_ok) {
           if (p.mask_hi) {
-            const __nv_bfloat16* mrow = p.mask_hi + out_row * p.ld_mask + nc;
 #pragma unroll
             for (int g = 0; g < 4; ++g) {
-              if (nc + g * 8 < p.ld_mask) {
-                const uint4 mk = *reinterpret_cast<const uint4*>(mrow + g * 8);
-                const uint32_t w[4] = {mk.x, mk.y, mk.z, mk.w};
+              const uint32_t w[4] = {mcur[g].x, mcur[g].y, mcur[g].z, mcur[g].w};
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                  // bf16 > 0  <=>  sign bit clear and magnitude non-zero
-                  const uint32_t lo16 = w[i] & 0xffffu, hi16 = w[i] >> 16;
-                  if (!(lo16 != 0 && lo16 < 0x8000u)) v[g * 8 + 2 * i] = 0.f;
-                  if (!(hi16 != 0 && hi16 < 0x8000u)) v[g * 8 + 2 * i + 1] = 0.f;
-                }
+              for (int i = 0; i < 4; ++i) {
+                // bf16 > 0  <=>  sign bit clear and magnitude non-zero
+                const uint32_t lo16 = w[i] & 0xffffu, hi16 = w[i] >> 16;
+                if (!(lo16 != 0 && lo16 < 0x8000u)) v[g * 8 + 2 * i] = 0.f;
+                if (!(hi16 != 0 && hi16 < 0x8000u)) v[g * 8 + 2 * i + 1] = 0.f;
               }
             }
           }
@@ -297,15 +315,31 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  // stream-K: the (tile, k-iteration) space is cut into gridDim.x equal contiguous ranges, so every SM gets the same
-  // number of MMAs whatever the tile count; a tile covered by a single CTA is stored, a shared one accumulated
-  // with fp32 atomics into the (pre-zeroed) gradient buffer.
+  // Wave-aligned split-K.  Whole waves of gridDim.x tiles run data-parallel (one tile per CTA, all CTAs sweep the
+  // contraction index in phase, so tiles that share an operand slab hit it in L2 at the same time); the remaining
+  // R = tiles % gridDim.x tiles are cut into S = gridDim.x / R aligned K slices each so that the last wave also
+  // fills the machine.  Sliced tiles accumulate with fp32 atomics into the pre-zeroed gradient, whole tiles store.
   const int tiles_mn = p.m_tiles * p.n_tiles;
   const int num_tiles = p.taps * tiles_mn;
   const int total_iters = p.B * p.t_chunks;
-  const int64_t space = (int64_t)num_tiles * total_iters;
-  const int64_t range_begin = space * blockIdx.x / gridDim.x;
-  const int64_t range_end = space * (blockIdx.x + 1) / gridDim.x;
+  const int G = gridDim.x;
+  const int full_waves = num_tiles / G;
+  const int tail_tiles = num_tiles - full_waves * G;
+  const int tail_split = tail_tiles > 0 ? max(1, min(G / tail_tiles, total_iters / 4 > 0 ? total_iters / 4 : 1)) : 1;
+  const int my_items = full_waves + ((int)blockIdx.x < tail_tiles * tail_split ? 1 : 0);
+  // item i of this CTA -> (tile, q0, q1)
+  auto item = [&](int i, int& tile, int& q0, int& q1) {
+    if (i < full_waves) {
+      tile = i * G + blockIdx.x;
+      q0 = 0;
+      q1 = total_iters;
+    } else {
+      const int slice = blockIdx.x / tail_tiles;          // CTAs of one slice are consecutive: same K range in phase
+      tile = full_waves * G + blockIdx.x % tail_tiles;
+      q0 = (int)((int64_t)total_iters * slice / tail_split);
+      q1 = (int)((int64_t)total_iters * (slice + 1) / tail_split);
+    }
+  };
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmX);
@@ -326,24 +360,22 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  // tile -> (tap, n tile, m tile)
+  // tile -> (n tile, tap, m tile), n slowest: a wave touches few dZ column slabs
   auto decode = [&](int tile, int& j, int& mt, int& nt) {
-    j = tile / tiles_mn;
-    const int rem = tile - j * tiles_mn;
-    nt = rem / p.m_tiles;
-    mt = rem - nt * p.m_tiles;
+    const int per_n = p.taps * p.m_tiles;
+    nt = tile / per_n;
+    const int rem = tile - nt * per_n;
+    j = rem / p.m_tiles;
+    mt = rem - j * p.m_tiles;
   };
 
   if (warp == 0) {
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int64_t pos = range_begin; pos < range_end;) {
-        const int tile = (int)(pos / total_iters);
-        const int q0 = (int)(pos - (int64_t)tile * total_iters);
-        const int q1 = (int)min((int64_t)total_iters, q0 + (range_end - pos));
-        pos += q1 - q0;
-        int j, mt, nt;
+      for (int i = 0; i < my_items; ++i) {
+        int tile, q0, q1, j, mt, nt;
+        item(i, tile, q0, q1);
         decode(tile, j, mt, nt);
         const int m = j - p.pad_left;
         const int shift = p.a_stride == 1 ? m : floordiv(m, p.a_stride);
@@ -378,11 +410,9 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
       int stage = 0;
       uint32_t phase = 0;
       int local = 0;
-      for (int64_t pos = range_begin; pos < range_end; ++local) {
-        const int tile = (int)(pos / total_iters);
-        const int q0 = (int)(pos - (int64_t)tile * total_iters);
-        const int q1 = (int)min((int64_t)total_iters, q0 + (range_end - pos));
-        pos += q1 - q0;
+      for (; local < my_items; ++local) {
+        int tile, q0, q1;
+        item(local, tile, q0, q1);
         const int acc = local & 1;
         const uint32_t acc_phase = (local >> 1) & 1;
         mbar_wait(tmem_empty + acc, acc_phase ^ 1);
@@ -419,12 +449,9 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
     const int quarter = warp & 3;
     const int row = quarter * 32 + lane;
     int local = 0;
-    for (int64_t pos = range_begin; pos < range_end; ++local) {
-      const int tile = (int)(pos / total_iters);
-      const int q0 = (int)(pos - (int64_t)tile * total_iters);
-      const int q1 = (int)min((int64_t)total_iters, q0 + (range_end - pos));
-      pos += q1 - q0;
-      int j, mt, nt;
+    for (; local < my_items; ++local) {
+      int tile, q0, q1, j, mt, nt;
+      item(local, tile, q0, q1);
       decode(tile, j, mt, nt);
       const bool whole_tile = q0 == 0 && q1 == total_iters;
       const int acc = local & 1;
@@ -638,10 +665,7 @@ int launch_wgrad_t(const CUtensorMap& tmX, const CUtensorMap& tmDZ, const WgradP
                                       Cfg::SMEM_BYTES));
     configured = true;
   }
-  // at least 4 k-iterations per CTA, at most one CTA per SM
-  const int64_t space = (int64_t)p.taps * p.m_tiles * p.n_tiles * p.B * p.t_chunks;
-  const int ctas = (int)(space / 4 < 1 ? 1 : (space / 4 > st_num_sms() ? st_num_sms() : space / 4));
-  tc_wgrad_kernel<BLOCK_N, NPL><<<ctas, kThreads, Cfg::SMEM_BYTES, stream>>>(tmX, tmDZ, p);
+  tc_wgrad_kernel<BLOCK_N, NPL><<<st_num_sms(), kThreads, Cfg::SMEM_BYTES, stream>>>(tmX, tmDZ, p);
   ST_CUDA_LAUNCH_CHECK("tc_wgrad_kernel");
   return ST_OK;
 }

@@ -17,6 +17,7 @@ struct ConvParams {
   int b_row_step, b_col_step, b_plane_rows;
   // output tiling
   int B, To, N, m_tiles_per_utt, n_tiles;
+  int n_fastest;                 // tile order: 1 = n tile index fastest, 0 = m tile index fastest
   // epilogue
   const float* bias;
   int relu;
@@ -35,7 +36,7 @@ struct WgradParams {
   int taps, pad_left, a_stride, a_cin;
   int m_tiles, n_tiles;
   int Cin, Cout;
-  float* dW;                     // must be zero on entry (stream-K accumulates shared tiles with atomics)
+  float* dW;                     // must be zero on entry (K-sliced tiles accumulate with atomics)
 };
 
 int make_map_3d(CUtensorMap* map, const void* base, int C, int T, int Bn, int64_t ld, int64_t batch_stride,

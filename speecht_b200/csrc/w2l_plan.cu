@@ -241,6 +241,7 @@ ST_API int st_plan_forward(st_plan* p, const float* inputs, st_stream_t stream) 
     c.B = p->B; c.To = L.To; c.N = L.Cout;
     c.m_tiles_per_utt = (L.To + tc::kTileM - 1) / tc::kTileM;
     c.n_tiles = (L.Cout + block_n - 1) / block_n;
+    c.n_fastest = (size_t)p->npl * p->B * L.Ti * L.ld_in * 2 > (size_t)48 << 20;   // A planes too big for L2
     c.bias = p->params + L.b_off;
     c.relu = L.relu;
     if (l < 10) {
@@ -308,6 +309,7 @@ ST_API int st_plan_backward_range(st_plan* p, int hi, int lo, st_stream_t stream
       c.B = p->B; c.To = L.Ti; c.N = L.Cin;
       c.m_tiles_per_utt = (L.Ti + tc::kTileM - 1) / tc::kTileM;
       c.n_tiles = (L.Cin + 255) / 256;
+      c.n_fastest = (size_t)p->npl * p->B * L.To * ld_dz * 2 > (size_t)48 << 20;
       c.bias = nullptr;
       c.relu = 0;
       c.out_planes = bf(p, p->off_dz[nxt]);

@@ -86,9 +86,14 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   // SWIZZLE_128B tiles need 1024-byte alignment in the shared window
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
-  uint64_t* empty_bar = full_bar + STAGES;
-  uint64_t* tmem_full = empty_bar + STAGES;
+  // Each pipeline stage holds two independently signalled load groups (NPL == 2):
+  //   group X = {A_hi, B_lo}, group Y = {A_lo, B_hi};  products are issued hi*lo (X), hi*hi (X+Y), lo*hi (Y),
+  // so X is released after the 2nd product and Y after the 3rd: the refill that is on the critical path is 48 KB
+  // instead of 96 KB and a two-stage ring keeps the tensor pipe fed.  NPL == 1 uses group X only.
+  constexpr int NG = NPL == 2 ? 2 : 1;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);   // [STAGES][NG]
+  uint64_t* empty_bar = full_bar + STAGES * NG;                                         // [STAGES][NG]
+  uint64_t* tmem_full = empty_bar + STAGES * NG;
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
@@ -100,7 +105,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmA);
     prefetch_tmap(&tmB);
-    for (int s = 0; s < STAGES; ++s) {
+    for (int s = 0; s < STAGES * NG; ++s) {
       mbar_init(full_bar + s, 1);
       mbar_init(empty_bar + s, 1);
     }
@@ -136,16 +141,18 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const int m = p.a_sign * (j - p.pad_left);
           const int shift = p.a_stride == 1 ? m : floordiv(m, p.a_stride);
           const int a_col = (m - shift * p.a_stride) * p.a_cin + cc * kChunkK;
-          mbar_wait(empty_bar + stage, phase ^ 1);
-          mbar_expect_tx(full_bar + stage, Cfg::STAGE_BYTES);
           uint8_t* st = smem + stage * Cfg::STAGE_BYTES;
+          const int b_c0 = j * p.b_col_step + cc * kChunkK, b_c1 = n0 + j * p.b_row_step;
 #pragma unroll
-          for (int pl = 0; pl < NPL; ++pl)
-            tma_load_3d(&tmA, full_bar + stage, st + pl * Cfg::A_BYTES, a_col, t0 + shift, pl * p.B + b);
-#pragma unroll
-          for (int pl = 0; pl < NPL; ++pl)
-            tma_load_2d(&tmB, full_bar + stage, st + NPL * Cfg::A_BYTES + pl * Cfg::B_BYTES,
-                        j * p.b_col_step + cc * kChunkK, pl * p.b_plane_rows + n0 + j * p.b_row_step);
+          for (int g = 0; g < NG; ++g) {
+            // group 0 (X): A plane 0 + B plane NPL-1;  group 1 (Y): A plane 1 + B plane 0
+            const int pa = g, pb = NPL - 1 - g;
+            uint64_t* fb = full_bar + stage * NG + g;
+            mbar_wait(empty_bar + stage * NG + g, phase ^ 1);
+            mbar_expect_tx(fb, Cfg::A_BYTES + Cfg::B_BYTES);
+            tma_load_3d(&tmA, fb, st + pa * Cfg::A_BYTES, a_col, t0 + shift, pa * p.B + b);
+            tma_load_2d(&tmB, fb, st + NPL * Cfg::A_BYTES + pb * Cfg::B_BYTES, b_c0, pb * p.b_plane_rows + b_c1);
+          }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -165,16 +172,16 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
         for (int it = 0; it < nk; ++it) {
-          mbar_wait(full_bar + stage, phase);
-          tc_fence_after();
           const uint32_t a_addr = smem_u32(smem + stage * Cfg::STAGE_BYTES);
           const uint32_t b_addr = a_addr + NPL * Cfg::A_BYTES;
           uint32_t accumulate = it > 0 ? 1u : 0u;
-          // products, smallest first: lo*hi, hi*lo, hi*hi (NPL==2) / hi*hi (NPL==1)
+          // NPL==2 products in issue order: hi*lo (group X), hi*hi (X+Y), lo*hi (Y); NPL==1: hi*hi (X)
 #pragma unroll
           for (int pr = 0; pr < (NPL == 2 ? 3 : 1); ++pr) {
-            const int pa = (NPL == 2) ? (pr == 0 ? 1 : 0) : 0;
-            const int pb = (NPL == 2) ? (pr == 1 ? 1 : 0) : 0;
+            const int pa = (NPL == 2 && pr == 2) ? 1 : 0;
+            const int pb = (NPL == 2 && pr == 0) ? 1 : 0;
+            if (pr == 0) { mbar_wait(full_bar + stage * NG, phase); tc_fence_after(); }
+            if (NPL == 2 && pr == 1) { mbar_wait(full_bar + stage * NG + 1, phase); tc_fence_after(); }
             const uint64_t da = make_smem_desc_sw128(a_addr + pa * Cfg::A_BYTES, 16, 1024);
             const uint64_t db = make_smem_desc_sw128(b_addr + pb * Cfg::B_BYTES, 16, 1024);
 #pragma unroll
@@ -183,8 +190,10 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               umma_bf16(d_tmem, da + (uint64_t)(kk * 2), db + (uint64_t)(kk * 2), idesc, accumulate);
               accumulate = 1u;
             }
+            // a group's smem is reusable once the MMAs issued so far have read it
+            if (NPL == 1 || pr == 1) umma_commit(empty_bar + stage * NG);
+            if (NPL == 2 && pr == 2) umma_commit(empty_bar + stage * NG + 1);
           }
-          umma_commit(empty_bar + stage);                 // smem slot reusable once these MMAs have read it
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
         umma_commit(tmem_full + acc);                     // accumulator complete -> epilogue
@@ -308,9 +317,10 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+  constexpr int NG = NPL == 2 ? 2 : 1;              // load groups per stage, see tc_conv_kernel
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
-  uint64_t* empty_bar = full_bar + STAGES;
-  uint64_t* tmem_full = empty_bar + STAGES;
+  uint64_t* empty_bar = full_bar + STAGES * NG;
+  uint64_t* tmem_full = empty_bar + STAGES * NG;
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
@@ -344,7 +354,7 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmX);
     prefetch_tmap(&tmDZ);
-    for (int s = 0; s < STAGES; ++s) {
+    for (int s = 0; s < STAGES * NG; ++s) {
       mbar_init(full_bar + s, 1);
       mbar_init(empty_bar + s, 1);
     }
@@ -384,21 +394,22 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
         for (int q = q0; q < q1; ++q) {
           const int b = q / p.t_chunks;
           const int t0 = (q - b * p.t_chunks) * kChunkK;
-          mbar_wait(empty_bar + stage, phase ^ 1);
-          mbar_expect_tx(full_bar + stage, Cfg::STAGE_BYTES);
           uint8_t* st = smem + stage * Cfg::STAGE_BYTES;
 #pragma unroll
-          for (int pl = 0; pl < NPL; ++pl)
+          for (int g = 0; g < NG; ++g) {
+            const int pa = g, pb = NPL - 1 - g;           // group X = {X_hi, dZ_lo}, group Y = {X_lo, dZ_hi}
+            uint64_t* fb = full_bar + stage * NG + g;
+            mbar_wait(empty_bar + stage * NG + g, phase ^ 1);
+            mbar_expect_tx(fb, Cfg::A_BYTES + Cfg::B_BYTES);
 #pragma unroll
             for (int h = 0; h < kTileM / 64; ++h)
-              tma_load_3d(&tmX, full_bar + stage, st + pl * Cfg::A_BYTES + h * Cfg::BOX_BYTES, a_col + h * 64,
-                          t0 + shift, pl * p.B + b);
-#pragma unroll
-          for (int pl = 0; pl < NPL; ++pl)
+              tma_load_3d(&tmX, fb, st + pa * Cfg::A_BYTES + h * Cfg::BOX_BYTES, a_col + h * 64, t0 + shift,
+                          pa * p.B + b);
 #pragma unroll
             for (int h = 0; h < BLOCK_N / 64; ++h)
-              tma_load_3d(&tmDZ, full_bar + stage, st + NPL * Cfg::A_BYTES + pl * Cfg::B_BYTES + h * Cfg::BOX_BYTES,
-                          n0 + h * 64, t0, pl * p.B + b);
+              tma_load_3d(&tmDZ, fb, st + NPL * Cfg::A_BYTES + pb * Cfg::B_BYTES + h * Cfg::BOX_BYTES, n0 + h * 64, t0,
+                          pb * p.B + b);
+          }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -420,14 +431,14 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
         const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
         uint32_t accumulate = 0u;
         for (int q = q0; q < q1; ++q) {
-          mbar_wait(full_bar + stage, phase);
-          tc_fence_after();
           const uint32_t a_addr = smem_u32(smem + stage * Cfg::STAGE_BYTES);
           const uint32_t b_addr = a_addr + NPL * Cfg::A_BYTES;
 #pragma unroll
           for (int pr = 0; pr < (NPL == 2 ? 3 : 1); ++pr) {
-            const int pa = (NPL == 2) ? (pr == 0 ? 1 : 0) : 0;
-            const int pb = (NPL == 2) ? (pr == 1 ? 1 : 0) : 0;
+            const int pa = (NPL == 2 && pr == 2) ? 1 : 0;
+            const int pb = (NPL == 2 && pr == 0) ? 1 : 0;
+            if (pr == 0) { mbar_wait(full_bar + stage * NG, phase); tc_fence_after(); }
+            if (NPL == 2 && pr == 1) { mbar_wait(full_bar + stage * NG + 1, phase); tc_fence_after(); }
 #pragma unroll
             for (int kk = 0; kk < kChunkK / 16; ++kk) {
               // MN-major SW128: a K step of 16 rows = 2 swizzle atoms of 8 rows x 128 B = 2048 bytes;
@@ -437,8 +448,9 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
               umma_bf16(d_tmem, da, db, idesc, accumulate);
               accumulate = 1u;
             }
+            if (NPL == 1 || pr == 1) umma_commit(empty_bar + stage * NG);
+            if (NPL == 2 && pr == 2) umma_commit(empty_bar + stage * NG + 1);
           }
-          umma_commit(empty_bar + stage);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
         umma_commit(tmem_full + acc);

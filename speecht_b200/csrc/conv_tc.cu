@@ -530,50 +530,77 @@ split_input_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ plan
   }
 }
 
-// W [K][Cin][Cout] -> fwd[pl][co][k*cin_p + ci] via a 32x32 shared-memory transpose; block (32, 8)
+// ---- filter packing for ALL layers in two launches (PackTable lists the layers) ----
+// forward layout: W [K][Cin][Cout] -> fwd[pl][co][k*cin_p + ci] through a 64(ci) x 32(co) shared-memory transpose;
+// block (32, 8): 128-byte coalesced reads along co, 128-byte bf16x2 writes along ci
 template <int NPL>
-__global__ void pack_filter_fwd_kernel(const float* __restrict__ w, int K, int Cin, int Cout,
-                                       __nv_bfloat16* __restrict__ fwd, int cin_p) {
-  __shared__ float tile[32][33];
-  const int k = blockIdx.z;
-  const int ci0 = blockIdx.y * 32, co0 = blockIdx.x * 32;
-  for (int i = threadIdx.y; i < 32; i += 8) {
-    const int ci = ci0 + i, co = co0 + threadIdx.x;
-    tile[i][threadIdx.x] = (ci < Cin && co < Cout) ? w[((int64_t)k * Cin + ci) * Cout + co] : 0.f;
+__global__ void __launch_bounds__(256)
+pack_filter_fwd_all_kernel(const PackTable tab) {
+  __shared__ float tile[64][33];
+  int l = 0;
+  while (l + 1 < tab.n && (int)blockIdx.x >= tab.e[l + 1].fwd_blk0) ++l;
+  const PackEntry& e = tab.e[l];
+  int lb = blockIdx.x - e.fwd_blk0;
+  const int co_tiles = (e.Cout + 31) / 32, ci_tiles = e.cin_p / 64;
+  const int co0 = (lb % co_tiles) * 32;
+  lb /= co_tiles;
+  const int ci0 = (lb % ci_tiles) * 64;
+  const int k = lb / ci_tiles;
+  const int tx = threadIdx.x, ty = threadIdx.y;
+#pragma unroll
+  for (int r = 0; r < 64; r += 8) {
+    const int ci = ci0 + r + ty, co = co0 + tx;
+    tile[r + ty][tx] = (ci < e.Cin && co < e.Cout) ? __ldg(e.w + ((int64_t)k * e.Cin + ci) * e.Cout + co) : 0.f;
   }
   __syncthreads();
-  const int64_t ld = (int64_t)K * cin_p;
-  const int64_t plane_stride = (int64_t)Cout * ld;
-  for (int i = threadIdx.y; i < 32; i += 8) {
-    const int co = co0 + i, ci = ci0 + threadIdx.x;
-    if (co < Cout && ci < cin_p) {
-      float rem = tile[threadIdx.x][i];
+  const int64_t ld = (int64_t)e.K * e.cin_p;
+  const int64_t plane_stride = (int64_t)e.Cout * ld;
+#pragma unroll
+  for (int r = 0; r < 32; r += 8) {
+    const int co = co0 + r + ty;
+    if (co < e.Cout) {
+      float v0 = tile[2 * tx][r + ty], v1 = tile[2 * tx + 1][r + ty];
+      __nv_bfloat16* dst = e.fwd + (int64_t)co * ld + (int64_t)k * e.cin_p + ci0 + 2 * tx;
 #pragma unroll
       for (int pl = 0; pl < NPL; ++pl) {
-        const __nv_bfloat16 h = __float2bfloat16_rn(rem);
-        fwd[pl * plane_stride + (int64_t)co * ld + (int64_t)k * cin_p + ci] = h;
-        rem -= __bfloat162float(h);
+        const __nv_bfloat16 h0 = __float2bfloat16_rn(v0), h1 = __float2bfloat16_rn(v1);
+        *reinterpret_cast<uint32_t*>(dst + pl * plane_stride) = pack_bf16x2(h0, h1);
+        v0 -= __bfloat162float(h0);
+        v1 -= __bfloat162float(h1);
       }
     }
   }
 }
 
-// W [K*Cin][Cout] -> bwd[pl][row][ld_co] (columns >= Cout zero)
+// backward layout: W [K*Cin][Cout] -> bwd[pl][row][ld_co] (columns >= Cout zero); 4 columns per thread
 template <int NPL>
 __global__ void __launch_bounds__(256)
-pack_filter_bwd_kernel(const float* __restrict__ w, int64_t rows, int Cout, __nv_bfloat16* __restrict__ bwd, int ld_co) {
-  const int64_t total = rows * ld_co;
-  const int64_t plane_stride = total;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int co = (int)(i % ld_co);
-    const int64_t r = i / ld_co;
-    float rem = co < Cout ? __ldg(w + r * Cout + co) : 0.f;
+pack_filter_bwd_all_kernel(const PackTable tab) {
+  int l = 0;
+  while (l + 1 < tab.n && (int)blockIdx.x >= tab.e[l + 1].bwd_blk0) ++l;
+  const PackEntry& e = tab.e[l];
+  if (!e.bwd) return;
+  const int64_t rows = (int64_t)e.K * e.Cin;
+  const int64_t total = rows * e.ld_co;
+  const int64_t i = ((int64_t)(blockIdx.x - e.bwd_blk0) * 256 + threadIdx.x) * 4;
+  if (i >= total) return;
+  const int co = (int)(i % e.ld_co);
+  const int64_t r = i / e.ld_co;
+  float v[4];
 #pragma unroll
-    for (int pl = 0; pl < NPL; ++pl) {
-      const __nv_bfloat16 h = __float2bfloat16_rn(rem);
-      bwd[pl * plane_stride + i] = h;
-      rem -= __bfloat162float(h);
+  for (int q = 0; q < 4; ++q) v[q] = (co + q < e.Cout) ? __ldg(e.w + r * e.Cout + co + q) : 0.f;
+#pragma unroll
+  for (int pl = 0; pl < NPL; ++pl) {
+    __nv_bfloat16 h[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      h[q] = __float2bfloat16_rn(v[q]);
+      v[q] -= __bfloat162float(h[q]);
     }
+    uint2 pk;
+    pk.x = pack_bf16x2(h[0], h[1]);
+    pk.y = pack_bf16x2(h[2], h[3]);
+    *reinterpret_cast<uint2*>(e.bwd + pl * total + i) = pk;
   }
 }
 
@@ -760,29 +787,30 @@ int launch_split_input(const float* x, __nv_bfloat16* planes, int B, int T, int 
   return ST_OK;
 }
 
-int launch_pack_filter(const float* w, int K, int Cin, int Cout, __nv_bfloat16* fwd, int cin_p, __nv_bfloat16* bwd,
-                       int ld_co, int n_planes, cudaStream_t stream) {
-  if (fwd) {
-    dim3 grid((Cout + 31) / 32, (cin_p + 31) / 32, K);
-    if (n_planes == 2) pack_filter_fwd_kernel<2><<<grid, dim3(32, 8), 0, stream>>>(w, K, Cin, Cout, fwd, cin_p);
-    else pack_filter_fwd_kernel<1><<<grid, dim3(32, 8), 0, stream>>>(w, K, Cin, Cout, fwd, cin_p);
-    ST_CUDA_LAUNCH_CHECK("pack_filter_fwd_kernel");
+int launch_pack_filters(PackTable& tab, int n_planes, cudaStream_t stream) {
+  int fb = 0, bb = 0;
+  for (int l = 0; l < tab.n; ++l) {
+    PackEntry& e = tab.e[l];
+    ST_CHECK_ARG(e.cin_p % 64 == 0 && e.ld_co % 4 == 0, "launch_pack_filters: bad padded sizes");
+    e.fwd_blk0 = fb;
+    e.bwd_blk0 = bb;
+    fb += e.K * (e.cin_p / 64) * ((e.Cout + 31) / 32);
+    if (e.bwd) bb += (int)(((int64_t)e.K * e.Cin * e.ld_co / 4 + 255) / 256);
   }
-  if (bwd) {
-    const int64_t rows = (int64_t)K * Cin;
-    int blocks = (int)((rows * ld_co + 255) / 256);
-    const int cap = 16 * st_num_sms();
-    blocks = blocks > cap ? cap : blocks;
-    if (n_planes == 2) pack_filter_bwd_kernel<2><<<blocks, 256, 0, stream>>>(w, rows, Cout, bwd, ld_co);
-    else pack_filter_bwd_kernel<1><<<blocks, 256, 0, stream>>>(w, rows, Cout, bwd, ld_co);
-    ST_CUDA_LAUNCH_CHECK("pack_filter_bwd_kernel");
+  if (n_planes == 2) pack_filter_fwd_all_kernel<2><<<fb, dim3(32, 8), 0, stream>>>(tab);
+  else pack_filter_fwd_all_kernel<1><<<fb, dim3(32, 8), 0, stream>>>(tab);
+  ST_CUDA_LAUNCH_CHECK("pack_filter_fwd_all_kernel");
+  if (bb > 0) {
+    if (n_planes == 2) pack_filter_bwd_all_kernel<2><<<bb, 256, 0, stream>>>(tab);
+    else pack_filter_bwd_all_kernel<1><<<bb, 256, 0, stream>>>(tab);
+    ST_CUDA_LAUNCH_CHECK("pack_filter_bwd_all_kernel");
   }
   return ST_OK;
 }
 
 int launch_bias_grad(const __nv_bfloat16* dz, int64_t rows, int N, int ld, int n_planes, float* db,
                      cudaStream_t stream) {
-  ST_CUDA_CALL(cudaMemsetAsync(db, 0, (size_t)N * sizeof(float), stream));
+  // db must be zero on entry (the plan zeroes the whole flat gradient buffer once per backward)
   int chunks = (int)((rows + 63) / 64);
   const int cap = 8 * st_num_sms() / ((ld + 255) / 256);
   chunks = chunks > cap ? cap : (chunks < 1 ? 1 : chunks);

@@ -52,9 +52,20 @@ int launch_wgrad(const CUtensorMap& tmX, const CUtensorMap& tmDZ, const WgradPar
 // fp32 [B][T][F] -> planes [n_planes][B][Tpad][F] (rows t >= T zero)
 int launch_split_input(const float* x, __nv_bfloat16* planes, int B, int T, int Tpad, int F, int n_planes,
                        cudaStream_t stream);
-// W [K][Cin][Cout] fp32 -> forward layout planes [n][Cout][K*cin_p] (K-major), backward layout planes [n][K*Cin][ld_co]
-int launch_pack_filter(const float* w, int K, int Cin, int Cout, __nv_bfloat16* fwd, int cin_p, __nv_bfloat16* bwd,
-                       int ld_co, int n_planes, cudaStream_t stream);
+// W [K][Cin][Cout] fp32 -> forward layout planes [n][Cout][K*cin_p] (K-major), backward layout planes
+// [n][K*Cin][ld_co] (bwd may be null); all layers of the table in two launches
+struct PackEntry {
+  const float* w;
+  __nv_bfloat16* fwd;
+  __nv_bfloat16* bwd;
+  int K, Cin, Cout, cin_p, ld_co;
+  int fwd_blk0, bwd_blk0;        // filled by launch_pack_filters
+};
+struct PackTable {
+  int n;
+  PackEntry e[12];
+};
+int launch_pack_filters(PackTable& tab, int n_planes, cudaStream_t stream);
 // db[n] = sum over rows and planes of dz planes [n_planes][rows][ld]
 int launch_bias_grad(const __nv_bfloat16* dz, int64_t rows, int N, int ld, int n_planes, float* db,
                      cudaStream_t stream);

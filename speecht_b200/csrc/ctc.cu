@@ -47,15 +47,17 @@ __device__ __forceinline__ double lse3(double a0, double a1, double a2) {
 }
 
 // dynamic smem: double buf[2][s_pad + 4]; int ext[s_pad]; unsigned char skip[s_pad + 2]; [float lsm_s[len*C]]
-// NS = extended-label positions per thread (S <= NS*256).  LSM_SMEM: the utterance's log-softmax rows are staged in
+// NS = extended-label positions per thread (S <= NS*blockDim.x; the launcher sizes the block to the longest
+// extended label so that NS == 1 up to 511 characters).  LSM_SMEM: the utterance's log-softmax rows are staged in
 // shared memory up front (one coalesced pass) so that the serial recursion never waits on an L2 round trip.
 template <int NS, bool LSM_SMEM>
-__global__ void __launch_bounds__(kABThreads)
+__global__ void __launch_bounds__(1024)
 ctc_alpha_beta_kernel(const float* __restrict__ lsm, int T, int C, const int32_t* __restrict__ labels,
                       const int32_t* __restrict__ label_offsets, const int32_t* __restrict__ seq_len, int blank,
                       int s_pad, double* __restrict__ alpha, double* __restrict__ beta,
                       double* __restrict__ logp, float* __restrict__ loss, int32_t* __restrict__ status) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int nthr = blockDim.x;                      // = extended-label length rounded up to a warp (NS == 1)
   const int b = blockIdx.x;
   const bool is_beta = blockIdx.y == 1;
   const int l0 = label_offsets[b];
@@ -74,7 +76,7 @@ ctc_alpha_beta_kernel(const float* __restrict__ lsm, int T, int C, const int32_t
 
   // extended label sequence + feasibility (device-side mirror of st_ctc_validate_labels_host)
   int repeats = 0, bad = 0;
-  for (int s = threadIdx.x; s < S + 2 && S <= s_pad; s += kABThreads) {
+  for (int s = threadIdx.x; s < S + 2 && S <= s_pad; s += nthr) {
     int e = blank;
     if (s < S && (s & 1)) {
       e = labels[l0 + (s >> 1)];
@@ -87,15 +89,15 @@ ctc_alpha_beta_kernel(const float* __restrict__ lsm, int T, int C, const int32_t
   if (repeats) atomicAdd(&s_bad, repeats << 1);
   __syncthreads();
   const int n_rep = s_bad >> 1;
-  const bool infeasible = (s_bad & 1) || (L + n_rep > len) || len < 0 || S > s_pad || S > NS * kABThreads;
-  for (int s = threadIdx.x; s < S + 2 && S <= s_pad; s += kABThreads) {
+  const bool infeasible = (s_bad & 1) || (L + n_rep > len) || len < 0 || S > s_pad || S > NS * nthr;
+  for (int s = threadIdx.x; s < S + 2 && S <= s_pad; s += nthr) {
     // skip[s]: transition s-2 -> s allowed
     skip[s] = (s >= 2 && s < S && ext[s] != blank && ext[s] != ext[s - 2]) ? 1 : 0;
   }
-  for (int i = threadIdx.x; i < 2 * bstride; i += kABThreads) buf[i] = -INFINITY;
+  for (int i = threadIdx.x; i < 2 * bstride; i += nthr) buf[i] = -INFINITY;
   const float* lrow = lsm + (int64_t)b * T * C;
   if (LSM_SMEM && !infeasible && len > 0) {
-    for (int i = threadIdx.x; i < len * C; i += kABThreads) lsm_s[i] = lrow[i];
+    for (int i = threadIdx.x; i < len * C; i += nthr) lsm_s[i] = lrow[i];
     lrow = lsm_s;
   }
   __syncthreads();
@@ -115,7 +117,7 @@ ctc_alpha_beta_kernel(const float* __restrict__ lsm, int T, int C, const int32_t
   bool my_skip[NS], live[NS];
 #pragma unroll
   for (int j = 0; j < NS; ++j) {
-    const int s = threadIdx.x + j * kABThreads;
+    const int s = threadIdx.x + j * nthr;
     live[j] = s < S;
     my_ext[j] = live[j] ? ext[s] : blank;
     my_skip[j] = false;
@@ -125,7 +127,7 @@ ctc_alpha_beta_kernel(const float* __restrict__ lsm, int T, int C, const int32_t
     // alpha_0
 #pragma unroll
     for (int j = 0; j < NS; ++j) {
-      const int s = threadIdx.x + j * kABThreads;
+      const int s = threadIdx.x + j * nthr;
       if (live[j]) {
         my_skip[j] = skip[s] != 0;
         const double v = (s < 2) ? (double)lrow[my_ext[j]] : -INFINITY;
@@ -142,7 +144,7 @@ ctc_alpha_beta_kernel(const float* __restrict__ lsm, int T, int C, const int32_t
       float lp[NS];
 #pragma unroll
       for (int j = 0; j < NS; ++j) {
-        const int s = threadIdx.x + j * kABThreads;
+        const int s = threadIdx.x + j * nthr;
         if (live[j]) {
           a0[j] = prev[2 + s];
           a1[j] = prev[1 + s];
@@ -155,7 +157,7 @@ ctc_alpha_beta_kernel(const float* __restrict__ lsm, int T, int C, const int32_t
         if (live[j]) v[j] = lse3(a0[j], a1[j], a2[j]) + (double)lp[j];
 #pragma unroll
       for (int j = 0; j < NS; ++j) {
-        const int s = threadIdx.x + j * kABThreads;
+        const int s = threadIdx.x + j * nthr;
         if (live[j]) {
           cur[2 + s] = v[j];
           lat[(int64_t)t * s_pad + s] = v[j];
@@ -175,7 +177,7 @@ ctc_alpha_beta_kernel(const float* __restrict__ lsm, int T, int C, const int32_t
     const float* last = lrow + (int64_t)(len - 1) * C;
 #pragma unroll
     for (int j = 0; j < NS; ++j) {
-      const int s = threadIdx.x + j * kABThreads;
+      const int s = threadIdx.x + j * nthr;
       if (live[j]) {
         my_skip[j] = skip[s + 2] != 0;                                  // transition s -> s+2
         const double v = (s >= S - 2) ? 0.0 : -INFINITY;
@@ -192,7 +194,7 @@ ctc_alpha_beta_kernel(const float* __restrict__ lsm, int T, int C, const int32_t
       float lp[NS];
 #pragma unroll
       for (int j = 0; j < NS; ++j) {
-        const int s = threadIdx.x + j * kABThreads;
+        const int s = threadIdx.x + j * nthr;
         if (live[j]) {
           b0[j] = nxt[s];
           b1[j] = nxt[s + 1];
@@ -205,7 +207,7 @@ ctc_alpha_beta_kernel(const float* __restrict__ lsm, int T, int C, const int32_t
         if (live[j]) v[j] = lse3(b0[j], b1[j], b2[j]);
 #pragma unroll
       for (int j = 0; j < NS; ++j) {
-        const int s = threadIdx.x + j * kABThreads;
+        const int s = threadIdx.x + j * nthr;
         if (live[j]) {
           lat[(int64_t)t * s_pad + s] = v[j];
           cur[s] = v[j] + (double)lp[j];
@@ -369,13 +371,14 @@ ST_API int st_ctc_loss(const float* logits, int64_t stride_t, int64_t stride_b, 
   const bool lsm_in_smem = smem_base + smem_lsm + 64 <= 200 * 1024;
   const size_t smem = smem_base + (lsm_in_smem ? smem_lsm : 0) + 64;
   const int S_max = 2 * max_label_len + 1;
-  const int ns = S_max <= kABThreads ? 1 : (S_max <= 2 * kABThreads ? 2 : (S_max <= 4 * kABThreads ? 4 : 8));
+  const int threads = S_max >= 1024 ? 1024 : (S_max + 31) / 32 * 32;
+  const int ns = S_max <= threads ? 1 : (S_max <= 2 * threads ? 2 : (S_max <= 4 * threads ? 4 : 8));
 #define ST_CTC_LAUNCH(NS_, SM_)                                                                                      \
   do {                                                                                                               \
     if (smem > 48 * 1024)                                                                                            \
       ST_CUDA_CALL(cudaFuncSetAttribute(ctc_alpha_beta_kernel<NS_, SM_>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                         (int)smem));                                                                 \
-    ctc_alpha_beta_kernel<NS_, SM_><<<dim3(B, 2), kABThreads, smem, s>>>(lsm, T, C, labels, label_offsets, seq_len,  \
+    ctc_alpha_beta_kernel<NS_, SM_><<<dim3(B, 2), threads, smem, s>>>(lsm, T, C, labels, label_offsets, seq_len,  \
                                                                        blank, s_pad, alpha, beta, logp, loss, status); \
   } while (0)
   if (lsm_in_smem) {

@@ -208,14 +208,16 @@ ST_API int st_plan_bind(st_plan* p, void* arena, size_t arena_bytes, float* para
 // fp32 parameters -> bf16 operand planes (forward K-major layout for every layer, backward layout for layers 1..10)
 ST_API int st_plan_pack_weights(st_plan* p, st_stream_t stream) {
   ST_CHECK_ARG(p && p->bound, "st_plan_pack_weights: plan is not bound");
-  cudaStream_t s = st_cu(stream);
+  tc::PackTable tab{};
+  tab.n = 11;
   for (int l = 0; l < 11; ++l) {
     Layer& L = p->layers[l];
-    int rc = tc::launch_pack_filter(p->params + L.w_off, L.K, L.Cin, L.Cout, bf(p, L.off_wfwd), L.cin_p,
-                                    l > 0 ? bf(p, L.off_wbwd) : nullptr, L.ld_co, p->npl, s);
-    if (rc) return rc;
-    p->launches += l > 0 ? 2 : 1;
+    tab.e[l] = tc::PackEntry{p->params + L.w_off, bf(p, L.off_wfwd), l > 0 ? bf(p, L.off_wbwd) : nullptr,
+                             L.K, L.Cin, L.Cout, L.cin_p, L.ld_co, 0, 0};
   }
+  const int rc = tc::launch_pack_filters(tab, p->npl, st_cu(stream));
+  if (rc) return rc;
+  p->launches += 2;
   return ST_OK;
 }
 
@@ -268,7 +270,11 @@ ST_API int st_plan_backward_range(st_plan* p, int hi, int lo, st_stream_t stream
   ST_CHECK_ARG(p && p->bound, "st_plan_backward: plan is not bound");
   ST_CHECK_ARG(hi <= 10 && lo >= 0 && hi >= lo, "st_plan_backward_range: need 10 >= hi >= lo >= 0");
   cudaStream_t s = st_cu(stream);
-  if (hi == 10) p->cur_dz = 0;
+  if (hi == 10) {
+    p->cur_dz = 0;
+    // filter gradients of K-sliced tiles accumulate with atomics: zero the whole flat buffer once per backward
+    ST_CUDA_CALL(cudaMemsetAsync(p->grads, 0, (size_t)st_plan_param_floats(p) * sizeof(float), s));
+  }
   int cur = p->cur_dz;                          // dz buffer holding the gradient wrt layer l's output (l < 10)
   for (int l = hi; l >= lo; --l) {
     Layer& L = p->layers[l];
@@ -286,7 +292,6 @@ ST_API int st_plan_backward_range(st_plan* p, int hi, int lo, st_stream_t stream
     w.n_tiles = l == 10 ? 1 : (L.Cout + 255) / 256;
     w.Cin = L.Cin; w.Cout = L.Cout;
     w.dW = p->grads + L.w_off;
-    ST_CUDA_CALL(cudaMemsetAsync(w.dW, 0, (size_t)L.K * L.Cin * L.Cout * sizeof(float), s));
     int ti = timed_begin(p, s);
     rc = tc::launch_wgrad(L.tm_wg_x, L.tm_wg_dz[l == 10 ? 0 : cur], w, l == 10 ? 64 : 256, p->npl, s);
     if (rc) return rc;

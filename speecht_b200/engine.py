@@ -305,11 +305,12 @@ class W2LEngine:
     Returns dict(avg_loss device scalar (LOCAL batch mean), loss [B], decoded|None)."""
     if self.precision != 'fp32':
       return self._tc().train_step(inputs, sequence_lengths, labels, learning_rate, max_gradient_norm, decode)
-    B = inputs.shape[0]
-    logits = self.forward(inputs, keep_activations=True)
+    B, T = inputs.shape[0], inputs.shape[1]
     ctc_len = np.asarray(sequence_lengths, dtype=np.int32) // 2
+    batch = ops.CTCBatch(labels, ctc_len, -(-T // 2), self.num_classes, self.device)
+    logits = self.forward(inputs, keep_activations=True)
     scale = 1.0 / (B * self.world_size)                                # tf.reduce_mean folded into the gradient
-    loss, dlogits = ops.ctc_loss(labels, logits, ctc_len, want_grad=True, grad_scale=scale)
+    loss, dlogits = ops.ctc_loss(batch, logits, want_grad=True, grad_scale=scale)
     self.launches += 3
     out = {'loss': loss, 'avg_loss': loss.mean(), 'decoded': None, 'logits': logits}
     if decode:

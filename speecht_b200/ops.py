@@ -107,12 +107,39 @@ def _workspace(key, nbytes, device):
   return buf
 
 
-def ctc_loss(labels, logits, sequence_length, want_grad=True, grad_scale=1.0, grad_planes=None, time_major=True,
+class CTCBatch:
+  """Device-side label / length tensors of one batch, uploaded asynchronously from pinned memory so that no host
+  synchronisation sits between the forward pass and the loss kernels."""
+
+  def __init__(self, labels, sequence_length, T, C, device, validate=True):
+    flat, offsets = flatten_labels(labels)
+    seq_host = np.ascontiguousarray(np.asarray(sequence_length.cpu() if torch.is_tensor(sequence_length)
+                                               else sequence_length, dtype=np.int32))
+    self.B = int(seq_host.shape[0])
+    if validate:
+      check(lib().st_ctc_validate_labels_host(flat.ctypes.data, offsets.ctypes.data, seq_host.ctypes.data, self.B, T,
+                                              C - 1))
+    self.max_len = int(np.max(np.diff(offsets))) if self.B else 0
+    n_lab = max(int(flat.size), 1)
+    # one pinned staging buffer, one async copy: [labels | offsets | seq_len]
+    host = torch.empty((n_lab + 2 * self.B + 1,), dtype=torch.int32).pin_memory()
+    host[:flat.size] = torch.from_numpy(flat) if flat.size else host[:0]
+    host[n_lab:n_lab + self.B + 1] = torch.from_numpy(offsets)
+    host[n_lab + self.B + 1:] = torch.from_numpy(seq_host)
+    self._host = host
+    dev = host.to(device, non_blocking=True)
+    self.labels = dev[:n_lab]
+    self.offsets = dev[n_lab:n_lab + self.B + 1]
+    self.seq_len = dev[n_lab + self.B + 1:]
+    self.T, self.C = T, C
+
+
+def ctc_loss(labels, logits, sequence_length=None, want_grad=True, grad_scale=1.0, grad_planes=None, time_major=True,
              validate=True):
   """tf.nn.ctc_loss(labels, logits, sequence_length) (speech_model.py:74) and its gradient.
 
   logits: [T,B,C] (time_major, may be a transposed VIEW of a [B,T,C] buffer -- strides are honoured, no copy).
-  labels: list of int lists, or the sparse triple of speech_input.py:48-69.  Blank = C-1.
+  labels: list of int lists, the sparse triple of speech_input.py:48-69, or a prepared CTCBatch.  Blank = C-1.
   Returns (loss [B], grad like logits or None).  Raises CTCLabelError like TF's InvalidArgumentError when a label
   does not fit its sequence."""
   _require_cuda(logits)
@@ -121,27 +148,22 @@ def ctc_loss(labels, logits, sequence_length, want_grad=True, grad_scale=1.0, gr
   T, B, C = logits.shape
   if logits.stride(2) != 1 or logits.dtype != torch.float32:
     raise ValueError('logits must be float32 with unit class stride')
-  flat, offsets = flatten_labels(labels)
-  seq_host = np.ascontiguousarray(np.asarray(sequence_length.cpu() if torch.is_tensor(sequence_length)
-                                             else sequence_length, dtype=np.int32))
-  if validate:
-    check(lib().st_ctc_validate_labels_host(flat.ctypes.data, offsets.ctypes.data, seq_host.ctypes.data, B, T, C - 1))
   dev = logits.device
-  max_len = int(np.max(np.diff(offsets))) if B else 0
-  d_flat = torch.from_numpy(flat if flat.size else np.zeros((1,), np.int32)).to(dev)
-  d_off = torch.from_numpy(offsets).to(dev)
-  d_seq = torch.from_numpy(seq_host).to(dev)
+  batch = labels if isinstance(labels, CTCBatch) else CTCBatch(labels, sequence_length, T, C, dev, validate)
+  if batch.B != B or batch.T != T:
+    raise ValueError('prepared CTC batch does not match the logits shape')
   loss = torch.empty((B,), dtype=torch.float32, device=dev)
   status = torch.empty((B,), dtype=torch.int32, device=dev)
   grad = None
   if want_grad:
     grad = torch.empty_strided(logits.shape, logits.stride(), dtype=torch.float32, device=dev)
-  nbytes = lib().st_ctc_workspace_bytes(T, B, C, max_len)
+  nbytes = lib().st_ctc_workspace_bytes(T, B, C, batch.max_len)
   ws = _workspace(('ctc', dev), nbytes, dev)
   n_planes, c_pad = (0, 0) if grad_planes is None else (grad_planes.shape[0], grad_planes.shape[-1])
-  check(lib().st_ctc_loss(ptr(logits), logits.stride(0), logits.stride(1), T, B, C, ptr(d_flat), ptr(d_off), max_len,
-                          ptr(d_seq), C - 1, ptr(loss), ptr(grad), float(grad_scale), ptr(grad_planes), n_planes,
-                          c_pad, ptr(status), ptr(ws), ws.numel(), stream_ptr()))
+  check(lib().st_ctc_loss(ptr(logits), logits.stride(0), logits.stride(1), T, B, C, ptr(batch.labels),
+                          ptr(batch.offsets), batch.max_len, ptr(batch.seq_len), C - 1, ptr(loss), ptr(grad),
+                          float(grad_scale), ptr(grad_planes), n_planes, c_pad, ptr(status), ptr(ws), ws.numel(),
+                          stream_ptr()))
   return loss, grad
 
 

@@ -127,11 +127,13 @@ class TCPlan:
   def train_step(self, inputs, sequence_lengths, labels, learning_rate, max_gradient_norm=5.0, decode=False):
     eng = self.engine
     B, T, _ = inputs.shape
+    ctc_len = np.asarray(sequence_lengths, dtype=np.int32) // 2
+    # labels go up first (pinned, async) so that nothing synchronises the host between forward and loss
+    batch = ops.CTCBatch(labels, ctc_len, -(-T // 2), eng.num_classes, eng.device)
     logits = self.forward(inputs.contiguous(), keep_activations=True)
     sh = self._last
-    ctc_len = np.asarray(sequence_lengths, dtype=np.int32) // 2
     scale = 1.0 / (B * eng.world_size)
-    loss, _ = ops.ctc_loss(labels, logits, ctc_len, want_grad=False, grad_scale=scale, grad_planes=sh.dlogits_planes)
+    loss, _ = ops.ctc_loss(batch, logits, want_grad=False, grad_scale=scale, grad_planes=sh.dlogits_planes)
     eng.launches += 3
     out = {'loss': loss, 'avg_loss': loss.mean(), 'decoded': None, 'logits': logits}
     if decode:

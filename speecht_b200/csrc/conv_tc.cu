@@ -280,6 +280,25 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               if (nc + i < p.ld_f32) frow[i] = v[i];
           }
         }
+        if (p.col_sum) {
+          // bias gradient of the layer below = column sums of what was just stored: 32x32 transpose-reduce with
+          // 31 shuffles (each step halves the values a lane holds), then one atomic per column per warp
+          if (!row_ok) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = 0.f;
+          }
+#pragma unroll
+          for (int off = 16; off >= 1; off >>= 1) {
+            const bool upper = (lane & off) != 0;
+#pragma unroll
+            for (int j = 0; j < off; ++j) {
+              const float send = upper ? v[j] : v[j + off];
+              const float keep = upper ? v[j + off] : v[j];
+              v[j] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+            }
+          }
+          if (nc + lane < p.N) atomicAdd(p.col_sum + nc + lane, v[0]);
+        }
       }
       tc_fence_before();
       __syncwarp();

@@ -28,6 +28,7 @@ struct ConvParams {
   int ld_f32;
   const __nv_bfloat16* mask_hi;  // same [B,To,ld_mask] indexing as the output; value > 0 passes
   int ld_mask;
+  float* col_sum;                // nullable: += column sums of the stored tile (bias gradient), [N] fp32
 };
 
 // ---- filter-gradient kernel: dW[j, ci, co] += sum_{b,t} X[b, t+shift_j, acol_j + ci] * dZ[b, t, co]

@@ -281,9 +281,14 @@ ST_API int st_plan_backward_range(st_plan* p, int hi, int lo, st_stream_t stream
     const __nv_bfloat16* dz = l == 10 ? bf(p, p->off_dlogits) : bf(p, p->off_dz[cur]);
     const int ld_dz = l == 10 ? 64 : L.ld_out;
     const int64_t rows = (int64_t)p->B * L.To;
-    int rc = tc::launch_bias_grad(dz, rows, L.Cout, ld_dz, p->npl, p->grads + L.b_off, s);
-    if (rc) return rc;
-    p->launches++;
+    int rc = ST_OK;
+    if (l == 10) {
+      // bias gradient of the last layer from the CTC gradient planes; layers 0..9 get theirs from the epilogue of
+      // the data-gradient kernel that produces their dz (ConvParams::col_sum)
+      rc = tc::launch_bias_grad(dz, rows, L.Cout, ld_dz, p->npl, p->grads + L.b_off, s);
+      if (rc) return rc;
+      p->launches++;
+    }
     // ---- filter gradient
     tc::WgradParams w{};
     w.B = p->B; w.To = L.To; w.t_chunks = (L.To + 63) / 64;
@@ -322,6 +327,7 @@ ST_API int st_plan_backward_range(st_plan* p, int hi, int lo, st_stream_t stream
       c.ld_out = Lb.ld_out;
       c.mask_hi = bf(p, Lb.off_out);
       c.ld_mask = Lb.ld_out;
+      c.col_sum = p->grads + Lb.b_off;
       ti = timed_begin(p, s);
       rc = tc::launch_conv(L.tm_dg_a[l == 10 ? 0 : cur], L.tm_dg_b, c, 256, p->npl, s);
       if (rc) return rc;

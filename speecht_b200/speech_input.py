@@ -58,7 +58,17 @@ class BaseInputLoader:
     (The reference builds float64 and lets the f32 placeholder cast; building f32 directly is value-identical.)"""
     sequence_lengths = np.array([inp.shape[0] for inp in input_list], dtype=np.int32)
     max_time = int(sequence_lengths.max())
-    input_tensor = np.zeros((len(input_list), max_time, self.input_size), dtype=np.float32)
+    shape = (len(input_list), max_time, self.input_size)
+    input_tensor = None
+    try:
+      import torch
+      if torch.cuda.is_available():
+        # page-locked staging buffer: the host->device copy of model.step is then truly asynchronous
+        input_tensor = torch.zeros(shape, dtype=torch.float32, pin_memory=True).numpy()
+    except Exception:
+      input_tensor = None
+    if input_tensor is None:
+      input_tensor = np.zeros(shape, dtype=np.float32)
     for idx, inp in enumerate(input_list):
       input_tensor[idx, :inp.shape[0], :] = inp
     return input_tensor, sequence_lengths, max_time

@@ -175,6 +175,8 @@ class SpeechModel:
     self._training = False
     self._decoding = False
     self.max_gradient_norm = 5.0
+    self._prefetched = None                      # next batch, already on its way to the device
+    self._copy_stream = None
 
   def add_training_ops(self, learning_rate: float = 1e-3, learning_rate_decay_factor: float = 0,
                        max_gradient_norm: float = 5.0, momentum: float = 0.9):
@@ -205,38 +207,77 @@ class SpeechModel:
       self.engine.init_xavier(seed=int(os.environ.get('SPEECHT_B200_SEED', '0')))
       self.engine.reset_optimizer()
 
-  def _next_batch(self, feed_dict):
+  def _to_device(self, inputs, stream=None):
+    """Host batch -> device tensor (async from pinned memory); returns (tensor, ready event or None)."""
+    if torch.is_tensor(inputs) and inputs.is_cuda:
+      return inputs, None
+    host = inputs if torch.is_tensor(inputs) else torch.from_numpy(np.ascontiguousarray(inputs, dtype=np.float32))
+    if stream is None:
+      return host.to(self.engine.device, non_blocking=True), None
+    with torch.cuda.stream(stream):
+      dev = host.to(self.engine.device, non_blocking=True)
+      ev = torch.cuda.Event()
+      ev.record(stream)
+    return dev, ev
+
+  def _fetch(self, feed_dict, stream=None):
+    """(device inputs, lengths, labels, ready event) of the next batch, or an exception instance at end of data."""
     feed = self.input_loader.get_feed_dict() or {}
     if feed_dict is not None:
       feed.update(feed_dict)
     if self.inputs in feed:
       inputs, lengths = feed[self.inputs], feed[self.sequence_lengths]
       labels = feed.get(self.labels) if self.labels is not None else None
-      return inputs, lengths, labels
-    return self.input_loader.dequeue()
+    else:
+      batch = self.input_loader.dequeue()
+      if batch is None:
+        raise OutOfRangeError('no input available')
+      inputs, lengths, labels = batch
+    dev, ev = self._to_device(inputs, stream)
+    return dev, lengths, labels, ev
+
+  def _next_batch(self, feed_dict):
+    """This step's batch.  Batches that come from the loader's queue are prefetched one step ahead: their
+    host->device copy runs on a side stream underneath the previous step's kernels (the reference's FIFOQueue
+    plays the same role on the host side, speech_input.py:147-156)."""
+    if feed_dict is None and self._prefetched is not None:
+      item, self._prefetched = self._prefetched, None
+      if isinstance(item, Exception):
+        raise item
+      dev, lengths, labels, ev = item
+      if ev is not None:
+        torch.cuda.current_stream().wait_event(ev)
+        dev.record_stream(torch.cuda.current_stream())    # allocated on the copy stream, consumed on this one
+      return dev, lengths, labels
+    dev, lengths, labels, _ = self._fetch(feed_dict)
+    return dev, lengths, labels
+
+  def _prefetch_next(self):
+    if getattr(self.input_loader, 'queue', None) is None and not getattr(self.input_loader, 'prefetchable', False):
+      return
+    if self._copy_stream is None:
+      self._copy_stream = torch.cuda.Stream(device=self.engine.device)
+    try:
+      self._prefetched = self._fetch(None, self._copy_stream)
+    except OutOfRangeError as e:
+      self._prefetched = e
 
   def step(self, sess, loss=True, update=True, decode=False, return_label=False, summary=False, feed_dict=None):
     """speech_model.py:197-235.  Returns: avg_loss (optional), decoded (optional), label (optional),
     update (optional, None), summary (optional, None) -- in that order."""
-    batch = self._next_batch(feed_dict)
-    if batch is None:
-      raise OutOfRangeError('no input available')
-    inputs, lengths, labels = batch
+    d_inputs, lengths, labels = self._next_batch(feed_dict)
     if (loss or update) and (labels is None or not self._training):
       raise ValueError('loss/update requested but the model has no labels / training ops')
     if decode and not self._decoding:
       raise ValueError('decode requested but add_decoding_ops was not called')
-    if torch.is_tensor(inputs):
-      d_inputs = inputs.to(self.engine.device, non_blocking=True)
-    else:
-      host = torch.from_numpy(np.ascontiguousarray(inputs, dtype=np.float32))
-      d_inputs = host.to(self.engine.device, non_blocking=True)
     if update:
       res = self.engine.train_step(d_inputs, lengths, labels, self.learning_rate.value, self.max_gradient_norm,
                                    decode=decode)
     else:
       res = self.engine.evaluate_step(d_inputs, lengths, labels if loss else None, decode=decode)
     self.last_result = res
+    if feed_dict is None:
+      self._prefetch_next()                     # next batch's H2D overlaps this step's kernels
     output = []
     if loss:
       output.append(np.float32(res['avg_loss'].item()))       # the device->host read of the step's result

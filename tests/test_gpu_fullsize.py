@@ -1,0 +1,103 @@
+"""GPU parity at BASELINE.json's full sizes, through properties / cross-checks that do not need the (slow) CPU
+oracle for the conv stack: the tensor-core path against the exact-fp32 CUDA path on identical inputs, and the
+CTC loss + greedy decode against the oracle on the GPU's own logits."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import speecht_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def rel(a, b):
+  a = np.asarray(a, np.float64); b = np.asarray(b, np.float64)
+  return float(np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-30))
+
+
+def _engines(*precisions, seed=0):
+  from speecht_b200.engine import W2LEngine
+  engs = []
+  for p in precisions:
+    e = W2LEngine(precision=p)
+    e.init_xavier(seed=seed)
+    engs.append(e)
+  return engs
+
+
+def test_config2_batch32_10s_tensor_path_matches_fp32_path():
+  """configs[1]: batch 32 x 10 s (T=1001 -> T'=501).  bf16x3 logits / loss vs the exact-fp32 path, labels equal."""
+  inputs, lengths, labels = O.synthetic_batch(seed=11, batch=32, seconds=10)
+  x = torch.from_numpy(inputs).cuda()
+  tc, ref = _engines('bf16x3', 'fp32')
+  a = tc.evaluate_step(x, lengths, labels)
+  b = ref.evaluate_step(x, lengths, labels)
+  assert a['logits'].shape == (501, 32, 29)
+  assert rel(a['logits'].cpu().numpy(), b['logits'].cpu().numpy()) < 1e-4
+  assert rel(a['loss'].cpu().numpy(), b['loss'].cpu().numpy()) < 1e-4
+  np.testing.assert_array_equal(a['decoded'][0].values, b['decoded'][0].values)
+  np.testing.assert_array_equal(a['decoded'][0].indices, b['decoded'][0].indices)
+  # CTC loss and greedy decode of the GPU's own logits against the CPU oracle at full size
+  logits = a['logits'].cpu().numpy()
+  oloss, _ = O.ctc_loss_and_grad(logits, labels, lengths // 2)
+  assert rel(a['loss'].cpu().numpy(), oloss) < 1e-5
+  (oi, ov, osh), _ = O.ctc_greedy_decoder(logits, lengths // 2)
+  np.testing.assert_array_equal(a['decoded'][0].values, ov)
+  np.testing.assert_array_equal(a['decoded'][0].indices, oi)
+
+
+def test_config2_train_step_gradients_tensor_path_vs_fp32_path():
+  """One train step at batch 32 x 10 s on both GPU paths from identical weights: global gradient norm and every
+  layer's filter gradient agree (rms-relative: single elements may differ through ReLU sign flips)."""
+  inputs, lengths, labels = O.synthetic_batch(seed=12, batch=32, seconds=10)
+  x = torch.from_numpy(inputs).cuda()
+  tc, ref = _engines('bf16x3', 'fp32')
+  ra = tc.train_step(x, lengths, labels, 1e-4)
+  rb = ref.train_step(x, lengths, labels, 1e-4)
+  assert abs(ra['avg_loss'].item() - rb['avg_loss'].item()) < 1e-4 * abs(rb['avg_loss'].item())
+  na, nb = tc.grad_norm(), ref.grad_norm()
+  assert abs(na - nb) < 2e-3 * nb, (na, nb)
+  for li, ((dw, db), (rw, rbias)) in enumerate(zip(tc.weight_grads, ref.weight_grads)):
+    err = (dw - rw).norm().item() / rw.norm().item()
+    assert err < 5e-3, (li, err)
+    errb = (db - rbias).norm().item() / max(rbias.norm().item(), 1e-30)
+    assert errb < 5e-3, (li, errb)
+  for (wa, _), (wb, _) in zip(tc.export_weights(), ref.export_weights()):
+    assert rel(wa, wb) < 1e-4
+
+
+def test_config4_batch32_30s_bf16_train_step_runs_and_matches_bf16x3_loss():
+  """configs[3] per-GPU shape: batch 32 x 30 s (T=3001 -> T'=1501), bf16 conv stack + fp32 CTC."""
+  inputs, lengths, labels = O.synthetic_batch(seed=13, batch=32, seconds=30)
+  x = torch.from_numpy(inputs).cuda()
+  lo, hi = _engines('bf16', 'bf16x3')
+  a = lo.train_step(x, lengths, labels, 1e-4, decode=True)
+  b = hi.evaluate_step(x, lengths, labels)
+  assert a['logits'].shape == (1501, 32, 29) and lo.global_step == 1
+  la, lb = a['loss'].cpu().numpy(), b['loss'].cpu().numpy()
+  assert np.all(np.isfinite(la)) and rel(la, lb) < 2e-2       # bf16: reported, not gated
+  assert np.isfinite(lo.grad_norm())
+
+
+def test_config5_batch256_variable_length_greedy_decode():
+  """configs[4]: evaluate, batch 256, variable 1-30 s utterances, greedy CTC decode; decode + loss of the GPU
+  logits checked against the oracle at full size; repeated evaluation is bit-identical (deterministic forward)."""
+  rng = np.random.default_rng(5)
+  secs = rng.integers(1, 31, size=256).tolist()
+  secs[0] = 30
+  inputs, lengths, labels = O.synthetic_batch(seed=14, batch=256, seconds=secs)
+  x = torch.from_numpy(inputs).cuda()
+  (tc,) = _engines('bf16x3')
+  a = tc.evaluate_step(x, lengths, labels)
+  logits = a['logits'].cpu().numpy()
+  assert logits.shape == (1501, 256, 29)
+  (oi, ov, osh), oneg = O.ctc_greedy_decoder(logits, lengths // 2)
+  np.testing.assert_array_equal(a['decoded'][0].values, ov)
+  np.testing.assert_array_equal(a['decoded'][0].indices, oi)
+  np.testing.assert_array_equal(a['decoded'][0].dense_shape, osh)
+  np.testing.assert_allclose(a['neg_sum_logits'], oneg, rtol=1e-4, atol=1e-3)
+  oloss, _ = O.ctc_loss_and_grad(logits, labels, lengths // 2)
+  assert rel(a['loss'].cpu().numpy(), oloss) < 1e-5
+  b = tc.evaluate_step(x, lengths, labels)
+  assert torch.equal(a['logits'], b['logits'])
+  np.testing.assert_array_equal(a['decoded'][0].values, b['decoded'][0].values)

@@ -35,9 +35,21 @@ def test_config2_batch32_10s_tensor_path_matches_fp32_path():
   assert a['logits'].shape == (501, 32, 29)
   assert rel(a['logits'].cpu().numpy(), b['logits'].cpu().numpy()) < 1e-4
   assert rel(a['loss'].cpu().numpy(), b['loss'].cpu().numpy()) < 1e-4
-  np.testing.assert_array_equal(a['decoded'][0].values, b['decoded'][0].values)
-  np.testing.assert_array_equal(a['decoded'][0].indices, b['decoded'][0].indices)
-  # CTC loss and greedy decode of the GPU's own logits against the CPU oracle at full size
+  # Greedy labels: the two paths sum in different orders, so frames whose two largest logits are closer than the
+  # arithmetic tolerance may pick the other class (report such flips, do not reseed around
+  # them).  Every differing frame must be such a near-tie, and there may only be a handful in 16032 frames.
+  la, lb = a['logits'].cpu().numpy(), b['logits'].cpu().numpy()
+  flips = np.argwhere(la.argmax(axis=2) != lb.argmax(axis=2))
+  scale = np.abs(lb).max()
+  for t, bb in flips:
+    top2 = np.sort(lb[t, bb])[-2:]
+    assert top2[1] - top2[0] < 2e-4 * scale, ('argmax flip that is not a near-tie', t, bb, top2)
+  assert len(flips) <= 8, len(flips)
+  print('near-tie argmax flips bf16x3 vs fp32 at config 2: %d of %d frames' % (len(flips), la.shape[0] * la.shape[1]))
+  if len(flips) == 0:
+    np.testing.assert_array_equal(a['decoded'][0].values, b['decoded'][0].values)
+    np.testing.assert_array_equal(a['decoded'][0].indices, b['decoded'][0].indices)
+  # CTC loss and greedy decode of the GPU's own logits against the CPU oracle at full size (bit-exact)
   logits = a['logits'].cpu().numpy()
   oloss, _ = O.ctc_loss_and_grad(logits, labels, lengths // 2)
   assert rel(a['loss'].cpu().numpy(), oloss) < 1e-5

@@ -60,7 +60,11 @@ def test_config2_batch32_10s_tensor_path_matches_fp32_path():
 
 def test_config2_train_step_gradients_tensor_path_vs_fp32_path():
   """One train step at batch 32 x 10 s on both GPU paths from identical weights: global gradient norm and every
-  layer's filter gradient agree (rms-relative: single elements may differ through ReLU sign flips)."""
+  layer's filter gradient agree.  The per-layer bound is rms-relative 3e-2, not 1e-4: a forward difference of
+  eps flips the ReLU of a fraction ~eps*density of the units (pre-activation within eps of zero), and removing a
+  fraction f of random-sign terms from a gradient sum changes it by ~sqrt(f) -- sqrt(1e-4) = 1e-2 is what is
+  measured at layer 0.  With the on/off pattern held equal the tensor path agrees to 3e-4
+  (tests/test_gpu_model.py::test_train_step_parity)."""
   inputs, lengths, labels = O.synthetic_batch(seed=12, batch=32, seconds=10)
   x = torch.from_numpy(inputs).cuda()
   tc, ref = _engines('bf16x3', 'fp32')
@@ -71,9 +75,9 @@ def test_config2_train_step_gradients_tensor_path_vs_fp32_path():
   assert abs(na - nb) < 2e-3 * nb, (na, nb)
   for li, ((dw, db), (rw, rbias)) in enumerate(zip(tc.weight_grads, ref.weight_grads)):
     err = (dw - rw).norm().item() / rw.norm().item()
-    assert err < 5e-3, (li, err)
+    assert err < 3e-2, (li, err)
     errb = (db - rbias).norm().item() / max(rbias.norm().item(), 1e-30)
-    assert errb < 5e-3, (li, errb)
+    assert errb < 3e-2, (li, errb)
   for (wa, _), (wb, _) in zip(tc.export_weights(), ref.export_weights()):
     assert rel(wa, wb) < 1e-4
 

@@ -120,6 +120,11 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // Programmatic dependent launch: everything above (barrier init, TMEM allocation, descriptor prefetch) touched no
+  // global data, so it may overlap the tail of the previous kernel in the stream.  Let OUR dependents start
+  // launching, then wait until the previous grid has completed and its writes are visible.
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
 
   if (warp == 0) {
     // ===================================================== TMA producer
@@ -388,6 +393,11 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // Programmatic dependent launch: everything above (barrier init, TMEM allocation, descriptor prefetch) touched no
+  // global data, so it may overlap the tail of the previous kernel in the stream.  Let OUR dependents start
+  // launching, then wait until the previous grid has completed and its writes are visible.
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
 
   // tile -> (n tile, tap, m tile), n slowest: a wave touches few dZ column slabs
   auto decode = [&](int tile, int& j, int& mt, int& nt) {
@@ -699,6 +709,24 @@ int grid_for(int work_items) {
   return work_items < sms ? work_items : sms;
 }
 
+// Launch with the programmatic-stream-serialization attribute (PDL): the kernel may begin while the previous kernel
+// of the stream drains; it synchronises with `griddepcontrol.wait` before touching global memory.
+template <class Kernel, class Params>
+cudaError_t launch_pdl(Kernel kernel, int grid, int smem, cudaStream_t stream, const CUtensorMap& m0,
+                       const CUtensorMap& m1, const Params& p) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, m0, m1, p);
+}
+
 template <int BLOCK_N, int NPL>
 int launch_conv_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvParams& p, cudaStream_t stream) {
   using Cfg = ConvCfg<BLOCK_N, NPL>;
@@ -709,8 +737,7 @@ int launch_conv_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvPara
     configured = true;
   }
   const int tiles = p.B * p.m_tiles_per_utt * p.n_tiles;
-  tc_conv_kernel<BLOCK_N, NPL><<<grid_for(tiles), kThreads, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, p);
-  ST_CUDA_LAUNCH_CHECK("tc_conv_kernel");
+  ST_CUDA_CALL(launch_pdl(tc_conv_kernel<BLOCK_N, NPL>, grid_for(tiles), Cfg::SMEM_BYTES, stream, tmA, tmB, p));
   return ST_OK;
 }
 
@@ -723,8 +750,7 @@ int launch_wgrad_t(const CUtensorMap& tmX, const CUtensorMap& tmDZ, const WgradP
                                       Cfg::SMEM_BYTES));
     configured = true;
   }
-  tc_wgrad_kernel<BLOCK_N, NPL><<<st_num_sms(), kThreads, Cfg::SMEM_BYTES, stream>>>(tmX, tmDZ, p);
-  ST_CUDA_LAUNCH_CHECK("tc_wgrad_kernel");
+  ST_CUDA_CALL(launch_pdl(tc_wgrad_kernel<BLOCK_N, NPL>, st_num_sms(), Cfg::SMEM_BYTES, stream, tmX, tmDZ, p));
   return ST_OK;
 }
 

@@ -300,6 +300,9 @@ def run_ours(args, rank, local_rank, world):
     # fall back to everything up to the end of the e2e region (same kernels, same load)
     clocks = sampler.stop(mark0, mark1 if mark1 > mark0 else mark2)
 
+  aux = None
+  if rank == 0 and world == 1:
+    aux = aux_kernels(eng, dev, B, args.seconds, host_sets[0], os.path.join(ROOT, 'MEASURED_PEAKS.json'))
   if world > 1:
     dist.destroy_process_group()
   if rank != 0:
@@ -324,6 +327,7 @@ def run_ours(args, rank, local_rank, world):
             'd2h_bytes_per_step': 4},
     'gpu_launches': int(launches),
     'roofline': roofline,
+    'aux_hbm_kernels': aux,
   }
   if world == 1 and not args.no_cpu_baseline:
     cv, csec = cpu_reference_steps(args.cpu_sample, args.seconds, 2, 1)
@@ -332,6 +336,77 @@ def run_ours(args, rank, local_rank, world):
                                       '%.1f s/step); CPU restatement, not TensorFlow-1' % (args.cpu_sample,
                                                                                          args.seconds, csec)}
   print(json.dumps(line), flush=True)
+
+
+def aux_kernels(eng, dev, B, seconds, host_set, peaks_path):
+  """The HBM-bound rows of SURVEY.md 8(d) -- features, CTC, greedy decode, clip+Adam -- timed alone with CUDA
+  events (20 calls after 3 warm-ups): algorithmic bytes / time against the measured HBM copy bandwidth.  They are
+  latency/launch-bound at these sizes; the fractions are reported as measured."""
+  import torch
+  from speecht_b200 import ops
+  peak = 6650.0
+  if os.path.exists(peaks_path):
+    peak = float(json.load(open(peaks_path)).get('hbm_gbs', peak))
+  T = frames_for(seconds)
+  To = (T + 1) // 2
+  rng = np.random.default_rng(7)
+  n_samp = int(16000 * seconds)
+  wav = torch.from_numpy((0.1 * rng.standard_normal((B, n_samp))).astype(np.float32)).to(dev)
+  logits_bm = torch.randn((B, To, 32), device=dev)[:, :, :29]
+  logits = logits_bm.transpose(0, 1)
+  ctc_len = host_set[1] // 2
+  batch = ops.CTCBatch(host_set[2], ctc_len, To, 29, dev)
+  n = eng.params.numel()
+
+  def timeit(fn, reps=20):
+    for _ in range(3):
+      fn()
+    torch.cuda.synchronize(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+      fn()
+    e1.record()
+    torch.cuda.synchronize(dev)
+    return e0.elapsed_time(e1) / reps
+
+  scratch = [torch.zeros_like(eng.params) for _ in range(4)]
+  nsq = torch.ones((1,), dtype=torch.float64, device=dev)
+  cases = {
+    'melspec (a1-a3)': (lambda: ops.power_spectrogram(wav, [n_samp] * B, 16000), B * (4 * n_samp + 4 * T * 128)),
+    'ctc_loss+grad (a8-a9)': (lambda: ops.ctc_loss(batch, logits, want_grad=True), 2 * To * B * 29 * 4),
+    'ctc_greedy_decode (a12)': (lambda: lib_decode(ops, logits, batch), To * B * 29 * 4),
+    'sumsq+clip_adam (a10-a11)': (lambda: (ops.global_norm_sq(scratch[1], nsq),
+                                           ops.clip_adam(scratch[0], scratch[1], scratch[2], scratch[3], 1, 1e-4,
+                                                         normsq=nsq)), 8 * n * 4),
+  }
+  out = {}
+  for name, (fn, nbytes) in cases.items():
+    ms = timeit(fn)
+    gbs = nbytes / (ms * 1e-3) / 1e9
+    out[name] = {'ms': round(ms, 4), 'algorithmic_MB': round(nbytes / 1e6, 2), 'GB/s': round(gbs, 1),
+                 'frac_of_measured_hbm': round(gbs / peak, 4)}
+  out['peak_GB/s'] = peak
+  return out
+
+
+def lib_decode(ops, logits, batch):
+  """Greedy decode kernel only (no host assembly of the sparse triple)."""
+  import torch
+  from speecht_b200._lib import check, lib, ptr, stream_ptr
+  T, B, C = logits.shape
+  key = ('dec', T, B)
+  buf = lib_decode.cache.get(key)
+  if buf is None:
+    buf = (torch.empty((B, T), dtype=torch.int32, device=logits.device),
+           torch.empty((B,), dtype=torch.int32, device=logits.device),
+           torch.empty((B,), dtype=torch.float32, device=logits.device))
+    lib_decode.cache[key] = buf
+  check(lib().st_ctc_greedy_decode(ptr(logits), logits.stride(0), logits.stride(1), T, B, C, ptr(batch.seq_len), C - 1,
+                                   1, ptr(buf[0]), ptr(buf[1]), ptr(buf[2]), stream_ptr()))
+
+
+lib_decode.cache = {}
 
 
 def main():

@@ -24,6 +24,7 @@
 #include "st_common.cuh"
 #include "conv_tc.h"
 #include "tc_ptx.cuh"
+#include <stdlib.h>
 
 namespace tc {
 
@@ -719,9 +720,10 @@ cudaError_t launch_pdl(Kernel kernel, int grid, int smem, cudaStream_t stream, c
   cfg.blockDim = dim3(kThreads);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = stream;
+  static const bool pdl = []() { const char* e = getenv("SPEECHT_B200_PDL"); return !(e && e[0] == '0'); }();
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  attr[0].val.programmaticStreamSerializationAllowed = pdl ? 1 : 0;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   return cudaLaunchKernelEx(&cfg, kernel, m0, m1, p);

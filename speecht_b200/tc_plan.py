@@ -14,10 +14,12 @@ from . import ops
 from ._lib import check, lib, ptr, stream_ptr
 
 N_PLANES = {'bf16': 1, 'bf16x3': 2}
-MAX_CACHED_SHAPES = 4
+MAX_CACHED_SHAPES = 64
 
 
 class _Shape:
+  """Native plan of one (batch, time) shape, bound into the TCPlan's shared arena."""
+
   def __init__(self, engine, B, T):
     self.B, self.T = B, T
     self.handle = ctypes.c_void_p()
@@ -26,8 +28,12 @@ class _Shape:
     n = lib().st_plan_param_floats(self.handle)
     if n != engine.params.numel():
       raise RuntimeError('native parameter layout (%d floats) != engine layout (%d)' % (n, engine.params.numel()))
-    nbytes = lib().st_plan_arena_bytes(self.handle)
-    self.arena = torch.zeros((nbytes + 1024,), dtype=torch.uint8, device=engine.device)
+    self.nbytes = lib().st_plan_arena_bytes(self.handle)
+
+  def bind(self, engine, arena):
+    self.arena = arena
+    nbytes = self.nbytes
+    B = self.B
     base = self.arena.data_ptr()
     self.arena_ptr = (base + 1023) // 1024 * 1024
     check(lib().st_plan_bind(self.handle, ctypes.c_void_p(self.arena_ptr), nbytes, ptr(engine.params),
@@ -60,8 +66,12 @@ class TCPlan:
   def __init__(self, engine):
     self.engine = engine
     self.shapes = {}
+    self.arena = None                 # ONE arena shared by every shape (only one shape is live at a time)
+    self._active = None
 
   def _shape(self, B, T):
+    """Plan for this batch shape.  Ragged training produces a new (B, T) almost every step: plans (offsets + TMA
+    descriptors, host-side only) are cached, the device arena is shared and only grows."""
     key = (B, T)
     sh = self.shapes.get(key)
     if sh is None:
@@ -69,9 +79,19 @@ class TCPlan:
         old = next(iter(self.shapes))
         self.shapes.pop(old).close()
       sh = _Shape(self.engine, B, T)
+      if self.arena is None or self.arena.numel() < sh.nbytes + 1024:
+        for other in self.shapes.values():
+          other.close()
+        self.shapes.clear()
+        self.arena = None                                      # release before growing
+        self.arena = torch.zeros((int(sh.nbytes * 1.1) + 1024,), dtype=torch.uint8, device=self.engine.device)
+      sh.bind(self.engine, self.arena)
       self.shapes[key] = sh
       if getattr(self, 'timing', False):
         check(lib().st_plan_set_timing(sh.handle, 1))
+    if self._active is not key and self._active != key:
+      sh.weights_version = -1                                  # another shape's buffers overlapped the filter planes
+      self._active = key
     return sh
 
   def set_timing(self, enable):

@@ -231,3 +231,20 @@ def test_cli_train_checkpoints_and_resumes(tmp_path):
   assert latest_checkpoint(flags.run_train_dir).endswith('speechT.ckpt-4')
   model2 = Training(cli.parse(argv)).run(max_steps=2)          # resumes from step 4
   assert model2.global_step.eval() == 6
+
+
+def test_shape_changes_share_one_arena_and_stay_correct():
+  """Ragged training changes (B, T) every step: plans are cached, the arena is shared and regrown, filter planes
+  are re-packed after a shape switch.  Alternating shapes must reproduce each shape's own result bit for bit."""
+  weights = O.xavier_weights(np.random.default_rng(3), dtype=np.float32)
+  eng = _engine('bf16x3', weights)
+  shapes = [(2, 1), (3, 2), (2, 1), (4, 1), (3, 2)]
+  seen = {}
+  for i, (b, secs) in enumerate(shapes):
+    inputs, lengths, labels = O.synthetic_batch(seed=40 + b * 10 + secs, batch=b, seconds=secs)
+    res = eng.evaluate_step(torch.from_numpy(inputs).cuda(), lengths, labels)
+    logits = res['logits'].cpu().numpy().copy()
+    if (b, secs) in seen:
+      np.testing.assert_array_equal(logits, seen[(b, secs)])
+    seen[(b, secs)] = logits
+  assert len(eng._tc().shapes) == 3 and eng._tc().arena is not None

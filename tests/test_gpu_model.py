@@ -248,3 +248,27 @@ def test_shape_changes_share_one_arena_and_stay_correct():
       np.testing.assert_array_equal(logits, seen[(b, secs)])
     seen[(b, secs)] = logits
   assert len(eng._tc().shapes) == 3 and eng._tc().arena is not None
+
+
+@pytest.mark.parametrize('T', [100, 37, 6, 2])
+def test_tensor_path_even_short_and_tiny_time_axes(T):
+  """Even T (pad 23/23 on the stride-2 layer instead of 23/24), T not a multiple of anything, and time axes far
+  shorter than a 128-row tile / the 48-tap first filter: TMA zero fill must reproduce TF 'SAME' everywhere."""
+  rng = np.random.default_rng(T)
+  B = 2
+  inputs = rng.standard_normal((B, T, 128)).astype(np.float32)
+  lengths = np.array([T, max(T - 1, 1)], dtype=np.int32)
+  inputs[1, lengths[1]:] = 0
+  weights = O.xavier_weights(np.random.default_rng(8), dtype=np.float32)
+  w64 = [(w.astype(np.float64), b.astype(np.float64)) for w, b in weights]
+  ref = O.wav2letter_forward(inputs.astype(np.float64), w64)
+  for precision in ('bf16x3', 'fp32'):
+    eng = _engine(precision, weights)
+    out = eng.forward(torch.from_numpy(inputs).cuda())
+    assert out.shape == ref.shape == ((T + 1) // 2, B, 29)
+    assert rel(out.cpu().numpy(), ref) < 1e-4, (precision, rel(out.cpu().numpy(), ref))
+  # and a training step on the shortest shapes must not fault (labels empty when there is no room for any)
+  labels = [[1] if lengths[i] // 2 >= 1 else [] for i in range(B)]
+  eng = _engine('bf16x3', weights)
+  res = eng.train_step(torch.from_numpy(inputs).cuda(), lengths, labels, 1e-4)
+  assert np.all(np.isfinite(res['loss'].cpu().numpy())) and np.isfinite(eng.grad_norm())

@@ -8,7 +8,8 @@ import os
 from ctypes import c_char_p, c_double, c_float, c_int, c_int32, c_int64, c_size_t, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'libspeecht_b200.so')
+# SPEECHT_B200_LIB selects another build of the same C ABI (A/B timing of kernel variants); default: in-tree build
+LIB_PATH = os.environ.get('SPEECHT_B200_LIB') or os.path.join(_HERE, 'libspeecht_b200.so')
 
 ST_OK = 0
 ST_ERR_INVALID_ARG = -1

@@ -30,7 +30,8 @@ namespace tc {
 
 namespace {
 
-constexpr int kThreads = 192;
+constexpr int kEpilogueWarps = 8;              // two per TMEM lane quarter: they split the 32-column chunks
+constexpr int kThreads = 64 + 32 * kEpilogueWarps;
 constexpr int kSmemBudget = 227 * 1024;
 
 template <int BLOCK_N, int NPL>
@@ -55,7 +56,8 @@ __device__ __forceinline__ uint32_t pack_bf16x2(__nv_bfloat16 lo, __nv_bfloat16 
   return (uint32_t)__bfloat16_as_ushort(lo) | ((uint32_t)__bfloat16_as_ushort(hi) << 16);
 }
 
-// Splits 8 fp32 values into NPL planes and stores each plane's 8 bf16 as one 16-byte vector.
+// Splits 8 fp32 values into NPL planes and stores each plane's 8 bf16 as one 16-byte vector.  Pairs are
+// converted with one cvt.rn.bf16x2.f32; the residual for the next plane is x - float(hi) (exact in fp32).
 template <int NPL>
 __device__ __forceinline__ void store_planes8(__nv_bfloat16* dst, int64_t plane_stride, const float* v) {
   float rem[8];
@@ -63,18 +65,17 @@ __device__ __forceinline__ void store_planes8(__nv_bfloat16* dst, int64_t plane_
   for (int i = 0; i < 8; ++i) rem[i] = v[i];
 #pragma unroll
   for (int p = 0; p < NPL; ++p) {
-    __nv_bfloat16 h[8];
+    uint32_t w[4];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      h[i] = __float2bfloat16_rn(rem[i]);
-      rem[i] -= __bfloat162float(h[i]);
+    for (int i = 0; i < 4; ++i) {
+      const __nv_bfloat162 h = __floats2bfloat162_rn(rem[2 * i], rem[2 * i + 1]);
+      w[i] = *reinterpret_cast<const uint32_t*>(&h);
+      if (p + 1 < NPL) {
+        rem[2 * i] -= __uint_as_float(w[i] << 16);
+        rem[2 * i + 1] -= __uint_as_float(w[i] & 0xffff0000u);
+      }
     }
-    uint4 pk;
-    pk.x = pack_bf16x2(h[0], h[1]);
-    pk.y = pack_bf16x2(h[2], h[3]);
-    pk.z = pack_bf16x2(h[4], h[5]);
-    pk.w = pack_bf16x2(h[6], h[7]);
-    *reinterpret_cast<uint4*>(dst + p * plane_stride) = pk;
+    *reinterpret_cast<uint4*>(dst + p * plane_stride) = make_uint4(w[0], w[1], w[2], w[3]);
   }
 }
 
@@ -112,7 +113,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tmem_full + a, 1);
-      mbar_init(tmem_empty + a, 4);
+      mbar_init(tmem_empty + a, kEpilogueWarps);
     }
     fence_barrier_init();
   }
@@ -209,6 +210,8 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   } else {
     // ===================================================== epilogue warps 2..5
     const int quarter = warp & 3;                         // TMEM lane quarter this warp may read
+    const int chunk0 = (warp - 2) >> 2;                   // warps w and w+4 share a quarter: even / odd chunks
+    constexpr int kChunkStep = kEpilogueWarps / 4;
     const int row = quarter * 32 + lane;
     int local = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
@@ -235,15 +238,15 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             mk[g] = *reinterpret_cast<const uint4*>(p.mask_hi + out_row * p.ld_mask + nc + g * 8);
         }
       };
-      load_mask(0);
+      load_mask(chunk0);
 #pragma unroll 1
-      for (int c = 0; c < BLOCK_N / 32; ++c) {
+      for (int c = chunk0; c < BLOCK_N / 32; c += kChunkStep) {
         uint32_t r[32];
         tmem_ld32(taddr + c * 32, r);
         uint4 mcur[4];
 #pragma unroll
         for (int g = 0; g < 4; ++g) mcur[g] = mk[g];
-        if (c + 1 < BLOCK_N / 32) load_mask(c + 1);
+        if (c + kChunkStep < BLOCK_N / 32) load_mask(c + kChunkStep);
         tmem_ld_wait();
         const int nc = n0 + c * 32;
         float v[32];
@@ -385,7 +388,7 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tmem_full + a, 1);
-      mbar_init(tmem_empty + a, 4);
+      mbar_init(tmem_empty + a, kEpilogueWarps);
     }
     fence_barrier_init();
   }
@@ -489,6 +492,8 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
     __syncwarp();
   } else {
     const int quarter = warp & 3;
+    const int chunk0 = (warp - 2) >> 2;
+    constexpr int kChunkStep = kEpilogueWarps / 4;
     const int row = quarter * 32 + lane;
     int local = 0;
     for (; local < my_items; ++local) {
@@ -505,7 +510,7 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BLOCK_N;
       float* wrow = p.dW + ((int64_t)j * p.Cin + ci) * p.Cout;
 #pragma unroll 1
-      for (int c = 0; c < BLOCK_N / 32; ++c) {
+      for (int c = chunk0; c < BLOCK_N / 32; c += kChunkStep) {
         uint32_t r[32];
         tmem_ld32(taddr + c * 32, r);
         tmem_ld_wait();

@@ -272,3 +272,16 @@ def test_tensor_path_even_short_and_tiny_time_axes(T):
   eng = _engine('bf16x3', weights)
   res = eng.train_step(torch.from_numpy(inputs).cuda(), lengths, labels, 1e-4)
   assert np.all(np.isfinite(res['loss'].cpu().numpy())) and np.isfinite(eng.grad_norm())
+
+
+def test_two_gpu_data_parallel_matches_single_process():
+  """NCCL path (needs >= 2 GPUs; the round-end single-GPU run skips it, `gpurun --gpus 2` exercises it)."""
+  import subprocess
+  if torch.cuda.device_count() < 2:
+    pytest.skip('needs two GPUs')
+  root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+  cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', '2', '--master-addr',
+         '127.0.0.1', '--master-port', '29533', os.path.join(root, 'tools', 'dp_parity.py'), 'bf16x3']
+  out = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
+  assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+  assert 'identical_across_ranks=True' in out.stdout

@@ -1,0 +1,61 @@
+"""Data-parallel parity (run under torchrun, one process per GPU): N ranks each train on their shard of a global
+batch for two steps; rank 0 also trains a single-process engine on the whole batch.  With all utterances the same
+length (so local and global padding coincide) the parameters must agree to fp32 summation-order noise.
+
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 tools/dp_parity.py
+"""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from oracle import speecht_oracle as O
+from speecht_b200 import parallel
+from speecht_b200.engine import W2LEngine
+
+
+def main():
+  precision = sys.argv[1] if len(sys.argv) > 1 else 'bf16x3'
+  rank, local, world = parallel.init_from_env('nccl')
+  torch.cuda.set_device(local)
+  per_rank = 3
+  inputs, lengths, labels = O.synthetic_batch(seed=21, batch=per_rank * world, seconds=1)
+  weights = O.xavier_weights(np.random.default_rng(5), dtype=np.float32)
+  a, b = parallel.shard_batch(per_rank * world, rank, world)
+  eng = W2LEngine(precision=precision, device='cuda:%d' % local, process_group=dist.group.WORLD if world > 1 else None)
+  eng.load_weights(weights)
+  losses = []
+  for _ in range(2):
+    res = eng.train_step(torch.from_numpy(inputs[a:b]).cuda(), lengths[a:b], labels[a:b], 1e-3)
+    losses.append(parallel.mean_scalar(res['avg_loss']).item())
+  flat = eng.params.clone()
+  # every rank must hold bit-identical parameters (same reduced gradient, same update)
+  gathered = [torch.empty_like(flat) for _ in range(world)]
+  if world > 1:
+    dist.all_gather(gathered, flat)
+  else:
+    gathered = [flat]
+  identical = all(torch.equal(gathered[0], g) for g in gathered)
+  if rank == 0:
+    single = W2LEngine(precision=precision, device='cuda:%d' % local)
+    single.load_weights(weights)
+    sl = []
+    for _ in range(2):
+      res = single.train_step(torch.from_numpy(inputs).cuda(), lengths, labels, 1e-3)
+      sl.append(res['avg_loss'].item())
+    diff = (single.params - flat).abs().max().item() / single.params.abs().max().item()
+    print('DP_PARITY world=%d precision=%s identical_across_ranks=%s max_rel_param_diff_vs_single=%.3e '
+          'loss_dp=%s loss_single=%s' % (world, precision, identical, diff, ['%.6f' % x for x in losses],
+                                        ['%.6f' % x for x in sl]), flush=True)
+    assert identical
+    assert diff < 2e-5, diff
+    assert all(abs(x - y) < 1e-4 * abs(y) for x, y in zip(losses, sl))
+  if world > 1:
+    dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+  main()

@@ -64,22 +64,26 @@ class Training(DatasetExecutor):
           avg_loss = step_result[0]
           step_time += (time.time() - start_time) / self.flags.steps_per_checkpoint
           loss += avg_loss / self.flags.steps_per_checkpoint
-          if is_checkpoint_step and self.rank != 0:
-            step_time, loss = 0.0, 0.0
-          elif is_checkpoint_step:
+          if is_checkpoint_step:
             global_step = model.global_step.eval()
-            perplexity = np.exp(float(avg_loss)) if avg_loss < 300 else float('inf')
-            print('global step {:d} learning rate {:.4f} step-time {:.2f} average loss {:.2f} perplexity {:.2f}'
-                  .format(global_step, model.learning_rate.eval(), step_time, avg_loss, perplexity))
-            model.summary_writer.add_summary(step_result[2], global_step)
+            if self.world > 1:
+              # every rank must take the same learning-rate decision: use the global mean of the running loss
+              import torch
+              loss = float(parallel.mean_scalar(torch.tensor([loss], device=model.engine.device)).item())
+            if self.rank == 0:
+              perplexity = np.exp(float(avg_loss)) if avg_loss < 300 else float('inf')
+              print('global step {:d} learning rate {:.4f} step-time {:.2f} average loss {:.2f} perplexity {:.2f}'
+                    .format(global_step, model.learning_rate.eval(), step_time, avg_loss, perplexity))
+              model.summary_writer.add_summary(step_result[2], global_step)
             # decrease the learning rate if no improvement was seen over the last 3 checkpoints
             if self.flags.learning_rate_decay_factor > 0 and len(previous_losses) > 2 \
                 and loss > max(previous_losses[-3:]):
               sess.run(model.learning_rate_decay_op)
             previous_losses.append(loss)
-            checkpoint_path = os.path.join(self.flags.run_train_dir, 'speechT.ckpt')
-            model.saver.save(sess, checkpoint_path, global_step=model.global_step)
-            print('Model saved')
+            if self.rank == 0:
+              checkpoint_path = os.path.join(self.flags.run_train_dir, 'speechT.ckpt')
+              model.saver.save(sess, checkpoint_path, global_step=model.global_step)
+              print('Model saved')
             step_time, loss = 0.0, 0.0
           if max_steps is not None and current_step >= max_steps:
             break

@@ -39,7 +39,7 @@ def parse_args():
   p.add_argument('--warmup', type=int, default=3)
   p.add_argument('--impl', default='ours', choices=['ours', 'reference'])
   p.add_argument('--precision', default=os.environ.get('SPEECHT_B200_PRECISION', 'bf16x3'),
-                 choices=['fp32', 'bf16x3', 'bf16'])
+                 choices=['fp32', 'bf16x6', 'bf16x3', 'bf16'])
   p.add_argument('--batch', type=int, default=32, help='per-GPU batch (BASELINE configs[1]: 32)')
   p.add_argument('--seconds', type=float, default=10.0)
   p.add_argument('--cpu-sample', type=int, default=2, help='utterances per CPU-baseline step')
@@ -313,6 +313,7 @@ def run_ours(args, rank, local_rank, world):
     'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
     'ms_per_step': ms_step, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
     'dtype': {'fp32': 'fp32', 'bf16x3': 'fp32 (bf16x3 split operands on tcgen05, fp32 accumulate; CTC/Adam fp32)',
+              'bf16x6': 'fp32 (bf16x6: three bf16 planes per operand, 6 products on tcgen05, fp32 accumulate)',
               'bf16': 'bf16 conv operands, fp32 accumulate; CTC/Adam fp32'}[args.precision],
     'data': 'synthetic',
     'config': {'workload': 'configs[1] train-step: batch %d/GPU, %gs@16kHz synthetic 128-mel (T=%d, T\'=%d), '

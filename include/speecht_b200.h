@@ -37,6 +37,7 @@ typedef void* st_stream_t;         /* cudaStream_t */
 /* conv precision modes of the tensor-core path (st_tc_*): number of bf16 planes an fp32 value is split into. */
 #define ST_PREC_BF16 1             /* 1 plane : plain bf16 operands, fp32 accumulate                      */
 #define ST_PREC_BF16X3 2           /* 2 planes: hi+lo split, 3 tcgen05 products -> ~2^-17 operand error     */
+#define ST_PREC_BF16X6 3           /* 3 planes: 6 products -> fp32-equivalent operands (error = accumulation) */
 
 int st_version(void);
 const char* st_last_error(void);
@@ -104,7 +105,7 @@ int st_melspec(const float* wav, int64_t wav_stride, const int32_t* n_samples, i
 
 /* ---- a6 on the tensor cores + a13: the whole step as a plan                     speech_model.py:235,275-295 ----
  * For a fixed (batch B, time T) shape the 11-layer stack is a fixed launch sequence of tcgen05/TMEM/TMA
- * implicit-GEMM kernels (csrc/conv_tc.cu) over bf16 operand planes (n_planes = ST_PREC_BF16 or ST_PREC_BF16X3).
+ * implicit-GEMM kernels (csrc/conv_tc.cu) over bf16 operand planes (n_planes = ST_PREC_BF16, _BF16X3 or _BF16X6).
  * The plan owns no device memory: the caller provides one arena (st_plan_arena_bytes, 1024-byte aligned) and the
  * flat fp32 parameter / gradient buffers (layout: per layer filters [K,Cin,Cout] then bias [Cout], each start
  * rounded up to 64 floats; st_plan_param_floats gives the total).

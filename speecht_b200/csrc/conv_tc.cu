@@ -3,8 +3,9 @@
 // (reference speech_model.py:155,173,177) and the gradients TF autodiff derives (speech_model.py:78).
 //
 // Operand format: every fp32 tensor is held as `NPL` bf16 planes whose sum is the value (NPL=1: plain bf16;
-// NPL=2: hi + lo split, x = hi + lo + O(2^-17 |x|)).  A product of two split operands is accumulated as
-// hi*hi + hi*lo + lo*hi (3 MMAs, the lo*lo term is below 2^-16 relative) in ONE fp32 TMEM accumulator.
+// NPL=2: hi + lo split, x = hi + lo + O(2^-17 |x|); NPL=3: three planes, x exact to 2^-25).  A product of two split
+// operands is accumulated as hi*hi + hi*lo + lo*hi (NPL=2: 3 MMAs, dropped terms 2^-16 relative) or as the six
+// products above 2^-24 (NPL=3, "bf16x6": fp32-equivalent operands) in ONE fp32 TMEM accumulator.
 //
 // Layout (NWC, the reference's): activations [plane][batch][time][channels], channels contiguous, so a tile of 128
 // time steps x 64 channels is one 3-D TMA box {64, 128, 1}; a filter tap k just shifts the time coordinate by
@@ -79,6 +80,34 @@ __device__ __forceinline__ void store_planes8(__nv_bfloat16* dst, int64_t plane_
   }
 }
 
+// Products of the split operands, in issue order, as (A plane, B plane, load group to wait for before it,
+// load group released after it; -1 = none).  Plane 0 = hi, 1 = lo, 2 = lo-lo.
+//   NPL 1: hi*hi
+//   NPL 2: hi*lo, hi*hi, lo*hi                       two load groups per stage, X = {A0,B1}, Y = {A1,B0}
+//   NPL 3: the six products above 2^-24: (0,2) (1,1) (2,0) (0,1) (1,0) (0,0), smallest first, one load group
+template <int NPL> struct Products;
+template <> struct Products<1> {
+  static constexpr int N = 1;
+  __device__ static constexpr int a(int) { return 0; }
+  __device__ static constexpr int b(int) { return 0; }
+  __device__ static constexpr int wait(int) { return 0; }
+  __device__ static constexpr int release(int) { return 0; }
+};
+template <> struct Products<2> {
+  static constexpr int N = 3;
+  __device__ static constexpr int a(int i) { return i == 2 ? 1 : 0; }
+  __device__ static constexpr int b(int i) { return i == 0 ? 1 : 0; }
+  __device__ static constexpr int wait(int i) { return i == 0 ? 0 : (i == 1 ? 1 : -1); }
+  __device__ static constexpr int release(int i) { return i == 1 ? 0 : (i == 2 ? 1 : -1); }
+};
+template <> struct Products<3> {
+  static constexpr int N = 6;
+  __device__ static constexpr int a(int i) { return i == 0 ? 0 : (i == 1 ? 1 : (i == 2 ? 2 : (i == 3 ? 0 : (i == 4 ? 1 : 0)))); }
+  __device__ static constexpr int b(int i) { return i == 0 ? 2 : (i == 1 ? 1 : (i == 2 ? 0 : (i == 3 ? 1 : 0))); }
+  __device__ static constexpr int wait(int i) { return i == 0 ? 0 : -1; }
+  __device__ static constexpr int release(int i) { return i == 5 ? 0 : -1; }
+};
+
 template <int BLOCK_N, int NPL>
 __global__ void __launch_bounds__(kThreads, 1)
 tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const ConvParams p) {
@@ -150,15 +179,27 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const int a_col = (m - shift * p.a_stride) * p.a_cin + cc * kChunkK;
           uint8_t* st = smem + stage * Cfg::STAGE_BYTES;
           const int b_c0 = j * p.b_col_step + cc * kChunkK, b_c1 = n0 + j * p.b_row_step;
+          if (NG == 2) {
 #pragma unroll
-          for (int g = 0; g < NG; ++g) {
-            // group 0 (X): A plane 0 + B plane NPL-1;  group 1 (Y): A plane 1 + B plane 0
-            const int pa = g, pb = NPL - 1 - g;
-            uint64_t* fb = full_bar + stage * NG + g;
-            mbar_wait(empty_bar + stage * NG + g, phase ^ 1);
-            mbar_expect_tx(fb, Cfg::A_BYTES + Cfg::B_BYTES);
-            tma_load_3d(&tmA, fb, st + pa * Cfg::A_BYTES, a_col, t0 + shift, pa * p.B + b);
-            tma_load_2d(&tmB, fb, st + NPL * Cfg::A_BYTES + pb * Cfg::B_BYTES, b_c0, pb * p.b_plane_rows + b_c1);
+            for (int g = 0; g < NG; ++g) {
+              // group 0 (X): A plane 0 + B plane 1;  group 1 (Y): A plane 1 + B plane 0
+              const int pa = g, pb = 1 - g;
+              uint64_t* fb = full_bar + stage * NG + g;
+              mbar_wait(empty_bar + stage * NG + g, phase ^ 1);
+              mbar_expect_tx(fb, Cfg::A_BYTES + Cfg::B_BYTES);
+              tma_load_3d(&tmA, fb, st + pa * Cfg::A_BYTES, a_col, t0 + shift, pa * p.B + b);
+              tma_load_2d(&tmB, fb, st + NPL * Cfg::A_BYTES + pb * Cfg::B_BYTES, b_c0, pb * p.b_plane_rows + b_c1);
+            }
+          } else {
+            uint64_t* fb = full_bar + stage;
+            mbar_wait(empty_bar + stage, phase ^ 1);
+            mbar_expect_tx(fb, Cfg::STAGE_BYTES);
+#pragma unroll
+            for (int pl = 0; pl < NPL; ++pl)
+              tma_load_3d(&tmA, fb, st + pl * Cfg::A_BYTES, a_col, t0 + shift, pl * p.B + b);
+#pragma unroll
+            for (int pl = 0; pl < NPL; ++pl)
+              tma_load_2d(&tmB, fb, st + NPL * Cfg::A_BYTES + pl * Cfg::B_BYTES, b_c0, pl * p.b_plane_rows + b_c1);
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
@@ -182,13 +223,11 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const uint32_t a_addr = smem_u32(smem + stage * Cfg::STAGE_BYTES);
           const uint32_t b_addr = a_addr + NPL * Cfg::A_BYTES;
           uint32_t accumulate = it > 0 ? 1u : 0u;
-          // NPL==2 products in issue order: hi*lo (group X), hi*hi (X+Y), lo*hi (Y); NPL==1: hi*hi (X)
+          using PR = Products<NPL>;
 #pragma unroll
-          for (int pr = 0; pr < (NPL == 2 ? 3 : 1); ++pr) {
-            const int pa = (NPL == 2 && pr == 2) ? 1 : 0;
-            const int pb = (NPL == 2 && pr == 0) ? 1 : 0;
-            if (pr == 0) { mbar_wait(full_bar + stage * NG, phase); tc_fence_after(); }
-            if (NPL == 2 && pr == 1) { mbar_wait(full_bar + stage * NG + 1, phase); tc_fence_after(); }
+          for (int pr = 0; pr < PR::N; ++pr) {
+            const int pa = PR::a(pr), pb = PR::b(pr);
+            if (PR::wait(pr) >= 0) { mbar_wait(full_bar + stage * NG + PR::wait(pr), phase); tc_fence_after(); }
             const uint64_t da = make_smem_desc_sw128(a_addr + pa * Cfg::A_BYTES, 16, 1024);
             const uint64_t db = make_smem_desc_sw128(b_addr + pb * Cfg::B_BYTES, 16, 1024);
 #pragma unroll
@@ -198,8 +237,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               accumulate = 1u;
             }
             // a group's smem is reusable once the MMAs issued so far have read it
-            if (NPL == 1 || pr == 1) umma_commit(empty_bar + stage * NG);
-            if (NPL == 2 && pr == 2) umma_commit(empty_bar + stage * NG + 1);
+            if (PR::release(pr) >= 0) umma_commit(empty_bar + stage * NG + PR::release(pr));
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
@@ -430,18 +468,26 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
           uint8_t* st = smem + stage * Cfg::STAGE_BYTES;
 #pragma unroll
           for (int g = 0; g < NG; ++g) {
-            const int pa = g, pb = NPL - 1 - g;           // group X = {X_hi, dZ_lo}, group Y = {X_lo, dZ_hi}
+            // NG == 2: group X = {X_hi, dZ_lo}, group Y = {X_lo, dZ_hi};  NG == 1: every plane in one group
             uint64_t* fb = full_bar + stage * NG + g;
             mbar_wait(empty_bar + stage * NG + g, phase ^ 1);
-            mbar_expect_tx(fb, Cfg::A_BYTES + Cfg::B_BYTES);
+            mbar_expect_tx(fb, NG == 2 ? Cfg::A_BYTES + Cfg::B_BYTES : Cfg::STAGE_BYTES);
 #pragma unroll
-            for (int h = 0; h < kTileM / 64; ++h)
-              tma_load_3d(&tmX, fb, st + pa * Cfg::A_BYTES + h * Cfg::BOX_BYTES, a_col + h * 64, t0 + shift,
-                          pa * p.B + b);
+            for (int pl = 0; pl < NPL; ++pl) {
+              if (NG == 2 && pl != g) continue;
 #pragma unroll
-            for (int h = 0; h < BLOCK_N / 64; ++h)
-              tma_load_3d(&tmDZ, fb, st + NPL * Cfg::A_BYTES + pb * Cfg::B_BYTES + h * Cfg::BOX_BYTES, n0 + h * 64, t0,
-                          pb * p.B + b);
+              for (int h = 0; h < kTileM / 64; ++h)
+                tma_load_3d(&tmX, fb, st + pl * Cfg::A_BYTES + h * Cfg::BOX_BYTES, a_col + h * 64, t0 + shift,
+                            pl * p.B + b);
+            }
+#pragma unroll
+            for (int pl = 0; pl < NPL; ++pl) {
+              if (NG == 2 && pl != 1 - g) continue;
+#pragma unroll
+              for (int h = 0; h < BLOCK_N / 64; ++h)
+                tma_load_3d(&tmDZ, fb, st + NPL * Cfg::A_BYTES + pl * Cfg::B_BYTES + h * Cfg::BOX_BYTES, n0 + h * 64,
+                            t0, pl * p.B + b);
+            }
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
@@ -466,12 +512,11 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
         for (int q = q0; q < q1; ++q) {
           const uint32_t a_addr = smem_u32(smem + stage * Cfg::STAGE_BYTES);
           const uint32_t b_addr = a_addr + NPL * Cfg::A_BYTES;
+          using PR = Products<NPL>;
 #pragma unroll
-          for (int pr = 0; pr < (NPL == 2 ? 3 : 1); ++pr) {
-            const int pa = (NPL == 2 && pr == 2) ? 1 : 0;
-            const int pb = (NPL == 2 && pr == 0) ? 1 : 0;
-            if (pr == 0) { mbar_wait(full_bar + stage * NG, phase); tc_fence_after(); }
-            if (NPL == 2 && pr == 1) { mbar_wait(full_bar + stage * NG + 1, phase); tc_fence_after(); }
+          for (int pr = 0; pr < PR::N; ++pr) {
+            const int pa = PR::a(pr), pb = PR::b(pr);
+            if (PR::wait(pr) >= 0) { mbar_wait(full_bar + stage * NG + PR::wait(pr), phase); tc_fence_after(); }
 #pragma unroll
             for (int kk = 0; kk < kChunkK / 16; ++kk) {
               // MN-major SW128: a K step of 16 rows = 2 swizzle atoms of 8 rows x 128 B = 2048 bytes;
@@ -481,8 +526,7 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
               umma_bf16(d_tmem, da, db, idesc, accumulate);
               accumulate = 1u;
             }
-            if (NPL == 1 || pr == 1) umma_commit(empty_bar + stage * NG);
-            if (NPL == 2 && pr == 2) umma_commit(empty_bar + stage * NG + 1);
+            if (PR::release(pr) >= 0) umma_commit(empty_bar + stage * NG + PR::release(pr));
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
@@ -812,6 +856,8 @@ int launch_conv(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvParams
   if (block_n == 256 && n_planes == 1) return launch_conv_t<256, 1>(tmA, tmB, p, stream);
   if (block_n == 32 && n_planes == 2) return launch_conv_t<32, 2>(tmA, tmB, p, stream);
   if (block_n == 32 && n_planes == 1) return launch_conv_t<32, 1>(tmA, tmB, p, stream);
+  if (block_n == 128 && n_planes == 3) return launch_conv_t<128, 3>(tmA, tmB, p, stream);
+  if (block_n == 32 && n_planes == 3) return launch_conv_t<32, 3>(tmA, tmB, p, stream);
   st_set_error("launch_conv: unsupported (block_n=%d, n_planes=%d)", block_n, n_planes);
   return ST_ERR_UNSUPPORTED;
 }
@@ -822,6 +868,8 @@ int launch_wgrad(const CUtensorMap& tmX, const CUtensorMap& tmDZ, const WgradPar
   if (block_n == 256 && n_planes == 1) return launch_wgrad_t<256, 1>(tmX, tmDZ, p, stream);
   if (block_n == 64 && n_planes == 2) return launch_wgrad_t<64, 2>(tmX, tmDZ, p, stream);
   if (block_n == 64 && n_planes == 1) return launch_wgrad_t<64, 1>(tmX, tmDZ, p, stream);
+  if (block_n == 128 && n_planes == 3) return launch_wgrad_t<128, 3>(tmX, tmDZ, p, stream);
+  if (block_n == 64 && n_planes == 3) return launch_wgrad_t<64, 3>(tmX, tmDZ, p, stream);
   st_set_error("launch_wgrad: unsupported (block_n=%d, n_planes=%d)", block_n, n_planes);
   return ST_ERR_UNSUPPORTED;
 }
@@ -833,7 +881,8 @@ int launch_split_input(const float* x, __nv_bfloat16* planes, int B, int T, int 
   int blocks = (int)((groups + 255) / 256);
   const int cap = 16 * st_num_sms();
   blocks = blocks > cap ? cap : blocks;
-  if (n_planes == 2) split_input_kernel<2><<<blocks, 256, 0, stream>>>(x, planes, B, T, Tpad, F);
+  if (n_planes == 3) split_input_kernel<3><<<blocks, 256, 0, stream>>>(x, planes, B, T, Tpad, F);
+  else if (n_planes == 2) split_input_kernel<2><<<blocks, 256, 0, stream>>>(x, planes, B, T, Tpad, F);
   else split_input_kernel<1><<<blocks, 256, 0, stream>>>(x, planes, B, T, Tpad, F);
   ST_CUDA_LAUNCH_CHECK("split_input_kernel");
   return ST_OK;
@@ -849,11 +898,13 @@ int launch_pack_filters(PackTable& tab, int n_planes, cudaStream_t stream) {
     fb += e.K * (e.cin_p / 64) * ((e.Cout + 31) / 32);
     if (e.bwd) bb += (int)(((int64_t)e.K * e.Cin * e.ld_co / 4 + 255) / 256);
   }
-  if (n_planes == 2) pack_filter_fwd_all_kernel<2><<<fb, dim3(32, 8), 0, stream>>>(tab);
+  if (n_planes == 3) pack_filter_fwd_all_kernel<3><<<fb, dim3(32, 8), 0, stream>>>(tab);
+  else if (n_planes == 2) pack_filter_fwd_all_kernel<2><<<fb, dim3(32, 8), 0, stream>>>(tab);
   else pack_filter_fwd_all_kernel<1><<<fb, dim3(32, 8), 0, stream>>>(tab);
   ST_CUDA_LAUNCH_CHECK("pack_filter_fwd_all_kernel");
   if (bb > 0) {
-    if (n_planes == 2) pack_filter_bwd_all_kernel<2><<<bb, 256, 0, stream>>>(tab);
+    if (n_planes == 3) pack_filter_bwd_all_kernel<3><<<bb, 256, 0, stream>>>(tab);
+    else if (n_planes == 2) pack_filter_bwd_all_kernel<2><<<bb, 256, 0, stream>>>(tab);
     else pack_filter_bwd_all_kernel<1><<<bb, 256, 0, stream>>>(tab);
     ST_CUDA_LAUNCH_CHECK("pack_filter_bwd_all_kernel");
   }

@@ -71,6 +71,9 @@ void timed_end(st_plan* p, int i, int kind, int layer, double flops, cudaStream_
   p->recs.push_back({kind, layer, flops, i, i + 1});
 }
 
+// N tile of the tensor-core kernels: three planes per operand only fit two pipeline stages with 128-wide tiles
+int wide_n(const st_plan* p) { return p->npl == 3 ? 128 : 256; }
+
 __nv_bfloat16* bf(st_plan* p, size_t off) { return reinterpret_cast<__nv_bfloat16*>(p->arena + off); }
 
 const __nv_bfloat16* act_in(st_plan* p, int l) { return l == 0 ? bf(p, p->off_in) : bf(p, p->layers[l - 1].off_out); }
@@ -79,7 +82,7 @@ const __nv_bfloat16* act_in(st_plan* p, int l) { return l == 0 ? bf(p, p->off_in
 
 ST_API int st_plan_create(st_plan** out, int B, int T, int input_size, int num_classes, int n_planes) {
   ST_CHECK_ARG(out && B > 0 && T > 1, "st_plan_create: bad shape");
-  ST_CHECK_ARG(n_planes == 1 || n_planes == 2, "st_plan_create: n_planes must be 1 (bf16) or 2 (bf16x3)");
+  ST_CHECK_ARG(n_planes >= 1 && n_planes <= 3, "st_plan_create: n_planes must be 1 (bf16), 2 (bf16x3) or 3 (bf16x6)");
   ST_CHECK_ARG(input_size % 64 == 0, "st_plan_create: input_size must be a multiple of 64 (got %d)", input_size);
   ST_CHECK_ARG(num_classes >= 2 && num_classes <= 32, "st_plan_create: num_classes must be in [2,32]");
   st_plan* p = new st_plan();
@@ -160,7 +163,7 @@ ST_API int st_plan_bind(st_plan* p, void* arena, size_t arena_bytes, float* para
   for (int l = 0; l < 11; ++l) {
     Layer& L = p->layers[l];
     const __nv_bfloat16* xin = act_in(p, l);
-    const int block_n = l == 10 ? 32 : 256;
+    const int block_n = l == 10 ? 32 : wide_n(p);
     // ---- forward: A = input activation planes, B = forward filter planes [Cout rows][K*cin_p]
     if (L.stride == 1) {
       rc = tc::make_map_3d(&L.tm_fwd_a, xin, L.Cin, L.Ti, npl * B, L.ld_in, (int64_t)L.Ti * L.ld_in, 64, 128);
@@ -197,7 +200,8 @@ ST_API int st_plan_bind(st_plan* p, void* arena, size_t arena_bytes, float* para
       }
     }
     if (l > 0) {
-      rc = tc::make_map_2d(&L.tm_dg_b, bf(p, L.off_wbwd), l == 10 ? 64 : L.Cout, npl * L.K * L.Cin, L.ld_co, 64, 256);
+      rc = tc::make_map_2d(&L.tm_dg_b, bf(p, L.off_wbwd), l == 10 ? 64 : L.Cout, npl * L.K * L.Cin, L.ld_co, 64,
+                           wide_n(p));
       if (rc) return rc;
     }
   }
@@ -229,7 +233,7 @@ ST_API int st_plan_forward(st_plan* p, const float* inputs, st_stream_t stream) 
   p->launches++;
   for (int l = 0; l < 11; ++l) {
     Layer& L = p->layers[l];
-    const int block_n = l == 10 ? 32 : 256;
+    const int block_n = l == 10 ? 32 : wide_n(p);
     tc::ConvParams c{};
     c.taps = L.K;
     c.chunks_per_tap = L.cin_p / 64;
@@ -294,11 +298,11 @@ ST_API int st_plan_backward_range(st_plan* p, int hi, int lo, st_stream_t stream
     w.B = p->B; w.To = L.To; w.t_chunks = (L.To + 63) / 64;
     w.taps = L.K; w.pad_left = L.pad_left; w.a_stride = L.stride; w.a_cin = L.Cin;
     w.m_tiles = (L.Cin + 127) / 128;
-    w.n_tiles = l == 10 ? 1 : (L.Cout + 255) / 256;
+    w.n_tiles = l == 10 ? 1 : (L.Cout + wide_n(p) - 1) / wide_n(p);
     w.Cin = L.Cin; w.Cout = L.Cout;
     w.dW = p->grads + L.w_off;
     int ti = timed_begin(p, s);
-    rc = tc::launch_wgrad(L.tm_wg_x, L.tm_wg_dz[l == 10 ? 0 : cur], w, l == 10 ? 64 : 256, p->npl, s);
+    rc = tc::launch_wgrad(L.tm_wg_x, L.tm_wg_dz[l == 10 ? 0 : cur], w, l == 10 ? 64 : wide_n(p), p->npl, s);
     if (rc) return rc;
     timed_end(p, ti, 2, l, 2.0 * L.K * L.Cin * L.Cout * (double)L.To * p->B, s);
     p->launches++;
@@ -318,7 +322,7 @@ ST_API int st_plan_backward_range(st_plan* p, int hi, int lo, st_stream_t stream
       c.b_plane_rows = L.K * L.Cin;
       c.B = p->B; c.To = L.Ti; c.N = L.Cin;
       c.m_tiles_per_utt = (L.Ti + tc::kTileM - 1) / tc::kTileM;
-      c.n_tiles = (L.Cin + 255) / 256;
+      c.n_tiles = (L.Cin + wide_n(p) - 1) / wide_n(p);
       c.n_fastest = (size_t)p->npl * p->B * L.To * ld_dz * 2 > (size_t)48 << 20;
       c.bias = nullptr;
       c.relu = 0;
@@ -329,7 +333,7 @@ ST_API int st_plan_backward_range(st_plan* p, int hi, int lo, st_stream_t stream
       c.ld_mask = Lb.ld_out;
       c.col_sum = p->grads + Lb.b_off;
       ti = timed_begin(p, s);
-      rc = tc::launch_conv(L.tm_dg_a[l == 10 ? 0 : cur], L.tm_dg_b, c, 256, p->npl, s);
+      rc = tc::launch_conv(L.tm_dg_a[l == 10 ? 0 : cur], L.tm_dg_b, c, wide_n(p), p->npl, s);
       if (rc) return rc;
       timed_end(p, ti, 1, l, 2.0 * L.K * L.Cin * L.Cout * (double)L.To * p->B, s);
       p->launches++;

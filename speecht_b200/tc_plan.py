@@ -13,7 +13,7 @@ import torch
 from . import ops
 from ._lib import check, lib, ptr, stream_ptr
 
-N_PLANES = {'bf16': 1, 'bf16x3': 2}
+N_PLANES = {'bf16': 1, 'bf16x3': 2, 'bf16x6': 3}
 MAX_CACHED_SHAPES = 64
 
 

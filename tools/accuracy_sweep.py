@@ -18,7 +18,7 @@ def main():
     ref = W2LEngine(precision='fp32'); ref.init_xavier(seed=seed)
     ref.forward(x, keep_activations=True)
     ref_acts = [a.clone() for a in ref._acts[1:11]] + [ref._logits_bm.clone()]
-    for precision in ('bf16x3', 'bf16'):
+    for precision in ('bf16x6', 'bf16x3', 'bf16'):
       eng = W2LEngine(precision=precision); eng.init_xavier(seed=seed)
       out = eng.forward(x, keep_activations=True)
       errs = []

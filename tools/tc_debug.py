@@ -31,7 +31,7 @@ def accumulation_probe():
   weights = [(bf16_round(w), b) for w, b in weights]
   w64 = [(w.astype(np.float64), b.astype(np.float64)) for w, b in weights]
   ref0 = O.conv1d_same(inputs.astype(np.float64), w64[0][0], w64[0][1], 2, True)
-  for precision in ('bf16x3', 'bf16', 'fp32'):
+  for precision in ('bf16x6', 'bf16x3', 'bf16', 'fp32'):
     eng = W2LEngine(precision=precision)
     eng.load_weights(weights)
     eng.forward(torch.from_numpy(inputs).cuda(), keep_activations=True)
@@ -54,7 +54,7 @@ def main():
   loss, dlog = O.ctc_loss_and_grad(logits, labels, lengths // 2)
   grads = O.wav2letter_backward(acts, w64, dlog / batch)
   accumulation_probe()
-  for precision in sys.argv[3:] or ['bf16x3', 'bf16']:
+  for precision in sys.argv[3:] or ['bf16x6', 'bf16x3', 'bf16']:
     eng = W2LEngine(precision=precision)
     eng.load_weights(weights)
     out = eng.forward(torch.from_numpy(inputs).cuda(), keep_activations=True)

@@ -43,9 +43,17 @@ struct ConvCfg {
   static constexpr int STAGES_RAW = (kSmemBudget - 2048) / STAGE_BYTES;
   static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 2048;  // 1024 alignment slack + barriers
-  static constexpr int TMEM_COLS = 2 * BLOCK_N < 32 ? 32 : 2 * BLOCK_N;
+  // Split modes keep TWO fp32 accumulators per tile: `main` takes the hi*hi products only, `side` every product
+  // that involves a lo plane.  The tensor core truncates its fp32 accumulation, one error of up to an ulp of the
+  // ACCUMULATOR per MMA whatever the size of the addend -- with a single accumulator the 2 (or 5) small products per
+  // K step cost as much accuracy as the hi*hi product itself (measured: bf16x6 was worse than bf16x3).  `side` stays
+  // 2^-8 times smaller, so its truncation is negligible; the epilogue adds the two in round-to-nearest fp32.
+  static constexpr int ACC_COLS = (NPL > 1 ? 2 : 1) * BLOCK_N;          // TMEM columns of one accumulator stage
+  static constexpr int ACC_STAGES = 2 * ACC_COLS <= 512 ? 2 : 1;        // double-buffered when TMEM allows
+  static constexpr int TMEM_RAW = ACC_STAGES * ACC_COLS;
+  static constexpr int TMEM_COLS = TMEM_RAW <= 32 ? 32 : (TMEM_RAW <= 64 ? 64 : (TMEM_RAW <= 128 ? 128 : (TMEM_RAW <= 256 ? 256 : 512)));
   static_assert(STAGES >= 2, "pipeline needs at least two stages");
-  static_assert(TMEM_COLS == 64 || TMEM_COLS == 128 || TMEM_COLS == 256 || TMEM_COLS == 512, "TMEM columns");
+  static_assert(TMEM_RAW <= 512, "TMEM columns");
 };
 
 __device__ __forceinline__ int floordiv(int a, int b) {
@@ -214,15 +222,16 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       uint32_t phase = 0;
       int local = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
-        const int acc = local & 1;
-        const uint32_t acc_phase = (local >> 1) & 1;
+        const int acc = local % Cfg::ACC_STAGES;
+        const uint32_t acc_phase = (local / Cfg::ACC_STAGES) & 1;
         mbar_wait(tmem_empty + acc, acc_phase ^ 1);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+        const uint32_t d_main = tmem_base + acc * Cfg::ACC_COLS;
+        const uint32_t d_side = d_main + BLOCK_N;
         for (int it = 0; it < nk; ++it) {
           const uint32_t a_addr = smem_u32(smem + stage * Cfg::STAGE_BYTES);
           const uint32_t b_addr = a_addr + NPL * Cfg::A_BYTES;
-          uint32_t accumulate = it > 0 ? 1u : 0u;
+          uint32_t acc_main = it > 0 ? 1u : 0u, acc_side = acc_main;
           using PR = Products<NPL>;
 #pragma unroll
           for (int pr = 0; pr < PR::N; ++pr) {
@@ -233,8 +242,13 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
             for (int kk = 0; kk < kChunkK / 16; ++kk) {
               // advancing 16 bf16 along K = 32 bytes inside the 128-byte swizzled row = +2 in the address field
-              umma_bf16(d_tmem, da + (uint64_t)(kk * 2), db + (uint64_t)(kk * 2), idesc, accumulate);
-              accumulate = 1u;
+              if (pa == 0 && pb == 0) {
+                umma_bf16(d_main, da + (uint64_t)(kk * 2), db + (uint64_t)(kk * 2), idesc, acc_main);
+                acc_main = 1u;
+              } else {
+                umma_bf16(d_side, da + (uint64_t)(kk * 2), db + (uint64_t)(kk * 2), idesc, acc_side);
+                acc_side = 1u;
+              }
             }
             // a group's smem is reusable once the MMAs issued so far have read it
             if (PR::release(pr) >= 0) umma_commit(empty_bar + stage * NG + PR::release(pr));
@@ -253,8 +267,8 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int row = quarter * 32 + lane;
     int local = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
-      const int acc = local & 1;
-      const uint32_t acc_phase = (local >> 1) & 1;
+      const int acc = local % Cfg::ACC_STAGES;
+      const uint32_t acc_phase = (local / Cfg::ACC_STAGES) & 1;
       const int nt = p.n_fastest ? tile % p.n_tiles : tile / m_tiles;
       const int mt = p.n_fastest ? tile / p.n_tiles : tile % m_tiles;
       const int b = mt / p.m_tiles_per_utt;
@@ -264,7 +278,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int64_t out_row = (int64_t)b * p.To + t;
       mbar_wait(tmem_full + acc, acc_phase);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BLOCK_N;
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * Cfg::ACC_COLS;
       // ReLU-mask vectors (data gradient only) are fetched one 32-column chunk ahead of their use
       uint4 mk[4];
       auto load_mask = [&](int c) {
@@ -281,6 +295,8 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       for (int c = chunk0; c < BLOCK_N / 32; c += kChunkStep) {
         uint32_t r[32];
         tmem_ld32(taddr + c * 32, r);
+        uint32_t q[32];
+        if (NPL > 1) tmem_ld32(taddr + BLOCK_N + c * 32, q);
         uint4 mcur[4];
 #pragma unroll
         for (int g = 0; g < 4; ++g) mcur[g] = mk[g];
@@ -292,6 +308,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int i = 0; i < 32; ++i) {
           const int n = nc + i;
           float x = __uint_as_float(r[i]);
+          if (NPL > 1) x += __uint_as_float(q[i]);          // main + side accumulator, round-to-nearest
           if (n < p.N) {
             if (p.bias) x += __ldg(p.bias + n);
             if (p.relu) x = fmaxf(x, 0.f);
@@ -370,7 +387,15 @@ struct WgradCfg {
   static constexpr int STAGES_RAW = (kSmemBudget - 2048) / STAGE_BYTES;
   static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 2048;
-  static constexpr int TMEM_COLS = 2 * BLOCK_N < 32 ? 32 : 2 * BLOCK_N;
+  // Split modes keep TWO fp32 accumulators per tile: `main` takes the hi*hi products only, `side` every product
+  // that involves a lo plane.  The tensor core truncates its fp32 accumulation, one error of up to an ulp of the
+  // ACCUMULATOR per MMA whatever the size of the addend -- with a single accumulator the 2 (or 5) small products per
+  // K step cost as much accuracy as the hi*hi product itself (measured: bf16x6 was worse than bf16x3).  `side` stays
+  // 2^-8 times smaller, so its truncation is negligible; the epilogue adds the two in round-to-nearest fp32.
+  static constexpr int ACC_COLS = (NPL > 1 ? 2 : 1) * BLOCK_N;          // TMEM columns of one accumulator stage
+  static constexpr int ACC_STAGES = 2 * ACC_COLS <= 512 ? 2 : 1;        // double-buffered when TMEM allows
+  static constexpr int TMEM_RAW = ACC_STAGES * ACC_COLS;
+  static constexpr int TMEM_COLS = TMEM_RAW <= 32 ? 32 : (TMEM_RAW <= 64 ? 64 : (TMEM_RAW <= 128 ? 128 : (TMEM_RAW <= 256 ? 256 : 512)));
   static constexpr int BOX_BYTES = 64 * 128;                     // one {64 ch, 64 rows} box
 };
 
@@ -503,12 +528,13 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
       for (; local < my_items; ++local) {
         int tile, q0, q1;
         item(local, tile, q0, q1);
-        const int acc = local & 1;
-        const uint32_t acc_phase = (local >> 1) & 1;
+        const int acc = local % Cfg::ACC_STAGES;
+        const uint32_t acc_phase = (local / Cfg::ACC_STAGES) & 1;
         mbar_wait(tmem_empty + acc, acc_phase ^ 1);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
-        uint32_t accumulate = 0u;
+        const uint32_t d_main = tmem_base + acc * Cfg::ACC_COLS;
+        const uint32_t d_side = d_main + BLOCK_N;
+        uint32_t acc_main = 0u, acc_side = 0u;
         for (int q = q0; q < q1; ++q) {
           const uint32_t a_addr = smem_u32(smem + stage * Cfg::STAGE_BYTES);
           const uint32_t b_addr = a_addr + NPL * Cfg::A_BYTES;
@@ -523,8 +549,13 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
               // LBO = distance between 64-wide MN blocks (one TMA box), SBO = 1024 (next 8 K rows)
               const uint64_t da = make_smem_desc_sw128(a_addr + pa * Cfg::A_BYTES + kk * 2048, Cfg::BOX_BYTES, 1024);
               const uint64_t db = make_smem_desc_sw128(b_addr + pb * Cfg::B_BYTES + kk * 2048, Cfg::BOX_BYTES, 1024);
-              umma_bf16(d_tmem, da, db, idesc, accumulate);
-              accumulate = 1u;
+              if (pa == 0 && pb == 0) {
+                umma_bf16(d_main, da, db, idesc, acc_main);
+                acc_main = 1u;
+              } else {
+                umma_bf16(d_side, da, db, idesc, acc_side);
+                acc_side = 1u;
+              }
             }
             if (PR::release(pr) >= 0) umma_commit(empty_bar + stage * NG + PR::release(pr));
           }
@@ -545,25 +576,27 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
       item(local, tile, q0, q1);
       decode(tile, j, mt, nt);
       const bool whole_tile = q0 == 0 && q1 == total_iters;
-      const int acc = local & 1;
-      const uint32_t acc_phase = (local >> 1) & 1;
+      const int acc = local % Cfg::ACC_STAGES;
+      const uint32_t acc_phase = (local / Cfg::ACC_STAGES) & 1;
       const int ci = mt * kTileM + row;
       const int n0 = nt * BLOCK_N;
       mbar_wait(tmem_full + acc, acc_phase);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BLOCK_N;
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * Cfg::ACC_COLS;
       float* wrow = p.dW + ((int64_t)j * p.Cin + ci) * p.Cout;
 #pragma unroll 1
       for (int c = chunk0; c < BLOCK_N / 32; c += kChunkStep) {
         uint32_t r[32];
         tmem_ld32(taddr + c * 32, r);
+        uint32_t q[32];
+        if (NPL > 1) tmem_ld32(taddr + BLOCK_N + c * 32, q);
         tmem_ld_wait();
         if (ci < p.Cin) {
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
             const int co = n0 + c * 32 + i;
             if (co < p.Cout) {
-              const float x = __uint_as_float(r[i]);
+              const float x = __uint_as_float(r[i]) + (NPL > 1 ? __uint_as_float(q[i]) : 0.f);
               if (whole_tile) wrow[co] = x;
               else atomicAdd(wrow + co, x);
             }

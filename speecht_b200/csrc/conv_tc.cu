@@ -890,6 +890,7 @@ int launch_conv(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvParams
   if (block_n == 32 && n_planes == 2) return launch_conv_t<32, 2>(tmA, tmB, p, stream);
   if (block_n == 32 && n_planes == 1) return launch_conv_t<32, 1>(tmA, tmB, p, stream);
   if (block_n == 128 && n_planes == 3) return launch_conv_t<128, 3>(tmA, tmB, p, stream);
+  if (block_n == 128 && n_planes == 2) return launch_conv_t<128, 2>(tmA, tmB, p, stream);
   if (block_n == 32 && n_planes == 3) return launch_conv_t<32, 3>(tmA, tmB, p, stream);
   st_set_error("launch_conv: unsupported (block_n=%d, n_planes=%d)", block_n, n_planes);
   return ST_ERR_UNSUPPORTED;
@@ -902,6 +903,7 @@ int launch_wgrad(const CUtensorMap& tmX, const CUtensorMap& tmDZ, const WgradPar
   if (block_n == 64 && n_planes == 2) return launch_wgrad_t<64, 2>(tmX, tmDZ, p, stream);
   if (block_n == 64 && n_planes == 1) return launch_wgrad_t<64, 1>(tmX, tmDZ, p, stream);
   if (block_n == 128 && n_planes == 3) return launch_wgrad_t<128, 3>(tmX, tmDZ, p, stream);
+  if (block_n == 128 && n_planes == 2) return launch_wgrad_t<128, 2>(tmX, tmDZ, p, stream);
   if (block_n == 64 && n_planes == 3) return launch_wgrad_t<64, 3>(tmX, tmDZ, p, stream);
   st_set_error("launch_wgrad: unsupported (block_n=%d, n_planes=%d)", block_n, n_planes);
   return ST_ERR_UNSUPPORTED;

@@ -73,14 +73,9 @@ void timed_end(st_plan* p, int i, int kind, int layer, double flops, cudaStream_
 }
 
 // N tile of the tensor-core kernels: three planes per operand only fit two pipeline stages with 128-wide tiles
-int wide_n(const st_plan* p) {
-  if (p->npl == 3) return 128;
-  if (p->npl == 2) {
-    static const int forced = []() { const char* e = getenv("SPEECHT_B200_WIDE_N"); return e ? atoi(e) : 0; }();
-    if (forced == 128 || forced == 256) return forced;
-  }
-  return 256;
-}
+// (bf16x3 keeps 256-wide tiles with single-buffered main+side accumulators: 128-wide, double-buffered tiles were
+// measured 17 % slower over the step, profiles/r01_tile_width_ab.txt)
+int wide_n(const st_plan* p) { return p->npl == 3 ? 128 : 256; }
 
 __nv_bfloat16* bf(st_plan* p, size_t off) { return reinterpret_cast<__nv_bfloat16*>(p->arena + off); }
 

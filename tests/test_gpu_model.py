@@ -69,7 +69,7 @@ def _gpu_activations(eng):
   return [plan.activation(l).cpu().numpy() for l in range(10)]
 
 
-# measured: 7.6e-5 worst layer for bf16x3 (tensor-core fp32 accumulation + hi/lo split), 2.3e-6 for fp32
+# measured: 2.5e-5 worst layer for bf16x3, 2.0e-5 for bf16x6, 2.3e-6 for fp32
 @pytest.mark.parametrize('precision', ['fp32', 'bf16x6', 'bf16x3'])
 def test_conv_activations_parity_every_layer(precision):
   """BASELINE gate: conv activations within 1e-4 (max|a-b| / max|b| per tensor), all 10 hidden layers + logits."""
@@ -81,13 +81,16 @@ def test_conv_activations_parity_every_layer(precision):
   logits, acts = O.wav2letter_forward(inputs.astype(np.float64), w64, keep_activations=True)
   eng = _engine(precision, weights)
   out = eng.forward(torch.from_numpy(inputs).cuda(), keep_activations=True)
+  # the BASELINE gate is 1e-4; the tighter bound guards the measured level (fp32 2e-6; split modes 2.5e-5 since the
+  # hi*hi products have their own accumulator)
+  bound = 5e-5
   for l, a in enumerate(_gpu_activations(eng)):
     assert a.shape == acts[l + 1].shape
-    assert rel(a, acts[l + 1]) < 1e-4, (l, rel(a, acts[l + 1]))
-  assert rel(out.cpu().numpy(), logits) < 1e-4
+    assert rel(a, acts[l + 1]) < bound, (l, rel(a, acts[l + 1]))
+  assert rel(out.cpu().numpy(), logits) < bound
 
 
-GRAD_TOL = {'fp32': 1e-4, 'bf16x6': 1e-3, 'bf16x3': 1e-3}
+GRAD_TOL = {'fp32': 1e-4, 'bf16x6': 3e-4, 'bf16x3': 3e-4}
 
 
 @pytest.mark.parametrize('precision', ['fp32', 'bf16x6', 'bf16x3'])
@@ -97,7 +100,7 @@ def test_train_step_parity(precision):
   Gradients are compared "same-mask": the oracle backward uses the ReLU on/off pattern of the GPU forward, because
   a pre-activation within rounding distance of zero (|z| ~ 1e-6) legitimately flips between any two
   implementations and changes single gradient elements by O(1) -- that is non-smoothness of ReLU, not kernel error.
-  Tolerances: fp32 path 1e-4; bf16x3 path 1e-3 (measured 3e-4: eleven layers of ~2e-5 tensor-core error)."""
+  Tolerances: fp32 path 1e-4; split tensor-core modes 3e-4 (measured 7e-5)."""
   inputs, lengths, labels = O.synthetic_batch(seed=3, batch=3, seconds=1)
   weights = O.xavier_weights(np.random.default_rng(99), dtype=np.float32)
   weights = [(w, (0.01 * np.random.default_rng(i).standard_normal(b.shape)).astype(np.float32))

@@ -279,36 +279,53 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       mbar_wait(tmem_full + acc, acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * Cfg::ACC_COLS;
-      // ReLU-mask vectors (data gradient only) are fetched one 32-column chunk ahead of their use
-      uint4 mk[4];
-      auto load_mask = [&](int c) {
+      // Phase 1: drain this warp's share of the accumulators into registers (main + side summed in round-to-nearest
+      // fp32) and hand TMEM back to the MMA warp at once -- with the two 256-column accumulators of the split modes
+      // there is no second accumulator stage, so everything after this point overlaps the next tile's MMAs.
+      constexpr int kChunks = BLOCK_N / 32;
+      constexpr int kMine = (kChunks + kChunkStep - 1) / kChunkStep;       // chunks per warp (compile time)
+      float sum[kMine][32];
+#pragma unroll
+      for (int ci = 0; ci < kMine; ++ci) {
+        const int c = chunk0 + ci * kChunkStep;
+        if (c < kChunks) {
+          uint32_t r[32];
+          tmem_ld32(taddr + c * 32, r);
+          if (NPL > 1) {
+            uint32_t q[32];
+            tmem_ld32(taddr + BLOCK_N + c * 32, q);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) sum[ci][i] = __uint_as_float(r[i]) + __uint_as_float(q[i]);
+          } else {
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) sum[ci][i] = __uint_as_float(r[i]);
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tmem_empty + acc);
+
+      // Phase 2: bias / ReLU / ReLU-mask / plane split / stores / bias-gradient column sums, from registers
+#pragma unroll
+      for (int ci = 0; ci < kMine; ++ci) {
+        const int c = chunk0 + ci * kChunkStep;
+        if (c >= kChunks) continue;
         const int nc = n0 + c * 32;
+        uint4 mk[4];
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
           mk[g] = make_uint4(0x3f803f80u, 0x3f803f80u, 0x3f803f80u, 0x3f803f80u);      // bf16 1.0 pairs: pass
           if (p.mask_hi && row_ok && nc + g * 8 < p.ld_mask)
             mk[g] = *reinterpret_cast<const uint4*>(p.mask_hi + out_row * p.ld_mask + nc + g * 8);
         }
-      };
-      load_mask(chunk0);
-#pragma unroll 1
-      for (int c = chunk0; c < BLOCK_N / 32; c += kChunkStep) {
-        uint32_t r[32];
-        tmem_ld32(taddr + c * 32, r);
-        uint32_t q[32];
-        if (NPL > 1) tmem_ld32(taddr + BLOCK_N + c * 32, q);
-        uint4 mcur[4];
-#pragma unroll
-        for (int g = 0; g < 4; ++g) mcur[g] = mk[g];
-        if (c + kChunkStep < BLOCK_N / 32) load_mask(c + kChunkStep);
-        tmem_ld_wait();
-        const int nc = n0 + c * 32;
-        float v[32];
+        float* v = sum[ci];
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
           const int n = nc + i;
-          float x = __uint_as_float(r[i]);
-          if (NPL > 1) x += __uint_as_float(q[i]);          // main + side accumulator, round-to-nearest
+          float x = v[i];
           if (n < p.N) {
             if (p.bias) x += __ldg(p.bias + n);
             if (p.relu) x = fmaxf(x, 0.f);
@@ -321,7 +338,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (p.mask_hi) {
 #pragma unroll
             for (int g = 0; g < 4; ++g) {
-              const uint32_t w[4] = {mcur[g].x, mcur[g].y, mcur[g].z, mcur[g].w};
+              const uint32_t w[4] = {mk[g].x, mk[g].y, mk[g].z, mk[g].w};
 #pragma unroll
               for (int i = 0; i < 4; ++i) {
                 // bf16 > 0  <=>  sign bit clear and magnitude non-zero
@@ -364,9 +381,6 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (nc + lane < p.N) atomicAdd(p.col_sum + nc + lane, v[0]);
         }
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(tmem_empty + acc);
     }
   }
 
@@ -584,28 +598,46 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * Cfg::ACC_COLS;
       float* wrow = p.dW + ((int64_t)j * p.Cin + ci) * p.Cout;
-#pragma unroll 1
-      for (int c = chunk0; c < BLOCK_N / 32; c += kChunkStep) {
-        uint32_t r[32];
-        tmem_ld32(taddr + c * 32, r);
-        uint32_t q[32];
-        if (NPL > 1) tmem_ld32(taddr + BLOCK_N + c * 32, q);
-        tmem_ld_wait();
-        if (ci < p.Cin) {
+      // drain to registers, release TMEM, then write / accumulate (see tc_conv_kernel)
+      constexpr int kChunks = BLOCK_N / 32;
+      constexpr int kMine = (kChunks + kChunkStep - 1) / kChunkStep;
+      float sum[kMine][32];
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            const int co = n0 + c * 32 + i;
-            if (co < p.Cout) {
-              const float x = __uint_as_float(r[i]) + (NPL > 1 ? __uint_as_float(q[i]) : 0.f);
-              if (whole_tile) wrow[co] = x;
-              else atomicAdd(wrow + co, x);
-            }
+      for (int ci2 = 0; ci2 < kMine; ++ci2) {
+        const int c = chunk0 + ci2 * kChunkStep;
+        if (c < kChunks) {
+          uint32_t r[32];
+          tmem_ld32(taddr + c * 32, r);
+          if (NPL > 1) {
+            uint32_t q[32];
+            tmem_ld32(taddr + BLOCK_N + c * 32, q);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) sum[ci2][i] = __uint_as_float(r[i]) + __uint_as_float(q[i]);
+          } else {
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) sum[ci2][i] = __uint_as_float(r[i]);
           }
         }
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tmem_empty + acc);
+#pragma unroll
+      for (int ci2 = 0; ci2 < kMine; ++ci2) {
+        const int c = chunk0 + ci2 * kChunkStep;
+        if (c >= kChunks || ci >= p.Cin) continue;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const int co = n0 + c * 32 + i;
+          if (co < p.Cout) {
+            if (whole_tile) wrow[co] = sum[ci2][i];
+            else atomicAdd(wrow + co, sum[ci2][i]);
+          }
+        }
+      }
+
     }
   }
 

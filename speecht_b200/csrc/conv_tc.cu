@@ -116,7 +116,10 @@ template <> struct Products<3> {
   __device__ static constexpr int release(int i) { return i == 5 ? 0 : -1; }
 };
 
-template <int BLOCK_N, int NPL>
+// EARLY: two-phase epilogue (drain the accumulators to registers, release TMEM, then store) -- chosen by the host
+// for launches where a CTA processes several tiles and the split modes leave no second accumulator stage; the
+// streaming epilogue (lower register pressure, TMEM loads overlapped with the stores) is used everywhere else.
+template <int BLOCK_N, int NPL, bool EARLY>
 __global__ void __launch_bounds__(kThreads, 1)
 tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const ConvParams p) {
   using Cfg = ConvCfg<BLOCK_N, NPL>;
@@ -279,6 +282,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       mbar_wait(tmem_full + acc, acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * Cfg::ACC_COLS;
+      if constexpr (EARLY) {
       // Phase 1: drain this warp's share of the accumulators into registers (main + side summed in round-to-nearest
       // fp32) and hand TMEM back to the MMA warp at once -- with the two 256-column accumulators of the split modes
       // there is no second accumulator stage, so everything after this point overlaps the next tile's MMAs.
@@ -380,6 +384,96 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
           if (nc + lane < p.N) atomicAdd(p.col_sum + nc + lane, v[0]);
         }
+      }
+      } else {
+      // ReLU-mask vectors (data gradient only) are fetched one 32-column chunk ahead of their use
+      uint4 mk[4];
+      auto load_mask = [&](int c) {
+        const int nc = n0 + c * 32;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          mk[g] = make_uint4(0x3f803f80u, 0x3f803f80u, 0x3f803f80u, 0x3f803f80u);      // bf16 1.0 pairs: pass
+          if (p.mask_hi && row_ok && nc + g * 8 < p.ld_mask)
+            mk[g] = *reinterpret_cast<const uint4*>(p.mask_hi + out_row * p.ld_mask + nc + g * 8);
+        }
+      };
+      load_mask(chunk0);
+#pragma unroll 1
+      for (int c = chunk0; c < BLOCK_N / 32; c += kChunkStep) {
+        uint32_t r[32];
+        tmem_ld32(taddr + c * 32, r);
+        uint32_t q[32];
+        if (NPL > 1) tmem_ld32(taddr + BLOCK_N + c * 32, q);
+        uint4 mcur[4];
+#pragma unroll
+        for (int g = 0; g < 4; ++g) mcur[g] = mk[g];
+        if (c + kChunkStep < BLOCK_N / 32) load_mask(c + kChunkStep);
+        tmem_ld_wait();
+        const int nc = n0 + c * 32;
+        float v[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const int n = nc + i;
+          float x = __uint_as_float(r[i]);
+          if (NPL > 1) x += __uint_as_float(q[i]);          // main + side accumulator, round-to-nearest
+          if (n < p.N) {
+            if (p.bias) x += __ldg(p.bias + n);
+            if (p.relu) x = fmaxf(x, 0.f);
+          } else {
+            x = 0.f;
+          }
+          v[i] = x;
+        }
+        if (row_ok) {
+          if (p.mask_hi) {
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              const uint32_t w[4] = {mcur[g].x, mcur[g].y, mcur[g].z, mcur[g].w};
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                // bf16 > 0  <=>  sign bit clear and magnitude non-zero
+                const uint32_t lo16 = w[i] & 0xffffu, hi16 = w[i] >> 16;
+                if (!(lo16 != 0 && lo16 < 0x8000u)) v[g * 8 + 2 * i] = 0.f;
+                if (!(hi16 != 0 && hi16 < 0x8000u)) v[g * 8 + 2 * i + 1] = 0.f;
+              }
+            }
+          }
+          if (p.out_planes) {
+            __nv_bfloat16* orow = p.out_planes + out_row * p.ld_out + nc;
+#pragma unroll
+            for (int g = 0; g < 4; ++g)
+              if (nc + g * 8 < p.ld_out) store_planes8<NPL>(orow + g * 8, p.out_plane_stride, v + g * 8);
+          }
+          if (p.out_f32) {
+            float* frow = p.out_f32 + out_row * p.ld_f32 + nc;
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (nc + i < p.ld_f32) frow[i] = v[i];
+          }
+        }
+        if (p.col_sum) {
+          // bias gradient of the layer below = column sums of what was just stored: 32x32 transpose-reduce with
+          // 31 shuffles (each step halves the values a lane holds), then one atomic per column per warp
+          if (!row_ok) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = 0.f;
+          }
+#pragma unroll
+          for (int off = 16; off >= 1; off >>= 1) {
+            const bool upper = (lane & off) != 0;
+#pragma unroll
+            for (int j = 0; j < off; ++j) {
+              const float send = upper ? v[j] : v[j + off];
+              const float keep = upper ? v[j + off] : v[j];
+              v[j] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+            }
+          }
+          if (nc + lane < p.N) atomicAdd(p.col_sum + nc + lane, v[0]);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tmem_empty + acc);
       }
     }
   }
@@ -598,46 +692,28 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * Cfg::ACC_COLS;
       float* wrow = p.dW + ((int64_t)j * p.Cin + ci) * p.Cout;
-      // drain to registers, release TMEM, then write / accumulate (see tc_conv_kernel)
-      constexpr int kChunks = BLOCK_N / 32;
-      constexpr int kMine = (kChunks + kChunkStep - 1) / kChunkStep;
-      float sum[kMine][32];
+#pragma unroll 1
+      for (int c = chunk0; c < BLOCK_N / 32; c += kChunkStep) {
+        uint32_t r[32];
+        tmem_ld32(taddr + c * 32, r);
+        uint32_t q[32];
+        if (NPL > 1) tmem_ld32(taddr + BLOCK_N + c * 32, q);
+        tmem_ld_wait();
+        if (ci < p.Cin) {
 #pragma unroll
-      for (int ci2 = 0; ci2 < kMine; ++ci2) {
-        const int c = chunk0 + ci2 * kChunkStep;
-        if (c < kChunks) {
-          uint32_t r[32];
-          tmem_ld32(taddr + c * 32, r);
-          if (NPL > 1) {
-            uint32_t q[32];
-            tmem_ld32(taddr + BLOCK_N + c * 32, q);
-            tmem_ld_wait();
-#pragma unroll
-            for (int i = 0; i < 32; ++i) sum[ci2][i] = __uint_as_float(r[i]) + __uint_as_float(q[i]);
-          } else {
-            tmem_ld_wait();
-#pragma unroll
-            for (int i = 0; i < 32; ++i) sum[ci2][i] = __uint_as_float(r[i]);
+          for (int i = 0; i < 32; ++i) {
+            const int co = n0 + c * 32 + i;
+            if (co < p.Cout) {
+              const float x = __uint_as_float(r[i]) + (NPL > 1 ? __uint_as_float(q[i]) : 0.f);
+              if (whole_tile) wrow[co] = x;
+              else atomicAdd(wrow + co, x);
+            }
           }
         }
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tmem_empty + acc);
-#pragma unroll
-      for (int ci2 = 0; ci2 < kMine; ++ci2) {
-        const int c = chunk0 + ci2 * kChunkStep;
-        if (c >= kChunks || ci >= p.Cin) continue;
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const int co = n0 + c * 32 + i;
-          if (co < p.Cout) {
-            if (whole_tile) wrow[co] = sum[ci2][i];
-            else atomicAdd(wrow + co, sum[ci2][i]);
-          }
-        }
-      }
-
     }
   }
 
@@ -843,18 +919,30 @@ cudaError_t launch_pdl(Kernel kernel, int grid, int smem, cudaStream_t stream, c
   return cudaLaunchKernelEx(&cfg, kernel, m0, m1, p);
 }
 
-template <int BLOCK_N, int NPL>
-int launch_conv_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvParams& p, cudaStream_t stream) {
+template <int BLOCK_N, int NPL, bool EARLY>
+int launch_conv_e(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvParams& p, cudaStream_t stream) {
   using Cfg = ConvCfg<BLOCK_N, NPL>;
   static bool configured = false;
   if (!configured) {
-    ST_CUDA_CALL(cudaFuncSetAttribute(tc_conv_kernel<BLOCK_N, NPL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    ST_CUDA_CALL(cudaFuncSetAttribute(tc_conv_kernel<BLOCK_N, NPL, EARLY>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       Cfg::SMEM_BYTES));
     configured = true;
   }
   const int tiles = p.B * p.m_tiles_per_utt * p.n_tiles;
-  ST_CUDA_CALL(launch_pdl(tc_conv_kernel<BLOCK_N, NPL>, grid_for(tiles), Cfg::SMEM_BYTES, stream, tmA, tmB, p));
+  ST_CUDA_CALL(launch_pdl(tc_conv_kernel<BLOCK_N, NPL, EARLY>, grid_for(tiles), Cfg::SMEM_BYTES, stream, tmA, tmB, p));
   return ST_OK;
+}
+
+template <int BLOCK_N, int NPL>
+int launch_conv_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvParams& p, cudaStream_t stream) {
+  // early TMEM release pays when a CTA has several tiles, no second accumulator stage, and a main loop long enough
+  // to hide the register-resident epilogue behind it
+  const int tiles = p.B * p.m_tiles_per_utt * p.n_tiles;
+  const bool early = ConvCfg<BLOCK_N, NPL>::ACC_STAGES == 1 && tiles > st_num_sms() && p.taps * p.chunks_per_tap >= 16;
+  if constexpr (ConvCfg<BLOCK_N, NPL>::ACC_STAGES == 1) {
+    if (early) return launch_conv_e<BLOCK_N, NPL, true>(tmA, tmB, p, stream);
+  }
+  return launch_conv_e<BLOCK_N, NPL, false>(tmA, tmB, p, stream);
 }
 
 template <int BLOCK_N, int NPL>

@@ -12,16 +12,19 @@
 // (k - pad_left) and TMA's out-of-bounds zero fill IS the 'SAME' zero padding (no halo buffers, no im2col).
 // Stride 2 (layer 0) is expressed on the pair view [B, T/2, 2*Cin] of the same memory.
 //
-// tc_conv_kernel (forward and data gradient): persistent, one CTA per SM, 192 threads:
-//   warp 0   : TMA producer  (A planes + B planes of one 64-wide K chunk per pipeline stage)
-//   warp 1   : TMEM allocator + single-thread tcgen05.mma issuer (128 x BLOCK_N x 16 per instruction)
-//   warps 2-5: epilogue: tcgen05.ld 32 lanes x 32 columns, +bias, ReLU / ReLU-mask, split to planes, 16-byte stores
-// Two accumulator stages in TMEM (2 x BLOCK_N columns) overlap the epilogue of tile i with the MMAs of tile i+1.
+// tc_conv_kernel (forward and data gradient): persistent, one CTA per SM, 320 threads:
+//   warp 0   : TMA producer  (one 64-wide K chunk per pipeline stage; in bf16x3 mode a stage is two independently
+//              released load groups {A_hi,B_lo} / {A_lo,B_hi}, so the refill on the critical path is 48 KB)
+//   warp 1   : TMEM allocator + single-thread tcgen05.mma issuer (128 x BLOCK_N x 16 per instruction); hi*hi products
+//              go to the `main` accumulator, every product with a lo plane to the `side` accumulator
+//   warps 2-9: epilogue, two warps per TMEM lane quarter: tcgen05.ld 32 lanes x 32 columns of main (+ side),
+//              +bias, ReLU / ReLU-mask, split to planes, 16-byte stores, bias-gradient column sums
 // tc_wgrad_kernel (filter gradient): same roles; both operands are MN-major (the contraction runs over time, the
-// slow axis), expressed through the MN-major SWIZZLE_128B shared-memory descriptors; split-K over (batch, time).
+// slow axis), expressed through the MN-major SWIZZLE_128B shared-memory descriptors; wave-aligned split-K.
+// Both are launched with programmatic stream serialization (griddepcontrol.wait after the prologue).
 //
 // Roofline: tensor-pipe bound.  Algorithmic FLOPs per launch = 2*K*Cin*Cout*T'*B (unpadded); the tensor pipe
-// executes NPL==2 ? 3x : 1x that (plus <= 2.4 % channel / 2.2 % time padding).
+// executes 3x (bf16x3) / 6x (bf16x6) / 1x (bf16) that, plus <= 2.4 % channel and 2.2 % time padding.
 #include "st_common.cuh"
 #include "conv_tc.h"
 #include "tc_ptx.cuh"

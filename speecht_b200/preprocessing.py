@@ -10,6 +10,7 @@ delegated to an injectable `load_audio(path) -> (samples, samplerate)`; WAV file
 The MFCC feature type (preprocessing.py:61-84) is out of scope (not the default, not on the hot path).
 """
 import fnmatch
+import itertools
 import logging
 import os
 import random
@@ -140,25 +141,27 @@ class SpeechCorpusReader:
         np.savez(out_directory + '/' + audio_id, audio_fragments=fragments, transcript=transcript_dict[audio_id])
 
   def load_samples(self, directory, max_size=False, loop_infinitely=False, limit_count=0, feature_type='mfcc'):
-    """Iterator of (audio_fragments, transcript) over the stored .npz files, shuffled; preprocessing.py:243-279."""
+    """Generator of (audio_fragments [T, n_features], transcript [L]) over the stored .npz files of `directory`
+    (preprocessing.py:243-279): shuffled once, optionally truncated to `limit_count` files, over-long utterances
+    (more than `max_size` frames) skipped with a warning; with `loop_infinitely` reshuffled after every pass."""
     load_directory = self._get_directory(feature_type, directory)
     if not os.path.exists(load_directory):
       raise ValueError('Directory {} does not exist'.format(load_directory))
     files = list(iglob_recursive(load_directory, '*.npz'))
     random.shuffle(files)
-    if limit_count:
-      files = files[:limit_count]
-    while True:
-      for file in files:
-        with np.load(file) as data:
-          audio_length = data['audio_fragments'].shape[0]
-          if not max_size or audio_length <= max_size:
-            yield data['audio_fragments'], data['transcript']
-          else:
-            logging.warning('Audio snippet too long: {}'.format(audio_length))
-      if not loop_infinitely:
-        break
-      random.shuffle(files)
+    files = files[:limit_count] if limit_count else files
+    for epoch in itertools.count():
+      if epoch and not loop_infinitely:
+        return
+      if epoch:
+        random.shuffle(files)
+      for path in files:
+        with np.load(path) as stored:
+          fragments, transcript = stored['audio_fragments'], stored['transcript']
+        if max_size and fragments.shape[0] > max_size:
+          logging.warning('Audio snippet too long: {}'.format(fragments.shape[0]))
+          continue
+        yield fragments, transcript
 
 
 class Preprocessing:

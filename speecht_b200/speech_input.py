@@ -75,17 +75,19 @@ class BaseInputLoader:
 
   @staticmethod
   def _get_labels_feed_item(label_list, max_time):
-    """speech_input.py:48-69 -> SparseTensorValue(indices [N,2], values [N], dense_shape [B, max_time])."""
-    label_shape = np.array([len(label_list), max_time], dtype=np.int64)
-    label_indices = []
-    label_values = []
-    for label_idx, label in enumerate(label_list):
-      for id_idx, identifier in enumerate(label):
-        label_indices.append([label_idx, id_idx])
-        label_values.append(identifier)
-    label_indices = np.array(label_indices, dtype=np.int64).reshape(-1, 2)
-    label_values = np.array(label_values, dtype=np.int64)
-    return SparseTensorValue(label_indices, label_values, label_shape)
+    """Sparse COO labels as the reference feeds them (speech_input.py:48-69): indices [N,2] = (utterance, position),
+    values [N], dense_shape [batch, max_time] -- the dense width is the INPUT max_time, not the longest label."""
+    lengths = [len(label) for label in label_list]
+    total = int(sum(lengths))
+    indices = np.zeros((total, 2), dtype=np.int64)
+    values = np.zeros((total,), dtype=np.int64)
+    cursor = 0
+    for row, (label, n) in enumerate(zip(label_list, lengths)):
+      indices[cursor:cursor + n, 0] = row
+      indices[cursor:cursor + n, 1] = np.arange(n)
+      values[cursor:cursor + n] = np.asarray(label, dtype=np.int64).reshape(-1)
+      cursor += n
+    return SparseTensorValue(indices, values, np.array([len(label_list), max_time], dtype=np.int64))
 
   @abstractmethod
   def get_inputs(self):

@@ -1,20 +1,41 @@
-"""Training loop -- mirror of reference speecht/training.py:26-99 (step timing, LR decay on no improvement over the
-last three checkpoints, checkpoint cadence).
+"""`train`: the optimisation loop around model.step.
 
-New (the reference is single-process): under torchrun (WORLD_SIZE > 1) every rank runs this loop on its own GPU,
-reads every WORLD_SIZE-th sample of one commonly shuffled stream, and the gradient is allreduced inside model.step
-(speecht_b200/parallel.py); rank 0 alone prints and writes checkpoints."""
+Policy follows reference speecht/training.py:44-99 -- time every step, and every `steps_per_checkpoint` steps: report
+(global step, learning rate, mean step time, loss, perplexity), multiply the learning rate by
+`learning_rate_decay_factor` when the windowed mean loss is worse than each of the last three windows, append the
+window loss to the history and write `speechT.ckpt-<global_step>`.
+
+New (the reference is single-process): under torchrun (WORLD_SIZE > 1) every rank runs this loop on its own GPU and
+reads every WORLD_SIZE-th sample of one commonly seeded shuffle stream; the gradient allreduce happens inside
+model.step (speecht_b200/parallel.py); the learning-rate decision uses the loss averaged over ranks so that all ranks
+take it together; rank 0 alone prints and writes checkpoints.
+"""
 import itertools
+import math
 import os
 import random
 import time
-
-import numpy as np
 
 from . import parallel
 from .errors import OutOfRangeError
 from .execution import DatasetExecutor
 from .speech_model import Session, create_default_model
+
+
+class _Window:
+  """Running means over one checkpoint window."""
+
+  def __init__(self, length):
+    self.length = length
+    self.reset()
+
+  def reset(self):
+    self.step_time = 0.0
+    self.loss = 0.0
+
+  def add(self, seconds, loss):
+    self.step_time += seconds / self.length
+    self.loss += loss / self.length
 
 
 class Training(DatasetExecutor):
@@ -29,64 +50,77 @@ class Training(DatasetExecutor):
       random.seed(int(os.environ.get('SPEECHT_B200_DATA_SEED', '1234')))   # same shuffle order on every rank
     super().__init__(flags)
 
+  # ---- DatasetExecutor hooks ---------------------------------------------------------------------
   def create_sample_generator(self, limit_count: int):
-    gen = self.reader.load_samples('train', loop_infinitely=True, limit_count=limit_count,
-                                   feature_type=self.flags.feature_type)
+    samples = self.reader.load_samples('train', loop_infinitely=True, limit_count=limit_count,
+                                       feature_type=self.flags.feature_type)
     if self.world > 1:
-      gen = itertools.islice(gen, self.rank, None, self.world)
-    return gen
+      samples = itertools.islice(samples, self.rank, None, self.world)
+    return samples
 
   def get_loader_limit_count(self) -> int:
     return self.flags.limit_training_set
 
   def create_model(self, sess):
+    """Resume from the run directory if it holds a checkpoint, otherwise start from Xavier weights."""
     model = create_default_model(self.flags, self.input_size, self.speech_input)
-    model.restore_or_create(sess, self.flags.run_train_dir,
-                            self.flags.learning_rate if self.flags.reset_learning_rate else None)
+    reset_to = self.flags.learning_rate if self.flags.reset_learning_rate else None
+    model.restore_or_create(sess, self.flags.run_train_dir, reset_to)
     return model
 
+  # ---- checkpoint-time policy --------------------------------------------------------------------
+  def _window_loss(self, model, window):
+    if self.world == 1:
+      return window.loss
+    import torch
+    local = torch.tensor([window.loss], device=model.engine.device)
+    return float(parallel.mean_scalar(local).item())
+
+  def _report(self, model, window, last_loss):
+    perplexity = math.exp(float(last_loss)) if last_loss < 300 else float('inf')
+    print('global step {:d} learning rate {:.4f} step-time {:.2f} average loss {:.2f} perplexity {:.2f}'
+          .format(model.global_step.eval(), model.learning_rate.eval(), window.step_time, last_loss, perplexity))
+
+  def _maybe_decay(self, sess, model, window_loss, history):
+    factor = self.flags.learning_rate_decay_factor
+    if factor > 0 and len(history) > 2 and window_loss > max(history[-3:]):
+      sess.run(model.learning_rate_decay_op)
+
+  def _save(self, sess, model):
+    path = os.path.join(self.flags.run_train_dir, 'speechT.ckpt')
+    model.saver.save(sess, path, global_step=model.global_step)
+    print('Model saved')
+
+  # ---- the loop ----------------------------------------------------------------------------------
   def run(self, max_steps=None):
+    per_checkpoint = self.flags.steps_per_checkpoint
+    window = _Window(per_checkpoint)
+    history = []
     with Session() as sess:
       model = self.create_model(sess)
-      # two feeder threads like the reference (training.py:49) -- one under data parallelism, where the threads of
-      # a rank must not race for the commonly seeded shuffle stream
-      coord = self.start_pipeline(sess, n_threads=2 if self.world == 1 else 1)
-      step_time, loss = 0.0, 0.0
-      current_step = 0
-      previous_losses = []
+      # two feeder threads like the reference (training.py:49); one per rank under data parallelism, where the
+      # threads of a rank must not race for the commonly seeded shuffle stream
+      coord = self.start_pipeline(sess, n_threads=1 if self.world > 1 else 2)
+      print('Begin training')
       try:
-        print('Begin training')
-        while not coord.should_stop():
-          current_step += 1
-          is_checkpoint_step = current_step % self.flags.steps_per_checkpoint == 0
-          start_time = time.time()
-          step_result = model.step(sess, summary=is_checkpoint_step)
-          avg_loss = step_result[0]
-          step_time += (time.time() - start_time) / self.flags.steps_per_checkpoint
-          loss += avg_loss / self.flags.steps_per_checkpoint
-          if is_checkpoint_step:
-            global_step = model.global_step.eval()
-            if self.world > 1:
-              # every rank must take the same learning-rate decision: use the global mean of the running loss
-              import torch
-              loss = float(parallel.mean_scalar(torch.tensor([loss], device=model.engine.device)).item())
-            if self.rank == 0:
-              perplexity = np.exp(float(avg_loss)) if avg_loss < 300 else float('inf')
-              print('global step {:d} learning rate {:.4f} step-time {:.2f} average loss {:.2f} perplexity {:.2f}'
-                    .format(global_step, model.learning_rate.eval(), step_time, avg_loss, perplexity))
-              model.summary_writer.add_summary(step_result[2], global_step)
-            # decrease the learning rate if no improvement was seen over the last 3 checkpoints
-            if self.flags.learning_rate_decay_factor > 0 and len(previous_losses) > 2 \
-                and loss > max(previous_losses[-3:]):
-              sess.run(model.learning_rate_decay_op)
-            previous_losses.append(loss)
-            if self.rank == 0:
-              checkpoint_path = os.path.join(self.flags.run_train_dir, 'speechT.ckpt')
-              model.saver.save(sess, checkpoint_path, global_step=model.global_step)
-              print('Model saved')
-            step_time, loss = 0.0, 0.0
-          if max_steps is not None and current_step >= max_steps:
+        for step in itertools.count(1):
+          if coord.should_stop() or (max_steps is not None and step > max_steps):
             break
+          at_checkpoint = step % per_checkpoint == 0
+          began = time.time()
+          fetched = model.step(sess, summary=at_checkpoint)
+          window.add(time.time() - began, fetched[0])
+          if not at_checkpoint:
+            continue
+          window_loss = self._window_loss(model, window)
+          if self.rank == 0:
+            self._report(model, window, fetched[0])
+            model.summary_writer.add_summary(fetched[2], model.global_step.eval())
+          self._maybe_decay(sess, model, window_loss, history)
+          history.append(window_loss)
+          if self.rank == 0:
+            self._save(sess, model)
+          window.reset()
       except OutOfRangeError:
         print('Done training -- step limit reached')
       finally:

@@ -1,31 +1,33 @@
-"""Character vocabulary of the acoustic model (mirror of reference speecht/vocabulary.py:16-81).
+"""Character vocabulary of the acoustic model: the same id assignment as the reference (speecht/vocabulary.py:16-21):
+ids 0-25 = a-z, 26 = apostrophe, 27 = space; 28 symbols, and the CTC blank is class 28 (speech_model.py:301).
 
-ids 0-25 = a-z, 26 = apostrophe, 27 = space; SIZE = 28 and the CTC blank is class 28 (speech_model.py:301)."""
-APOSTROPHE = 26
-SPACE_ID = 27
+Table-driven: one alphabet string defines both directions.
+"""
+ALPHABET = "abcdefghijklmnopqrstuvwxyz' "
+
+SIZE = len(ALPHABET)
+APOSTROPHE = ALPHABET.index("'")
+SPACE_ID = ALPHABET.index(' ')
 A_ASCII_CODE = ord('a')
-SIZE = 28
+
+_TO_ID = {symbol: index for index, symbol in enumerate(ALPHABET)}
 
 
 def letter_to_id(letter):
-  if letter == ' ':
-    return SPACE_ID
-  if letter == '\'':
-    return APOSTROPHE
-  return ord(letter) - A_ASCII_CODE
+  """Vocabulary id of one character (a-z, apostrophe, space); raises KeyError for anything else."""
+  return _TO_ID[letter]
 
 
 def id_to_letter(identifier):
-  if identifier == SPACE_ID:
-    return ' '
-  if identifier == APOSTROPHE:
-    return '\''
-  return chr(identifier + A_ASCII_CODE)
+  """Character of one vocabulary id."""
+  return ALPHABET[int(identifier)]
 
 
 def sentence_to_ids(sentence):
-  return [letter_to_id(letter) for letter in sentence.lower()]
+  """Lower-cases `sentence` and encodes it character by character."""
+  return [_TO_ID[symbol] for symbol in sentence.lower()]
 
 
 def ids_to_sentence(identifiers):
-  return ''.join(id_to_letter(int(identifier)) for identifier in identifiers)
+  """Inverse of sentence_to_ids for any iterable of ids (ints or numpy integers)."""
+  return ''.join(ALPHABET[int(identifier)] for identifier in identifiers)

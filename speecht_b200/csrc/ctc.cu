@@ -173,10 +173,19 @@ ctc_alpha_beta_kernel(const float* __restrict__ lsm, int T, int C, const int32_t
       }
     }
     __syncthreads();
-    for (int t = 1; t < len; ++t) {
+    int2* lat_t = lat + s_pad;                                          // row t of the lattice
+    for (int t = 1; t < len; ++t, lat_t += s_pad) {
       const int2* prev = buf + ((t - 1) & 1) * bstride;
       int2* cur = buf + (t & 1) * bstride;
       const float* next_row = lrow + (int64_t)(t + 1) * C;
+      // emission of step t+1 first: independent of the recursion, its MUFU / conversions fill the chain's stalls
+      float pn[NS];
+      int en[NS];
+#pragma unroll
+      for (int j = 0; j < NS; ++j) {
+        pn[j] = 0.f; en[j] = 0;
+        if (live[j] && t + 1 < len) sf_from_log(next_row[my_ext[j]], pn[j], en[j]);
+      }
       SF v[NS];
 #pragma unroll
       for (int j = 0; j < NS; ++j) {
@@ -186,18 +195,16 @@ ctc_alpha_beta_kernel(const float* __restrict__ lsm, int T, int C, const int32_t
           SF a2 = sf_load(prev + s);
           if (!my_skip[j]) { a2.p = 0.f; a2.e = kZeroExp; }
           v[j] = sf_add3_mul(a0, a1, a2, py[j], ey[j]);
-        }
-      }
-#pragma unroll
-      for (int j = 0; j < NS; ++j) {
-        const int s = threadIdx.x + j * nthr;
-        if (live[j]) {
           sf_store(cur + 2 + s, v[j]);
-          sf_store(lat + (int64_t)t * s_pad + s, v[j]);
-          if (t + 1 < len) sf_from_log(next_row[my_ext[j]], py[j], ey[j]);   // off the critical path
         }
       }
       __syncthreads();
+#pragma unroll
+      for (int j = 0; j < NS; ++j) {
+        const int s = threadIdx.x + j * nthr;
+        if (live[j]) sf_store(lat_t + s, v[j]);                          // global store after the barrier: off the chain
+        py[j] = pn[j]; ey[j] = en[j];
+      }
     }
     if (threadIdx.x == 0) {
       const int2* fin = buf + ((len - 1) & 1) * bstride;
@@ -225,9 +232,17 @@ ctc_alpha_beta_kernel(const float* __restrict__ lsm, int T, int C, const int32_t
       }
     }
     __syncthreads();
-    for (int t = len - 2; t >= 0; --t) {
+    int2* lat_t = lat + (int64_t)(len - 2) * s_pad;
+    for (int t = len - 2; t >= 0; --t, lat_t -= s_pad) {
       const int2* nxt = buf + ((t + 1) & 1) * bstride;                  // entries S..S+3 stay zero
       int2* cur = buf + (t & 1) * bstride;
+      float pn[NS];
+      int en[NS];
+#pragma unroll
+      for (int j = 0; j < NS; ++j) {
+        pn[j] = 0.f; en[j] = 0;
+        if (live[j] && t > 0) sf_from_log(lrow[(int64_t)(t - 1) * C + my_ext[j]], pn[j], en[j]);
+      }
       SF v[NS];
 #pragma unroll
       for (int j = 0; j < NS; ++j) {
@@ -237,18 +252,16 @@ ctc_alpha_beta_kernel(const float* __restrict__ lsm, int T, int C, const int32_t
           SF b2 = sf_load(nxt + s + 2);
           if (!my_skip[j]) { b2.p = 0.f; b2.e = kZeroExp; }
           v[j] = sf_add3_mul(b0, b1, b2, 1.f, 0);
-        }
-      }
-#pragma unroll
-      for (int j = 0; j < NS; ++j) {
-        const int s = threadIdx.x + j * nthr;
-        if (live[j]) {
-          sf_store(lat + (int64_t)t * s_pad + s, v[j]);
           sf_store(cur + s, sf_norm(v[j].p * py[j], v[j].e + ey[j]));
-          if (t > 0) sf_from_log(lrow[(int64_t)(t - 1) * C + my_ext[j]], py[j], ey[j]);
         }
       }
       __syncthreads();
+#pragma unroll
+      for (int j = 0; j < NS; ++j) {
+        const int s = threadIdx.x + j * nthr;
+        if (live[j]) sf_store(lat_t + s, v[j]);
+        py[j] = pn[j]; ey[j] = en[j];
+      }
     }
   }
 }

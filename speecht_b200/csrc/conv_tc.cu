@@ -37,15 +37,21 @@ namespace {
 constexpr int kEpilogueWarps = 8;              // two per TMEM lane quarter: they split the 32-column chunks
 constexpr int kThreads = 64 + 32 * kEpilogueWarps;
 constexpr int kSmemBudget = 227 * 1024;
+constexpr int kBarrierBytes = 1024;                // mbarriers + TMEM slot, after the pipeline stages
+constexpr int kStageTileBytes = 2 * 32 * 32 * 2;   // per epilogue warp: 2 planes x 32 rows x 32 bf16 columns
 
 template <int BLOCK_N, int NPL>
 struct ConvCfg {
   static constexpr int A_BYTES = kTileM * kChunkK * 2;           // 16 KB: 128 rows x 128 B
   static constexpr int B_BYTES = BLOCK_N * kChunkK * 2;
   static constexpr int STAGE_BYTES = NPL * (A_BYTES + B_BYTES);
-  static constexpr int STAGES_RAW = (kSmemBudget - 2048) / STAGE_BYTES;
+  // epilogue staging tiles for the TMA stores (one [2 planes][32][32] bf16 tile per epilogue warp); the three-plane
+  // mode has no shared memory left for them and keeps the direct stores
+  static constexpr int STAGING_BYTES = NPL <= 2 ? kEpilogueWarps * kStageTileBytes : 0;
+  static constexpr int STAGES_RAW = (kSmemBudget - 1024 - kBarrierBytes - STAGING_BYTES) / STAGE_BYTES;
   static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 2048;  // 1024 alignment slack + barriers
+  // [<= 1023 alignment slack][STAGES x stage][barriers, 1 KB][staging tiles]
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + kBarrierBytes + STAGING_BYTES;
   // Split modes keep TWO fp32 accumulators per tile: `main` takes the hi*hi products only, `side` every product
   // that involves a lo plane.  The tensor core truncates its fp32 accumulation, one error of up to an ulp of the
   // ACCUMULATOR per MMA whatever the size of the addend -- with a single accumulator the 2 (or 5) small products per
@@ -57,6 +63,8 @@ struct ConvCfg {
   static constexpr int TMEM_COLS = TMEM_RAW <= 32 ? 32 : (TMEM_RAW <= 64 ? 64 : (TMEM_RAW <= 128 ? 128 : (TMEM_RAW <= 256 ? 256 : 512)));
   static_assert(STAGES >= 2, "pipeline needs at least two stages");
   static_assert(TMEM_RAW <= 512, "TMEM columns");
+  static_assert(SMEM_BYTES <= kSmemBudget, "shared memory budget");
+  static_assert((STAGES * 2 * 2 + 4) * 8 + 8 <= kBarrierBytes, "barrier area");
 };
 
 __device__ __forceinline__ int floordiv(int a, int b) {
@@ -91,6 +99,91 @@ __device__ __forceinline__ void store_planes8(__nv_bfloat16* dst, int64_t plane_
   }
 }
 
+// One 32-column chunk of the epilogue for this lane's output row, from the summed accumulators v[32]:
+// + bias, ReLU or ReLU-mask, then
+//   * bf16 planes: staged [plane][32 rows][32 cols] in the warp's shared-memory tile and written with ONE TMA store
+//     per plane (box {32 ch, 32 t, 1}; rows t >= T' and channel padding beyond ld are clipped by the tensor map), or
+//     -- bf16x6 / SPEECHT_B200_TMA_STORE=0 -- direct 16-byte stores from the lane that owns the row;
+//   * fp32 logits (last layer): direct stores;
+//   * bias gradient of the layer below (data gradient): column sums by a 32x32 transpose-reduce.
+template <int NPL>
+__device__ __forceinline__ void epilogue_chunk(const ConvParams& p, const CUtensorMap* tmOut, uint8_t* stage,
+                                               float (&v)[32], const uint4 (&mk)[4], int nc, int lane, bool row_ok,
+                                               int64_t out_row, int t_warp, int b) {
+#pragma unroll
+  for (int i = 0; i < 32; ++i) {
+    const int n = nc + i;
+    float x = v[i];
+    if (n < p.N) {
+      if (p.bias) x += __ldg(p.bias + n);
+      if (p.relu) x = fmaxf(x, 0.f);
+    } else {
+      x = 0.f;
+    }
+    v[i] = x;
+  }
+  if (p.mask_hi) {
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      const uint32_t w[4] = {mk[g].x, mk[g].y, mk[g].z, mk[g].w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        // bf16 > 0  <=>  sign bit clear and magnitude non-zero
+        const uint32_t lo16 = w[i] & 0xffffu, hi16 = w[i] >> 16;
+        if (!(lo16 != 0 && lo16 < 0x8000u)) v[g * 8 + 2 * i] = 0.f;
+        if (!(hi16 != 0 && hi16 < 0x8000u)) v[g * 8 + 2 * i + 1] = 0.f;
+      }
+    }
+  }
+  if (p.out_planes) {
+    if (NPL <= 2 && p.tma_store) {
+      // the previous TMA store out of this warp's tile must have finished reading it
+      if (lane == 0) bulk_wait_read0();
+      __syncwarp();
+      __nv_bfloat16* srow = reinterpret_cast<__nv_bfloat16*>(stage + lane * 64);
+#pragma unroll
+      for (int g = 0; g < 4; ++g) store_planes8<NPL>(srow + g * 8, 32 * 32, v + g * 8);
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0 && t_warp < p.To && nc < p.ld_out) {
+#pragma unroll
+        for (int pl = 0; pl < NPL; ++pl) tma_store_3d(tmOut, stage + pl * (32 * 32 * 2), nc, t_warp, pl * p.B + b);
+        bulk_commit();
+      }
+    } else if (row_ok) {
+      __nv_bfloat16* orow = p.out_planes + out_row * p.ld_out + nc;
+#pragma unroll
+      for (int g = 0; g < 4; ++g)
+        if (nc + g * 8 < p.ld_out) store_planes8<NPL>(orow + g * 8, p.out_plane_stride, v + g * 8);
+    }
+  }
+  if (p.out_f32 && row_ok) {
+    float* frow = p.out_f32 + out_row * p.ld_f32 + nc;
+#pragma unroll
+    for (int i = 0; i < 32; ++i)
+      if (nc + i < p.ld_f32) frow[i] = v[i];
+  }
+  if (p.col_sum) {
+    // bias gradient of the layer below = column sums of what was just stored: 32x32 transpose-reduce with
+    // 31 shuffles (each step halves the values a lane holds), then one atomic per column per warp
+    if (!row_ok) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v[i] = 0.f;
+    }
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) {
+      const bool upper = (lane & off) != 0;
+#pragma unroll
+      for (int j = 0; j < off; ++j) {
+        const float send = upper ? v[j] : v[j + off];
+        const float keep = upper ? v[j + off] : v[j];
+        v[j] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+      }
+    }
+    if (nc + lane < p.N) atomicAdd(p.col_sum + nc + lane, v[0]);
+  }
+}
+
 // Products of the split operands, in issue order, as (A plane, B plane, load group to wait for before it,
 // load group released after it; -1 = none).  Plane 0 = hi, 1 = lo, 2 = lo-lo.
 //   NPL 1: hi*hi
@@ -122,9 +215,12 @@ template <> struct Products<3> {
 // EARLY: two-phase epilogue (drain the accumulators to registers, release TMEM, then store) -- chosen by the host
 // for launches where a CTA processes several tiles and the split modes leave no second accumulator stage; the
 // streaming epilogue (lower register pressure, TMEM loads overlapped with the stores) is used everywhere else.
+// 168 registers is the ceiling for 10 warps: each SM sub-partition holds 16384 registers and gets 3 of the warps
+// (a 200-register build fails to launch), so the two-phase epilogue's 64 live accumulators spill ~450 bytes.
 template <int BLOCK_N, int NPL, bool EARLY>
 __global__ void __launch_bounds__(kThreads, 1)
-tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const ConvParams p) {
+tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const __grid_constant__ CUtensorMap tmOut, const ConvParams p) {
   using Cfg = ConvCfg<BLOCK_N, NPL>;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
@@ -150,6 +246,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmA);
     prefetch_tmap(&tmB);
+    if (p.tma_store) prefetch_tmap(&tmOut);
     for (int s = 0; s < STAGES * NG; ++s) {
       mbar_init(full_bar + s, 1);
       mbar_init(empty_bar + s, 1);
@@ -266,132 +363,53 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     __syncwarp();
   } else {
-    // ===================================================== epilogue warps 2..5
+    // ===================================================== epilogue warps 2..9
     const int quarter = warp & 3;                         // TMEM lane quarter this warp may read
     const int chunk0 = (warp - 2) >> 2;                   // warps w and w+4 share a quarter: even / odd chunks
     constexpr int kChunkStep = kEpilogueWarps / 4;
+    constexpr int kChunks = BLOCK_N / 32;
     const int row = quarter * 32 + lane;
+    uint8_t* stage = smem + STAGES * Cfg::STAGE_BYTES + kBarrierBytes + (warp - 2) * kStageTileBytes;
+    auto tile_coords = [&](int tile, int& b, int& t0, int& n0) {
+      const int nt = p.n_fastest ? tile % p.n_tiles : tile / m_tiles;
+      const int mt = p.n_fastest ? tile / p.n_tiles : tile % m_tiles;
+      b = mt / p.m_tiles_per_utt;
+      t0 = (mt - b * p.m_tiles_per_utt) * kTileM;
+      n0 = nt * BLOCK_N;
+    };
+    // ReLU-mask rows of a tile (data gradient only) are pulled into L2 one tile ahead: the forward activations they
+    // come from were written a whole forward+loss ago and would otherwise be an HBM round trip in the epilogue
+    auto prefetch_mask = [&](int tile) {
+      if (!p.mask_hi || tile >= num_tiles) return;
+      int b, t0, n0;
+      tile_coords(tile, b, t0, n0);
+      if (t0 + row >= p.To) return;
+      const __nv_bfloat16* mrow = p.mask_hi + ((int64_t)b * p.To + t0 + row) * p.ld_mask;
+#pragma unroll
+      for (int q = chunk0; q < (BLOCK_N + 63) / 64; q += kChunkStep) {
+        const int c = n0 + q * 64;
+        if (c < p.ld_mask) {
+          prefetch_l2(mrow + c);
+          prefetch_l2(mrow + min(c + 63, p.ld_mask - 1));     // rows are not 128-byte aligned when ld % 64 != 0
+        }
+      }
+    };
+    prefetch_mask(blockIdx.x);
     int local = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
       const int acc = local % Cfg::ACC_STAGES;
       const uint32_t acc_phase = (local / Cfg::ACC_STAGES) & 1;
-      const int nt = p.n_fastest ? tile % p.n_tiles : tile / m_tiles;
-      const int mt = p.n_fastest ? tile / p.n_tiles : tile % m_tiles;
-      const int b = mt / p.m_tiles_per_utt;
-      const int t = (mt - b * p.m_tiles_per_utt) * kTileM + row;
-      const int n0 = nt * BLOCK_N;
+      int b, t0, n0;
+      tile_coords(tile, b, t0, n0);
+      const int t = t0 + row;
+      const int t_warp = t0 + quarter * 32;               // first row of this warp's 32-row slab
       const bool row_ok = t < p.To;
       const int64_t out_row = (int64_t)b * p.To + t;
+      prefetch_mask(tile + gridDim.x);
       mbar_wait(tmem_full + acc, acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * Cfg::ACC_COLS;
-      if constexpr (EARLY) {
-      // Phase 1: drain this warp's share of the accumulators into registers (main + side summed in round-to-nearest
-      // fp32) and hand TMEM back to the MMA warp at once -- with the two 256-column accumulators of the split modes
-      // there is no second accumulator stage, so everything after this point overlaps the next tile's MMAs.
-      constexpr int kChunks = BLOCK_N / 32;
-      constexpr int kMine = (kChunks + kChunkStep - 1) / kChunkStep;       // chunks per warp (compile time)
-      float sum[kMine][32];
-#pragma unroll
-      for (int ci = 0; ci < kMine; ++ci) {
-        const int c = chunk0 + ci * kChunkStep;
-        if (c < kChunks) {
-          uint32_t r[32];
-          tmem_ld32(taddr + c * 32, r);
-          if (NPL > 1) {
-            uint32_t q[32];
-            tmem_ld32(taddr + BLOCK_N + c * 32, q);
-            tmem_ld_wait();
-#pragma unroll
-            for (int i = 0; i < 32; ++i) sum[ci][i] = __uint_as_float(r[i]) + __uint_as_float(q[i]);
-          } else {
-            tmem_ld_wait();
-#pragma unroll
-            for (int i = 0; i < 32; ++i) sum[ci][i] = __uint_as_float(r[i]);
-          }
-        }
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(tmem_empty + acc);
-
-      // Phase 2: bias / ReLU / ReLU-mask / plane split / stores / bias-gradient column sums, from registers
-#pragma unroll
-      for (int ci = 0; ci < kMine; ++ci) {
-        const int c = chunk0 + ci * kChunkStep;
-        if (c >= kChunks) continue;
-        const int nc = n0 + c * 32;
-        uint4 mk[4];
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          mk[g] = make_uint4(0x3f803f80u, 0x3f803f80u, 0x3f803f80u, 0x3f803f80u);      // bf16 1.0 pairs: pass
-          if (p.mask_hi && row_ok && nc + g * 8 < p.ld_mask)
-            mk[g] = *reinterpret_cast<const uint4*>(p.mask_hi + out_row * p.ld_mask + nc + g * 8);
-        }
-        float* v = sum[ci];
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const int n = nc + i;
-          float x = v[i];
-          if (n < p.N) {
-            if (p.bias) x += __ldg(p.bias + n);
-            if (p.relu) x = fmaxf(x, 0.f);
-          } else {
-            x = 0.f;
-          }
-          v[i] = x;
-        }
-        if (row_ok) {
-          if (p.mask_hi) {
-#pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              const uint32_t w[4] = {mk[g].x, mk[g].y, mk[g].z, mk[g].w};
-#pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                // bf16 > 0  <=>  sign bit clear and magnitude non-zero
-                const uint32_t lo16 = w[i] & 0xffffu, hi16 = w[i] >> 16;
-                if (!(lo16 != 0 && lo16 < 0x8000u)) v[g * 8 + 2 * i] = 0.f;
-                if (!(hi16 != 0 && hi16 < 0x8000u)) v[g * 8 + 2 * i + 1] = 0.f;
-              }
-            }
-          }
-          if (p.out_planes) {
-            __nv_bfloat16* orow = p.out_planes + out_row * p.ld_out + nc;
-#pragma unroll
-            for (int g = 0; g < 4; ++g)
-              if (nc + g * 8 < p.ld_out) store_planes8<NPL>(orow + g * 8, p.out_plane_stride, v + g * 8);
-          }
-          if (p.out_f32) {
-            float* frow = p.out_f32 + out_row * p.ld_f32 + nc;
-#pragma unroll
-            for (int i = 0; i < 32; ++i)
-              if (nc + i < p.ld_f32) frow[i] = v[i];
-          }
-        }
-        if (p.col_sum) {
-          // bias gradient of the layer below = column sums of what was just stored: 32x32 transpose-reduce with
-          // 31 shuffles (each step halves the values a lane holds), then one atomic per column per warp
-          if (!row_ok) {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = 0.f;
-          }
-#pragma unroll
-          for (int off = 16; off >= 1; off >>= 1) {
-            const bool upper = (lane & off) != 0;
-#pragma unroll
-            for (int j = 0; j < off; ++j) {
-              const float send = upper ? v[j] : v[j + off];
-              const float keep = upper ? v[j + off] : v[j];
-              v[j] = keep + __shfl_xor_sync(0xffffffffu, send, off);
-            }
-          }
-          if (nc + lane < p.N) atomicAdd(p.col_sum + nc + lane, v[0]);
-        }
-      }
-      } else {
-      // ReLU-mask vectors (data gradient only) are fetched one 32-column chunk ahead of their use
-      uint4 mk[4];
-      auto load_mask = [&](int c) {
+      auto load_mask = [&](int c, uint4 (&mk)[4]) {
         const int nc = n0 + c * 32;
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
@@ -400,85 +418,75 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             mk[g] = *reinterpret_cast<const uint4*>(p.mask_hi + out_row * p.ld_mask + nc + g * 8);
         }
       };
-      load_mask(chunk0);
+      if constexpr (EARLY) {
+        // Phase 1: drain this warp's share of the accumulators into registers (main + side summed in round-to-nearest
+        // fp32) and hand TMEM back to the MMA warp at once -- with the two 256-column accumulators of the split modes
+        // there is no second accumulator stage, so everything after this point overlaps the next tile's MMAs.
+        constexpr int kMine = (kChunks + kChunkStep - 1) / kChunkStep;       // chunks per warp (compile time)
+        float sum[kMine][32];
+#pragma unroll
+        for (int ci = 0; ci < kMine; ++ci) {
+          const int c = chunk0 + ci * kChunkStep;
+          if (c < kChunks) {
+            uint32_t r[32];
+            tmem_ld32(taddr + c * 32, r);
+            if (NPL > 1) {
+              uint32_t q[32];
+              tmem_ld32(taddr + BLOCK_N + c * 32, q);
+              tmem_ld_wait();
+#pragma unroll
+              for (int i = 0; i < 32; ++i) sum[ci][i] = __uint_as_float(r[i]) + __uint_as_float(q[i]);
+            } else {
+              tmem_ld_wait();
+#pragma unroll
+              for (int i = 0; i < 32; ++i) sum[ci][i] = __uint_as_float(r[i]);
+            }
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tmem_empty + acc);
+
+        // Phase 2: bias / ReLU / ReLU-mask / plane split / stores / bias-gradient column sums, from registers
+#pragma unroll
+        for (int ci = 0; ci < kMine; ++ci) {
+          const int c = chunk0 + ci * kChunkStep;
+          if (c >= kChunks) continue;
+          uint4 mk[4];
+          load_mask(c, mk);
+          epilogue_chunk<NPL>(p, &tmOut, stage, sum[ci], mk, n0 + c * 32, lane, row_ok, out_row, t_warp, b);
+        }
+      } else {
+        // ReLU-mask vectors (data gradient only) are fetched one 32-column chunk ahead of their use
+        uint4 mk[4];
+        load_mask(chunk0, mk);
 #pragma unroll 1
-      for (int c = chunk0; c < BLOCK_N / 32; c += kChunkStep) {
-        uint32_t r[32];
-        tmem_ld32(taddr + c * 32, r);
-        uint32_t q[32];
-        if (NPL > 1) tmem_ld32(taddr + BLOCK_N + c * 32, q);
-        uint4 mcur[4];
+        for (int c = chunk0; c < kChunks; c += kChunkStep) {
+          uint32_t r[32];
+          tmem_ld32(taddr + c * 32, r);
+          uint32_t q[32];
+          if (NPL > 1) tmem_ld32(taddr + BLOCK_N + c * 32, q);
+          uint4 mcur[4];
 #pragma unroll
-        for (int g = 0; g < 4; ++g) mcur[g] = mk[g];
-        if (c + kChunkStep < BLOCK_N / 32) load_mask(c + kChunkStep);
-        tmem_ld_wait();
-        const int nc = n0 + c * 32;
-        float v[32];
+          for (int g = 0; g < 4; ++g) mcur[g] = mk[g];
+          if (c + kChunkStep < kChunks) load_mask(c + kChunkStep, mk);
+          tmem_ld_wait();
+          float v[32];
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const int n = nc + i;
-          float x = __uint_as_float(r[i]);
-          if (NPL > 1) x += __uint_as_float(q[i]);          // main + side accumulator, round-to-nearest
-          if (n < p.N) {
-            if (p.bias) x += __ldg(p.bias + n);
-            if (p.relu) x = fmaxf(x, 0.f);
-          } else {
-            x = 0.f;
+          for (int i = 0; i < 32; ++i) {
+            v[i] = __uint_as_float(r[i]);
+            if (NPL > 1) v[i] += __uint_as_float(q[i]);        // main + side accumulator, round-to-nearest
           }
-          v[i] = x;
+          epilogue_chunk<NPL>(p, &tmOut, stage, v, mcur, n0 + c * 32, lane, row_ok, out_row, t_warp, b);
         }
-        if (row_ok) {
-          if (p.mask_hi) {
-#pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              const uint32_t w[4] = {mcur[g].x, mcur[g].y, mcur[g].z, mcur[g].w};
-#pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                // bf16 > 0  <=>  sign bit clear and magnitude non-zero
-                const uint32_t lo16 = w[i] & 0xffffu, hi16 = w[i] >> 16;
-                if (!(lo16 != 0 && lo16 < 0x8000u)) v[g * 8 + 2 * i] = 0.f;
-                if (!(hi16 != 0 && hi16 < 0x8000u)) v[g * 8 + 2 * i + 1] = 0.f;
-              }
-            }
-          }
-          if (p.out_planes) {
-            __nv_bfloat16* orow = p.out_planes + out_row * p.ld_out + nc;
-#pragma unroll
-            for (int g = 0; g < 4; ++g)
-              if (nc + g * 8 < p.ld_out) store_planes8<NPL>(orow + g * 8, p.out_plane_stride, v + g * 8);
-          }
-          if (p.out_f32) {
-            float* frow = p.out_f32 + out_row * p.ld_f32 + nc;
-#pragma unroll
-            for (int i = 0; i < 32; ++i)
-              if (nc + i < p.ld_f32) frow[i] = v[i];
-          }
-        }
-        if (p.col_sum) {
-          // bias gradient of the layer below = column sums of what was just stored: 32x32 transpose-reduce with
-          // 31 shuffles (each step halves the values a lane holds), then one atomic per column per warp
-          if (!row_ok) {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = 0.f;
-          }
-#pragma unroll
-          for (int off = 16; off >= 1; off >>= 1) {
-            const bool upper = (lane & off) != 0;
-#pragma unroll
-            for (int j = 0; j < off; ++j) {
-              const float send = upper ? v[j] : v[j + off];
-              const float keep = upper ? v[j + off] : v[j];
-              v[j] = keep + __shfl_xor_sync(0xffffffffu, send, off);
-            }
-          }
-          if (nc + lane < p.N) atomicAdd(p.col_sum + nc + lane, v[0]);
-        }
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(tmem_empty + acc);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tmem_empty + acc);
       }
     }
+    // outstanding TMA stores of this warp must have been performed before the CTA (and its shared memory) goes away
+    if (lane == 0) bulk_wait0();
+    __syncwarp();
   }
 
   tc_fence_before();
@@ -703,13 +711,33 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
         if (NPL > 1) tmem_ld32(taddr + BLOCK_N + c * 32, q);
         tmem_ld_wait();
         if (ci < p.Cin) {
+          const int cb = n0 + c * 32;
+          float x[32];
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            const int co = n0 + c * 32 + i;
-            if (co < p.Cout) {
-              const float x = __uint_as_float(r[i]) + (NPL > 1 ? __uint_as_float(q[i]) : 0.f);
-              if (whole_tile) wrow[co] = x;
-              else atomicAdd(wrow + co, x);
+          for (int i = 0; i < 32; ++i) x[i] = __uint_as_float(r[i]) + (NPL > 1 ? __uint_as_float(q[i]) : 0.f);
+          // a lane owns one filter row (ci) and 32 consecutive output channels of it: they leave as 16- or 8-byte
+          // vectors when the row pitch keeps them aligned (Cout % 4 / % 2) -- plain stores for whole tiles, vector
+          // reductions (red.global.add.v4/.v2.f32) for K-sliced tiles -- and as scalars otherwise
+          if (cb + 32 <= p.Cout && (p.Cout & 3) == 0) {
+#pragma unroll
+            for (int i = 0; i < 32; i += 4) {
+              if (whole_tile) *reinterpret_cast<float4*>(wrow + cb + i) = make_float4(x[i], x[i + 1], x[i + 2], x[i + 3]);
+              else red_add_v4(wrow + cb + i, x[i], x[i + 1], x[i + 2], x[i + 3]);
+            }
+          } else if (cb + 32 <= p.Cout && (p.Cout & 1) == 0) {
+#pragma unroll
+            for (int i = 0; i < 32; i += 2) {
+              if (whole_tile) *reinterpret_cast<float2*>(wrow + cb + i) = make_float2(x[i], x[i + 1]);
+              else red_add_v2(wrow + cb + i, x[i], x[i + 1]);
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              const int co = cb + i;
+              if (co < p.Cout) {
+                if (whole_tile) wrow[co] = x[i];
+                else atomicAdd(wrow + co, x[i]);
+              }
             }
           }
         }
@@ -827,6 +855,74 @@ pack_filter_bwd_all_kernel(const PackTable tab) {
   }
 }
 
+// Both layouts in ONE pass over W: a block owns a 64(ci) x 64(co) tile of one tap, stages it in shared memory and
+// writes it out twice -- transposed for the forward layout (warp = one co row, lanes along ci, 128-byte bf16x2
+// rows) and as is for the backward layout (warp = one (k,ci) row, lanes along co).  Padding (ci >= Cin in the
+// forward rows, co >= Cout in the backward rows) is written as zeros every time: the arena is shared between shapes.
+template <int NPL>
+__global__ void __launch_bounds__(256)
+pack_filter_both_kernel(const PackTable tab) {
+  __shared__ float tile[64][65];
+  int l = 0;
+  while (l + 1 < tab.n && (int)blockIdx.x >= tab.e[l + 1].fwd_blk0) ++l;
+  const PackEntry& e = tab.e[l];
+  int lb = blockIdx.x - e.fwd_blk0;
+  const int co_tiles = (e.ld_co + 63) / 64, ci_tiles = e.cin_p / 64;
+  const int co0 = (lb % co_tiles) * 64;
+  lb /= co_tiles;
+  const int ci0 = (lb % ci_tiles) * 64;
+  const int k = lb / ci_tiles;
+  const int tx = threadIdx.x, ty = threadIdx.y;
+#pragma unroll
+  for (int r = 0; r < 64; r += 8) {
+    const int ci = ci0 + r + ty;
+    const float* src = e.w + ((int64_t)k * e.Cin + ci) * e.Cout + co0;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int c = tx + 32 * h;
+      tile[r + ty][c] = (ci < e.Cin && co0 + c < e.Cout) ? __ldg(src + c) : 0.f;
+    }
+  }
+  __syncthreads();
+  {
+    const int64_t ld = (int64_t)e.K * e.cin_p;
+    const int64_t plane_stride = (int64_t)e.Cout * ld;
+#pragma unroll
+    for (int r = 0; r < 64; r += 8) {
+      const int c = r + ty, co = co0 + c;
+      if (co < e.Cout) {
+        float v0 = tile[2 * tx][c], v1 = tile[2 * tx + 1][c];
+        __nv_bfloat16* dst = e.fwd + (int64_t)co * ld + (int64_t)k * e.cin_p + ci0 + 2 * tx;
+#pragma unroll
+        for (int pl = 0; pl < NPL; ++pl) {
+          const __nv_bfloat16 h0 = __float2bfloat16_rn(v0), h1 = __float2bfloat16_rn(v1);
+          *reinterpret_cast<uint32_t*>(dst + pl * plane_stride) = pack_bf16x2(h0, h1);
+          v0 -= __bfloat162float(h0);
+          v1 -= __bfloat162float(h1);
+        }
+      }
+    }
+  }
+  if (e.bwd && co0 + 2 * tx < e.ld_co) {
+    const int64_t plane_stride = (int64_t)e.K * e.Cin * e.ld_co;
+#pragma unroll
+    for (int r = 0; r < 64; r += 8) {
+      const int ci = ci0 + r + ty;
+      if (ci < e.Cin) {
+        float v0 = tile[r + ty][2 * tx], v1 = tile[r + ty][2 * tx + 1];
+        __nv_bfloat16* dst = e.bwd + ((int64_t)k * e.Cin + ci) * e.ld_co + co0 + 2 * tx;
+#pragma unroll
+        for (int pl = 0; pl < NPL; ++pl) {
+          const __nv_bfloat16 h0 = __float2bfloat16_rn(v0), h1 = __float2bfloat16_rn(v1);
+          *reinterpret_cast<uint32_t*>(dst + pl * plane_stride) = pack_bf16x2(h0, h1);
+          v0 -= __bfloat162float(h0);
+          v1 -= __bfloat162float(h1);
+        }
+      }
+    }
+  }
+}
+
 // db[n] += sum_rows sum_planes dz[pl][row][n]; block (32 column octets, 8 row lanes): each thread streams 16-byte
 // vectors (8 bf16 columns) down its rows; grid (ceil(ld/256), row chunks)
 __global__ void __launch_bounds__(256)
@@ -905,9 +1001,8 @@ int grid_for(int work_items) {
 
 // Launch with the programmatic-stream-serialization attribute (PDL): the kernel may begin while the previous kernel
 // of the stream drains; it synchronises with `griddepcontrol.wait` before touching global memory.
-template <class Kernel, class Params>
-cudaError_t launch_pdl(Kernel kernel, int grid, int smem, cudaStream_t stream, const CUtensorMap& m0,
-                       const CUtensorMap& m1, const Params& p) {
+template <class Kernel, class... Args>
+cudaError_t launch_pdl(Kernel kernel, int grid, int smem, cudaStream_t stream, const Args&... args) {
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(grid);
   cfg.blockDim = dim3(kThreads);
@@ -919,11 +1014,12 @@ cudaError_t launch_pdl(Kernel kernel, int grid, int smem, cudaStream_t stream, c
   attr[0].val.programmaticStreamSerializationAllowed = pdl ? 1 : 0;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  return cudaLaunchKernelEx(&cfg, kernel, m0, m1, p);
+  return cudaLaunchKernelEx(&cfg, kernel, args...);
 }
 
 template <int BLOCK_N, int NPL, bool EARLY>
-int launch_conv_e(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvParams& p, cudaStream_t stream) {
+int launch_conv_e(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmOut, const ConvParams& p,
+                  cudaStream_t stream) {
   using Cfg = ConvCfg<BLOCK_N, NPL>;
   static bool configured = false;
   if (!configured) {
@@ -932,20 +1028,26 @@ int launch_conv_e(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvPara
     configured = true;
   }
   const int tiles = p.B * p.m_tiles_per_utt * p.n_tiles;
-  ST_CUDA_CALL(launch_pdl(tc_conv_kernel<BLOCK_N, NPL, EARLY>, grid_for(tiles), Cfg::SMEM_BYTES, stream, tmA, tmB, p));
+  ST_CUDA_CALL(launch_pdl(tc_conv_kernel<BLOCK_N, NPL, EARLY>, grid_for(tiles), Cfg::SMEM_BYTES, stream, tmA, tmB,
+                          tmOut, p));
   return ST_OK;
 }
 
 template <int BLOCK_N, int NPL>
-int launch_conv_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvParams& p, cudaStream_t stream) {
+int launch_conv_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap* tmOut, const ConvParams& p0,
+                  cudaStream_t stream) {
+  // the TMA-store epilogue needs a store map, bf16 output planes and the staging tiles (<= 2 planes)
+  ConvParams p = p0;
+  if (!tmOut || !p.out_planes || NPL > 2) p.tma_store = 0;
+  const CUtensorMap& tmO = p.tma_store ? *tmOut : tmA;          // placeholder when unused
   // early TMEM release pays when a CTA has several tiles, no second accumulator stage, and a main loop long enough
   // to hide the register-resident epilogue behind it
   const int tiles = p.B * p.m_tiles_per_utt * p.n_tiles;
   const bool early = ConvCfg<BLOCK_N, NPL>::ACC_STAGES == 1 && tiles > st_num_sms() && p.taps * p.chunks_per_tap >= 16;
   if constexpr (ConvCfg<BLOCK_N, NPL>::ACC_STAGES == 1) {
-    if (early) return launch_conv_e<BLOCK_N, NPL, true>(tmA, tmB, p, stream);
+    if (early) return launch_conv_e<BLOCK_N, NPL, true>(tmA, tmB, tmO, p, stream);
   }
-  return launch_conv_e<BLOCK_N, NPL, false>(tmA, tmB, p, stream);
+  return launch_conv_e<BLOCK_N, NPL, false>(tmA, tmB, tmO, p, stream);
 }
 
 template <int BLOCK_N, int NPL>
@@ -985,6 +1087,29 @@ int make_map_3d(CUtensorMap* map, const void* base, int C, int T, int Bn, int64_
   return ST_OK;
 }
 
+// Store map of activation planes [Bn][T][C] for the epilogue: box {32 ch, 32 t, 1}, no swizzle (the staging tile in
+// shared memory is dense [32 rows][32 cols] bf16).
+int make_map_3d_store(CUtensorMap* map, const void* base, int C, int T, int Bn, int64_t ld, int64_t batch_stride) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) {
+    st_set_error("cuTensorMapEncodeTiled is not available from the CUDA driver");
+    return ST_ERR_CUDA;
+  }
+  const cuuint64_t dims[3] = {(cuuint64_t)C, (cuuint64_t)T, (cuuint64_t)Bn};
+  const cuuint64_t strides[2] = {(cuuint64_t)ld * 2, (cuuint64_t)batch_stride * 2};
+  const cuuint32_t box[3] = {32, 32, 1};
+  const cuuint32_t estr[3] = {1, 1, 1};
+  const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    st_set_error("cuTensorMapEncodeTiled(store 3d: C=%d T=%d B=%d ld=%lld) failed with CUresult %d", C, T, Bn,
+                 (long long)ld, (int)r);
+    return ST_ERR_CUDA;
+  }
+  return ST_OK;
+}
+
 int make_map_2d(CUtensorMap* map, const void* base, int cols, int rows, int64_t ld, int box_c, int box_r) {
   EncodeTiledFn fn = encode_fn();
   if (!fn) {
@@ -1006,15 +1131,15 @@ int make_map_2d(CUtensorMap* map, const void* base, int cols, int rows, int64_t 
   return ST_OK;
 }
 
-int launch_conv(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvParams& p, int block_n, int n_planes,
-                cudaStream_t stream) {
-  if (block_n == 256 && n_planes == 2) return launch_conv_t<256, 2>(tmA, tmB, p, stream);
-  if (block_n == 256 && n_planes == 1) return launch_conv_t<256, 1>(tmA, tmB, p, stream);
-  if (block_n == 32 && n_planes == 2) return launch_conv_t<32, 2>(tmA, tmB, p, stream);
-  if (block_n == 32 && n_planes == 1) return launch_conv_t<32, 1>(tmA, tmB, p, stream);
-  if (block_n == 128 && n_planes == 3) return launch_conv_t<128, 3>(tmA, tmB, p, stream);
-  if (block_n == 128 && n_planes == 2) return launch_conv_t<128, 2>(tmA, tmB, p, stream);
-  if (block_n == 32 && n_planes == 3) return launch_conv_t<32, 3>(tmA, tmB, p, stream);
+int launch_conv(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap* tmOut, const ConvParams& p,
+                int block_n, int n_planes, cudaStream_t stream) {
+  if (block_n == 256 && n_planes == 2) return launch_conv_t<256, 2>(tmA, tmB, tmOut, p, stream);
+  if (block_n == 256 && n_planes == 1) return launch_conv_t<256, 1>(tmA, tmB, tmOut, p, stream);
+  if (block_n == 32 && n_planes == 2) return launch_conv_t<32, 2>(tmA, tmB, tmOut, p, stream);
+  if (block_n == 32 && n_planes == 1) return launch_conv_t<32, 1>(tmA, tmB, tmOut, p, stream);
+  if (block_n == 128 && n_planes == 3) return launch_conv_t<128, 3>(tmA, tmB, tmOut, p, stream);
+  if (block_n == 128 && n_planes == 2) return launch_conv_t<128, 2>(tmA, tmB, tmOut, p, stream);
+  if (block_n == 32 && n_planes == 3) return launch_conv_t<32, 3>(tmA, tmB, tmOut, p, stream);
   st_set_error("launch_conv: unsupported (block_n=%d, n_planes=%d)", block_n, n_planes);
   return ST_ERR_UNSUPPORTED;
 }
@@ -1046,7 +1171,25 @@ int launch_split_input(const float* x, __nv_bfloat16* planes, int B, int T, int 
   return ST_OK;
 }
 
-int launch_pack_filters(PackTable& tab, int n_planes, cudaStream_t stream) {
+int launch_pack_filters(PackTable& tab, int n_planes, cudaStream_t stream, int* launches) {
+  *launches = 0;
+  static const bool merged = []() { const char* e = getenv("SPEECHT_B200_PACK_MERGED"); return !(e && e[0] == '0'); }();
+  if (merged) {
+    int blocks = 0;
+    for (int l = 0; l < tab.n; ++l) {
+      PackEntry& e = tab.e[l];
+      ST_CHECK_ARG(e.cin_p % 64 == 0 && e.ld_co % 4 == 0 && e.ld_co >= e.Cout, "launch_pack_filters: bad padded sizes");
+      e.fwd_blk0 = blocks;
+      e.bwd_blk0 = 0;
+      blocks += e.K * (e.cin_p / 64) * ((e.ld_co + 63) / 64);
+    }
+    if (n_planes == 3) pack_filter_both_kernel<3><<<blocks, dim3(32, 8), 0, stream>>>(tab);
+    else if (n_planes == 2) pack_filter_both_kernel<2><<<blocks, dim3(32, 8), 0, stream>>>(tab);
+    else pack_filter_both_kernel<1><<<blocks, dim3(32, 8), 0, stream>>>(tab);
+    ST_CUDA_LAUNCH_CHECK("pack_filter_both_kernel");
+    *launches = 1;
+    return ST_OK;
+  }
   int fb = 0, bb = 0;
   for (int l = 0; l < tab.n; ++l) {
     PackEntry& e = tab.e[l];
@@ -1060,11 +1203,13 @@ int launch_pack_filters(PackTable& tab, int n_planes, cudaStream_t stream) {
   else if (n_planes == 2) pack_filter_fwd_all_kernel<2><<<fb, dim3(32, 8), 0, stream>>>(tab);
   else pack_filter_fwd_all_kernel<1><<<fb, dim3(32, 8), 0, stream>>>(tab);
   ST_CUDA_LAUNCH_CHECK("pack_filter_fwd_all_kernel");
+  *launches = 1;
   if (bb > 0) {
     if (n_planes == 3) pack_filter_bwd_all_kernel<3><<<bb, 256, 0, stream>>>(tab);
     else if (n_planes == 2) pack_filter_bwd_all_kernel<2><<<bb, 256, 0, stream>>>(tab);
     else pack_filter_bwd_all_kernel<1><<<bb, 256, 0, stream>>>(tab);
     ST_CUDA_LAUNCH_CHECK("pack_filter_bwd_all_kernel");
+    *launches = 2;
   }
   return ST_OK;
 }

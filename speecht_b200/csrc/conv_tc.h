@@ -29,6 +29,7 @@ struct ConvParams {
   const __nv_bfloat16* mask_hi;  // same [B,To,ld_mask] indexing as the output; value > 0 passes
   int ld_mask;
   float* col_sum;                // nullable: += column sums of the stored tile (bias gradient), [N] fp32
+  int tma_store;                 // 1: bf16 planes leave through the store tensor map (launch_conv's tmOut)
 };
 
 // ---- filter-gradient kernel: dW[j, ci, co] += sum_{b,t} X[b, t+shift_j, acol_j + ci] * dZ[b, t, co]
@@ -43,10 +44,13 @@ struct WgradParams {
 int make_map_3d(CUtensorMap* map, const void* base, int C, int T, int Bn, int64_t ld, int64_t batch_stride,
                 int box_c, int box_t);
 int make_map_2d(CUtensorMap* map, const void* base, int cols, int rows, int64_t ld, int box_c, int box_r);
+// store map over output planes [Bn][T][C] (C = padded channel count ld), box {32, 32, 1}
+int make_map_3d_store(CUtensorMap* map, const void* base, int C, int T, int Bn, int64_t ld, int64_t batch_stride);
 
 // block_n: 32 or 256 (conv) / 64 or 256 (wgrad); n_planes: 1 or 2.
-int launch_conv(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvParams& p, int block_n, int n_planes,
-                cudaStream_t stream);
+// tmOut: store map of p.out_planes (nullable; used when p.tma_store is set)
+int launch_conv(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap* tmOut, const ConvParams& p,
+                int block_n, int n_planes, cudaStream_t stream);
 int launch_wgrad(const CUtensorMap& tmX, const CUtensorMap& tmDZ, const WgradParams& p, int block_n, int n_planes,
                  cudaStream_t stream);
 
@@ -54,7 +58,7 @@ int launch_wgrad(const CUtensorMap& tmX, const CUtensorMap& tmDZ, const WgradPar
 int launch_split_input(const float* x, __nv_bfloat16* planes, int B, int T, int Tpad, int F, int n_planes,
                        cudaStream_t stream);
 // W [K][Cin][Cout] fp32 -> forward layout planes [n][Cout][K*cin_p] (K-major), backward layout planes
-// [n][K*Cin][ld_co] (bwd may be null); all layers of the table in two launches
+// [n][K*Cin][ld_co] (bwd may be null); all layers of the table in one launch (two with SPEECHT_B200_PACK_MERGED=0)
 struct PackEntry {
   const float* w;
   __nv_bfloat16* fwd;
@@ -66,7 +70,7 @@ struct PackTable {
   int n;
   PackEntry e[12];
 };
-int launch_pack_filters(PackTable& tab, int n_planes, cudaStream_t stream);
+int launch_pack_filters(PackTable& tab, int n_planes, cudaStream_t stream, int* launches);
 // db[n] = sum over rows and planes of dz planes [n_planes][rows][ld]
 int launch_bias_grad(const __nv_bfloat16* dz, int64_t rows, int N, int ld, int n_planes, float* db,
                      cudaStream_t stream);

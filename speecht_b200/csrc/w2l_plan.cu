@@ -25,6 +25,8 @@ struct Layer {
   CUtensorMap tm_fwd_a, tm_fwd_b;     // forward
   CUtensorMap tm_dg_a[2], tm_dg_b;    // data gradient (A = dz ping or pong)
   CUtensorMap tm_wg_x, tm_wg_dz[2];   // filter gradient
+  CUtensorMap tm_fwd_out;             // store map of this layer's output planes (layers 0..9)
+  CUtensorMap tm_dg_out[2];           // store map of the dz buffer the data gradient of this layer writes (1..10)
 };
 
 int round_up(int x, int m) { return (x + m - 1) / m * m; }
@@ -49,6 +51,13 @@ struct st_plan {
   std::vector<Rec> recs;
   int ev_used;
   int cur_dz;                  // ping/pong buffer holding the gradient wrt the next layer to process
+  bool tma_store;              // epilogues write bf16 planes with TMA stores (SPEECHT_B200_TMA_STORE=0 disables)
+  // Experiment switch SPEECHT_B200_PACK_OVERLAP=1: filter packing of the three big layers (8..10: 87 % of the
+  // parameters) runs on a side stream under the forward of layers 0..7, which only need their own (small) filters.
+  bool pack_overlap;
+  cudaStream_t side;
+  cudaEvent_t ev_fork, ev_join;
+  bool join_pending;
 };
 
 namespace {
@@ -91,6 +100,13 @@ ST_API int st_plan_create(st_plan** out, int B, int T, int input_size, int num_c
   st_plan* p = new st_plan();
   p->B = B; p->T = T; p->Tpad = round_up(T, 2); p->F = input_size; p->C = num_classes; p->npl = n_planes;
   p->arena = nullptr; p->params = nullptr; p->grads = nullptr; p->launches = 0; p->bound = false; p->cur_dz = 0; p->timing = false; p->ev_used = 0;
+  {
+    const char* e = getenv("SPEECHT_B200_TMA_STORE");
+    p->tma_store = !(e && e[0] == '0') && n_planes <= 2;
+    e = getenv("SPEECHT_B200_PACK_OVERLAP");
+    p->pack_overlap = e && e[0] == '1';
+  }
+  p->side = nullptr; p->ev_fork = nullptr; p->ev_join = nullptr; p->join_pending = false;
   // reference speech_model.py:275-292
   const int table[11][5] = {{48, 2, input_size, 250, 1}, {7, 1, 250, 250, 1}, {7, 1, 250, 250, 1}, {7, 1, 250, 250, 1},
                             {7, 1, 250, 250, 1},         {7, 1, 250, 250, 1}, {7, 1, 250, 250, 1}, {7, 1, 250, 250, 1},
@@ -138,7 +154,15 @@ ST_API int st_plan_create(st_plan** out, int B, int T, int input_size, int num_c
 }
 
 ST_API int st_plan_destroy(st_plan* p) {
-  if (p) for (cudaEvent_t e : p->ev_pool) cudaEventDestroy(e);
+  if (p) {
+    for (cudaEvent_t e : p->ev_pool) cudaEventDestroy(e);
+    if (p->side) {
+      cudaStreamSynchronize(p->side);
+      cudaStreamDestroy(p->side);
+    }
+    if (p->ev_fork) cudaEventDestroy(p->ev_fork);
+    if (p->ev_join) cudaEventDestroy(p->ev_join);
+  }
   delete p;
   return ST_OK;
 }
@@ -158,6 +182,8 @@ ST_API int st_plan_bind(st_plan* p, void* arena, size_t arena_bytes, float* para
   ST_CHECK_ARG(p && arena && params && grads, "st_plan_bind: null pointer");
   ST_CHECK_ARG(arena_bytes >= p->arena_bytes, "st_plan_bind: arena %zu < required %zu bytes", arena_bytes, p->arena_bytes);
   ST_CHECK_ARG((reinterpret_cast<uintptr_t>(arena) & 1023) == 0, "st_plan_bind: arena must be 1024-byte aligned");
+  ST_CHECK_ARG((reinterpret_cast<uintptr_t>(params) & 15) == 0 && (reinterpret_cast<uintptr_t>(grads) & 15) == 0,
+               "st_plan_bind: parameter / gradient buffers must be 16-byte aligned");
   p->arena = static_cast<char*>(arena);
   p->params = params;
   p->grads = grads;
@@ -207,25 +233,78 @@ ST_API int st_plan_bind(st_plan* p, void* arena, size_t arena_bytes, float* para
                            wide_n(p));
       if (rc) return rc;
     }
+    // ---- store maps for the epilogues (planes are dense [npl][B][T][ld] inside their buffer)
+    if (p->tma_store) {
+      if (l < 10) {
+        rc = tc::make_map_3d_store(&L.tm_fwd_out, bf(p, L.off_out), L.ld_out, L.To, npl * B, L.ld_out,
+                                   (int64_t)L.To * L.ld_out);
+        if (rc) return rc;
+      }
+      if (l > 0) {
+        const Layer& Lb = p->layers[l - 1];
+        for (int s = 0; s < 2; ++s) {
+          rc = tc::make_map_3d_store(&L.tm_dg_out[s], bf(p, p->off_dz[s]), Lb.ld_out, Lb.To, npl * B, Lb.ld_out,
+                                     (int64_t)Lb.To * Lb.ld_out);
+          if (rc) return rc;
+        }
+      }
+    }
+  }
+  if (p->pack_overlap && !p->side) {
+    ST_CUDA_CALL(cudaStreamCreateWithFlags(&p->side, cudaStreamNonBlocking));
+    ST_CUDA_CALL(cudaEventCreateWithFlags(&p->ev_fork, cudaEventDisableTiming));
+    ST_CUDA_CALL(cudaEventCreateWithFlags(&p->ev_join, cudaEventDisableTiming));
   }
   p->bound = true;
   return ST_OK;
 }
 
 // fp32 parameters -> bf16 operand planes (forward K-major layout for every layer, backward layout for layers 1..10)
+namespace {
+
+int pack_layers(st_plan* p, int l0, int l1, cudaStream_t s) {
+  tc::PackTable tab{};
+  tab.n = l1 - l0;
+  for (int l = l0; l < l1; ++l) {
+    Layer& L = p->layers[l];
+    tab.e[l - l0] = tc::PackEntry{p->params + L.w_off, bf(p, L.off_wfwd), l > 0 ? bf(p, L.off_wbwd) : nullptr,
+                                  L.K, L.Cin, L.Cout, L.cin_p, L.ld_co, 0, 0};
+  }
+  int n = 0;
+  const int rc = tc::launch_pack_filters(tab, p->npl, s, &n);
+  if (rc) return rc;
+  p->launches += n;
+  return ST_OK;
+}
+
+// The side-stream packing of layers 8..10 must be complete before anything on `s` touches their filter planes.
+int join_pack(st_plan* p, cudaStream_t s) {
+  if (p->join_pending) {
+    ST_CUDA_CALL(cudaStreamWaitEvent(s, p->ev_join, 0));
+    p->join_pending = false;
+  }
+  return ST_OK;
+}
+
+constexpr int kFirstBigLayer = 8;
+
+}  // namespace
+
 ST_API int st_plan_pack_weights(st_plan* p, st_stream_t stream) {
   ST_CHECK_ARG(p && p->bound, "st_plan_pack_weights: plan is not bound");
-  tc::PackTable tab{};
-  tab.n = 11;
-  for (int l = 0; l < 11; ++l) {
-    Layer& L = p->layers[l];
-    tab.e[l] = tc::PackEntry{p->params + L.w_off, bf(p, L.off_wfwd), l > 0 ? bf(p, L.off_wbwd) : nullptr,
-                             L.K, L.Cin, L.Cout, L.cin_p, L.ld_co, 0, 0};
-  }
-  const int rc = tc::launch_pack_filters(tab, p->npl, st_cu(stream));
+  cudaStream_t s = st_cu(stream);
+  if (!p->pack_overlap) return pack_layers(p, 0, 11, s);
+  // everything queued on `s` so far (the optimizer step that produced the parameters, earlier users of the filter
+  // planes) precedes the side-stream work
+  int rc = join_pack(p, s);
   if (rc) return rc;
-  p->launches += 2;
-  return ST_OK;
+  ST_CUDA_CALL(cudaEventRecord(p->ev_fork, s));
+  ST_CUDA_CALL(cudaStreamWaitEvent(p->side, p->ev_fork, 0));
+  rc = pack_layers(p, kFirstBigLayer, 11, p->side);
+  if (rc) return rc;
+  ST_CUDA_CALL(cudaEventRecord(p->ev_join, p->side));
+  p->join_pending = true;
+  return pack_layers(p, 0, kFirstBigLayer, s);
 }
 
 ST_API int st_plan_forward(st_plan* p, const float* inputs, st_stream_t stream) {
@@ -261,8 +340,13 @@ ST_API int st_plan_forward(st_plan* p, const float* inputs, st_stream_t stream) 
       c.out_f32 = reinterpret_cast<float*>(p->arena + p->off_logits);
       c.ld_f32 = 32;
     }
+    c.tma_store = p->tma_store && l < 10;
+    if (l == kFirstBigLayer) {
+      rc = join_pack(p, s);
+      if (rc) return rc;
+    }
     const int ti = timed_begin(p, s);
-    rc = tc::launch_conv(L.tm_fwd_a, L.tm_fwd_b, c, block_n, p->npl, s);
+    rc = tc::launch_conv(L.tm_fwd_a, L.tm_fwd_b, l < 10 ? &L.tm_fwd_out : nullptr, c, block_n, p->npl, s);
     if (rc) return rc;
     timed_end(p, ti, 0, l, 2.0 * L.K * L.Cin * L.Cout * (double)L.To * p->B, s);
     p->launches++;
@@ -277,6 +361,10 @@ ST_API int st_plan_backward_range(st_plan* p, int hi, int lo, st_stream_t stream
   ST_CHECK_ARG(p && p->bound, "st_plan_backward: plan is not bound");
   ST_CHECK_ARG(hi <= 10 && lo >= 0 && hi >= lo, "st_plan_backward_range: need 10 >= hi >= lo >= 0");
   cudaStream_t s = st_cu(stream);
+  {
+    const int rc = join_pack(p, s);
+    if (rc) return rc;
+  }
   if (hi == 10) {
     p->cur_dz = 0;
     // filter gradients of K-sliced tiles accumulate with atomics: zero the whole flat buffer once per backward
@@ -335,8 +423,9 @@ ST_API int st_plan_backward_range(st_plan* p, int hi, int lo, st_stream_t stream
       c.mask_hi = bf(p, Lb.off_out);
       c.ld_mask = Lb.ld_out;
       c.col_sum = p->grads + Lb.b_off;
+      c.tma_store = p->tma_store;
       ti = timed_begin(p, s);
-      rc = tc::launch_conv(L.tm_dg_a[l == 10 ? 0 : cur], L.tm_dg_b, c, wide_n(p), p->npl, s);
+      rc = tc::launch_conv(L.tm_dg_a[l == 10 ? 0 : cur], L.tm_dg_b, &L.tm_dg_out[nxt], c, wide_n(p), p->npl, s);
       if (rc) return rc;
       timed_end(p, ti, 1, l, 2.0 * L.K * L.Cin * L.Cout * (double)L.To * p->B, s);
       p->launches++;

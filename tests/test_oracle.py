@@ -177,3 +177,38 @@ def test_train_step_gradients_vs_torch_autograd_tiny_net():
   for (dw, db), (w, b) in zip(grads, tw):
     np.testing.assert_allclose(dw, w.grad.numpy(), rtol=1e-7, atol=1e-10)
     np.testing.assert_allclose(db, b.grad.numpy(), rtol=1e-7, atol=1e-10)
+
+
+def test_features_vs_torchaudio_librosa_compatible_pipeline():
+  """Second opinion on the librosa semantics the oracle restates from memory (reference preprocessing.py:50-58):
+  torchaudio's MelSpectrogram(norm='slaney', mel_scale='slaney', center=True, pad_mode='reflect', power=2) is
+  torchaudio's documented librosa.feature.melspectrogram equivalent and AmplitudeToDB('power', top_db=80) its
+  power_to_db; ref=np.max only subtracts the maximum.  Agreement pins: reflect padding, periodic Hann, the Slaney
+  mel scale + area normalisation, fmax = sr/2, amin = 1e-10, the 80 dB floor.  (Not the reference itself: librosa
+  is not installable here.)"""
+  torch = pytest.importorskip('torch')
+  ta = pytest.importorskip('torchaudio')
+  rng = np.random.default_rng(11)
+  wav = (0.1 * rng.standard_normal(16000 + 123)).astype(np.float32)
+  wav[4000:6000] *= 1e-4                      # a quiet stretch so that the 80 dB floor actually clips something
+  old = torch.get_default_dtype()
+  torch.set_default_dtype(torch.float64)      # torchaudio builds window and filterbank in the default dtype
+  try:
+    fb = ta.functional.melscale_fbanks(n_freqs=257, f_min=0.0, f_max=8000.0, n_mels=128, sample_rate=16000,
+                                       norm='slaney', mel_scale='slaney').numpy().T
+    mel = ta.transforms.MelSpectrogram(sample_rate=16000, n_fft=512, hop_length=160, n_mels=128, f_min=0.0,
+                                       f_max=8000.0, power=2.0, center=True, pad_mode='reflect', norm='slaney',
+                                       mel_scale='slaney')
+    S = mel(torch.from_numpy(wav).double())                               # [128, T]
+    db = ta.transforms.AmplitudeToDB(stype='power', top_db=80.0)(S)       # ref = 1.0, amin = 1e-10
+  finally:
+    torch.set_default_dtype(old)
+  assert fb.dtype == np.float64
+  np.testing.assert_allclose(O.mel_filterbank(16000, 512, 128), fb, rtol=1e-9, atol=1e-12)
+  db = db - 10.0 * torch.log10(torch.clamp(S.max(), min=1e-10))           # ref = np.max
+  x = db.numpy()
+  ref = ((x - x.mean()) / x.std()).T                                      # normalize(), then .T (preprocessing.py:29-33,58)
+  got = O.calc_power_spectrogram(wav, 16000)
+  assert got.shape == ref.shape == (1 + len(wav) // 160, 128)
+  assert (x <= x.max() - 80.0 + 1e-9).any()                               # the floor was active in this case
+  np.testing.assert_allclose(got, ref, rtol=0, atol=1e-9)

@@ -106,35 +106,39 @@ __device__ __forceinline__ void store_planes8(__nv_bfloat16* dst, int64_t plane_
 //     -- bf16x6 / SPEECHT_B200_TMA_STORE=0 -- direct 16-byte stores from the lane that owns the row;
 //   * fp32 logits (last layer): direct stores;
 //   * bias gradient of the layer below (data gradient): column sums by a 32x32 transpose-reduce.
+// Bit i of the result = mask element i > 0 (bf16: sign clear and magnitude non-zero), for this lane's 32 columns.
+__device__ __forceinline__ uint32_t positive_bits(const uint4 (&mk)[4]) {
+  uint32_t bits = 0;
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    const uint32_t w[4] = {mk[g].x, mk[g].y, mk[g].z, mk[g].w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      // h > 0  <=>  1 <= h <= 0x7fff  <=>  (h - 1) < 0x7fff (unsigned)
+      bits |= (uint32_t)(((w[i] & 0xffffu) - 1u) < 0x7fffu) << (g * 8 + 2 * i);
+      bits |= (uint32_t)(((w[i] >> 16) - 1u) < 0x7fffu) << (g * 8 + 2 * i + 1);
+    }
+  }
+  return bits;
+}
+
 template <int NPL>
 __device__ __forceinline__ void epilogue_chunk(const ConvParams& p, const CUtensorMap* tmOut, uint8_t* stage,
-                                               float (&v)[32], const uint4 (&mk)[4], int nc, int lane, bool row_ok,
-                                               int64_t out_row, int t_warp, int b) {
+                                               float (&v)[32], float bias_lane, uint32_t keep, int nc, int lane,
+                                               bool row_ok, int64_t out_row, int t_warp, int b) {
+  // bias_lane: bias[nc + lane] (0 beyond N), fetched with one coalesced load per chunk before the accumulator was
+  // ready and broadcast by shuffles here -- 32 dependent uniform loads in the epilogue cost ~30 k cycles per tile.
+  // keep: bit i set = column nc+i is a real channel AND (data gradient) the ReLU below it was active.
+  if (p.bias) {
 #pragma unroll
-  for (int i = 0; i < 32; ++i) {
-    const int n = nc + i;
-    float x = v[i];
-    if (n < p.N) {
-      if (p.bias) x += __ldg(p.bias + n);
-      if (p.relu) x = fmaxf(x, 0.f);
-    } else {
-      x = 0.f;
-    }
-    v[i] = x;
+    for (int i = 0; i < 32; ++i) v[i] += __shfl_sync(0xffffffffu, bias_lane, i);
   }
-  if (p.mask_hi) {
+  if (p.relu) {
 #pragma unroll
-    for (int g = 0; g < 4; ++g) {
-      const uint32_t w[4] = {mk[g].x, mk[g].y, mk[g].z, mk[g].w};
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        // bf16 > 0  <=>  sign bit clear and magnitude non-zero
-        const uint32_t lo16 = w[i] & 0xffffu, hi16 = w[i] >> 16;
-        if (!(lo16 != 0 && lo16 < 0x8000u)) v[g * 8 + 2 * i] = 0.f;
-        if (!(hi16 != 0 && hi16 < 0x8000u)) v[g * 8 + 2 * i + 1] = 0.f;
-      }
-    }
+    for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
   }
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = (keep & (1u << i)) ? v[i] : 0.f;
   if (p.out_planes) {
     if (NPL <= 2 && p.tma_store) {
       // the previous TMA store out of this warp's tile must have finished reading it
@@ -406,23 +410,42 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const bool row_ok = t < p.To;
       const int64_t out_row = (int64_t)b * p.To + t;
       prefetch_mask(tile + gridDim.x);
+      // Per chunk of this warp, fetched while the MMAs of the tile are still running: the lane's bias element and
+      // the ReLU-mask row segment (data gradient), reduced to one keep-bit per column once it has arrived.
+      constexpr int kMine = (kChunks + kChunkStep - 1) / kChunkStep;       // chunks per warp (compile time)
+      float bias_l[kMine];
+      uint32_t keep[kMine];
+      {
+        uint4 mk[kMine][4];
+#pragma unroll
+        for (int ci = 0; ci < kMine; ++ci) {
+          const int nc = n0 + (chunk0 + ci * kChunkStep) * 32;
+          bias_l[ci] = (p.bias && nc + lane < p.N) ? __ldg(p.bias + nc + lane) : 0.f;
+          if (p.mask_hi) {
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              mk[ci][g] = make_uint4(0x3f803f80u, 0x3f803f80u, 0x3f803f80u, 0x3f803f80u);    // bf16 1.0 pairs: pass
+              if (row_ok && nc + g * 8 < p.ld_mask)
+                mk[ci][g] = *reinterpret_cast<const uint4*>(p.mask_hi + out_row * p.ld_mask + nc + g * 8);
+            }
+          }
+        }
+        // (the epilogue warps have nothing else to do until the accumulator is complete: the load latency overlaps
+        // the tile's MMAs either way, and the 16 mask vectors are dead before the accumulator registers are needed)
+#pragma unroll
+        for (int ci = 0; ci < kMine; ++ci) {
+          const int nvalid = p.N - (n0 + (chunk0 + ci * kChunkStep) * 32);
+          keep[ci] = nvalid >= 32 ? 0xffffffffu : (nvalid <= 0 ? 0u : ((1u << nvalid) - 1u));
+          if (p.mask_hi) keep[ci] &= positive_bits(mk[ci]);
+        }
+      }
       mbar_wait(tmem_full + acc, acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * Cfg::ACC_COLS;
-      auto load_mask = [&](int c, uint4 (&mk)[4]) {
-        const int nc = n0 + c * 32;
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          mk[g] = make_uint4(0x3f803f80u, 0x3f803f80u, 0x3f803f80u, 0x3f803f80u);      // bf16 1.0 pairs: pass
-          if (p.mask_hi && row_ok && nc + g * 8 < p.ld_mask)
-            mk[g] = *reinterpret_cast<const uint4*>(p.mask_hi + out_row * p.ld_mask + nc + g * 8);
-        }
-      };
       if constexpr (EARLY) {
         // Phase 1: drain this warp's share of the accumulators into registers (main + side summed in round-to-nearest
         // fp32) and hand TMEM back to the MMA warp at once -- with the two 256-column accumulators of the split modes
         // there is no second accumulator stage, so everything after this point overlaps the next tile's MMAs.
-        constexpr int kMine = (kChunks + kChunkStep - 1) / kChunkStep;       // chunks per warp (compile time)
         float sum[kMine][32];
 #pragma unroll
         for (int ci = 0; ci < kMine; ++ci) {
@@ -452,24 +475,18 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int ci = 0; ci < kMine; ++ci) {
           const int c = chunk0 + ci * kChunkStep;
           if (c >= kChunks) continue;
-          uint4 mk[4];
-          load_mask(c, mk);
-          epilogue_chunk<NPL>(p, &tmOut, stage, sum[ci], mk, n0 + c * 32, lane, row_ok, out_row, t_warp, b);
+          epilogue_chunk<NPL>(p, &tmOut, stage, sum[ci], bias_l[ci], keep[ci], n0 + c * 32, lane, row_ok, out_row,
+                              t_warp, b);
         }
       } else {
-        // ReLU-mask vectors (data gradient only) are fetched one 32-column chunk ahead of their use
-        uint4 mk[4];
-        load_mask(chunk0, mk);
-#pragma unroll 1
-        for (int c = chunk0; c < kChunks; c += kChunkStep) {
+#pragma unroll
+        for (int ci = 0; ci < kMine; ++ci) {
+          const int c = chunk0 + ci * kChunkStep;
+          if (c >= kChunks) continue;
           uint32_t r[32];
           tmem_ld32(taddr + c * 32, r);
           uint32_t q[32];
           if (NPL > 1) tmem_ld32(taddr + BLOCK_N + c * 32, q);
-          uint4 mcur[4];
-#pragma unroll
-          for (int g = 0; g < 4; ++g) mcur[g] = mk[g];
-          if (c + kChunkStep < kChunks) load_mask(c + kChunkStep, mk);
           tmem_ld_wait();
           float v[32];
 #pragma unroll
@@ -477,7 +494,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             v[i] = __uint_as_float(r[i]);
             if (NPL > 1) v[i] += __uint_as_float(q[i]);        // main + side accumulator, round-to-nearest
           }
-          epilogue_chunk<NPL>(p, &tmOut, stage, v, mcur, n0 + c * 32, lane, row_ok, out_row, t_warp, b);
+          epilogue_chunk<NPL>(p, &tmOut, stage, v, bias_l[ci], keep[ci], n0 + c * 32, lane, row_ok, out_row, t_warp, b);
         }
         tc_fence_before();
         __syncwarp();

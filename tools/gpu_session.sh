@@ -30,7 +30,7 @@ import json
 try:
   d=json.loads(open('$O/bench_$name.json').read().strip().splitlines()[-1])
   r=d['roofline']
-  print('ms/step %.3f  value %.0f  e2e %.0f  conv %.3f wgrad %.3f  launches %d' % (d['ms_per_step'], d['value'], d['e2e']['value'], r['kernels']['tc_conv_kernel']['ms_per_step'], r['kernels']['tc_wgrad_kernel']['ms_per_step'], d['gpu_launches']))
+  print('ms/step %.3f  value %.0f  e2e %.0f  conv %.3f wgrad %.3f  launches %d  ctc %.4f' % (d['ms_per_step'], d['value'], d['e2e']['value'], r['kernels']['tc_conv_kernel']['ms_per_step'], r['kernels']['tc_wgrad_kernel']['ms_per_step'], d['gpu_launches'], d['aux_hbm_kernels']['ctc_loss+grad (a8-a9)']['ms']))
 except Exception as e:
   print('unreadable', e)
 P
@@ -39,9 +39,10 @@ P
 bench default A=1
 bench base SPEECHT_B200_LIB=$PWD/speecht_b200/libspeecht_b200_base.so
 bench nostore SPEECHT_B200_TMA_STORE=0
-bench nomerge SPEECHT_B200_PACK_MERGED=0
-bench overlap SPEECHT_B200_PACK_OVERLAP=1
+bench ctcns2 SPEECHT_B200_CTC_NS=2
+bench ctcns4 SPEECHT_B200_CTC_NS=4
 bench default2 A=1
+bench base2 SPEECHT_B200_LIB=$PWD/speecht_b200/libspeecht_b200_base.so
 bench bf16 SPEECHT_B200_PRECISION=bf16
 
 timeout 1200 python -m pytest tests -x -q -m gpu > $O/t_all_default.log 2>&1

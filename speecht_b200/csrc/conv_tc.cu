@@ -123,7 +123,7 @@ __device__ __forceinline__ uint32_t positive_bits(const uint4 (&mk)[4]) {
 }
 
 template <int NPL>
-__device__ __forceinline__ void epilogue_chunk(const ConvParams& p, const CUtensorMap* tmOut, uint8_t* stage,
+__device__ __forceinline__ float epilogue_chunk(const ConvParams& p, const CUtensorMap* tmOut, uint8_t* stage,
                                                float (&v)[32], float bias_lane, uint32_t keep, int nc, int lane,
                                                bool row_ok, int64_t out_row, int t_warp, int b) {
   // bias_lane: bias[nc + lane] (0 beyond N), fetched with one coalesced load per chunk before the accumulator was
@@ -163,13 +163,20 @@ __device__ __forceinline__ void epilogue_chunk(const ConvParams& p, const CUtens
   }
   if (p.out_f32 && row_ok) {
     float* frow = p.out_f32 + out_row * p.ld_f32 + nc;
+    if (nc + 32 <= p.ld_f32 && (p.ld_f32 & 3) == 0) {
 #pragma unroll
-    for (int i = 0; i < 32; ++i)
-      if (nc + i < p.ld_f32) frow[i] = v[i];
+      for (int i = 0; i < 32; i += 4)
+        *reinterpret_cast<float4*>(frow + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 32; ++i)
+        if (nc + i < p.ld_f32) frow[i] = v[i];
+    }
   }
   if (p.col_sum) {
     // bias gradient of the layer below = column sums of what was just stored: 32x32 transpose-reduce with
-    // 31 shuffles (each step halves the values a lane holds), then one atomic per column per warp
+    // 31 shuffles (each step halves the values a lane holds); the one atomic per column per warp is issued by the
+    // caller after the last chunk (an atomic in flight makes the next chunk's proxy fence wait for its round trip)
     if (!row_ok) {
 #pragma unroll
       for (int i = 0; i < 32; ++i) v[i] = 0.f;
@@ -184,8 +191,9 @@ __device__ __forceinline__ void epilogue_chunk(const ConvParams& p, const CUtens
         v[j] = keep + __shfl_xor_sync(0xffffffffu, send, off);
       }
     }
-    if (nc + lane < p.N) atomicAdd(p.col_sum + nc + lane, v[0]);
+    return v[0];            // column nc + lane; the caller adds it to col_sum once the tile's stores are issued
   }
+  return 0.f;
 }
 
 // Products of the split operands, in issue order, as (A plane, B plane, load group to wait for before it,
@@ -442,6 +450,9 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       mbar_wait(tmem_full + acc, acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * Cfg::ACC_COLS;
+      float csum[kMine];
+#pragma unroll
+      for (int ci = 0; ci < kMine; ++ci) csum[ci] = 0.f;
       if constexpr (EARLY) {
         // Phase 1: drain this warp's share of the accumulators into registers (main + side summed in round-to-nearest
         // fp32) and hand TMEM back to the MMA warp at once -- with the two 256-column accumulators of the split modes
@@ -475,8 +486,8 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int ci = 0; ci < kMine; ++ci) {
           const int c = chunk0 + ci * kChunkStep;
           if (c >= kChunks) continue;
-          epilogue_chunk<NPL>(p, &tmOut, stage, sum[ci], bias_l[ci], keep[ci], n0 + c * 32, lane, row_ok, out_row,
-                              t_warp, b);
+          csum[ci] = epilogue_chunk<NPL>(p, &tmOut, stage, sum[ci], bias_l[ci], keep[ci], n0 + c * 32, lane, row_ok,
+                                         out_row, t_warp, b);
         }
       } else {
 #pragma unroll
@@ -494,11 +505,19 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             v[i] = __uint_as_float(r[i]);
             if (NPL > 1) v[i] += __uint_as_float(q[i]);        // main + side accumulator, round-to-nearest
           }
-          epilogue_chunk<NPL>(p, &tmOut, stage, v, bias_l[ci], keep[ci], n0 + c * 32, lane, row_ok, out_row, t_warp, b);
+          csum[ci] = epilogue_chunk<NPL>(p, &tmOut, stage, v, bias_l[ci], keep[ci], n0 + c * 32, lane, row_ok, out_row,
+                                         t_warp, b);
         }
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(tmem_empty + acc);
+      }
+      if (p.col_sum) {
+#pragma unroll
+        for (int ci = 0; ci < kMine; ++ci) {
+          const int n = n0 + (chunk0 + ci * kChunkStep) * 32 + lane;
+          if (chunk0 + ci * kChunkStep < kChunks && n < p.N) atomicAdd(p.col_sum + n, csum[ci]);
+        }
       }
     }
     // outstanding TMA stores of this warp must have been performed before the CTA (and its shared memory) goes away

@@ -425,16 +425,8 @@ ST_API int st_ctc_loss(const float* logits, int64_t stride_t, int64_t stride_b, 
   const bool lsm_in_smem = smem_base + smem_lsm + 64 <= 200 * 1024;
   const size_t smem = smem_base + (lsm_in_smem ? smem_lsm : 0) + 64;
   const int S_max = 2 * max_label_len + 1;
-  int threads = S_max >= 1024 ? 1024 : (S_max + 31) / 32 * 32;
-  int ns = S_max <= threads ? 1 : (S_max <= 2 * threads ? 2 : (S_max <= 4 * threads ? 4 : 8));
-  {
-    // experiment switch: more lattice positions per thread (fewer warps at the per-step barrier)
-    static const int force_ns = []() { const char* e = getenv("SPEECHT_B200_CTC_NS"); return e ? atoi(e) : 0; }();
-    if ((force_ns == 2 || force_ns == 4) && force_ns > ns) {
-      ns = force_ns;
-      threads = ((S_max + ns - 1) / ns + 31) / 32 * 32;
-    }
-  }
+  const int threads = S_max >= 1024 ? 1024 : (S_max + 31) / 32 * 32;
+  const int ns = S_max <= threads ? 1 : (S_max <= 2 * threads ? 2 : (S_max <= 4 * threads ? 4 : 8));
 #define ST_CTC_LAUNCH(NS_, SM_)                                                                                      \
   do {                                                                                                               \
     if (smem > 48 * 1024)                                                                                            \

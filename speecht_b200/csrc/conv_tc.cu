@@ -817,80 +817,7 @@ split_input_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ plan
   }
 }
 
-// ---- filter packing for ALL layers in two launches (PackTable lists the layers) ----
-// forward layout: W [K][Cin][Cout] -> fwd[pl][co][k*cin_p + ci] through a 64(ci) x 32(co) shared-memory transpose;
-// block (32, 8): 128-byte coalesced reads along co, 128-byte bf16x2 writes along ci
-template <int NPL>
-__global__ void __launch_bounds__(256)
-pack_filter_fwd_all_kernel(const PackTable tab) {
-  __shared__ float tile[64][33];
-  int l = 0;
-  while (l + 1 < tab.n && (int)blockIdx.x >= tab.e[l + 1].fwd_blk0) ++l;
-  const PackEntry& e = tab.e[l];
-  int lb = blockIdx.x - e.fwd_blk0;
-  const int co_tiles = (e.Cout + 31) / 32, ci_tiles = e.cin_p / 64;
-  const int co0 = (lb % co_tiles) * 32;
-  lb /= co_tiles;
-  const int ci0 = (lb % ci_tiles) * 64;
-  const int k = lb / ci_tiles;
-  const int tx = threadIdx.x, ty = threadIdx.y;
-#pragma unroll
-  for (int r = 0; r < 64; r += 8) {
-    const int ci = ci0 + r + ty, co = co0 + tx;
-    tile[r + ty][tx] = (ci < e.Cin && co < e.Cout) ? __ldg(e.w + ((int64_t)k * e.Cin + ci) * e.Cout + co) : 0.f;
-  }
-  __syncthreads();
-  const int64_t ld = (int64_t)e.K * e.cin_p;
-  const int64_t plane_stride = (int64_t)e.Cout * ld;
-#pragma unroll
-  for (int r = 0; r < 32; r += 8) {
-    const int co = co0 + r + ty;
-    if (co < e.Cout) {
-      float v0 = tile[2 * tx][r + ty], v1 = tile[2 * tx + 1][r + ty];
-      __nv_bfloat16* dst = e.fwd + (int64_t)co * ld + (int64_t)k * e.cin_p + ci0 + 2 * tx;
-#pragma unroll
-      for (int pl = 0; pl < NPL; ++pl) {
-        const __nv_bfloat16 h0 = __float2bfloat16_rn(v0), h1 = __float2bfloat16_rn(v1);
-        *reinterpret_cast<uint32_t*>(dst + pl * plane_stride) = pack_bf16x2(h0, h1);
-        v0 -= __bfloat162float(h0);
-        v1 -= __bfloat162float(h1);
-      }
-    }
-  }
-}
-
-// backward layout: W [K*Cin][Cout] -> bwd[pl][row][ld_co] (columns >= Cout zero); 4 columns per thread
-template <int NPL>
-__global__ void __launch_bounds__(256)
-pack_filter_bwd_all_kernel(const PackTable tab) {
-  int l = 0;
-  while (l + 1 < tab.n && (int)blockIdx.x >= tab.e[l + 1].bwd_blk0) ++l;
-  const PackEntry& e = tab.e[l];
-  if (!e.bwd) return;
-  const int64_t rows = (int64_t)e.K * e.Cin;
-  const int64_t total = rows * e.ld_co;
-  const int64_t i = ((int64_t)(blockIdx.x - e.bwd_blk0) * 256 + threadIdx.x) * 4;
-  if (i >= total) return;
-  const int co = (int)(i % e.ld_co);
-  const int64_t r = i / e.ld_co;
-  float v[4];
-#pragma unroll
-  for (int q = 0; q < 4; ++q) v[q] = (co + q < e.Cout) ? __ldg(e.w + r * e.Cout + co + q) : 0.f;
-#pragma unroll
-  for (int pl = 0; pl < NPL; ++pl) {
-    __nv_bfloat16 h[4];
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      h[q] = __float2bfloat16_rn(v[q]);
-      v[q] -= __bfloat162float(h[q]);
-    }
-    uint2 pk;
-    pk.x = pack_bf16x2(h[0], h[1]);
-    pk.y = pack_bf16x2(h[2], h[3]);
-    *reinterpret_cast<uint2*>(e.bwd + pl * total + i) = pk;
-  }
-}
-
+// ---- filter packing for ALL layers in one launch (PackTable lists the layers) ----
 // Both layouts in ONE pass over W: a block owns a 64(ci) x 64(co) tile of one tap, stages it in shared memory and
 // writes it out twice -- transposed for the forward layout (warp = one co row, lanes along ci, 128-byte bf16x2
 // rows) and as is for the backward layout (warp = one (k,ci) row, lanes along co).  Padding (ci >= Cin in the
@@ -900,9 +827,9 @@ __global__ void __launch_bounds__(256)
 pack_filter_both_kernel(const PackTable tab) {
   __shared__ float tile[64][65];
   int l = 0;
-  while (l + 1 < tab.n && (int)blockIdx.x >= tab.e[l + 1].fwd_blk0) ++l;
+  while (l + 1 < tab.n && (int)blockIdx.x >= tab.e[l + 1].blk0) ++l;
   const PackEntry& e = tab.e[l];
-  int lb = blockIdx.x - e.fwd_blk0;
+  int lb = blockIdx.x - e.blk0;
   const int co_tiles = (e.ld_co + 63) / 64, ci_tiles = e.cin_p / 64;
   const int co0 = (lb % co_tiles) * 64;
   lb /= co_tiles;
@@ -1209,44 +1136,18 @@ int launch_split_input(const float* x, __nv_bfloat16* planes, int B, int T, int 
 
 int launch_pack_filters(PackTable& tab, int n_planes, cudaStream_t stream, int* launches) {
   *launches = 0;
-  static const bool merged = []() { const char* e = getenv("SPEECHT_B200_PACK_MERGED"); return !(e && e[0] == '0'); }();
-  if (merged) {
-    int blocks = 0;
-    for (int l = 0; l < tab.n; ++l) {
-      PackEntry& e = tab.e[l];
-      ST_CHECK_ARG(e.cin_p % 64 == 0 && e.ld_co % 4 == 0 && e.ld_co >= e.Cout, "launch_pack_filters: bad padded sizes");
-      e.fwd_blk0 = blocks;
-      e.bwd_blk0 = 0;
-      blocks += e.K * (e.cin_p / 64) * ((e.ld_co + 63) / 64);
-    }
-    if (n_planes == 3) pack_filter_both_kernel<3><<<blocks, dim3(32, 8), 0, stream>>>(tab);
-    else if (n_planes == 2) pack_filter_both_kernel<2><<<blocks, dim3(32, 8), 0, stream>>>(tab);
-    else pack_filter_both_kernel<1><<<blocks, dim3(32, 8), 0, stream>>>(tab);
-    ST_CUDA_LAUNCH_CHECK("pack_filter_both_kernel");
-    *launches = 1;
-    return ST_OK;
-  }
-  int fb = 0, bb = 0;
+  int blocks = 0;
   for (int l = 0; l < tab.n; ++l) {
     PackEntry& e = tab.e[l];
-    ST_CHECK_ARG(e.cin_p % 64 == 0 && e.ld_co % 4 == 0, "launch_pack_filters: bad padded sizes");
-    e.fwd_blk0 = fb;
-    e.bwd_blk0 = bb;
-    fb += e.K * (e.cin_p / 64) * ((e.Cout + 31) / 32);
-    if (e.bwd) bb += (int)(((int64_t)e.K * e.Cin * e.ld_co / 4 + 255) / 256);
+    ST_CHECK_ARG(e.cin_p % 64 == 0 && e.ld_co % 4 == 0 && e.ld_co >= e.Cout, "launch_pack_filters: bad padded sizes");
+    e.blk0 = blocks;
+    blocks += e.K * (e.cin_p / 64) * ((e.ld_co + 63) / 64);
   }
-  if (n_planes == 3) pack_filter_fwd_all_kernel<3><<<fb, dim3(32, 8), 0, stream>>>(tab);
-  else if (n_planes == 2) pack_filter_fwd_all_kernel<2><<<fb, dim3(32, 8), 0, stream>>>(tab);
-  else pack_filter_fwd_all_kernel<1><<<fb, dim3(32, 8), 0, stream>>>(tab);
-  ST_CUDA_LAUNCH_CHECK("pack_filter_fwd_all_kernel");
+  if (n_planes == 3) pack_filter_both_kernel<3><<<blocks, dim3(32, 8), 0, stream>>>(tab);
+  else if (n_planes == 2) pack_filter_both_kernel<2><<<blocks, dim3(32, 8), 0, stream>>>(tab);
+  else pack_filter_both_kernel<1><<<blocks, dim3(32, 8), 0, stream>>>(tab);
+  ST_CUDA_LAUNCH_CHECK("pack_filter_both_kernel");
   *launches = 1;
-  if (bb > 0) {
-    if (n_planes == 3) pack_filter_bwd_all_kernel<3><<<bb, 256, 0, stream>>>(tab);
-    else if (n_planes == 2) pack_filter_bwd_all_kernel<2><<<bb, 256, 0, stream>>>(tab);
-    else pack_filter_bwd_all_kernel<1><<<bb, 256, 0, stream>>>(tab);
-    ST_CUDA_LAUNCH_CHECK("pack_filter_bwd_all_kernel");
-    *launches = 2;
-  }
   return ST_OK;
 }
 

@@ -58,13 +58,13 @@ int launch_wgrad(const CUtensorMap& tmX, const CUtensorMap& tmDZ, const WgradPar
 int launch_split_input(const float* x, __nv_bfloat16* planes, int B, int T, int Tpad, int F, int n_planes,
                        cudaStream_t stream);
 // W [K][Cin][Cout] fp32 -> forward layout planes [n][Cout][K*cin_p] (K-major), backward layout planes
-// [n][K*Cin][ld_co] (bwd may be null); all layers of the table in one launch (two with SPEECHT_B200_PACK_MERGED=0)
+// [n][K*Cin][ld_co] (bwd may be null); all layers of the table in one launch
 struct PackEntry {
   const float* w;
   __nv_bfloat16* fwd;
   __nv_bfloat16* bwd;
   int K, Cin, Cout, cin_p, ld_co;
-  int fwd_blk0, bwd_blk0;        // filled by launch_pack_filters
+  int blk0;                      // first block of this layer, filled by launch_pack_filters
 };
 struct PackTable {
   int n;

@@ -52,12 +52,6 @@ struct st_plan {
   int ev_used;
   int cur_dz;                  // ping/pong buffer holding the gradient wrt the next layer to process
   bool tma_store;              // epilogues write bf16 planes with TMA stores (SPEECHT_B200_TMA_STORE=0 disables)
-  // Experiment switch SPEECHT_B200_PACK_OVERLAP=1: filter packing of the three big layers (8..10: 87 % of the
-  // parameters) runs on a side stream under the forward of layers 0..7, which only need their own (small) filters.
-  bool pack_overlap;
-  cudaStream_t side;
-  cudaEvent_t ev_fork, ev_join;
-  bool join_pending;
 };
 
 namespace {
@@ -103,10 +97,7 @@ ST_API int st_plan_create(st_plan** out, int B, int T, int input_size, int num_c
   {
     const char* e = getenv("SPEECHT_B200_TMA_STORE");
     p->tma_store = !(e && e[0] == '0') && n_planes <= 2;
-    e = getenv("SPEECHT_B200_PACK_OVERLAP");
-    p->pack_overlap = e && e[0] == '1';
   }
-  p->side = nullptr; p->ev_fork = nullptr; p->ev_join = nullptr; p->join_pending = false;
   // reference speech_model.py:275-292
   const int table[11][5] = {{48, 2, input_size, 250, 1}, {7, 1, 250, 250, 1}, {7, 1, 250, 250, 1}, {7, 1, 250, 250, 1},
                             {7, 1, 250, 250, 1},         {7, 1, 250, 250, 1}, {7, 1, 250, 250, 1}, {7, 1, 250, 250, 1},
@@ -156,12 +147,6 @@ ST_API int st_plan_create(st_plan** out, int B, int T, int input_size, int num_c
 ST_API int st_plan_destroy(st_plan* p) {
   if (p) {
     for (cudaEvent_t e : p->ev_pool) cudaEventDestroy(e);
-    if (p->side) {
-      cudaStreamSynchronize(p->side);
-      cudaStreamDestroy(p->side);
-    }
-    if (p->ev_fork) cudaEventDestroy(p->ev_fork);
-    if (p->ev_join) cudaEventDestroy(p->ev_join);
   }
   delete p;
   return ST_OK;
@@ -250,11 +235,6 @@ ST_API int st_plan_bind(st_plan* p, void* arena, size_t arena_bytes, float* para
       }
     }
   }
-  if (p->pack_overlap && !p->side) {
-    ST_CUDA_CALL(cudaStreamCreateWithFlags(&p->side, cudaStreamNonBlocking));
-    ST_CUDA_CALL(cudaEventCreateWithFlags(&p->ev_fork, cudaEventDisableTiming));
-    ST_CUDA_CALL(cudaEventCreateWithFlags(&p->ev_join, cudaEventDisableTiming));
-  }
   p->bound = true;
   return ST_OK;
 }
@@ -268,7 +248,7 @@ int pack_layers(st_plan* p, int l0, int l1, cudaStream_t s) {
   for (int l = l0; l < l1; ++l) {
     Layer& L = p->layers[l];
     tab.e[l - l0] = tc::PackEntry{p->params + L.w_off, bf(p, L.off_wfwd), l > 0 ? bf(p, L.off_wbwd) : nullptr,
-                                  L.K, L.Cin, L.Cout, L.cin_p, L.ld_co, 0, 0};
+                                  L.K, L.Cin, L.Cout, L.cin_p, L.ld_co, 0};
   }
   int n = 0;
   const int rc = tc::launch_pack_filters(tab, p->npl, s, &n);
@@ -277,34 +257,11 @@ int pack_layers(st_plan* p, int l0, int l1, cudaStream_t s) {
   return ST_OK;
 }
 
-// The side-stream packing of layers 8..10 must be complete before anything on `s` touches their filter planes.
-int join_pack(st_plan* p, cudaStream_t s) {
-  if (p->join_pending) {
-    ST_CUDA_CALL(cudaStreamWaitEvent(s, p->ev_join, 0));
-    p->join_pending = false;
-  }
-  return ST_OK;
-}
-
-constexpr int kFirstBigLayer = 8;
-
 }  // namespace
 
 ST_API int st_plan_pack_weights(st_plan* p, st_stream_t stream) {
   ST_CHECK_ARG(p && p->bound, "st_plan_pack_weights: plan is not bound");
-  cudaStream_t s = st_cu(stream);
-  if (!p->pack_overlap) return pack_layers(p, 0, 11, s);
-  // everything queued on `s` so far (the optimizer step that produced the parameters, earlier users of the filter
-  // planes) precedes the side-stream work
-  int rc = join_pack(p, s);
-  if (rc) return rc;
-  ST_CUDA_CALL(cudaEventRecord(p->ev_fork, s));
-  ST_CUDA_CALL(cudaStreamWaitEvent(p->side, p->ev_fork, 0));
-  rc = pack_layers(p, kFirstBigLayer, 11, p->side);
-  if (rc) return rc;
-  ST_CUDA_CALL(cudaEventRecord(p->ev_join, p->side));
-  p->join_pending = true;
-  return pack_layers(p, 0, kFirstBigLayer, s);
+  return pack_layers(p, 0, 11, st_cu(stream));
 }
 
 ST_API int st_plan_forward(st_plan* p, const float* inputs, st_stream_t stream) {
@@ -341,10 +298,6 @@ ST_API int st_plan_forward(st_plan* p, const float* inputs, st_stream_t stream) 
       c.ld_f32 = 32;
     }
     c.tma_store = p->tma_store && l < 10;
-    if (l == kFirstBigLayer) {
-      rc = join_pack(p, s);
-      if (rc) return rc;
-    }
     const int ti = timed_begin(p, s);
     rc = tc::launch_conv(L.tm_fwd_a, L.tm_fwd_b, l < 10 ? &L.tm_fwd_out : nullptr, c, block_n, p->npl, s);
     if (rc) return rc;
@@ -361,10 +314,6 @@ ST_API int st_plan_backward_range(st_plan* p, int hi, int lo, st_stream_t stream
   ST_CHECK_ARG(p && p->bound, "st_plan_backward: plan is not bound");
   ST_CHECK_ARG(hi <= 10 && lo >= 0 && hi >= lo, "st_plan_backward_range: need 10 >= hi >= lo >= 0");
   cudaStream_t s = st_cu(stream);
-  {
-    const int rc = join_pack(p, s);
-    if (rc) return rc;
-  }
   if (hi == 10) {
     p->cur_dz = 0;
     // filter gradients of K-sliced tiles accumulate with atomics: zero the whole flat buffer once per backward

@@ -135,6 +135,12 @@ int st_plan_launches(const st_plan* plan);
 int st_plan_set_timing(st_plan* plan, int enable);
 int st_plan_read_timings(st_plan* plan, int* kind, int* layer, double* flops, float* ms, int max_records);
 
+/* Debug: per-CTA %globaltimer timeline of ONE tensor-core conv launch (the launch_index-th forward / data-gradient
+ * launch after this call): buf[grid][8] int64 device memory -- 0 entry, 1 previous grid complete, 2 first operands
+ * landed, 3 last MMA issued, 4 accumulator complete, 5 epilogue issued, 6 staging tiles drained, 7 exit.
+ * buf = NULL switches it off.  Used by tools/conv_timeline.py; no reference counterpart. */
+int st_debug_conv_timeline(int64_t* buf, int launch_index);
+
 #ifdef __cplusplus
 }
 #endif

@@ -29,10 +29,17 @@
 #include "conv_tc.h"
 #include "tc_ptx.cuh"
 #include <stdlib.h>
+#include <type_traits>
 
 namespace tc {
 
 namespace {
+
+__device__ __forceinline__ long long global_ns() {
+  long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
 
 constexpr int kEpilogueWarps = 8;              // two per TMEM lane quarter: they split the 32-column chunks
 constexpr int kThreads = 64 + 32 * kEpilogueWarps;
@@ -140,7 +147,7 @@ __device__ __forceinline__ float epilogue_chunk(const ConvParams& p, const CUten
 #pragma unroll
   for (int i = 0; i < 32; ++i) v[i] = (keep & (1u << i)) ? v[i] : 0.f;
   if (p.out_planes) {
-    if (NPL <= 2 && p.tma_store) {
+    if constexpr (NPL <= 2) {
       // the previous TMA store out of this warp's tile must have finished reading it
       if (lane == 0) bulk_wait_read0();
       __syncwarp();
@@ -154,7 +161,7 @@ __device__ __forceinline__ float epilogue_chunk(const ConvParams& p, const CUten
         for (int pl = 0; pl < NPL; ++pl) tma_store_3d(tmOut, stage + pl * (32 * 32 * 2), nc, t_warp, pl * p.B + b);
         bulk_commit();
       }
-    } else if (row_ok) {
+    } else if (row_ok) {       // three planes: no shared memory left for staging tiles
       __nv_bfloat16* orow = p.out_planes + out_row * p.ld_out + nc;
 #pragma unroll
       for (int g = 0; g < 4; ++g)
@@ -254,6 +261,9 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int num_tiles = p.B * p.m_tiles_per_utt * p.n_tiles;
   const int m_tiles = p.B * p.m_tiles_per_utt;
   const int nk = p.taps * p.chunks_per_tap;
+  // debug stamps of the first tile (streaming-epilogue instantiations only: the two-phase one has no register to spare)
+  long long* tl = (!EARLY && p.timeline) ? p.timeline + (int64_t)blockIdx.x * 8 : nullptr;
+  if (tl && threadIdx.x == 0) tl[0] = global_ns();                                   // 0: kernel entry
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmA);
@@ -279,6 +289,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   // launching, then wait until the previous grid has completed and its writes are visible.
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   asm volatile("griddepcontrol.wait;" ::: "memory");
+  if (tl && threadIdx.x == 0) tl[1] = global_ns();                                   // 1: previous grid complete
 
   if (warp == 0) {
     // ===================================================== TMA producer
@@ -332,18 +343,28 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   } else if (warp == 1) {
     // ===================================================== MMA issuer (one thread)
     if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(kTileM, BLOCK_N, 0, 0);
       int stage = 0;
       uint32_t phase = 0;
       int local = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
         const int acc = local % Cfg::ACC_STAGES;
         const uint32_t acc_phase = (local / Cfg::ACC_STAGES) & 1;
+        // Only real channels are multiplied: the N of the instruction is the tile's channel count rounded up to 16
+        // (2000 output channels = 7 tiles of 256 and one of 208), and K steps that would read only TMA zero fill
+        // (the last 64-wide chunk of a 2000-channel contraction holds 16 channels) are not issued.  The big layers
+        // are power-bound, so every MMA that is not executed is time.
+        const int nt = p.n_fastest ? tile % p.n_tiles : tile / m_tiles;
+        const int n_valid = min(BLOCK_N, p.N - nt * BLOCK_N);
+        const uint32_t idesc = make_idesc_bf16(kTileM, p.trim ? max(16, (n_valid + 15) & ~15) : BLOCK_N, 0, 0);
         mbar_wait(tmem_empty + acc, acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_main = tmem_base + acc * Cfg::ACC_COLS;
         const uint32_t d_side = d_main + BLOCK_N;
-        for (int it = 0; it < nk; ++it) {
+        // one pipeline iteration = the products of one 64-deep K chunk; FULL: all four K steps (unrolled, the hot
+        // path), otherwise only the first nkk (runtime loop) -- the issuing thread is close to critical (a division
+        // and four extra branches per iteration cost 3 % of the step), so the trimmed path must not tax the full one
+        auto iteration = [&](auto full_tag, int it, int nkk) {
+          constexpr bool FULL = decltype(full_tag)::value;
           const uint32_t a_addr = smem_u32(smem + stage * Cfg::STAGE_BYTES);
           const uint32_t b_addr = a_addr + NPL * Cfg::A_BYTES;
           uint32_t acc_main = it > 0 ? 1u : 0u, acc_side = acc_main;
@@ -352,10 +373,10 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           for (int pr = 0; pr < PR::N; ++pr) {
             const int pa = PR::a(pr), pb = PR::b(pr);
             if (PR::wait(pr) >= 0) { mbar_wait(full_bar + stage * NG + PR::wait(pr), phase); tc_fence_after(); }
+            if (tl && local == 0 && it == 0 && pr == 0) tl[2] = global_ns();         // 2: first operands landed
             const uint64_t da = make_smem_desc_sw128(a_addr + pa * Cfg::A_BYTES, 16, 1024);
             const uint64_t db = make_smem_desc_sw128(b_addr + pb * Cfg::B_BYTES, 16, 1024);
-#pragma unroll
-            for (int kk = 0; kk < kChunkK / 16; ++kk) {
+            auto step = [&](int kk) {
               // advancing 16 bf16 along K = 32 bytes inside the 128-byte swizzled row = +2 in the address field
               if (pa == 0 && pb == 0) {
                 umma_bf16(d_main, da + (uint64_t)(kk * 2), db + (uint64_t)(kk * 2), idesc, acc_main);
@@ -364,13 +385,31 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 umma_bf16(d_side, da + (uint64_t)(kk * 2), db + (uint64_t)(kk * 2), idesc, acc_side);
                 acc_side = 1u;
               }
+            };
+            if constexpr (FULL) {
+#pragma unroll
+              for (int kk = 0; kk < kChunkK / 16; ++kk) step(kk);
+            } else {
+#pragma unroll 1
+              for (int kk = 0; kk < nkk; ++kk) step(kk);
             }
             // a group's smem is reusable once the MMAs issued so far have read it
             if (PR::release(pr) >= 0) umma_commit(empty_bar + stage * NG + PR::release(pr));
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        };
+        // channel chunk outer, tap inner (the producer's order): the number of K steps only depends on the chunk
+        int it = 0;
+        for (int cc = 0; cc < p.chunks_per_tap; ++cc) {
+          const int nkk = p.trim ? min(kChunkK / 16, (p.k_cols - cc * kChunkK + 15) >> 4) : kChunkK / 16;
+          if (nkk == kChunkK / 16) {
+            for (int j = 0; j < p.taps; ++j, ++it) iteration(std::true_type{}, it, nkk);
+          } else {
+            for (int j = 0; j < p.taps; ++j, ++it) iteration(std::false_type{}, it, nkk);
+          }
         }
         umma_commit(tmem_full + acc);                     // accumulator complete -> epilogue
+        if (tl && local == 0) tl[3] = global_ns();                                   // 3: last MMA of the tile issued
       }
     }
     __syncwarp();
@@ -449,6 +488,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
       mbar_wait(tmem_full + acc, acc_phase);
       tc_fence_after();
+      if (tl && local == 0 && warp == 2 && lane == 0) tl[4] = global_ns();           // 4: accumulator complete
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * Cfg::ACC_COLS;
       float csum[kMine];
 #pragma unroll
@@ -490,10 +530,16 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                                          out_row, t_warp, b);
         }
       } else {
-#pragma unroll
+        // A real loop, not four unrolled copies: one chunk is ~500 instructions, and four copies per tile did not
+        // fit the instruction cache (stall_no_inst all over the epilogue in ncu's source view).  The per-chunk
+        // scalars are picked out of / put back into their registers with selects.
+        static_assert(kMine <= 4, "chunk scalars are selected by hand");
+#pragma unroll 1
         for (int ci = 0; ci < kMine; ++ci) {
           const int c = chunk0 + ci * kChunkStep;
-          if (c >= kChunks) continue;
+          if (c >= kChunks) break;
+          const float bias_c = ci == 0 ? bias_l[0] : (ci == 1 ? bias_l[1 % kMine] : (ci == 2 ? bias_l[2 % kMine] : bias_l[3 % kMine]));
+          const uint32_t keep_c = ci == 0 ? keep[0] : (ci == 1 ? keep[1 % kMine] : (ci == 2 ? keep[2 % kMine] : keep[3 % kMine]));
           uint32_t r[32];
           tmem_ld32(taddr + c * 32, r);
           uint32_t q[32];
@@ -505,8 +551,11 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             v[i] = __uint_as_float(r[i]);
             if (NPL > 1) v[i] += __uint_as_float(q[i]);        // main + side accumulator, round-to-nearest
           }
-          csum[ci] = epilogue_chunk<NPL>(p, &tmOut, stage, v, bias_l[ci], keep[ci], n0 + c * 32, lane, row_ok, out_row,
-                                         t_warp, b);
+          const float cs = epilogue_chunk<NPL>(p, &tmOut, stage, v, bias_c, keep_c, n0 + c * 32, lane, row_ok, out_row,
+                                               t_warp, b);
+#pragma unroll
+          for (int k = 0; k < kMine; ++k)
+            if (ci == k) csum[k] = cs;
         }
         tc_fence_before();
         __syncwarp();
@@ -519,10 +568,13 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (chunk0 + ci * kChunkStep < kChunks && n < p.N) atomicAdd(p.col_sum + n, csum[ci]);
         }
       }
+      if (tl && local == 0 && warp == 2 && lane == 0) tl[5] = global_ns();           // 5: warp 2's epilogue issued
     }
-    // outstanding TMA stores of this warp must have been performed before the CTA (and its shared memory) goes away
-    if (lane == 0) bulk_wait0();
+    // outstanding TMA stores of this warp must have finished reading the staging tile before the CTA (and its shared
+    // memory) goes away; their global writes are complete when the grid is
+    if (lane == 0) bulk_wait_read0();
     __syncwarp();
+    if (tl && warp == 2 && lane == 0) tl[6] = global_ns();                           // 6: staging tiles drained
   }
 
   tc_fence_before();
@@ -531,6 +583,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     tc_fence_after();
     tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
   }
+  if (tl && threadIdx.x == 0) tl[7] = global_ns();                                   // 7: exit
 }
 
 // ------------------------------------------------------------------------------------------------ filter gradient
@@ -676,13 +729,16 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
     __syncwarp();
   } else if (warp == 1) {
     if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(kTileM, BLOCK_N, 1, 1);      // both operands MN-major
       int stage = 0;
       uint32_t phase = 0;
       int local = 0;
       for (; local < my_items; ++local) {
-        int tile, q0, q1;
+        int tile, q0, q1, tj, tmt, tnt;
         item(local, tile, q0, q1);
+        decode(tile, tj, tmt, tnt);
+        // both operands MN-major; N trimmed to the real output channels of this n tile (rounded up to 16)
+        const int n_valid = min(BLOCK_N, p.Cout - tnt * BLOCK_N);
+        const uint32_t idesc = make_idesc_bf16(kTileM, p.trim ? max(16, (n_valid + 15) & ~15) : BLOCK_N, 1, 1);
         const int acc = local % Cfg::ACC_STAGES;
         const uint32_t acc_phase = (local / Cfg::ACC_STAGES) & 1;
         mbar_wait(tmem_empty + acc, acc_phase ^ 1);
@@ -690,7 +746,8 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
         const uint32_t d_main = tmem_base + acc * Cfg::ACC_COLS;
         const uint32_t d_side = d_main + BLOCK_N;
         uint32_t acc_main = 0u, acc_side = 0u;
-        for (int q = q0; q < q1; ++q) {
+        auto iteration = [&](auto full_tag, int nkk) {
+          constexpr bool FULL = decltype(full_tag)::value;
           const uint32_t a_addr = smem_u32(smem + stage * Cfg::STAGE_BYTES);
           const uint32_t b_addr = a_addr + NPL * Cfg::A_BYTES;
           using PR = Products<NPL>;
@@ -698,8 +755,7 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
           for (int pr = 0; pr < PR::N; ++pr) {
             const int pa = PR::a(pr), pb = PR::b(pr);
             if (PR::wait(pr) >= 0) { mbar_wait(full_bar + stage * NG + PR::wait(pr), phase); tc_fence_after(); }
-#pragma unroll
-            for (int kk = 0; kk < kChunkK / 16; ++kk) {
+            auto step = [&](int kk) {
               // MN-major SW128: a K step of 16 rows = 2 swizzle atoms of 8 rows x 128 B = 2048 bytes;
               // LBO = distance between 64-wide MN blocks (one TMA box), SBO = 1024 (next 8 K rows)
               const uint64_t da = make_smem_desc_sw128(a_addr + pa * Cfg::A_BYTES + kk * 2048, Cfg::BOX_BYTES, 1024);
@@ -711,10 +767,26 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
                 umma_bf16(d_side, da, db, idesc, acc_side);
                 acc_side = 1u;
               }
+            };
+            if constexpr (FULL) {
+#pragma unroll
+              for (int kk = 0; kk < kChunkK / 16; ++kk) step(kk);
+            } else {
+#pragma unroll 1
+              for (int kk = 0; kk < nkk; ++kk) step(kk);
             }
             if (PR::release(pr) >= 0) umma_commit(empty_bar + stage * NG + PR::release(pr));
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        };
+        // K = time: rows past the utterance's last logit frame are TMA zero fill in dZ, their K steps are skipped
+        // (only the last chunk of an utterance can be short)
+        const int last_nkk = p.trim ? min(kChunkK / 16, (p.To - (p.t_chunks - 1) * kChunkK + 15) >> 4) : kChunkK / 16;
+        int tc = q0 - (q0 / p.t_chunks) * p.t_chunks;
+        for (int q = q0; q < q1; ++q) {
+          if (tc == p.t_chunks - 1 && last_nkk != kChunkK / 16) iteration(std::false_type{}, last_nkk);
+          else iteration(std::true_type{}, kChunkK / 16);
+          if (++tc == p.t_chunks) tc = 0;
         }
         umma_commit(tmem_full + acc);
       }
@@ -996,12 +1068,16 @@ int launch_conv_e(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensor
   return ST_OK;
 }
 
+long long* g_timeline_buf = nullptr;
+int g_timeline_index = -1, g_timeline_count = 0;
+
 template <int BLOCK_N, int NPL>
 int launch_conv_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap* tmOut, const ConvParams& p0,
                   cudaStream_t stream) {
   // the TMA-store epilogue needs a store map, bf16 output planes and the staging tiles (<= 2 planes)
   ConvParams p = p0;
   if (!tmOut || !p.out_planes || NPL > 2) p.tma_store = 0;
+  p.timeline = (g_timeline_buf && g_timeline_count++ == g_timeline_index) ? g_timeline_buf : nullptr;
   const CUtensorMap& tmO = p.tma_store ? *tmOut : tmA;          // placeholder when unused
   // early TMEM release pays when a CTA has several tiles, no second accumulator stage, and a main loop long enough
   // to hide the register-resident epilogue behind it
@@ -1027,6 +1103,12 @@ int launch_wgrad_t(const CUtensorMap& tmX, const CUtensorMap& tmDZ, const WgradP
 }
 
 }  // namespace
+
+void set_conv_timeline(long long* buf, int launch_index) {
+  g_timeline_buf = buf;
+  g_timeline_index = launch_index;
+  g_timeline_count = 0;
+}
 
 int make_map_3d(CUtensorMap* map, const void* base, int C, int T, int Bn, int64_t ld, int64_t batch_stride,
                 int box_c, int box_t) {

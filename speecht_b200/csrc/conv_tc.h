@@ -30,6 +30,9 @@ struct ConvParams {
   int ld_mask;
   float* col_sum;                // nullable: += column sums of the stored tile (bias gradient), [N] fp32
   int tma_store;                 // 1: bf16 planes leave through the store tensor map (launch_conv's tmOut)
+  long long* timeline;           // debug (st_debug_conv_timeline): [grid][8] %globaltimer stamps of the CTA's first tile
+  int k_cols;                    // valid contraction columns per tap (A channels): zero-filled K steps are not issued
+  int trim;                      // 1: issue only the K steps / N columns that hold real channels (0: full tiles)
 };
 
 // ---- filter-gradient kernel: dW[j, ci, co] += sum_{b,t} X[b, t+shift_j, acol_j + ci] * dZ[b, t, co]
@@ -39,6 +42,7 @@ struct WgradParams {
   int m_tiles, n_tiles;
   int Cin, Cout;
   float* dW;                     // must be zero on entry (K-sliced tiles accumulate with atomics)
+  int trim;                      // 1: N of the last n tile rounded to 16, K steps past the last time row skipped
 };
 
 int make_map_3d(CUtensorMap* map, const void* base, int C, int T, int Bn, int64_t ld, int64_t batch_stride,
@@ -46,6 +50,9 @@ int make_map_3d(CUtensorMap* map, const void* base, int C, int T, int Bn, int64_
 int make_map_2d(CUtensorMap* map, const void* base, int cols, int rows, int64_t ld, int box_c, int box_r);
 // store map over output planes [Bn][T][C] (C = padded channel count ld), box {32, 32, 1}
 int make_map_3d_store(CUtensorMap* map, const void* base, int C, int T, int Bn, int64_t ld, int64_t batch_stride);
+
+// Debug hook: the conv launch number `launch_index` (counted from the call) writes its per-CTA timeline into buf.
+void set_conv_timeline(long long* buf, int launch_index);
 
 // block_n: 32 or 256 (conv) / 64 or 256 (wgrad); n_planes: 1 or 2.
 // tmOut: store map of p.out_planes (nullable; used when p.tma_store is set)

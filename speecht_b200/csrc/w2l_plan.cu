@@ -52,6 +52,7 @@ struct st_plan {
   int ev_used;
   int cur_dz;                  // ping/pong buffer holding the gradient wrt the next layer to process
   bool tma_store;              // epilogues write bf16 planes with TMA stores (SPEECHT_B200_TMA_STORE=0 disables)
+  bool trim;                   // MMAs over channel / time padding are not issued (SPEECHT_B200_TRIM=0 disables)
 };
 
 namespace {
@@ -97,6 +98,8 @@ ST_API int st_plan_create(st_plan** out, int B, int T, int input_size, int num_c
   {
     const char* e = getenv("SPEECHT_B200_TMA_STORE");
     p->tma_store = !(e && e[0] == '0') && n_planes <= 2;
+    e = getenv("SPEECHT_B200_TRIM");
+    p->trim = !(e && e[0] == '0');
   }
   // reference speech_model.py:275-292
   const int table[11][5] = {{48, 2, input_size, 250, 1}, {7, 1, 250, 250, 1}, {7, 1, 250, 250, 1}, {7, 1, 250, 250, 1},
@@ -298,6 +301,8 @@ ST_API int st_plan_forward(st_plan* p, const float* inputs, st_stream_t stream) 
       c.ld_f32 = 32;
     }
     c.tma_store = p->tma_store && l < 10;
+    c.k_cols = L.Cin;
+    c.trim = p->trim;
     const int ti = timed_begin(p, s);
     rc = tc::launch_conv(L.tm_fwd_a, L.tm_fwd_b, l < 10 ? &L.tm_fwd_out : nullptr, c, block_n, p->npl, s);
     if (rc) return rc;
@@ -341,6 +346,7 @@ ST_API int st_plan_backward_range(st_plan* p, int hi, int lo, st_stream_t stream
     w.n_tiles = l == 10 ? 1 : (L.Cout + wide_n(p) - 1) / wide_n(p);
     w.Cin = L.Cin; w.Cout = L.Cout;
     w.dW = p->grads + L.w_off;
+    w.trim = p->trim;
     int ti = timed_begin(p, s);
     rc = tc::launch_wgrad(L.tm_wg_x, L.tm_wg_dz[l == 10 ? 0 : cur], w, l == 10 ? 64 : wide_n(p), p->npl, s);
     if (rc) return rc;
@@ -373,6 +379,8 @@ ST_API int st_plan_backward_range(st_plan* p, int hi, int lo, st_stream_t stream
       c.ld_mask = Lb.ld_out;
       c.col_sum = p->grads + Lb.b_off;
       c.tma_store = p->tma_store;
+      c.k_cols = L.Cout;
+      c.trim = p->trim;
       ti = timed_begin(p, s);
       rc = tc::launch_conv(L.tm_dg_a[l == 10 ? 0 : cur], L.tm_dg_b, &L.tm_dg_out[nxt], c, wide_n(p), p->npl, s);
       if (rc) return rc;
@@ -424,4 +432,13 @@ ST_API int st_plan_read_timings(st_plan* p, int* kind, int* layer, double* flops
   p->recs.clear();
   p->ev_used = 0;
   return n;
+}
+
+// Debug: the `launch_index`-th tensor-core conv launch after this call (forward and data-gradient launches, in
+// stream order) writes eight %globaltimer stamps per CTA into buf[grid][8] (device memory, >= 148*8 int64):
+// 0 entry, 1 previous grid complete, 2 first operands landed, 3 last MMA issued, 4 accumulator complete,
+// 5 epilogue issued, 6 staging tiles drained, 7 exit.  buf = NULL switches it off.  tools/conv_timeline.py.
+ST_API int st_debug_conv_timeline(int64_t* buf, int launch_index) {
+  tc::set_conv_timeline(reinterpret_cast<long long*>(buf), launch_index);
+  return ST_OK;
 }

@@ -18,13 +18,17 @@
 //   warp 1   : TMEM allocator + single-thread tcgen05.mma issuer (128 x BLOCK_N x 16 per instruction); hi*hi products
 //              go to the `main` accumulator, every product with a lo plane to the `side` accumulator
 //   warps 2-9: epilogue, two warps per TMEM lane quarter: tcgen05.ld 32 lanes x 32 columns of main (+ side),
-//              +bias, ReLU / ReLU-mask, split to planes, 16-byte stores, bias-gradient column sums
+//              +bias, ReLU / ReLU-mask, split to planes, staged in a per-warp shared-memory tile and written with
+//              one TMA store per plane (ragged edges clipped by the tensor map), bias-gradient column sums
 // tc_wgrad_kernel (filter gradient): same roles; both operands are MN-major (the contraction runs over time, the
 // slow axis), expressed through the MN-major SWIZZLE_128B shared-memory descriptors; wave-aligned split-K.
 // Both are launched with programmatic stream serialization (griddepcontrol.wait after the prologue).
 //
-// Roofline: tensor-pipe bound.  Algorithmic FLOPs per launch = 2*K*Cin*Cout*T'*B (unpadded); the tensor pipe
-// executes 3x (bf16x3) / 6x (bf16x6) / 1x (bf16) that, plus <= 2.4 % channel and 2.2 % time padding.
+// Roofline: tensor-pipe bound (in practice: bound by the clock the power cap allows while the pipe is 95 % busy).
+// Algorithmic FLOPs per launch = 2*K*Cin*Cout*T'*B (unpadded); the tensor pipe executes 3x (bf16x3) / 6x (bf16x6) /
+// 1x (bf16) that, plus the padding of 250 channels to 256 and 2.2 % time padding -- MMAs that would only multiply
+// the padding of 2000 channels (N beyond 208 in the last tile, K steps beyond the 16 channels of the last chunk) are
+// not issued.
 #include "st_common.cuh"
 #include "conv_tc.h"
 #include "tc_ptx.cuh"

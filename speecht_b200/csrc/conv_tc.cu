@@ -114,7 +114,7 @@ __device__ __forceinline__ void store_planes8(__nv_bfloat16* dst, int64_t plane_
 // + bias, ReLU or ReLU-mask, then
 //   * bf16 planes: staged [plane][32 rows][32 cols] in the warp's shared-memory tile and written with ONE TMA store
 //     per plane (box {32 ch, 32 t, 1}; rows t >= T' and channel padding beyond ld are clipped by the tensor map), or
-//     -- bf16x6 / SPEECHT_B200_TMA_STORE=0 -- direct 16-byte stores from the lane that owns the row;
+//     -- bf16x6 only: no shared memory left -- direct 16-byte stores from the lane that owns the row;
 //   * fp32 logits (last layer): direct stores;
 //   * bias gradient of the layer below (data gradient): column sums by a 32x32 transpose-reduce.
 // Bit i of the result = mask element i > 0 (bf16: sign clear and magnitude non-zero), for this lane's 32 columns.
@@ -1080,7 +1080,12 @@ int launch_conv_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensor
                   cudaStream_t stream) {
   // the TMA-store epilogue needs a store map, bf16 output planes and the staging tiles (<= 2 planes)
   ConvParams p = p0;
-  if (!tmOut || !p.out_planes || NPL > 2) p.tma_store = 0;
+  // bf16 planes leave through the store map in the one- and two-plane builds (compile-time in the epilogue)
+  p.tma_store = p.out_planes && NPL <= 2;
+  if (p.tma_store && !tmOut) {
+    st_set_error("launch_conv: bf16 output planes need their store tensor map (n_planes <= 2)");
+    return ST_ERR_INVALID_ARG;
+  }
   p.timeline = (g_timeline_buf && g_timeline_count++ == g_timeline_index) ? g_timeline_buf : nullptr;
   const CUtensorMap& tmO = p.tma_store ? *tmOut : tmA;          // placeholder when unused
   // early TMEM release pays when a CTA has several tiles, no second accumulator stage, and a main loop long enough

@@ -29,7 +29,7 @@ struct ConvParams {
   const __nv_bfloat16* mask_hi;  // same [B,To,ld_mask] indexing as the output; value > 0 passes
   int ld_mask;
   float* col_sum;                // nullable: += column sums of the stored tile (bias gradient), [N] fp32
-  int tma_store;                 // 1: bf16 planes leave through the store tensor map (launch_conv's tmOut)
+  int tma_store;                 // set by launch_conv: bf16 planes leave through the store tensor map tmOut
   long long* timeline;           // debug (st_debug_conv_timeline): [grid][8] %globaltimer stamps of the CTA's first tile
   int k_cols;                    // valid contraction columns per tap (A channels): zero-filled K steps are not issued
   int trim;                      // 1: issue only the K steps / N columns that hold real channels (0: full tiles)
@@ -55,7 +55,7 @@ int make_map_3d_store(CUtensorMap* map, const void* base, int C, int T, int Bn, 
 void set_conv_timeline(long long* buf, int launch_index);
 
 // block_n: 32 or 256 (conv) / 64 or 256 (wgrad); n_planes: 1 or 2.
-// tmOut: store map of p.out_planes (nullable; used when p.tma_store is set)
+// tmOut: store map of p.out_planes, required when p.out_planes is set and n_planes <= 2 (see make_map_3d_store)
 int launch_conv(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap* tmOut, const ConvParams& p,
                 int block_n, int n_planes, cudaStream_t stream);
 int launch_wgrad(const CUtensorMap& tmX, const CUtensorMap& tmDZ, const WgradParams& p, int block_n, int n_planes,

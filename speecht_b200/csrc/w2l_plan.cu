@@ -51,7 +51,7 @@ struct st_plan {
   std::vector<Rec> recs;
   int ev_used;
   int cur_dz;                  // ping/pong buffer holding the gradient wrt the next layer to process
-  bool tma_store;              // epilogues write bf16 planes with TMA stores (SPEECHT_B200_TMA_STORE=0 disables)
+  bool tma_store;              // one / two planes: the epilogues write bf16 planes with TMA stores (store maps needed)
   bool trim;                   // MMAs over channel / time padding are not issued (SPEECHT_B200_TRIM=0 disables)
 };
 
@@ -96,9 +96,8 @@ ST_API int st_plan_create(st_plan** out, int B, int T, int input_size, int num_c
   p->B = B; p->T = T; p->Tpad = round_up(T, 2); p->F = input_size; p->C = num_classes; p->npl = n_planes;
   p->arena = nullptr; p->params = nullptr; p->grads = nullptr; p->launches = 0; p->bound = false; p->cur_dz = 0; p->timing = false; p->ev_used = 0;
   {
-    const char* e = getenv("SPEECHT_B200_TMA_STORE");
-    p->tma_store = !(e && e[0] == '0') && n_planes <= 2;
-    e = getenv("SPEECHT_B200_TRIM");
+    p->tma_store = n_planes <= 2;
+    const char* e = getenv("SPEECHT_B200_TRIM");
     p->trim = !(e && e[0] == '0');
   }
   // reference speech_model.py:275-292

@@ -212,3 +212,24 @@ def test_features_vs_torchaudio_librosa_compatible_pipeline():
   assert got.shape == ref.shape == (1 + len(wav) // 160, 128)
   assert (x <= x.max() - 80.0 + 1e-9).any()                               # the floor was active in this case
   np.testing.assert_allclose(got, ref, rtol=0, atol=1e-9)
+
+
+def test_same_padding_vs_transformers_tf_port():
+  """Second opinion on tf.nn.conv1d(padding='SAME') (reference speech_model.py:155): Hugging Face's MobileNetV2 port
+  carries `apply_tf_padding`, its restatement of TensorFlow's SAME rule (validated there against TF checkpoints).
+  The oracle's (left, right) padding must equal what that function pads along the height axis, for the layer shapes
+  of the network and for odd/even lengths.  (Not TensorFlow itself: TF is not installable here.)"""
+  torch = pytest.importorskip('torch')
+  mod = pytest.importorskip('transformers.models.mobilenet_v2.modeling_mobilenet_v2')
+  for k, s in [(48, 2), (7, 1), (32, 1), (1, 1), (6, 2), (4, 3), (3, 1)]:
+    conv = torch.nn.Conv2d(1, 1, kernel_size=(k, 1), stride=(s, 1))
+    for t in [1, 2, 5, 6, 37, 100, 101, 501, 1001, 3001]:
+      x = torch.ones((1, 1, t, 1))
+      y = mod.apply_tf_padding(x, conv)
+      col = y[0, 0, :, 0]
+      nz = torch.nonzero(col).flatten()
+      left = int(nz[0])
+      right = int(col.numel() - 1 - nz[-1])
+      out_len, pl, pr = O.same_padding(t, k, s)
+      assert (left, right) == (pl, pr), (k, s, t, left, right, pl, pr)
+      assert (t + left + right - k) // s + 1 == out_len == -(-t // s)

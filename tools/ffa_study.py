@@ -1,0 +1,92 @@
+"""CPU study for the fast-FIR split of the 32-tap layer: checks the index algebra of the
+three-convolution form against the direct 'SAME' correlation and compares their rounding error when every operand is
+a bf16 hi+lo pair, products hi*hi + hi*lo + lo*hi, fp32 accumulation (numpy emulation of the bf16x3 tensor path; the
+tensor core's own accumulate truncation is not modelled -- it adds the same ~2e-5 to both forms).
+
+  python tools/ffa_study.py [seed]
+"""
+import sys
+
+import numpy as np
+
+K, PAD_L = 32, 15
+
+
+def bf16_round(x):
+  """round-to-nearest-even to bfloat16, returned as float32"""
+  u = np.asarray(x, np.float32).view(np.uint32).astype(np.uint64)
+  r = ((u + 0x7fff + ((u >> 16) & 1)) >> 16) << 16
+  return r.astype(np.uint32).view(np.float32)
+
+
+def split(x):
+  hi = bf16_round(x)
+  lo = bf16_round(np.asarray(x, np.float32) - hi)
+  return hi, lo
+
+
+def mm3(a, b):
+  """a [M,Kc] @ b [Kc,N] with bf16x3 operands, fp32 accumulation: main (hi*hi) + side (hi*lo + lo*hi)"""
+  ah, al = split(a)
+  bh, bl = split(b)
+  main = ah @ bh
+  side = ah @ bl + al @ bh
+  return (main + side).astype(np.float32)
+
+
+def corr(xp, w, rows, mm):
+  """sum_j xp[u + j] @ w[j] for u in range(rows): xp [U, Cin], w [J, Cin, Cout]"""
+  J = w.shape[0]
+  out = None
+  for j in range(J):
+    term = mm(xp[j:j + rows], w[j])
+    out = term if out is None else out + term
+  return out
+
+
+def main():
+  seed = int(sys.argv[1]) if len(sys.argv) > 1 else 0
+  rng = np.random.default_rng(seed)
+  T, cin, cout = 501, 250, 192
+  x = np.maximum(rng.standard_normal((T, cin)), 0).astype(np.float32)          # a ReLU output
+  lim = np.sqrt(6.0 / (K * cin + K * 2000))
+  w = rng.uniform(-lim, lim, size=(K, cin, cout)).astype(np.float32)
+  xp = np.zeros((T + K, cin), np.float32)                                      # x'[n] = x[n - 15], zero outside
+  xp[PAD_L:PAD_L + T] = x
+
+  exact = corr(xp.astype(np.float64), w.astype(np.float64), T, lambda a, b: a @ b)
+  direct = corr(xp, w, T, mm3)
+
+  # fast-FIR form: even / odd phases of x' and of the taps
+  x0, x1 = xp[0::2], xp[1::2]                                                   # x'_0[u] = x'[2u], x'_1[u] = x'[2u+1]
+  w0, w1 = w[0::2], w[1::2]
+  n_even, n_odd = (T + 1) // 2, T // 2
+  x0s = x0[1:]                                                                  # x'_0[u + 1]
+  xs = (x1[:x0s.shape[0]] + x0s).astype(np.float32)                             # x'_1[u] + x'_0[u+1], re-split inside mm3
+  ws = (w0 + w1).astype(np.float32)
+
+  def run(mm, dt):
+    a00 = corr(x0.astype(dt), w0.astype(dt), n_even + 1, mm)                    # needed at u and u + 1
+    a11 = corr(x1.astype(dt), w1.astype(dt), n_even, mm)
+    s = corr(xs.astype(dt), ws.astype(dt), n_odd, mm)
+    y = np.empty((T, cout), dt)
+    y[0::2] = a00[:n_even] + a11[:n_even]
+    y[1::2] = s - a11[:n_odd] - a00[1:n_odd + 1]
+    return y
+
+  ffa64 = run(lambda a, b: a @ b, np.float64)
+  ffa = run(mm3, np.float32)
+  scale = np.max(np.abs(exact))
+  print('index algebra (float64 fast-FIR vs direct):   max abs diff / max |y| = %.2e' % (np.max(np.abs(ffa64 - exact)) / scale))
+  for name, y in (('direct   bf16x3', direct), ('fast-FIR bf16x3', ffa)):
+    e = np.abs(y - exact)
+    print('%s: max err / max|y| = %.2e   rms err / rms y = %.2e   even rows max %.2e   odd rows max %.2e'
+          % (name, e.max() / scale, np.sqrt(np.mean(e ** 2)) / np.sqrt(np.mean(exact ** 2)), e[0::2].max() / scale,
+             e[1::2].max() / scale))
+  it_direct, it_ffa = K * 4, 3 * (K // 2) * 4
+  print('pipeline iterations per 128 output rows x 256 channels: direct %d, fast-FIR %d per 2 x 128 rows -> %.0f %%'
+        % (it_direct, it_ffa, 100.0 * it_ffa / (2 * it_direct)))
+
+
+if __name__ == '__main__':
+  main()

@@ -74,6 +74,30 @@ def main():
     y[1::2] = s - a11[:n_odd] - a00[1:n_odd + 1]
     return y
 
+  # The same three convolutions as the plan would launch them: stride-1 'SAME'-style correlations with 16 taps over
+  # row VIEWS of the unpadded activation x (TMA zero fill outside [0, rows)):
+  #   A00[u] = sum_j odd [u + j - 8] w0[j]   odd [r] = x[2r + 1]   (pad_left 8)
+  #   A11[u] = sum_j even[u + j - 7] w1[j]   even[r] = x[2r]       (pad_left 7)
+  #   S[u]   = sum_j xs  [u + j - 7] ws[j]   xs  [r] = x[2r] + x[2r + 1]   (pad_left 7)
+  def view_corr(v, wj, pad_left, rows):
+    vp = np.zeros((rows + wj.shape[0] + pad_left + 1, v.shape[1]), np.float64)
+    n = min(v.shape[0], vp.shape[0] - pad_left)
+    vp[pad_left:pad_left + n] = v[:n]
+    return corr(vp, wj.astype(np.float64), rows, lambda a, b: a @ b)
+
+  x64 = x.astype(np.float64)
+  odd, even = x64[1::2], x64[0::2]
+  xs_v = even.copy()
+  xs_v[:odd.shape[0]] += odd
+  a00_v = view_corr(odd, w0, 8, n_even + 1)
+  a11_v = view_corr(even, w1, 7, n_even)
+  s_v = view_corr(xs_v, ws, 7, n_odd)
+  y_v = np.empty((T, cout), np.float64)
+  y_v[0::2] = a00_v[:n_even] + a11_v[:n_even]
+  y_v[1::2] = s_v - a11_v[:n_odd] - a00_v[1:n_odd + 1]
+  print('row-view formulation (odd/pad 8, even/pad 7, pair sums/pad 7) vs direct: max abs diff / max |y| = %.2e'
+        % (np.max(np.abs(y_v - exact)) / np.max(np.abs(exact))))
+
   ffa64 = run(lambda a, b: a @ b, np.float64)
   ffa = run(mm3, np.float32)
   scale = np.max(np.abs(exact))

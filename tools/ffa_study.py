@@ -4,6 +4,12 @@ a bf16 hi+lo pair, products hi*hi + hi*lo + lo*hi, fp32 accumulation (numpy emul
 tensor core's own accumulate truncation is not modelled -- it adds the same ~2e-5 to both forms).
 
   python tools/ffa_study.py [seed]
+
+Backward of the same form (not exercised here; plain linear algebra of the three correlations): with
+dA00[u] = dy[2u] - dy[2u-1], dA11[u] = dy[2u] - dy[2u+1], dS[u] = dy[2u+1] the data gradient is three half-rate
+transposed 16-tap convolutions d_odd = dA00 (*) w0, d_even = dA11 (*) w1, d_xs = dS (*) ws with dx[2r+1] = d_odd[r] +
+d_xs[r], dx[2r] = d_even[r] + d_xs[r], and the filter gradient three half-rate correlations dw[2j] = <odd, dA00>_j +
+<xs, dS>_j, dw[2j+1] = <even, dA11>_j + <xs, dS>_j -- 75 % of the MMAs in every pass.
 """
 import sys
 

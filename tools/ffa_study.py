@@ -5,7 +5,7 @@ tensor core's own accumulate truncation is not modelled -- it adds the same ~2e-
 
   python tools/ffa_study.py [seed]
 
-Backward of the same form (not exercised here; plain linear algebra of the three correlations): with
+Backward of the same form (checked against torch autograd on a small case by check_backward below): with
 dA00[u] = dy[2u] - dy[2u-1], dA11[u] = dy[2u] - dy[2u+1], dS[u] = dy[2u+1] the data gradient is three half-rate
 transposed 16-tap convolutions d_odd = dA00 (*) w0, d_even = dA11 (*) w1, d_xs = dS (*) ws with dx[2r+1] = d_odd[r] +
 d_xs[r], dx[2r] = d_even[r] + d_xs[r], and the filter gradient three half-rate correlations dw[2j] = <odd, dA00>_j +
@@ -118,5 +118,60 @@ def main():
         % (it_direct, it_ffa, 100.0 * it_ffa / (2 * it_direct)))
 
 
+def check_backward():
+  """dx and dw of the three-correlation form (docstring formulas) against autograd of the direct 32-tap correlation."""
+  import torch
+  torch.manual_seed(0)
+  K, PAD = 32, 15
+  T, cin, cout = 101, 6, 5
+  x = torch.randn(T, cin, dtype=torch.float64, requires_grad=True)
+  w = torch.randn(K, cin, cout, dtype=torch.float64, requires_grad=True)
+  xp = torch.zeros(T + K, cin, dtype=torch.float64)
+  xp = torch.cat([torch.zeros(PAD, cin, dtype=torch.float64), x, torch.zeros(K - PAD, cin, dtype=torch.float64)])
+  y = sum(xp[k:k + T] @ w[k] for k in range(K))
+  dy = torch.randn(T, cout, dtype=torch.float64)
+  (y * dy).sum().backward()
+  dx_ref, dw_ref = x.grad.numpy(), w.grad.numpy()
+  xn, wn, dyn = x.detach().numpy(), w.detach().numpy(), dy.numpy()
+  n_even, n_odd = (T + 1) // 2, T // 2
+  def get(a, i):  # zero outside
+      return a[i] if 0 <= i < a.shape[0] else np.zeros(a.shape[1])
+  dye = dyn[0::2]; dyo = dyn[1::2]
+  U = n_even + 1
+  dA00 = np.stack([get(dye, u) - get(dyo, u - 1) for u in range(U)])
+  dA11 = np.stack([get(dye, u) - get(dyo, u) for u in range(n_even)])
+  dS = np.stack([get(dyo, u) for u in range(n_odd)])
+  w0, w1 = wn[0::2], wn[1::2]; ws = w0 + w1
+  odd, even = xn[1::2], xn[0::2]
+  xs = even.copy(); xs[:odd.shape[0]] += odd
+  # forward views: A00[u] = sum_j odd[u+j-8] w0[j]; A11[u] = sum_j even[u+j-7] w1[j]; S[u] = sum_j xs[u+j-7] ws[j]
+  def tconv(dA, wj, pad, rows):   # d_view[r] = sum_j dA[r - j + pad] wj[j]^T
+      out = np.zeros((rows, wj.shape[1]))
+      for r in range(rows):
+          for j in range(wj.shape[0]):
+              u = r - j + pad
+              if 0 <= u < dA.shape[0]:
+                  out[r] += dA[u] @ wj[j].T
+      return out
+  d_odd = tconv(dA00, w0, 8, odd.shape[0]); d_even = tconv(dA11, w1, 7, even.shape[0]); d_xs = tconv(dS, ws, 7, even.shape[0])
+  dx = np.zeros_like(xn)
+  dx[1::2] = d_odd + d_xs[:odd.shape[0]]
+  dx[0::2] = d_even + d_xs
+  e_dx = np.abs(dx - dx_ref).max()
+  def wcorr(v, dA, pad, J):       # <v, dA>_j = sum_u v[u + j - pad]^T dA[u]
+      out = np.zeros((J, v.shape[1], dA.shape[1]))
+      for j in range(J):
+          for u in range(dA.shape[0]):
+              r = u + j - pad
+              if 0 <= r < v.shape[0]:
+                  out[j] += np.outer(v[r], dA[u])
+      return out
+  c0 = wcorr(odd, dA00, 8, 16); c1 = wcorr(even, dA11, 7, 16); cs = wcorr(xs, dS, 7, 16)
+  dw = np.zeros_like(wn); dw[0::2] = c0 + cs; dw[1::2] = c1 + cs
+  print('backward formulas vs autograd (float64, T=101): max |dx err| = %.1e, max |dw err| = %.1e' % (e_dx, np.abs(dw - dw_ref).max()))
+
+
+
 if __name__ == '__main__':
   main()
+  check_backward()

@@ -1015,6 +1015,91 @@ merge_planes_kernel(const __nv_bfloat16* __restrict__ planes, int64_t rows, int 
   }
 }
 
+// ---- fast-FIR split of a stride-1 K-tap layer (experimental, SPEECHT_B200_FFA=1) -------------
+// xs[pl][b][r][:] = planes of x[b][2r][:] + x[b][2r+1][:] (x[b][T][:] = 0); one thread per 8 channels
+template <int NPL>
+__global__ void __launch_bounds__(256)
+pair_sum_planes_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ xs, int B, int T, int Tx,
+                       int ld) {
+  const int64_t groups = (int64_t)B * Tx * (ld / 8);
+  const int64_t in_plane = (int64_t)B * T * ld, out_plane = (int64_t)B * Tx * ld;
+  for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < groups; g += (int64_t)gridDim.x * blockDim.x) {
+    const int c8 = (int)(g % (ld / 8));
+    const int64_t br = g / (ld / 8);
+    const int r = (int)(br % Tx);
+    const int b = (int)(br / Tx);
+    float v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = 0.f;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int t = 2 * r + h;
+      if (t >= T) continue;
+      for (int pl = NPL - 1; pl >= 0; --pl) {
+        const uint4 q = *reinterpret_cast<const uint4*>(x + pl * in_plane + ((int64_t)b * T + t) * ld + c8 * 8);
+        const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          v[2 * i] += __uint_as_float(w[i] << 16);
+          v[2 * i + 1] += __uint_as_float(w[i] & 0xffff0000u);
+        }
+      }
+    }
+    store_planes8<NPL>(xs + ((int64_t)b * Tx + r) * ld + c8 * 8, out_plane, v);
+  }
+}
+
+// w [2J][Cin][Cout] fp32 -> w0 = even taps, w1 = odd taps, ws = w0 + w1, each [J][Cin][Cout] fp32
+__global__ void __launch_bounds__(256)
+ffa_split_taps_kernel(const float* __restrict__ w, float* __restrict__ w0, float* __restrict__ w1,
+                      float* __restrict__ ws, int J, int64_t tap_elems) {
+  const int64_t total = (int64_t)J * tap_elems;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t j = i / tap_elems, e = i - j * tap_elems;
+    const float a = __ldg(w + (2 * j) * tap_elems + e), c = __ldg(w + (2 * j + 1) * tap_elems + e);
+    w0[i] = a;
+    w1[i] = c;
+    ws[i] = a + c;
+  }
+}
+
+// y[b][2u] = act(A00[u] + A11[u] + bias), y[b][2u+1] = act(S[u] - A11[u] - A00[u+1] + bias) -> bf16 planes
+// [NPL][B][To][ld_out]; the three partial products are fp32 [B][Tu][ld_p]; one thread per 8 channels of one u
+template <int NPL>
+__global__ void __launch_bounds__(256)
+ffa_combine_kernel(const float* __restrict__ a00, const float* __restrict__ a11, const float* __restrict__ sm,
+                   const float* __restrict__ bias, int relu, __nv_bfloat16* __restrict__ out, int B, int To, int Tu,
+                   int N, int ld_p, int ld_out) {
+  const int cg = ld_out / 8;
+  const int64_t groups = (int64_t)B * Tu * cg;
+  const int64_t out_plane = (int64_t)B * To * ld_out;
+  for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < groups; g += (int64_t)gridDim.x * blockDim.x) {
+    const int c8 = (int)(g % cg);
+    const int64_t bu = g / cg;
+    const int u = (int)(bu % Tu);
+    const int b = (int)(bu / Tu);
+    if (2 * u >= To) continue;
+    const int64_t row = ((int64_t)b * Tu + u) * ld_p + c8 * 8;
+    float p0[8], p0n[8], p1[8], ps[8], ye[8], yo[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const bool ok = c8 * 8 + i < N;
+      p0[i] = ok ? a00[row + i] : 0.f;
+      p1[i] = ok ? a11[row + i] : 0.f;
+      ps[i] = ok ? sm[row + i] : 0.f;
+      p0n[i] = (ok && u + 1 < Tu) ? a00[row + ld_p + i] : 0.f;
+      const float bv = (ok && bias) ? __ldg(bias + c8 * 8 + i) : 0.f;
+      ye[i] = p0[i] + p1[i] + bv;
+      yo[i] = ps[i] - p1[i] - p0n[i] + bv;
+      if (relu) { ye[i] = fmaxf(ye[i], 0.f); yo[i] = fmaxf(yo[i], 0.f); }
+      if (!ok) { ye[i] = 0.f; yo[i] = 0.f; }
+    }
+    __nv_bfloat16* o = out + ((int64_t)b * To + 2 * u) * ld_out + c8 * 8;
+    store_planes8<NPL>(o, out_plane, ye);
+    if (2 * u + 1 < To) store_planes8<NPL>(o + ld_out, out_plane, yo);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ host side
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -1222,6 +1307,46 @@ int launch_split_input(const float* x, __nv_bfloat16* planes, int B, int T, int 
   else if (n_planes == 2) split_input_kernel<2><<<blocks, 256, 0, stream>>>(x, planes, B, T, Tpad, F);
   else split_input_kernel<1><<<blocks, 256, 0, stream>>>(x, planes, B, T, Tpad, F);
   ST_CUDA_LAUNCH_CHECK("split_input_kernel");
+  return ST_OK;
+}
+
+int launch_pair_sum_planes(const __nv_bfloat16* x, __nv_bfloat16* xs, int B, int T, int Tx, int ld, int n_planes,
+                           cudaStream_t stream) {
+  ST_CHECK_ARG(ld % 8 == 0 && n_planes >= 1 && n_planes <= 2, "launch_pair_sum_planes: bad arguments");
+  const int64_t groups = (int64_t)B * Tx * (ld / 8);
+  int blocks = (int)((groups + 255) / 256);
+  const int cap = 16 * st_num_sms();
+  blocks = blocks > cap ? cap : blocks;
+  if (n_planes == 2) pair_sum_planes_kernel<2><<<blocks, 256, 0, stream>>>(x, xs, B, T, Tx, ld);
+  else pair_sum_planes_kernel<1><<<blocks, 256, 0, stream>>>(x, xs, B, T, Tx, ld);
+  ST_CUDA_LAUNCH_CHECK("pair_sum_planes_kernel");
+  return ST_OK;
+}
+
+int launch_ffa_split_taps(const float* w, float* w0, float* w1, float* ws, int J, int64_t tap_elems,
+                          cudaStream_t stream) {
+  const int64_t total = (int64_t)J * tap_elems;
+  int blocks = (int)((total + 255) / 256);
+  const int cap = 16 * st_num_sms();
+  blocks = blocks > cap ? cap : blocks;
+  ffa_split_taps_kernel<<<blocks, 256, 0, stream>>>(w, w0, w1, ws, J, tap_elems);
+  ST_CUDA_LAUNCH_CHECK("ffa_split_taps_kernel");
+  return ST_OK;
+}
+
+int launch_ffa_combine(const float* a00, const float* a11, const float* sm, const float* bias, int relu,
+                       __nv_bfloat16* out, int B, int To, int Tu, int N, int ld_p, int ld_out, int n_planes,
+                       cudaStream_t stream) {
+  ST_CHECK_ARG(ld_out % 8 == 0 && n_planes >= 1 && n_planes <= 2, "launch_ffa_combine: bad arguments");
+  const int64_t groups = (int64_t)B * Tu * (ld_out / 8);
+  int blocks = (int)((groups + 255) / 256);
+  const int cap = 16 * st_num_sms();
+  blocks = blocks > cap ? cap : blocks;
+  if (n_planes == 2)
+    ffa_combine_kernel<2><<<blocks, 256, 0, stream>>>(a00, a11, sm, bias, relu, out, B, To, Tu, N, ld_p, ld_out);
+  else
+    ffa_combine_kernel<1><<<blocks, 256, 0, stream>>>(a00, a11, sm, bias, relu, out, B, To, Tu, N, ld_p, ld_out);
+  ST_CUDA_LAUNCH_CHECK("ffa_combine_kernel");
   return ST_OK;
 }
 

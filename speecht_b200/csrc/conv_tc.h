@@ -78,6 +78,18 @@ struct PackTable {
   PackEntry e[12];
 };
 int launch_pack_filters(PackTable& tab, int n_planes, cudaStream_t stream, int* launches);
+// ---- fast-FIR split of a stride-1 layer (experimental, see w2l_plan.cu)
+// xs planes [n][B][Tx][ld] of x[b][2r] + x[b][2r+1] from x planes [n][B][T][ld]
+int launch_pair_sum_planes(const __nv_bfloat16* x, __nv_bfloat16* xs, int B, int T, int Tx, int ld, int n_planes,
+                           cudaStream_t stream);
+// w [2J][tap_elems] fp32 -> even taps, odd taps, their sum, each [J][tap_elems]
+int launch_ffa_split_taps(const float* w, float* w0, float* w1, float* ws, int J, int64_t tap_elems,
+                          cudaStream_t stream);
+// y[2u] = act(A00[u] + A11[u] + bias), y[2u+1] = act(S[u] - A11[u] - A00[u+1] + bias): fp32 [B][Tu][ld_p] partial
+// products -> bf16 planes [n][B][To][ld_out]
+int launch_ffa_combine(const float* a00, const float* a11, const float* sm, const float* bias, int relu,
+                       __nv_bfloat16* out, int B, int To, int Tu, int N, int ld_p, int ld_out, int n_planes,
+                       cudaStream_t stream);
 // db[n] = sum over rows and planes of dz planes [n_planes][rows][ld]
 int launch_bias_grad(const __nv_bfloat16* dz, int64_t rows, int N, int ld, int n_planes, float* db,
                      cudaStream_t stream);

@@ -53,6 +53,13 @@ struct st_plan {
   int cur_dz;                  // ping/pong buffer holding the gradient wrt the next layer to process
   bool tma_store;              // one / two planes: the epilogues write bf16 planes with TMA stores (store maps needed)
   bool trim;                   // MMAs over channel / time padding are not issued (SPEECHT_B200_TRIM=0 disables)
+  // EXPERIMENTAL, off by default, not yet run on a GPU (SPEECHT_B200_FFA=1): forward of the 32-tap layer 8 as a
+  // fast-FIR split -- three half-rate 16-tap convolutions (75 % of the MMAs) + one elementwise combine, DESIGN.md
+  // section 8 and tools/ffa_study.py.  Backward is unchanged.
+  bool ffa;
+  int ffa_Tx, ffa_Tu;                            // rows of the pair-sum planes / of the partial products
+  size_t off_ffa_xs, off_ffa_w32[3], off_ffa_w[3], off_ffa_p[3];
+  CUtensorMap tm_ffa_a[3], tm_ffa_b[3];
 };
 
 namespace {
@@ -99,6 +106,8 @@ ST_API int st_plan_create(st_plan** out, int B, int T, int input_size, int num_c
     p->tma_store = n_planes <= 2;
     const char* e = getenv("SPEECHT_B200_TRIM");
     p->trim = !(e && e[0] == '0');
+    e = getenv("SPEECHT_B200_FFA");
+    p->ffa = e && e[0] == '1' && n_planes <= 2;
   }
   // reference speech_model.py:275-292
   const int table[11][5] = {{48, 2, input_size, 250, 1}, {7, 1, 250, 250, 1}, {7, 1, 250, 250, 1}, {7, 1, 250, 250, 1},
@@ -141,6 +150,17 @@ ST_API int st_plan_create(st_plan** out, int B, int T, int input_size, int num_c
   p->dz_elems = (size_t)B * p->To * 2000;
   p->off_dz[0] = take((size_t)n_planes * p->dz_elems * 2);
   p->off_dz[1] = take((size_t)n_planes * p->dz_elems * 2);
+  if (p->ffa) {
+    const Layer& L8 = p->layers[8];
+    p->ffa_Tx = (L8.Ti + 1) / 2;
+    p->ffa_Tu = (L8.To + 1) / 2 + 1;
+    p->off_ffa_xs = take((size_t)n_planes * B * p->ffa_Tx * L8.ld_in * 2);
+    for (int i = 0; i < 3; ++i) {
+      p->off_ffa_w32[i] = take((size_t)(L8.K / 2) * L8.Cin * L8.Cout * sizeof(float));
+      p->off_ffa_w[i] = take((size_t)n_planes * L8.Cout * (L8.K / 2) * L8.cin_p * 2);
+      p->off_ffa_p[i] = take((size_t)B * p->ffa_Tu * L8.Cout * sizeof(float));
+    }
+  }
   p->arena_bytes = off;
   *out = p;
   return ST_OK;
@@ -237,6 +257,26 @@ ST_API int st_plan_bind(st_plan* p, void* arena, size_t arena_bytes, float* para
       }
     }
   }
+  if (p->ffa) {
+    // A operands of the three half-rate convolutions: row views of the layer-7 output x (odd rows, even rows) and
+    // the pair-sum planes; B operands: the packed even-tap, odd-tap and summed filters (forward layout, 16 taps)
+    Layer& L8 = p->layers[8];
+    const __nv_bfloat16* x = act_in(p, 8);
+    rc = tc::make_map_3d(&p->tm_ffa_a[0], x + L8.ld_in, L8.Cin, L8.Ti / 2, npl * B, 2 * L8.ld_in,
+                         (int64_t)L8.Ti * L8.ld_in, 64, 128);
+    if (rc) return rc;
+    rc = tc::make_map_3d(&p->tm_ffa_a[1], x, L8.Cin, (L8.Ti + 1) / 2, npl * B, 2 * L8.ld_in,
+                         (int64_t)L8.Ti * L8.ld_in, 64, 128);
+    if (rc) return rc;
+    rc = tc::make_map_3d(&p->tm_ffa_a[2], bf(p, p->off_ffa_xs), L8.Cin, p->ffa_Tx, npl * B, L8.ld_in,
+                         (int64_t)p->ffa_Tx * L8.ld_in, 64, 128);
+    if (rc) return rc;
+    for (int i = 0; i < 3; ++i) {
+      rc = tc::make_map_2d(&p->tm_ffa_b[i], bf(p, p->off_ffa_w[i]), (L8.K / 2) * L8.cin_p, npl * L8.Cout,
+                           (int64_t)(L8.K / 2) * L8.cin_p, 64, wide_n(p));
+      if (rc) return rc;
+    }
+  }
   p->bound = true;
   return ST_OK;
 }
@@ -263,8 +303,73 @@ int pack_layers(st_plan* p, int l0, int l1, cudaStream_t s) {
 
 ST_API int st_plan_pack_weights(st_plan* p, st_stream_t stream) {
   ST_CHECK_ARG(p && p->bound, "st_plan_pack_weights: plan is not bound");
-  return pack_layers(p, 0, 11, st_cu(stream));
+  int rc = pack_layers(p, 0, 11, st_cu(stream));
+  if (rc || !p->ffa) return rc;
+  // fast-FIR filters of layer 8: even taps, odd taps and their sum, each packed like a 16-tap forward filter
+  Layer& L8 = p->layers[8];
+  float* w32[3];
+  for (int i = 0; i < 3; ++i) w32[i] = reinterpret_cast<float*>(p->arena + p->off_ffa_w32[i]);
+  rc = tc::launch_ffa_split_taps(p->params + L8.w_off, w32[0], w32[1], w32[2], L8.K / 2, (int64_t)L8.Cin * L8.Cout,
+                                 st_cu(stream));
+  if (rc) return rc;
+  tc::PackTable tab{};
+  tab.n = 3;
+  for (int i = 0; i < 3; ++i)
+    tab.e[i] = tc::PackEntry{w32[i], bf(p, p->off_ffa_w[i]), nullptr, L8.K / 2, L8.Cin, L8.Cout, L8.cin_p, L8.ld_co, 0};
+  int n = 0;
+  rc = tc::launch_pack_filters(tab, p->npl, st_cu(stream), &n);
+  if (rc) return rc;
+  p->launches += n + 1;
+  return ST_OK;
 }
+
+namespace {
+
+// EXPERIMENTAL (SPEECHT_B200_FFA=1): y = x (*) w over 32 taps as
+//   A00[u] = sum_j odd [u+j-8] w[2j],  A11[u] = sum_j even[u+j-7] w[2j+1],  S[u] = sum_j xs[u+j-7] (w[2j]+w[2j+1])
+//   y[2u] = A00[u] + A11[u],           y[2u+1] = S[u] - A11[u] - A00[u+1]            (tools/ffa_study.py)
+// with odd[r] = x[2r+1], even[r] = x[2r], xs[r] = x[2r] + x[2r+1]: three 16-tap launches of tc_conv_kernel writing
+// fp32 partial products, then bias + ReLU + plane split in ffa_combine_kernel.
+int forward_layer8_ffa(st_plan* p, cudaStream_t s) {
+  Layer& L = p->layers[8];
+  int rc = tc::launch_pair_sum_planes(act_in(p, 8), bf(p, p->off_ffa_xs), p->B, L.Ti, p->ffa_Tx, L.ld_in, p->npl, s);
+  if (rc) return rc;
+  p->launches++;
+  float* part[3];
+  for (int i = 0; i < 3; ++i) {
+    part[i] = reinterpret_cast<float*>(p->arena + p->off_ffa_p[i]);
+    tc::ConvParams c{};
+    c.taps = L.K / 2;
+    c.chunks_per_tap = L.cin_p / 64;
+    c.pad_left = i == 0 ? 8 : 7;
+    c.a_sign = 1;
+    c.a_stride = 1;
+    c.a_cin = 0;
+    c.b_row_step = 0;
+    c.b_col_step = L.cin_p;
+    c.b_plane_rows = L.Cout;
+    c.B = p->B; c.To = p->ffa_Tu; c.N = L.Cout;
+    c.m_tiles_per_utt = (p->ffa_Tu + tc::kTileM - 1) / tc::kTileM;
+    c.n_tiles = (L.Cout + wide_n(p) - 1) / wide_n(p);
+    c.n_fastest = 0;
+    c.out_f32 = part[i];
+    c.ld_f32 = L.Cout;
+    c.k_cols = L.Cin;
+    c.trim = p->trim;
+    const int ti = timed_begin(p, s);
+    rc = tc::launch_conv(p->tm_ffa_a[i], p->tm_ffa_b[i], nullptr, c, wide_n(p), p->npl, s);
+    if (rc) return rc;
+    timed_end(p, ti, 0, 8, 2.0 * L.K * L.Cin * L.Cout * (double)L.To * p->B / 3.0, s);
+    p->launches++;
+  }
+  rc = tc::launch_ffa_combine(part[0], part[1], part[2], p->params + L.b_off, L.relu, bf(p, L.off_out), p->B, L.To,
+                              p->ffa_Tu, L.Cout, L.Cout, L.ld_out, p->npl, s);
+  if (rc) return rc;
+  p->launches++;
+  return ST_OK;
+}
+
+}  // namespace
 
 ST_API int st_plan_forward(st_plan* p, const float* inputs, st_stream_t stream) {
   ST_CHECK_ARG(p && p->bound && inputs, "st_plan_forward: plan is not bound / null input");
@@ -275,6 +380,11 @@ ST_API int st_plan_forward(st_plan* p, const float* inputs, st_stream_t stream) 
   for (int l = 0; l < 11; ++l) {
     Layer& L = p->layers[l];
     const int block_n = l == 10 ? 32 : wide_n(p);
+    if (l == 8 && p->ffa) {
+      rc = forward_layer8_ffa(p, s);
+      if (rc) return rc;
+      continue;
+    }
     tc::ConvParams c{};
     c.taps = L.K;
     c.chunks_per_tap = L.cin_p / 64;

@@ -305,3 +305,22 @@ def test_training_reduces_the_loss_on_a_fixed_batch(precision):
   assert all(np.isfinite(losses))
   assert losses[-1] < 0.5 * losses[0], (losses[0], losses[-1])
   assert np.mean(losses[-10:]) < np.mean(losses[:10])
+
+
+@pytest.mark.skipif(os.environ.get('SPEECHT_B200_TEST_EXPERIMENTAL') != '1',
+                    reason='experimental fast-FIR forward of layer 8 (SPEECHT_B200_FFA=1): opt-in until it has been '
+                           'validated on a GPU (DESIGN.md section 8)')
+@pytest.mark.parametrize('seconds', [1, 3])
+def test_experimental_fast_fir_layer8_forward_parity(seconds, monkeypatch):
+  """The three-convolution form of layer 8 must give the same activations (1e-4 gate; expected ~4e-5 on the odd rows
+  of layer 8) and the same greedy labels as the oracle.  The switch is read when a plan is created."""
+  monkeypatch.setenv('SPEECHT_B200_FFA', '1')
+  inputs, lengths, labels = O.synthetic_batch(seed=4, batch=3, seconds=seconds)
+  weights = O.xavier_weights(np.random.default_rng(98), dtype=np.float32)
+  w64 = [(w.astype(np.float64), b.astype(np.float64)) for w, b in weights]
+  logits, acts = O.wav2letter_forward(inputs.astype(np.float64), w64, keep_activations=True)
+  eng = _engine('bf16x3', weights)
+  out = eng.forward(torch.from_numpy(inputs).cuda(), keep_activations=True)
+  for l, a in enumerate(_gpu_activations(eng)):
+    assert rel(a, acts[l + 1]) < 1e-4, (l, rel(a, acts[l + 1]))
+  assert rel(out.cpu().numpy(), logits) < 1e-4

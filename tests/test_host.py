@@ -113,3 +113,37 @@ def test_no_product_module_imports_the_oracle():
     for line in path.read_text().splitlines():
       if 'import' in line:
         assert 'oracle' not in line, (path, line)
+
+
+def test_native_plan_host_logic_without_a_gpu(monkeypatch):
+  """st_plan_create is pure host code (shapes, SAME padding, arena offsets): it must agree with the Python side's
+  flat parameter layout and frame arithmetic for every shape class, on a box without a GPU."""
+  import ctypes
+  from speecht_b200._lib import check, lib
+  from speecht_b200.engine import ParamLayout, layer_table
+  layout = ParamLayout(layer_table(128, 29))
+  sizes = {}
+  for (B, T, npl) in [(4, 101, 2), (32, 1001, 2), (32, 1000, 1), (1, 2, 2), (3, 37, 3), (32, 3001, 1)]:
+    h = ctypes.c_void_p()
+    check(lib().st_plan_create(ctypes.byref(h), B, T, 128, 29, npl))
+    try:
+      assert lib().st_plan_param_floats(h) == layout.total
+      assert lib().st_plan_logit_frames(h) == -(-T // 2)                  # ceil(T/2), speech_model.py:275 stride 2
+      n = lib().st_plan_arena_bytes(h)
+      assert n > 0 and n % 1024 == 0
+      sizes[(B, T, npl)] = n
+    finally:
+      check(lib().st_plan_destroy(h))
+  assert sizes[(32, 1001, 2)] > sizes[(4, 101, 2)]
+  assert sizes[(32, 3001, 1)] > sizes[(32, 1000, 1)]
+  # bad arguments are rejected with the C ABI's error code, not a crash
+  h = ctypes.c_void_p()
+  assert lib().st_plan_create(ctypes.byref(h), 4, 101, 100, 29, 2) != 0    # input_size not a multiple of 64
+  assert lib().st_plan_create(ctypes.byref(h), 4, 101, 128, 29, 4) != 0    # n_planes outside 1..3
+  # the experimental fast-FIR forward only adds its buffers when it is switched on (read at plan creation)
+  monkeypatch.setenv('SPEECHT_B200_FFA', '1')
+  check(lib().st_plan_create(ctypes.byref(h), 32, 1001, 128, 29, 2))
+  try:
+    assert lib().st_plan_arena_bytes(h) > sizes[(32, 1001, 2)]
+  finally:
+    check(lib().st_plan_destroy(h))

@@ -1,18 +1,28 @@
 #!/usr/bin/env python3
-"""bench.py -- utterances/s of one Wav2Letter train step (BASELINE.json metric) on N B200s of one box.
+"""bench.py -- the reference's headline workloads (BASELINE.json `configs`) on N B200s of one box.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--precision bf16x3|fp32|bf16] [--impl ours|reference]
+  python bench.py [--config 2|3|4|5] [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
   N>1:  python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
-            bench.py --gpus N --steps K --warmup W
+            bench.py --gpus N --steps K --warmup W [--config C]
 
-A "step" is model.step(update=True): forward through the 11 conv layers, CTC loss, backward, [NCCL allreduce of the
-flat gradient], clip_by_global_norm, Adam -- on one batch of synthetic N(0,1) 128-mel inputs.  Workload at every N is
-BASELINE.json configs[1] per GPU: batch 32 x 10 s @ 16 kHz (T=1001 mel frames -> T'=501 logit frames), 11-layer net
-(weak scaling: per-GPU batch fixed).
+  --config 2 (default)  train step, batch 32/GPU x 10 s, 11-layer Wav2Letter, fp32-grade arithmetic (bf16x3 split)
+  --config 3            train step, batch 64/GPU x 10 s, bf16 operands + fp32 accumulate / CTC / Adam
+                        (the "17-layer large" net of BASELINE.json does not exist in the reference: SURVEY.md 0.3 #2;
+                        the reference's only network, 11 layers with 2000-channel tail, is what runs)
+  --config 4            train step, batch 32/GPU x 30 s, bf16, data parallel (NCCL gradient allreduce)
+  --config 5            evaluate step (forward + CTC loss + greedy decode), batch 256/GPU, lengths uniform in 1..30 s
+  --batch / --seconds / --precision override the config's values.
 
-Printed by rank 0: ONE JSON line, see the keys below; `value` is the device-resident throughput, `e2e` the same step
-driven through the reference-facing SpeechModel.step with HOST batches (H2D of the inputs and D2H of the loss inside
-the timed region).  `--impl reference` times the CPU restatement of the reference (oracle/, numpy on all host cores;
+A train "step" is model.step(update=True): forward through the 11 conv layers, CTC loss, backward, [NCCL allreduce of
+the flat gradient], clip_by_global_norm, Adam.  An evaluate "step" is model.step(update=False, decode=True,
+return_label=True) (evaluation.py:132-137 in the reference): ONE forward, the CTC loss and the greedy decode.
+
+Rank 0 prints ONE JSON line.  `value` is device-resident throughput (inputs already in HBM), `e2e` the same step through
+the reference-facing SpeechModel.step with HOST batches (H2D of the inputs and D2H of the result inside the timed
+region).  `ctc_loss_delta` compares the GPU path with the float64 oracle on a small sample of the same workload.
+`roofline` is measured live with CUDA events around the dominant kernel's launches; its `frac` uses the burst cuBLAS
+figure when the timed region is shorter than a second and the sustained one otherwise (both fractions are reported).
+`--impl reference` times the CPU restatement of the reference (oracle/, numpy on a pinned number of host threads;
 TensorFlow 1.x cannot be installed here) on a bounded sample of the same workload.
 """
 import argparse
@@ -28,8 +38,23 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-METRIC = 'utterances/sec (10s@16kHz, 128-mel) train-step'
 UNIT = 'utterances/s'
+PEAKS_PATH = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+TRAFFIC_PATH = os.path.join(ROOT, 'profiles', 'traffic.json')
+
+CONFIGS = {
+  2: dict(mode='train', batch=32, seconds=10.0, precision='bf16x3',
+          name='configs[1] train-step: batch 32/GPU, 10s@16kHz synthetic 128-mel, Wav2Letter 11 conv layers, fp32-grade '
+               '(bf16x3 split operands)'),
+  3: dict(mode='train', batch=64, seconds=10.0, precision='bf16',
+          name='configs[2] train-step: batch 64/GPU, 10s@16kHz, bf16 conv stack + fp32 CTC (the reference has ONE '
+               'network: 11 conv layers, 2000-channel tail; a 17-layer net does not exist in it)'),
+  4: dict(mode='train', batch=32, seconds=30.0, precision='bf16',
+          name='configs[3] data-parallel train-step: batch 32/GPU, 30s utterances, bf16, NCCL gradient allreduce'),
+  5: dict(mode='eval', batch=256, seconds=(1, 30), precision='bf16x3',
+          name='configs[4] evaluate: batch 256/GPU, greedy CTC decode, variable-length 1-30s synthetic utterances '
+               '(zero-padded to the batch maximum like speech_input.py:38-43; unbucketed)'),
+}
 
 
 def parse_args():
@@ -38,13 +63,26 @@ def parse_args():
   p.add_argument('--steps', type=int, default=10)
   p.add_argument('--warmup', type=int, default=3)
   p.add_argument('--impl', default='ours', choices=['ours', 'reference'])
-  p.add_argument('--precision', default=os.environ.get('SPEECHT_B200_PRECISION', 'bf16x3'),
+  p.add_argument('--config', type=int, default=2, choices=sorted(CONFIGS))
+  p.add_argument('--precision', default=os.environ.get('SPEECHT_B200_PRECISION'),
                  choices=['fp32', 'bf16x6', 'bf16x3', 'bf16'])
-  p.add_argument('--batch', type=int, default=32, help='per-GPU batch (BASELINE configs[1]: 32)')
-  p.add_argument('--seconds', type=float, default=10.0)
-  p.add_argument('--cpu-sample', type=int, default=2, help='utterances per CPU-baseline step')
+  p.add_argument('--batch', type=int, default=None, help='per-GPU batch (default: the config\'s)')
+  p.add_argument('--seconds', type=float, default=None, help='fixed utterance length (default: the config\'s)')
+  p.add_argument('--cpu-sample', type=int, default=8, help='utterances per CPU-baseline step')
+  p.add_argument('--cpu-threads', type=int, default=16, help='BLAS threads of the CPU arm (capped by the host)')
   p.add_argument('--no-cpu-baseline', action='store_true')
-  return p.parse_args()
+  p.add_argument('--no-sustained', action='store_true', help='skip the >= 2 s sustained pass')
+  p.add_argument('--sustained-seconds', type=float, default=2.5)
+  args = p.parse_args()
+  cfg = dict(CONFIGS[args.config])
+  if args.batch is not None:
+    cfg['batch'] = args.batch
+  if args.seconds is not None:
+    cfg['seconds'] = args.seconds
+  if args.precision is not None:
+    cfg['precision'] = args.precision
+  args.cfg = cfg
+  return args
 
 
 # ------------------------------------------------------------------------------------------------ workload
@@ -60,24 +98,42 @@ def make_labels(rng, n_chars, ctc_len):
 
 
 def make_batch(seed, batch, seconds):
-  """BASELINE.md synthetic inputs: N(0,1) mel [B,T,128] f32, 15 chars/s labels feasible for CTC."""
+  """BASELINE.md synthetic inputs: N(0,1) mel [B,T,128] f32, 15 chars/s labels feasible for CTC.
+  seconds: a number (fixed length) or (lo, hi): integer seconds uniform in [lo, hi], zero-padded to the batch max."""
   rng = np.random.default_rng(seed)
-  T = frames_for(seconds)
-  inputs = rng.standard_normal((batch, T, 128), dtype=np.float32)
-  lengths = np.full((batch,), T, dtype=np.int32)
-  labels = [make_labels(rng, int(15 * seconds), T // 2) for _ in range(batch)]
+  if isinstance(seconds, (tuple, list)):
+    secs = rng.integers(int(seconds[0]), int(seconds[1]) + 1, size=batch).astype(np.float64)
+  else:
+    secs = np.full((batch,), float(seconds))
+  lengths = np.array([frames_for(s) for s in secs], dtype=np.int32)
+  T = int(lengths.max())
+  inputs = np.zeros((batch, T, 128), dtype=np.float32)
+  for b in range(batch):
+    inputs[b, :lengths[b]] = rng.standard_normal((int(lengths[b]), 128), dtype=np.float32)
+  labels = [make_labels(rng, int(15 * secs[b]), int(lengths[b]) // 2) for b in range(batch)]
   return inputs, lengths, labels
 
 
 def conv_flops_forward(batch, T):
   from speecht_b200.engine import layer_table
-  total, per_layer, t = 0.0, [], T
+  total, t = 0.0, T
   for (k, s, cin, cout, _r) in layer_table():
     t = -(-t // s)
-    f = 2.0 * k * cin * cout * t * batch
-    per_layer.append(f)
-    total += f
-  return total, per_layer
+    total += 2.0 * k * cin * cout * t * batch
+  return total
+
+
+def metric_name(cfg):
+  if cfg['mode'] == 'eval':
+    return 'utterances/sec (1-30s@16kHz, 128-mel) evaluate-step: forward + CTC loss + greedy decode'
+  secs = cfg['seconds']
+  return 'utterances/sec (%gs@16kHz, 128-mel) train-step' % secs
+
+
+def reference_weights():
+  """Xavier weights from the SAME stream on the GPU arm, the CPU arm and the loss-delta check."""
+  from oracle import speecht_oracle as O
+  return O.xavier_weights(np.random.default_rng(0), dtype=np.float32)
 
 
 # ------------------------------------------------------------------------------------------------ clocks
@@ -107,18 +163,12 @@ class ClockSampler:
   def mark(self):
     return len(self.lines)
 
-  def stop(self, first=0, last=None):
-    self.lines = self.lines[first:last]
+  def summary(self, first=0, last=None):
     if self.proc is None:
       return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
-    self.proc.terminate()
-    try:
-      self.proc.wait(timeout=2)
-    except subprocess.TimeoutExpired:
-      self.proc.kill()
     sm, mx, power, reasons = [], [], [], set()
     names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
-    for line in self.lines:
+    for line in self.lines[first:last]:
       f = [x.strip() for x in line.split(',')]
       if len(f) < 9:
         continue
@@ -134,26 +184,17 @@ class ClockSampler:
     return {'sm_mhz': float(np.median(sm)), 'sm_max_mhz': float(max(mx)), 'power_w_max': float(max(power)),
             'samples': len(sm), 'reasons': sorted(reasons)}
 
+  def stop(self):
+    if self.proc is None:
+      return
+    self.proc.terminate()
+    try:
+      self.proc.wait(timeout=2)
+    except subprocess.TimeoutExpired:
+      self.proc.kill()
+
 
 # ------------------------------------------------------------------------------------------------ CPU arm
-def cpu_reference_steps(sample, seconds, steps, warmup):
-  """Times oracle.train_step (float32 numpy, BLAS on every host core) on `sample` utterances per step."""
-  from oracle import speecht_oracle as O
-  inputs, lengths, labels = make_batch(1000, sample, seconds)
-  weights = O.xavier_weights(np.random.default_rng(0), dtype=np.float32)
-  m = [(np.zeros_like(w), np.zeros_like(b)) for w, b in weights]
-  v = [(np.zeros_like(w), np.zeros_like(b)) for w, b in weights]
-  times = []
-  for i in range(warmup + steps):
-    t0 = time.perf_counter()
-    O.train_step(inputs, lengths, labels, weights, m, v, step=i + 1, lr=1e-4, dtype=np.float32)
-    dt = time.perf_counter() - t0
-    if i >= warmup:
-      times.append(dt)
-  sec = float(np.mean(times))
-  return sample / sec, sec
-
-
 def host_cores():
   try:
     return len(os.sched_getaffinity(0))
@@ -161,36 +202,115 @@ def host_cores():
     return os.cpu_count() or 1
 
 
+def cpu_threads(requested):
+  return max(1, min(int(requested), host_cores()))
+
+
+def cpu_reference_steps(mode, sample, seconds, steps, warmup, threads):
+  """Times the oracle's step (float32 numpy, BLAS pinned to `threads` threads) on `sample` utterances per step.
+  -> (utterances/s, seconds per step)."""
+  from threadpoolctl import threadpool_limits
+  from oracle import speecht_oracle as O
+  inputs, lengths, labels = make_batch(1000, sample, seconds)
+  weights = reference_weights()
+  m = [(np.zeros_like(w), np.zeros_like(b)) for w, b in weights]
+  v = [(np.zeros_like(w), np.zeros_like(b)) for w, b in weights]
+  times = []
+  with threadpool_limits(limits=threads):
+    for i in range(warmup + steps):
+      t0 = time.perf_counter()
+      if mode == 'eval':
+        O.evaluate_step(inputs, lengths, labels, weights, dtype=np.float32)
+      else:
+        O.train_step(inputs, lengths, labels, weights, m, v, step=i + 1, lr=1e-4, dtype=np.float32)
+      dt = time.perf_counter() - t0
+      if i >= warmup:
+        times.append(dt)
+  sec = float(np.mean(times))
+  return sample / sec, sec
+
+
+def cpu_sample_seconds(cfg):
+  """The CPU arm's bounded sample of the workload: fixed-length utterances; for the variable-length evaluate
+  workload its mean length (15.5 s), so that utterances/s stay comparable."""
+  secs = cfg['seconds']
+  return float(np.mean(secs)) if isinstance(secs, (tuple, list)) else float(secs)
+
+
+def cpu_baseline_record(cfg, sample, steps, warmup, threads):
+  secs = cpu_sample_seconds(cfg)
+  value, sec = cpu_reference_steps(cfg['mode'], sample, secs, steps, warmup, threads)
+  what = 'oracle.evaluate_step' if cfg['mode'] == 'eval' else 'oracle.train_step'
+  return {'value': value, 'unit': UNIT, 'cores': threads, 'kind': 'port', 'host_cores': host_cores(),
+          'sample': '%d steps of %s on %d x %gs utterances (numpy/OpenBLAS float32 pinned to %d threads, %.2f s/step); '
+                    'CPU restatement of the reference, NOT TensorFlow-1 (not installable, DESIGN.md)'
+                    % (steps, what, sample, secs, threads, sec)}, sec
+
+
 def run_reference(args, rank, world):
   if rank != 0:
     return
-  T = frames_for(args.seconds)
-  steps, warmup = max(1, min(args.steps, 3)), min(args.warmup, 1)
-  value, sec = cpu_reference_steps(args.cpu_sample, args.seconds, steps, warmup)
+  cfg = args.cfg
+  threads = cpu_threads(args.cpu_threads)
+  secs = cpu_sample_seconds(cfg)
+  # bounded: about a second per train step at 8 x 10 s on 16 threads; cap the whole run near a minute
+  per_step_guess = 1.2 * (args.cpu_sample / 8.0) * (secs / 10.0) * (0.4 if cfg['mode'] == 'eval' else 1.0)
+  steps = int(max(1, min(args.steps, 60.0 / max(per_step_guess, 1e-3))))
+  warmup = int(max(0, min(args.warmup, 1)))
+  rec, sec = cpu_baseline_record(cfg, args.cpu_sample, steps, warmup, threads)
   line = {
-    'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': steps,
-    'warmup': warmup, 'ms_per_step': sec * 1e3, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
-    'dtype': 'fp32', 'data': 'synthetic',
-    'config': {'workload': 'configs[1] train-step: 10s@16kHz synthetic 128-mel, Wav2Letter 11 conv layers, fp32; '
-                           'CPU sample of %d utterances/step (T=%d)' % (args.cpu_sample, T),
-               'global_batch': args.cpu_sample, 'seconds': args.seconds},
-    'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': host_cores(), 'kind': 'port',
-                     'sample': '%d steps of oracle.train_step on %d x %gs utterances (numpy/BLAS float32); CPU '
-                               'restatement of the reference, NOT TensorFlow-1 (not installable, DESIGN.md)'
-                               % (steps, args.cpu_sample, args.seconds)},
-    'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+    'impl': 'reference', 'metric': metric_name(cfg), 'value': rec['value'], 'unit': UNIT, 'n_gpus': args.gpus,
+    'steps': steps, 'warmup': warmup, 'ms_per_step': sec * 1e3, 'higher_is_better': True, 'scaling': 'weak',
+    'vs_baseline': None, 'dtype': 'fp32', 'data': 'synthetic',
+    'config': {'workload': cfg['name'] + '; CPU sample of %d x %gs utterances/step' % (args.cpu_sample, secs),
+               'global_batch': args.cpu_sample, 'seconds': secs, 'bench_config': args.config},
+    'cpu_baseline': rec,
+    'e2e': {'value': rec['value'], 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
     'gpu_launches': 0,
   }
   print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------ parity beside the number
+def ctc_loss_delta(eng_factory, cfg, sample=2):
+  """|CTC loss(GPU) - CTC loss(float64 oracle)| on `sample` utterances of the CPU arm's own batch, same weights
+  (BASELINE.json metric: "CTC-loss delta vs ref").  Greedy labels are compared too (bit-exact gate)."""
+  import torch
+  from oracle import speecht_oracle as O
+  secs = min(cpu_sample_seconds(cfg), 10.0)          # bounded: the float64 oracle forward is ~1 s per 10 s utterance
+  inputs, lengths, labels = make_batch(1000, sample, secs)
+  weights = reference_weights()
+  t0 = time.perf_counter()
+  ref = O.evaluate_step(inputs, lengths, labels, weights, dtype=np.float64)
+  t_ref = time.perf_counter() - t0
+  eng = eng_factory()
+  eng.load_weights(weights)
+  res = eng.evaluate_step(torch.from_numpy(inputs).to(eng.device), lengths, labels, decode=True)
+  loss = res['loss'].cpu().numpy().astype(np.float64)
+  logits = res['logits'].cpu().numpy().astype(np.float64)
+  d = np.abs(loss - ref['loss'])
+  out = {'max_abs': float(d.max()), 'max_rel': float((d / np.abs(ref['loss'])).max()),
+         'avg_loss_gpu': float(loss.mean()), 'avg_loss_oracle': float(ref['loss'].mean()),
+         'logits_max_rel': float(np.max(np.abs(logits - ref['logits'])) / np.max(np.abs(ref['logits']))),
+         'greedy_labels_equal': bool(np.array_equal(res['decoded'][0].values, ref['decoded'][1])
+                                     and np.array_equal(res['decoded'][0].indices, ref['decoded'][0])),
+         'sample': '%d x %gs utterances, float64 numpy oracle (%.1f s), precision %s' % (sample, secs, t_ref,
+                                                                                        eng.precision),
+         'gate': '1e-4 relative (north_star); greedy labels bit-exact'}
+  del eng
+  torch.cuda.empty_cache()
+  return out
 
 
 # ------------------------------------------------------------------------------------------------ GPU arm
 def run_ours(args, rank, local_rank, world):
   import torch
   import torch.distributed as dist
-  from speecht_b200 import speech_input, speech_model
+  from speecht_b200 import parallel, speech_input, speech_model
   from speecht_b200.engine import W2LEngine
 
+  cfg = args.cfg
+  mode, precision = cfg['mode'], cfg['precision']
   torch.cuda.set_device(local_rank)
   dev = torch.device('cuda', local_rank)
   group = None
@@ -198,14 +318,19 @@ def run_ours(args, rank, local_rank, world):
     dist.init_process_group('nccl', device_id=dev)
     group = dist.group.WORLD
 
-  B, T = args.batch, frames_for(args.seconds)
-  n_sets = 4                                                 # rotate distinct batches so inputs never sit in L2
-  host_sets = [make_batch(100 * rank + i, B, args.seconds) for i in range(n_sets)]
+  B = cfg['batch']
+  n_sets = 4 if mode == 'train' else 2                      # rotate distinct batches so inputs never sit in L2
+  host_sets = [make_batch(100 * rank + i, B, cfg['seconds']) for i in range(n_sets)]
   pinned = [torch.from_numpy(h[0]).pin_memory() for h in host_sets]
   dev_inputs = [p.to(dev) for p in pinned]
+  T = int(max(h[0].shape[1] for h in host_sets))
 
-  eng = W2LEngine(precision=args.precision, device=dev, process_group=group)
-  eng.init_xavier(seed=0)                                    # same weights on every rank
+  delta = None
+  if rank == 0:
+    delta = ctc_loss_delta(lambda: W2LEngine(precision=precision, device=dev), cfg)
+
+  eng = W2LEngine(precision=precision, device=dev, process_group=group)
+  eng.load_weights(reference_weights())                      # same weights on every rank (and on the CPU arm)
   lr = 1e-4
 
   def barrier():
@@ -221,17 +346,22 @@ def run_ours(args, rank, local_rank, world):
       fn(i)
     e1.record()
     barrier()
-    ms = e0.elapsed_time(e1)
-    if world > 1:
-      t = torch.tensor([ms], device=dev, dtype=torch.float64)
-      dist.all_reduce(t, op=dist.ReduceOp.MAX)
-      ms = float(t.item())
-    return ms
+    return parallel.max_scalar(e0.elapsed_time(e1), device=dev)
 
-  # ---- device-resident throughput (`value`)
-  def step_resident(i):
-    h = host_sets[i % n_sets]
-    eng.train_step(dev_inputs[i % n_sets], h[1], h[2], lr)
+  # ---- device-resident step (`value`)
+  if mode == 'train':
+    def step_resident(i):
+      h = host_sets[i % n_sets]
+      eng.train_step(dev_inputs[i % n_sets], h[1], h[2], lr)
+  else:
+    from speecht_b200 import ops
+    ctc_batches = [ops.CTCBatch(h[2], h[1] // 2, (h[0].shape[1] + 1) // 2, eng.num_classes, dev) for h in host_sets]
+
+    def step_resident(i):
+      # forward + CTC loss + greedy-decode kernels; the compacted label rows stay on the device (the host-side
+      # SparseTensor assembly and, at N > 1, the gather of the rows belong to the e2e number below)
+      k = i % n_sets
+      eng.evaluate_step_device(dev_inputs[k], ctc_batches[k])
 
   sampler = ClockSampler(local_rank)
   if rank == 0:
@@ -247,23 +377,38 @@ def run_ours(args, rank, local_rank, world):
   ms_step = ms_total / args.steps
   value = world * B / (ms_step * 1e-3)
   # pass 2 (roofline): the same K steps again with a CUDA-event pair recorded around every conv launch on the
-  # launch stream -- the ~70 extra stream commands per step cost a few % and are kept out of `value`
+  # launch stream -- the extra stream commands cost a few % and are kept out of `value`
   eng.start_kernel_timing()
   ms_instrumented = timed(step_resident, args.steps) / args.steps
   timings = eng.stop_kernel_timing()
+  # pass 3 (sustained): the same step for >= 2.5 s, so the power cap has settled (MEASURED_PEAKS' sustained figure
+  # is the denominator that goes with THIS number)
+  sustained = None
+  if not args.no_sustained:
+    n_sus = int(max(args.steps, np.ceil(args.sustained_seconds * 1e3 / ms_step)))
+    mark_s0 = sampler.mark()
+    ms_sus = timed(step_resident, n_sus) / n_sus
+    mark_s1 = sampler.mark()
+    sustained = {'steps': n_sus, 'ms_per_step': ms_sus, 'value': world * B / (ms_sus * 1e-3),
+                 'seconds': ms_sus * n_sus * 1e-3}
+    if rank == 0:
+      sustained['clocks'] = sampler.summary(mark_s0, mark_s1)
+
+  dp_identical = None
+  if world > 1 and mode == 'train':
+    dp_identical = bool(parallel.identical_across_ranks(eng.params, group))
 
   # ---- roofline of the dominant kernel, from events recorded inside the timed region
   roofline = None
   if rank == 0:
-    roofline = eng.roofline_report(timings, args.steps, os.path.join(ROOT, 'MEASURED_PEAKS.json'))
+    roofline = eng.roofline_report(timings, args.steps, PEAKS_PATH, region_seconds=ms_total * 1e-3,
+                                   train=(mode == 'train'))
     if roofline is not None:
       roofline['instrumented_ms_per_step'] = ms_instrumented
-    if roofline is not None and os.path.exists(os.path.join(ROOT, 'profiles', 'traffic.json')):
-      # dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed
-      # `ncu --set full` capture (profiles/), keyed by precision
-      tr = json.load(open(os.path.join(ROOT, 'profiles', 'traffic.json'))).get(args.precision, {})
-      roofline['traffic'] = tr.get('bytes_per_launch')
-      roofline['traffic_source'] = tr.get('source')
+      if sustained is not None:
+        roofline['frac_sustained_run'] = (roofline['achieved'] * ms_step / sustained['ms_per_step']) / \
+          roofline['peak_sustained'] if roofline.get('peak_sustained') else None
+      roofline['traffic'], roofline['traffic_source'] = lookup_traffic(precision, B, T, roofline.get('kernel'))
 
   # ---- end-to-end through SpeechModel.step with host batches (`e2e`)
   class HostFeed(speech_input.BaseInputLoader):
@@ -283,60 +428,87 @@ def run_ours(args, rank, local_rank, world):
       return pinned[k], host_sets[k][1], host_sets[k][2]
 
   import types
-  flags = types.SimpleNamespace(command='train', learning_rate=lr, learning_rate_decay_factor=0.0,
-                                max_gradient_norm=5.0, momentum=0.9, log_dir='log', run_name='bench',
-                                run_type='train', precision=args.precision, process_group=group, engine=eng)
+  flags = types.SimpleNamespace(command='train' if mode == 'train' else 'evaluate', learning_rate=lr,
+                                learning_rate_decay_factor=0.0, max_gradient_norm=5.0, momentum=0.9, log_dir='log',
+                                run_name='bench', run_type='train', precision=precision, process_group=group,
+                                engine=eng, language_model=None)
   feed = HostFeed()
   model = speech_model.create_default_model(flags, 128, feed)
   sess = speech_model.Session(dev)
+  d2h_bytes = [4]
+  if mode == 'train':
+    def step_e2e(i):
+      model.step(sess)
+  else:
+    def step_e2e(i):
+      _loss, decoded, _labels = model.step(sess, update=False, decode=True, return_label=True)
+      rows = decoded[0]
+      d2h_bytes[0] = 4 + 4 * B + 4 * int(rows.values.shape[0])
+      if world > 1:
+        parallel.gather_decoded_sparse(rows, group, device=dev)
   for i in range(args.warmup):
-    model.step(sess)
-  e2e_ms = timed(lambda i: model.step(sess), args.steps) / args.steps
+    step_e2e(i)
+  e2e_ms = timed(step_e2e, args.steps) / args.steps
   e2e_value = world * B / (e2e_ms * 1e-3)
   clocks = None
   if rank == 0:
     mark2 = sampler.mark()
-    # samples taken during the device-resident timed region; if it was shorter than the 100 ms sampling period,
-    # fall back to everything up to the end of the e2e region (same kernels, same load)
-    clocks = sampler.stop(mark0, mark1 if mark1 > mark0 else mark2)
+    # samples taken during the device-resident timed region; if it was shorter than the sampling period, everything
+    # up to the end of the e2e region (same kernels, same load)
+    clocks = sampler.summary(mark0, mark1 if mark1 > mark0 else mark2)
+    sampler.stop()
 
   aux = None
-  if rank == 0 and world == 1:
-    aux = aux_kernels(eng, dev, B, args.seconds, host_sets[0], os.path.join(ROOT, 'MEASURED_PEAKS.json'))
+  if rank == 0 and world == 1 and mode == 'train':
+    aux = aux_kernels(eng, dev, B, cfg['seconds'], host_sets[0], PEAKS_PATH)
   if world > 1:
     dist.destroy_process_group()
   if rank != 0:
     return
 
-  fwd_flops, _ = conv_flops_forward(B, T)
+  mean_frames = float(np.mean([h[1].mean() for h in host_sets]))
+  fwd_flops = conv_flops_forward(B, T)
+  h2d = int(pinned[0].numel() * 4 + sum(len(l) for l in host_sets[0][2]) * 4 + 8 * B + 4)
   line = {
-    'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
-    'ms_per_step': ms_step, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+    'metric': metric_name(cfg), 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
+    'warmup': args.warmup, 'ms_per_step': ms_step, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
     'dtype': {'fp32': 'fp32', 'bf16x3': 'fp32 (bf16x3 split operands on tcgen05, fp32 accumulate; CTC/Adam fp32)',
               'bf16x6': 'fp32 (bf16x6: three bf16 planes per operand, 6 products on tcgen05, fp32 accumulate)',
-              'bf16': 'bf16 conv operands, fp32 accumulate; CTC/Adam fp32'}[args.precision],
+              'bf16': 'bf16 conv operands, fp32 accumulate; CTC/Adam fp32'}[precision],
     'data': 'synthetic',
-    'config': {'workload': 'configs[1] train-step: batch %d/GPU, %gs@16kHz synthetic 128-mel (T=%d, T\'=%d), '
-                           'Wav2Letter 11 conv layers' % (B, args.seconds, T, (T + 1) // 2),
-               'global_batch': world * B, 'precision': args.precision, 'parallelism': 'dp%d' % world,
+    'config': {'workload': cfg['name'] + ' (T=%d mel frames -> T\'=%d logit frames)' % (T, (T + 1) // 2),
+               'bench_config': args.config, 'mode': mode, 'global_batch': world * B, 'precision': precision,
+               'parallelism': 'dp%d' % world, 'mean_frames': mean_frames,
                'l2': 'no explicit flush: per-step working set (activations+params+grads+Adam > 1 GB) exceeds the '
                      '126 MB L2 and %d distinct input batches rotate' % n_sets,
-               'train_tflop_per_step_per_gpu': 3 * fwd_flops / 1e12},
+               'conv_tflop_per_step_per_gpu': (3 if mode == 'train' else 1) * fwd_flops / 1e12},
     'clocks': clocks,
-    'e2e': {'value': e2e_value, 'unit': UNIT, 'ms_per_step': e2e_ms,
-            'h2d_bytes_per_step': int(pinned[0].numel() * 4 + sum(len(l) for l in host_sets[0][2]) * 4 + 8 * B + 4),
-            'd2h_bytes_per_step': 4},
+    'e2e': {'value': e2e_value, 'unit': UNIT, 'ms_per_step': e2e_ms, 'h2d_bytes_per_step': h2d,
+            'd2h_bytes_per_step': int(d2h_bytes[0])},
     'gpu_launches': int(launches),
+    'ctc_loss_delta': delta,
     'roofline': roofline,
+    'sustained': sustained,
     'aux_hbm_kernels': aux,
   }
+  if dp_identical is not None:
+    line['dp_identical'] = dp_identical
   if world == 1 and not args.no_cpu_baseline:
-    cv, csec = cpu_reference_steps(args.cpu_sample, args.seconds, 2, 1)
-    line['cpu_baseline'] = {'value': cv, 'unit': UNIT, 'cores': host_cores(), 'kind': 'port',
-                            'sample': '2 steps of oracle.train_step on %d x %gs utterances (numpy/BLAS float32, '
-                                      '%.1f s/step); CPU restatement, not TensorFlow-1' % (args.cpu_sample,
-                                                                                         args.seconds, csec)}
+    rec, _sec = cpu_baseline_record(cfg, args.cpu_sample, 2, 1, cpu_threads(args.cpu_threads))
+    line['cpu_baseline'] = rec
   print(json.dumps(line), flush=True)
+
+
+def lookup_traffic(precision, B, T, kernel):
+  """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel from the committed
+  `ncu --set full` capture of THIS shape (profiles/traffic.json, key "<precision>/B<batch>/T<frames>"); None when no
+  capture of this shape exists -- a number measured on another shape would be silently wrong."""
+  if not os.path.exists(TRAFFIC_PATH):
+    return None, None
+  tr = json.load(open(TRAFFIC_PATH)).get('%s/B%d/T%d' % (precision, B, T))
+  if not tr or (kernel and kernel not in tr.get('kernel', '')):
+    return None, None
+  return tr.get('bytes_per_launch'), tr.get('source')
 
 
 def aux_kernels(eng, dev, B, seconds, host_set, peaks_path):

@@ -37,7 +37,9 @@ def _stale(target, deps):
   return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
 
 
-def build(force=False, verbose=False):
+def build(force=False, verbose=False, report=None):
+  """Compile what is stale (everything with force=True) and link.  `report`, when a list, receives the names of
+  the sources that were actually recompiled and 'link' when the shared library was relinked."""
   os.makedirs(OBJ_DIR, exist_ok=True)
   nvcc = _nvcc()
   headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(('.cuh', '.h'))] + [HEADER]
@@ -63,6 +65,8 @@ def build(force=False, verbose=False):
     for msg in pool.map(compile_one, jobs):
       if verbose and msg:
         print(msg)
+  if report is not None:
+    report.extend(os.path.basename(path) for path, _obj in jobs)
   objs = [os.path.join(OBJ_DIR, s.replace('.cu', '.o')) for s in sources]
   if force or jobs or _stale(LIB_PATH, objs):
     cmd = [nvcc, '-shared', '-o', LIB_PATH] + objs + ['-cudart', 'static', '-gencode', 'arch=compute_100a,code=sm_100a']
@@ -71,6 +75,8 @@ def build(force=False, verbose=False):
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
       raise RuntimeError('link failed:\n%s\n%s' % (r.stdout, r.stderr))
+    if report is not None:
+      report.append('link')
   return LIB_PATH
 
 

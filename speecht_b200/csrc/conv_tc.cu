@@ -1118,6 +1118,13 @@ EncodeTiledFn encode_fn() {
   return fn;
 }
 
+constexpr int kMaxDevices = 64;
+int current_device() {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  return (dev >= 0 && dev < kMaxDevices) ? dev : 0;
+}
+
 int grid_for(int work_items) {
   const int sms = st_num_sms();
   return work_items < sms ? work_items : sms;
@@ -1145,11 +1152,13 @@ template <int BLOCK_N, int NPL, bool EARLY>
 int launch_conv_e(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmOut, const ConvParams& p,
                   cudaStream_t stream) {
   using Cfg = ConvCfg<BLOCK_N, NPL>;
-  static bool configured = false;
-  if (!configured) {
+  // the opt-in for > 48 KB of dynamic shared memory is a per-DEVICE function attribute
+  static bool configured[kMaxDevices] = {};
+  const int dev = current_device();
+  if (!configured[dev]) {
     ST_CUDA_CALL(cudaFuncSetAttribute(tc_conv_kernel<BLOCK_N, NPL, EARLY>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       Cfg::SMEM_BYTES));
-    configured = true;
+    configured[dev] = true;
   }
   const int tiles = p.B * p.m_tiles_per_utt * p.n_tiles;
   ST_CUDA_CALL(launch_pdl(tc_conv_kernel<BLOCK_N, NPL, EARLY>, grid_for(tiles), Cfg::SMEM_BYTES, stream, tmA, tmB,
@@ -1186,11 +1195,12 @@ int launch_conv_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensor
 template <int BLOCK_N, int NPL>
 int launch_wgrad_t(const CUtensorMap& tmX, const CUtensorMap& tmDZ, const WgradParams& p, cudaStream_t stream) {
   using Cfg = WgradCfg<BLOCK_N, NPL>;
-  static bool configured = false;
-  if (!configured) {
+  static bool configured[kMaxDevices] = {};
+  const int dev = current_device();
+  if (!configured[dev]) {
     ST_CUDA_CALL(cudaFuncSetAttribute(tc_wgrad_kernel<BLOCK_N, NPL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       Cfg::SMEM_BYTES));
-    configured = true;
+    configured[dev] = true;
   }
   ST_CUDA_CALL(launch_pdl(tc_wgrad_kernel<BLOCK_N, NPL>, st_num_sms(), Cfg::SMEM_BYTES, stream, tmX, tmDZ, p));
   return ST_OK;

@@ -29,6 +29,18 @@ from ._lib import check, lib, ptr, stream_ptr
 PRECISIONS = ('fp32', 'bf16x6', 'bf16x3', 'bf16')
 
 
+def _on_engine_device(fn):
+  """The native calls launch on torch's CURRENT device and stream: run the method with the engine's own device
+  current, so an engine created for cuda:1 works while cuda:0 is the process default."""
+  import functools
+
+  @functools.wraps(fn)
+  def wrapped(self, *args, **kwargs):
+    with torch.cuda.device(self.device):
+      return fn(self, *args, **kwargs)
+  return wrapped
+
+
 def layer_table(input_size=128, num_classes=29):
   """(filter_width, stride, cin, cout, relu) per layer -- reference speech_model.py:275-292."""
   layers = [(48, 2, input_size, 250, True)]
@@ -101,6 +113,7 @@ class W2LEngine:
     self.kernel_times = []                                    # (kernel name, algorithmic flops, start, stop)
 
   # ---------------------------------------------------------------- parameters
+  @_on_engine_device
   def init_xavier(self, seed=0):
     """tf.contrib.layers.xavier_initializer on [K,Cin,Cout] + zero bias (speech_model.py:150-152)."""
     rng = np.random.default_rng(seed)
@@ -110,6 +123,7 @@ class W2LEngine:
       b.zero_()
     self.mark_weights_changed()
 
+  @_on_engine_device
   def load_weights(self, weights):
     """weights: list of (filters [K,Cin,Cout], bias [Cout]) numpy arrays in the `export` .npy layout."""
     if len(weights) != len(self.layers):
@@ -169,10 +183,12 @@ class W2LEngine:
     self.kernel_times = []
     return out
 
-  def roofline_report(self, timings, steps, peaks_path=None):
+  def roofline_report(self, timings, steps, peaks_path=None, region_seconds=None, train=True):
     """Roofline of the dominant kernel from CUDA events recorded around its launches INSIDE the timed steps:
-    achieved = algorithmic FLOPs of those launches / their summed duration; peak = MEASURED_PEAKS.json
-    (bf16_tflops_sustained: the kernel is timed inside a long step) or the B200_PROFILING.md fallback."""
+    achieved = algorithmic FLOPs of those launches / their summed duration.  Denominator: MEASURED_PEAKS.json --
+    the BURST cuBLAS bf16 figure when the timed region is shorter than a second (the power cap has not settled, the
+    SM clock is still near its maximum), the SUSTAINED one otherwise; both fractions are reported.  Without the file:
+    the B200_PROFILING.md fallback (1.59 PFLOP/s burst, ~1.4 sustained), labelled as such."""
     import json
     import os
     by, per_layer = {}, {}
@@ -184,18 +200,24 @@ class W2LEngine:
         pl[0] += flops; pl[1] += ms
     if not by:
       return None
-    peak, src = 1590.0, 'fallback 1.59 PFLOP/s (B200_PROFILING.md)'
+    burst, sustained, src = 1590.0, 1400.0, 'fallback (B200_PROFILING.md: 1.59 PFLOP/s burst, ~1.4 sustained)'
     if peaks_path and os.path.exists(peaks_path):
       pk = json.load(open(peaks_path))
-      peak, src = float(pk.get('bf16_tflops_sustained', pk.get('bf16_tflops'))), \
-        'MEASURED_PEAKS.json bf16_tflops_sustained (cuBLAS bf16, back-to-back)'
+      burst = float(pk.get('bf16_tflops', burst))
+      sustained = float(pk.get('bf16_tflops_sustained', sustained))
+      src = 'measured (MEASURED_PEAKS.json: cuBLAS bf16 8192^3, burst best-of-10 / sustained 4 s back to back)'
+    use_burst = region_seconds is None or region_seconds < 1.0
+    peak = burst if use_burst else sustained
     name = max(by, key=lambda k: by[k][1])
     flops, ms, n = by[name]
     achieved = flops / (ms * 1e-3) / 1e12
     passes = {'fp32': None, 'bf16x6': 6, 'bf16x3': 3, 'bf16': 1}[self.precision]
     rep = {'kernel': name, 'bound': 'tensor', 'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s',
-           'frac': achieved / peak, 'traffic': None, 'launches_per_step': n / steps, 'avg_launch_ms': ms / n,
-           'ms_per_step': ms / steps, 'peak_source': src,
+           'frac': achieved / peak, 'traffic': None,
+           'peak_kind': ('burst' if use_burst else 'sustained') + ' (timed region %.2f s)' % (region_seconds or 0.0),
+           'peak_burst': burst, 'peak_sustained': sustained, 'frac_burst': achieved / burst,
+           'frac_sustained': achieved / sustained, 'peak_source': src,
+           'launches_per_step': n / steps, 'avg_launch_ms': ms / n, 'ms_per_step': ms / steps,
            'kernels': {k: {'tflops': v[0] / (v[1] * 1e-3) / 1e12, 'ms_per_step': v[1] / steps,
                            'launches_per_step': v[2] / steps} for k, v in by.items()},
            'layers_ms_per_step': {k: round(v[1] / steps, 4) for k, v in sorted(per_layer.items())}}
@@ -203,8 +225,8 @@ class W2LEngine:
       rep['mma_passes'] = passes
       rep['tensor_pipe_frac'] = passes * achieved / peak
       rep['note'] = ('achieved = algorithmic FLOPs (unpadded, 1 pass) / event time; in %s mode the tensor pipe '
-                     'executes %d MMAs per algorithmic MAC, tensor_pipe_frac = %d*frac' % (self.precision, passes,
-                                                                                         passes)) if passes > 1 else \
+                     'executes %d MMAs per algorithmic MAC, so the ceiling of frac is 1/%d and tensor_pipe_frac = '
+                     '%d*frac' % (self.precision, passes, passes, passes)) if passes > 1 else \
                     'plain bf16: one MMA pass'
     else:
       rep['note'] = 'exact-fp32 FFMA path: compared with the bf16 tensor peak for reference only'
@@ -239,6 +261,7 @@ class W2LEngine:
     return outs
 
   # ---------------------------------------------------------------- forward
+  @_on_engine_device
   def forward(self, inputs, keep_activations=False):
     """inputs [B,T,input_size] f32 CUDA -> logits [T',B,num_classes] (time-major VIEW, speech_model.py:295)."""
     if inputs.dim() != 3 or inputs.shape[2] != self.input_size:
@@ -288,6 +311,7 @@ class W2LEngine:
       self._plan = TCPlan(self)
     return self._plan
 
+  @_on_engine_device
   def evaluate_step(self, inputs, sequence_lengths, labels=None, decode=True):
     """model.step(update=False, decode=True): returns dict(loss [B] tensor|None, avg_loss, decoded, logits)."""
     logits = self.forward(inputs, keep_activations=False)
@@ -303,6 +327,18 @@ class W2LEngine:
       self.launches += 1
     return out
 
+  @_on_engine_device
+  def evaluate_step_device(self, inputs, ctc_batch, merge_repeated=True):
+    """The kernels of model.step(update=False, decode=True) with every result left on the device: forward, CTC loss
+    (no gradient) and greedy decode.  ctc_batch: ops.CTCBatch of this batch (labels + ctc lengths already uploaded).
+    -> (loss [B], label rows [B, T'] int32, counts [B] int32, neg_sum_logits [B])."""
+    logits = self.forward(inputs, keep_activations=False)
+    loss, _ = ops.ctc_loss(ctc_batch, logits, want_grad=False)
+    values, counts, neg = ops.ctc_greedy_decode_device(logits, ctc_batch.seq_len, merge_repeated)
+    self.launches += 3
+    return loss, values, counts, neg
+
+  @_on_engine_device
   def train_step(self, inputs, sequence_lengths, labels, learning_rate, max_gradient_norm=5.0, decode=False):
     """model.step(update=True): forward, CTC, backward, [allreduce], clip_by_global_norm, Adam.
     Returns dict(avg_loss device scalar (LOCAL batch mean), loss [B], decoded|None)."""
@@ -336,6 +372,7 @@ class W2LEngine:
       return []
     return handles
 
+  @_on_engine_device
   def apply_gradients(self, learning_rate, max_gradient_norm=5.0, reduced=False):
     """[allreduce] + tf.clip_by_global_norm + Adam(eps=1e-3) on the flat buffers (speech_model.py:77-82)."""
     if not reduced:
@@ -348,5 +385,6 @@ class W2LEngine:
     self.launches += 2
     self.mark_weights_changed()
 
+  @_on_engine_device
   def grad_norm(self):
     return float(torch.sqrt(ops.global_norm_sq(self.grads)).item())

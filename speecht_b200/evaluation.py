@@ -103,6 +103,7 @@ class Evaluation(DatasetExecutor):
         coord.request_stop()
       self.print_global_statistics(stats)
       coord.join()
+      self.speech_input.raise_if_failed()
     return stats
 
   @staticmethod

@@ -167,43 +167,61 @@ def ctc_loss(labels, logits, sequence_length=None, want_grad=True, grad_scale=1.
   return loss, grad
 
 
+_decode_bufs = {}
+
+
+def ctc_greedy_decode_device(logits, d_seq, merge_repeated=True):
+  """The decode kernel alone: logits [T,B,C] (strided view allowed), d_seq int32 [B] on the device ->
+  (label rows [B, max(T,1)] int32, counts [B] int32, neg_sum_logits [B] f32), all on the device (buffers are reused
+  per shape: copy what must survive the next call)."""
+  _require_cuda(logits)
+  T, B, C = logits.shape
+  if logits.stride(2) != 1 or logits.dtype != torch.float32:
+    raise ValueError('logits must be float32 with unit class stride')
+  dev = logits.device
+  key = (T, B, dev)
+  buf = _decode_bufs.get(key)
+  if buf is None:
+    if len(_decode_bufs) > 16:
+      _decode_bufs.clear()
+    buf = (torch.empty((B, max(T, 1)), dtype=torch.int32, device=dev),
+           torch.empty((B,), dtype=torch.int32, device=dev), torch.empty((B,), dtype=torch.float32, device=dev))
+    _decode_bufs[key] = buf
+  values, counts, neg = buf
+  check(lib().st_ctc_greedy_decode(ptr(logits), logits.stride(0), logits.stride(1), T, B, C, ptr(d_seq), C - 1,
+                                   int(bool(merge_repeated)), ptr(values), ptr(counts), ptr(neg), stream_ptr()))
+  return values, counts, neg
+
+
 def ctc_greedy_decoder(logits, sequence_length, merge_repeated=True):
   """tf.nn.ctc_greedy_decoder(logits [T,B,C], sequence_length, merge_repeated) (speech_model.py:113-115).
   Returns ([SparseTensorValue(indices int64 [N,2], values int64 [N], dense_shape int64 [2])], neg_sum_logits [B,1])
   as numpy, like sess.run would hand it to evaluation.py:144,161-171."""
   _require_cuda(logits)
   T, B, C = logits.shape
-  if logits.stride(2) != 1 or logits.dtype != torch.float32:
-    raise ValueError('logits must be float32 with unit class stride')
   dev = logits.device
   if torch.is_tensor(sequence_length):
     d_seq = sequence_length.to(device=dev, dtype=torch.int32)
   else:
     d_seq = torch.from_numpy(np.ascontiguousarray(np.asarray(sequence_length, dtype=np.int32))).to(dev)
-  values = torch.empty((B, max(T, 1)), dtype=torch.int32, device=dev)
-  counts = torch.empty((B,), dtype=torch.int32, device=dev)
-  neg = torch.empty((B,), dtype=torch.float32, device=dev)
-  check(lib().st_ctc_greedy_decode(ptr(logits), logits.stride(0), logits.stride(1), T, B, C, ptr(d_seq), C - 1,
-                                   int(bool(merge_repeated)), ptr(values), ptr(counts), ptr(neg), stream_ptr()))
+  values, counts, neg = ctc_greedy_decode_device(logits, d_seq, merge_repeated)
   return [sparse_from_rows(values, counts)], neg.cpu().numpy().reshape(B, 1)
 
 
 def sparse_from_rows(values, counts):
-  """[B,T] int32 rows + counts -> the SparseTensor triple TF returns (row-major order)."""
+  """[B,T] int32 rows + counts -> the SparseTensor triple TF returns (row-major order).  Only the counts and the
+  first max(count) columns of the rows cross to the host."""
   counts_h = counts.cpu().numpy().astype(np.int64)
-  values_h = values.cpu().numpy()
   B = counts_h.shape[0]
+  width = int(counts_h.max()) if B else 0
+  values_h = values[:, :max(width, 1)].cpu().numpy()
   n = int(counts_h.sum())
-  indices = np.zeros((n, 2), dtype=np.int64)
-  vals = np.zeros((n,), dtype=np.int64)
-  pos = 0
-  for b in range(B):
-    c = int(counts_h[b])
-    indices[pos:pos + c, 0] = b
-    indices[pos:pos + c, 1] = np.arange(c)
-    vals[pos:pos + c] = values_h[b, :c]
-    pos += c
-  shape = np.array([B, int(counts_h.max()) if B else 0], dtype=np.int64)
+  rows = np.repeat(np.arange(B, dtype=np.int64), counts_h)
+  starts = np.cumsum(counts_h) - counts_h
+  cols = np.arange(n, dtype=np.int64) - np.repeat(starts, counts_h)
+  indices = np.stack([rows, cols], axis=1).reshape(n, 2)
+  vals = values_h[rows, cols].astype(np.int64) if n else np.zeros((0,), dtype=np.int64)
+  shape = np.array([B, width], dtype=np.int64)
   return SparseTensorValue(indices, vals, shape)
 
 

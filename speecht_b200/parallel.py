@@ -78,3 +78,57 @@ def gather_decoded(decoded_rows, group=None):
   gathered = [None] * dist.get_world_size(group)
   dist.all_gather_object(gathered, [list(map(int, r)) for r in decoded_rows], group=group)
   return [row for part in gathered for row in part]
+
+
+def gather_decoded_sparse(sparse, group=None, device=None):
+  """Decode gather over tensors instead of pickled objects: every rank contributes the (indices, values, dense_shape)
+  triple of its greedy decode; returns the triple of the GLOBAL batch (rows offset by the batch sizes of the lower
+  ranks) on every rank.  Two collectives: the sizes, then the padded entries."""
+  if not dist.is_initialized() or dist.get_world_size(group) == 1:
+    return sparse
+  world = dist.get_world_size(group)
+  n, b = int(sparse.values.shape[0]), int(sparse.dense_shape[0])
+  meta = torch.tensor([n, b, int(sparse.dense_shape[1])], dtype=torch.int64, device=device)
+  metas = [torch.empty_like(meta) for _ in range(world)]
+  dist.all_gather(metas, meta, group=group)
+  metas = torch.stack(metas).cpu().numpy()
+  cap = int(metas[:, 0].max())
+  mine = torch.zeros((max(cap, 1), 3), dtype=torch.int64, device=device)
+  if n:
+    mine[:n, :2] = torch.from_numpy(np.ascontiguousarray(sparse.indices)).to(device)
+    mine[:n, 2] = torch.from_numpy(np.ascontiguousarray(sparse.values)).to(device)
+  parts = [torch.empty_like(mine) for _ in range(world)]
+  dist.all_gather(parts, mine, group=group)
+  indices, values, row0 = [], [], 0
+  for r in range(world):
+    part = parts[r][:int(metas[r, 0])].cpu().numpy()
+    idx = part[:, :2].copy()
+    idx[:, 0] += row0
+    indices.append(idx)
+    values.append(part[:, 2])
+    row0 += int(metas[r, 1])
+  from .ops import SparseTensorValue
+  return SparseTensorValue(np.concatenate(indices).reshape(-1, 2), np.concatenate(values),
+                           np.array([row0, int(metas[:, 2].max())], dtype=np.int64))
+
+
+def identical_across_ranks(tensor, group=None):
+  """True when every rank holds bit-identical contents (data-parallel invariant: identical parameters after every
+  update).  Compares the elementwise MAX and MIN over ranks of the raw bit patterns."""
+  if not dist.is_initialized() or dist.get_world_size(group) == 1:
+    return True
+  bits = tensor.detach().contiguous().view(torch.int32).clone()
+  hi, lo = bits.clone(), bits
+  dist.all_reduce(hi, op=dist.ReduceOp.MAX, group=group)
+  dist.all_reduce(lo, op=dist.ReduceOp.MIN, group=group)
+  return bool(torch.equal(hi, lo))
+
+
+def any_rank_true(flag, device=None, group=None):
+  """Logical OR of a per-rank python bool (data-parallel ranks agree on termination before entering a step, so that
+  no rank is left waiting in the gradient allreduce)."""
+  if not dist.is_initialized() or dist.get_world_size(group) == 1:
+    return bool(flag)
+  t = torch.tensor([1 if flag else 0], dtype=torch.int32, device=device)
+  dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
+  return bool(t.item())

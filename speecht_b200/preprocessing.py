@@ -140,22 +140,30 @@ class SpeechCorpusReader:
         audio_id = self._extract_audio_id(audio_file)
         np.savez(out_directory + '/' + audio_id, audio_fragments=fragments, transcript=transcript_dict[audio_id])
 
-  def load_samples(self, directory, max_size=False, loop_infinitely=False, limit_count=0, feature_type='mfcc'):
+  def load_samples(self, directory, max_size=False, loop_infinitely=False, limit_count=0, feature_type='mfcc',
+                   shard=None, rng=None):
     """Generator of (audio_fragments [T, n_features], transcript [L]) over the stored .npz files of `directory`
     (preprocessing.py:243-279): shuffled once, optionally truncated to `limit_count` files, over-long utterances
-    (more than `max_size` frames) skipped with a warning; with `loop_infinitely` reshuffled after every pass."""
+    (more than `max_size` frames) skipped with a warning; with `loop_infinitely` reshuffled after every pass.
+    `rng` (a random.Random) replaces the global generator; `shard` = (rank, world) keeps every world-th file."""
     load_directory = self._get_directory(feature_type, directory)
     if not os.path.exists(load_directory):
       raise ValueError('Directory {} does not exist'.format(load_directory))
     files = list(iglob_recursive(load_directory, '*.npz'))
-    random.shuffle(files)
+    if rng is not None:
+      files.sort()                              # os.walk order is not portable; the private generator defines the order
+    shuffle = rng.shuffle if rng is not None else random.shuffle
+    shuffle(files)
     files = files[:limit_count] if limit_count else files
+    rank, world = shard if shard is not None else (0, 1)
     for epoch in itertools.count():
       if epoch and not loop_infinitely:
         return
       if epoch:
-        random.shuffle(files)
-      for path in files:
+        shuffle(files)
+      # shard = (rank, world): this reader yields every world-th file of the commonly shuffled list (new; the
+      # reference is single-process)
+      for path in files[rank::world]:
         with np.load(path) as stored:
           fragments, transcript = stored['audio_fragments'], stored['transcript']
         if max_size and fragments.shape[0] > max_size:

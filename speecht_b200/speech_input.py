@@ -141,6 +141,8 @@ class InputBatchLoader(BaseInputLoader):
     self._lock = threading.Lock()
     self._live_threads = 0
     self._closed = False
+    self._error = None                      # first exception raised inside a feeder thread
+    self._held = None                       # item taken off the queue by at_end(), handed out by the next dequeue
 
   def get_inputs(self):
     return self.inputs, self.sequence_lengths, self.labels
@@ -157,6 +159,23 @@ class InputBatchLoader(BaseInputLoader):
       except queue.Full:
         if coord is not None and coord.should_stop():
           return False
+
+  def _close(self, coord):
+    """Append the end marker.  When the consumer has stopped (full queue, stop requested) one stale batch is
+    dropped to make room, so a feeder thread never blocks forever on a queue nobody reads."""
+    while True:
+      try:
+        self.queue.put_nowait(self._END)
+        return
+      except queue.Full:
+        if coord is None or coord.should_stop():
+          try:
+            self.queue.get_nowait()
+          except queue.Empty:
+            pass
+        else:
+          import time
+          time.sleep(0.05)
 
   def _enqueue(self, sess, coord):
     try:
@@ -176,13 +195,19 @@ class InputBatchLoader(BaseInputLoader):
               break
         if coord is not None and coord.should_stop():
           break
+    except BaseException as e:              # bad .npz, KeyError, ...: surfaces in the consumer, not a silent "done"
+      with self._lock:
+        if self._error is None:
+          self._error = e
+      if coord is not None:
+        coord.request_stop()
     finally:
       with self._lock:
         self._live_threads -= 1
         last = self._live_threads == 0
       if last:
         self._closed = True
-        self._put(self._END, None)
+        self._close(coord)
 
   def start_threads(self, sess, coord, n_threads=1):
     threads = []
@@ -196,9 +221,31 @@ class InputBatchLoader(BaseInputLoader):
       threads.append(t)
     return threads
 
+  def raise_if_failed(self):
+    if self._error is not None:
+      raise RuntimeError('input feeder thread failed') from self._error
+
+  def at_end(self):
+    """Blocks until the next batch or the end marker is available; True when the stream has ended (or a feeder
+    failed).  Data-parallel ranks use it to agree on termination BEFORE entering a step (training.py)."""
+    if self._error is not None:
+      return True
+    if self._held is None:
+      self._held = self.queue.get()
+    return self._held is self._END
+
   def dequeue(self):
-    item = self.queue.get()
+    self.raise_if_failed()
+    if self._held is not None:
+      item, self._held = self._held, None
+    else:
+      item = self.queue.get()
     if item is self._END:
-      self.queue.put(self._END)          # stay closed for any later step
+      try:
+        self.queue.put_nowait(self._END)   # stay closed for any later step
+      except queue.Full:
+        pass
+      if self._error is not None:
+        raise RuntimeError('input feeder thread failed') from self._error
       raise OutOfRangeError('input queue is closed and has insufficient elements')
     return item

@@ -93,18 +93,34 @@ class Saver:
   save(sess, path, global_step=) writes `<path>-<step>.npz` holding the flat parameter / Adam buffers, global_step
   and learning_rate, plus a `checkpoint` text file naming the latest one (like tf.train.get_checkpoint_state)."""
 
-  def __init__(self, model):
+  def __init__(self, model, max_to_keep=5):
     self.model = model
+    self.max_to_keep = max_to_keep              # tf.train.Saver default: the five most recent checkpoints stay
+    self._kept = []
 
   def save(self, sess, save_path, global_step=None):
     step = global_step.eval() if hasattr(global_step, 'eval') else global_step
     path = '%s-%d' % (save_path, step) if step is not None else save_path
     eng = self.model.engine
-    np.savez(path + '.npz', params=eng.params.cpu().numpy(), adam_m=eng.adam_m.cpu().numpy(),
+    # written under a temporary name and renamed: a crash mid-write never leaves a truncated file under the final name
+    tmp = path + '.tmp.npz'
+    np.savez(tmp, params=eng.params.cpu().numpy(), adam_m=eng.adam_m.cpu().numpy(),
              adam_v=eng.adam_v.cpu().numpy(), global_step=np.int64(eng.global_step),
              learning_rate=np.float64(self.model.learning_rate.value if hasattr(self.model, 'learning_rate') else 0))
-    with open(os.path.join(os.path.dirname(path) or '.', 'checkpoint'), 'w') as f:
+    os.replace(tmp, path + '.npz')
+    marker = os.path.join(os.path.dirname(path) or '.', 'checkpoint')
+    with open(marker + '.tmp', 'w') as f:
       f.write('model_checkpoint_path: "%s"\n' % os.path.basename(path))
+    os.replace(marker + '.tmp', marker)
+    if path in self._kept:
+      self._kept.remove(path)
+    self._kept.append(path)
+    while self.max_to_keep and len(self._kept) > self.max_to_keep:
+      old = self._kept.pop(0)
+      try:
+        os.remove(old + '.npz')
+      except OSError:
+        pass
     return path
 
   def restore(self, sess, path):
@@ -261,6 +277,13 @@ class SpeechModel:
       self._prefetched = self._fetch(None, self._copy_stream)
     except OutOfRangeError as e:
       self._prefetched = e
+
+  def input_exhausted(self):
+    """True when the NEXT step would find no batch (the prefetch already hit the end, or the loader says so)."""
+    if self._prefetched is not None:
+      return isinstance(self._prefetched, Exception)
+    at_end = getattr(self.input_loader, 'at_end', None)
+    return bool(at_end()) if at_end is not None else False
 
   def step(self, sess, loss=True, update=True, decode=False, return_label=False, summary=False, feed_dict=None):
     """speech_model.py:197-235.  Returns: avg_loss (optional), decoded (optional), label (optional),

@@ -47,16 +47,20 @@ class Training(DatasetExecutor):
       import torch.distributed as dist
       torch.cuda.set_device(self.local_rank)
       flags.process_group = dist.group.WORLD
-      random.seed(int(os.environ.get('SPEECHT_B200_DATA_SEED', '1234')))   # same shuffle order on every rank
     super().__init__(flags)
 
   # ---- DatasetExecutor hooks ---------------------------------------------------------------------
   def create_sample_generator(self, limit_count: int):
-    samples = self.reader.load_samples('train', loop_infinitely=True, limit_count=limit_count,
-                                       feature_type=self.flags.feature_type)
-    if self.world > 1:
-      samples = itertools.islice(samples, self.rank, None, self.world)
-    return samples
+    if self.world == 1:
+      return self.reader.load_samples('train', loop_infinitely=True, limit_count=limit_count,
+                                      feature_type=self.flags.feature_type)
+    # data parallel: every rank shuffles the FILE LIST with the same private generator and reads only its own
+    # every-world-th file -- no rank loads utterances it will discard, and the order does not depend on the global
+    # `random` state staying in step across ranks
+    seed = int(os.environ.get('SPEECHT_B200_DATA_SEED', '1234'))
+    return self.reader.load_samples('train', loop_infinitely=True, limit_count=limit_count,
+                                    feature_type=self.flags.feature_type, shard=(self.rank, self.world),
+                                    rng=random.Random(seed))
 
   def get_loader_limit_count(self) -> int:
     return self.flags.limit_training_set
@@ -106,6 +110,9 @@ class Training(DatasetExecutor):
         for step in itertools.count(1):
           if coord.should_stop() or (max_steps is not None and step > max_steps):
             break
+          if self.world > 1 and parallel.any_rank_true(model.input_exhausted(), device=model.engine.device):
+            print('Done training -- a rank ran out of input')      # all ranks leave together: nobody waits in NCCL
+            break
           at_checkpoint = step % per_checkpoint == 0
           began = time.time()
           fetched = model.step(sess, summary=at_checkpoint)
@@ -126,4 +133,5 @@ class Training(DatasetExecutor):
       finally:
         coord.request_stop()
       coord.join()
+      self.speech_input.raise_if_failed()       # a feeder-thread exception must not look like a clean end of data
     return model

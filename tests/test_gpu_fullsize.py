@@ -118,3 +118,62 @@ def test_config5_batch256_variable_length_greedy_decode():
   b = tc.evaluate_step(x, lengths, labels)
   assert torch.equal(first, b['logits'])
   np.testing.assert_array_equal(a['decoded'][0].values, b['decoded'][0].values)
+
+
+@pytest.mark.parametrize('precision', ['bf16x3', 'fp32'])
+def test_full_length_10s_every_layer_against_the_float64_oracle(precision):
+  """Closes the chain at FULL LENGTH (T=1001 mel frames, T'=501): activations of all 11 layers, logits, CTC loss and
+  greedy labels of the tensor-core path directly against the float64 numpy oracle -- not against the repo's own fp32
+  CUDA path.  Batch 2 keeps the oracle at a few seconds; the per-row arithmetic (K = 32 x 250 and 2000-deep
+  contractions, 501-row time axis with its ragged last tile) is that of config 2."""
+  from speecht_b200.engine import W2LEngine
+  inputs, lengths, labels = O.synthetic_batch(seed=21, batch=2, seconds=10)
+  weights = O.xavier_weights(np.random.default_rng(77), dtype=np.float32)
+  w64 = [(w.astype(np.float64), b.astype(np.float64)) for w, b in weights]
+  logits64, acts64 = O.wav2letter_forward(inputs.astype(np.float64), w64, keep_activations=True)
+  ref = O.evaluate_step(inputs, lengths, labels, weights, dtype=np.float64)
+  eng = W2LEngine(precision=precision)
+  eng.load_weights(weights)
+  res = eng.evaluate_step(torch.from_numpy(inputs).cuda(), lengths, labels)
+  if precision == 'fp32':
+    eng.forward(torch.from_numpy(inputs).cuda(), keep_activations=True)
+    gpu_acts = [a.cpu().numpy() for a in eng._acts[1:11]]
+  else:
+    gpu_acts = [eng._tc().activation(l).cpu().numpy() for l in range(10)]
+  errs = [rel(a, acts64[l + 1]) for l, a in enumerate(gpu_acts)]
+  errs.append(rel(res['logits'].cpu().numpy(), logits64))
+  print('%s vs float64 oracle at T=1001: per-layer rel err %s' % (precision, ' '.join('%.2e' % e for e in errs)))
+  assert res['logits'].shape == (501, 2, 29)
+  assert max(errs) < 1e-4, errs
+  assert rel(res['loss'].cpu().numpy(), ref['loss']) < 1e-4
+  # greedy labels: bit-exact unless a frame's two best logits are closer than the arithmetic tolerance (reported)
+  lg, lo = res['logits'].cpu().numpy(), ref['logits']
+  flips = np.argwhere(lg.argmax(axis=2) != lo.argmax(axis=2))
+  for t, b in flips:
+    top2 = np.sort(lo[t, b])[-2:]
+    assert top2[1] - top2[0] < 2e-4 * np.abs(lo).max(), ('argmax flip that is not a near-tie', t, b, top2)
+  if len(flips) == 0:
+    np.testing.assert_array_equal(res['decoded'][0].values, ref['decoded'][1])
+    np.testing.assert_array_equal(res['decoded'][0].indices, ref['decoded'][0])
+  assert len(flips) <= 1, flips
+
+
+def test_evaluate_step_device_equals_evaluate_step_on_ragged_batch():
+  """bench.py --config 5 times evaluate_step_device (results left on the device): same loss, same label rows as the
+  host-facing evaluate_step, on a ragged 1-4 s batch."""
+  from speecht_b200 import ops
+  from speecht_b200.engine import W2LEngine
+  inputs, lengths, labels = O.synthetic_batch(seed=3, batch=6, seconds=[1, 4, 2, 3, 1, 2])
+  eng = W2LEngine(precision='bf16x3')
+  eng.init_xavier(seed=2)
+  x = torch.from_numpy(inputs).cuda()
+  host = eng.evaluate_step(x, lengths, labels)
+  host_loss = host['loss'].cpu().numpy()
+  host_vals, host_idx = host['decoded'][0].values.copy(), host['decoded'][0].indices.copy()
+  To = (inputs.shape[1] + 1) // 2
+  batch = ops.CTCBatch(labels, lengths // 2, To, 29, x.device)
+  loss, values, counts, _neg = eng.evaluate_step_device(x, batch)
+  np.testing.assert_array_equal(loss.cpu().numpy(), host_loss)
+  sp = ops.sparse_from_rows(values, counts)
+  np.testing.assert_array_equal(sp.values, host_vals)
+  np.testing.assert_array_equal(sp.indices, host_idx)

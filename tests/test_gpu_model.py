@@ -321,6 +321,7 @@ def test_experimental_fast_fir_layer8_forward_parity(seconds, monkeypatch):
   logits, acts = O.wav2letter_forward(inputs.astype(np.float64), w64, keep_activations=True)
   eng = _engine('bf16x3', weights)
   out = eng.forward(torch.from_numpy(inputs).cuda(), keep_activations=True)
-  for l, a in enumerate(_gpu_activations(eng)):
-    assert rel(a, acts[l + 1]) < 1e-4, (l, rel(a, acts[l + 1]))
+  errs = [rel(a, acts[l + 1]) for l, a in enumerate(_gpu_activations(eng))]
+  print('fast-FIR layer 8: per-layer rel err vs float64 oracle', ' '.join('%.2e' % e for e in errs))
+  assert max(errs) < 1e-4, errs
   assert rel(out.cpu().numpy(), logits) < 1e-4

@@ -234,3 +234,23 @@ def test_power_spectrogram_vs_oracle_and_golden(ops):
     assert torch.all(feat[i, r.shape[0]:] == 0)
   with pytest.raises(ValueError):
     ops.power_spectrogram(dev(wavs[:, :200]), [200, 200, 200], 16000)
+
+
+# ----------------------------------------------------------------------------------------------- TF published vectors
+def test_ctc_kernels_reproduce_tensorflow_published_test_vectors(ops):
+  """The literals of TensorFlow's own ctc_loss / ctc_greedy_decoder kernel tests (tests/golden/
+  tf_published_vectors.py), through the C ABI: pins blank = last class, softmax inside the op, the gradient and the
+  decoder's merge / ignore-beyond-length rules on the CUDA path itself, not only on the oracle."""
+  import sys
+  sys.path.insert(0, GOLDEN)
+  import tf_published_vectors as TFV
+  logits, targets, seq_len, loss_truth, grad_truth = TFV.ctc_case()
+  loss, grad = ops.ctc_loss(targets, dev(logits), np.asarray(seq_len, np.int32), want_grad=True)
+  np.testing.assert_allclose(loss.cpu().numpy(), loss_truth, rtol=0, atol=5e-6)
+  np.testing.assert_allclose(grad.cpu().numpy(), grad_truth, rtol=0, atol=2e-6)
+  glogits, gseq, indices, values, shape, neg = TFV.greedy_case()
+  dec, gneg = ops.ctc_greedy_decoder(dev(glogits), np.asarray(gseq, np.int32), merge_repeated=True)
+  np.testing.assert_array_equal(dec[0].indices, indices)
+  np.testing.assert_array_equal(dec[0].values, values)
+  np.testing.assert_array_equal(dec[0].dense_shape, shape)
+  np.testing.assert_allclose(gneg, neg, rtol=1e-6)

@@ -116,3 +116,117 @@ def test_cli_flag_surface_matches_reference_defaults():
   assert f.dataset == 'test' and f.lm_weight == 0.8 and f.valid_word_count_weight == 2.3
   f = cli.parse(['preprocess', '--train-only'])
   assert f.train_only and not f.test_only and f.run_type == 'other'
+
+
+def test_learning_rate_decay_policy_matches_reference_training_loop():
+  """reference training.py:81-83: multiply the learning rate by learning_rate_decay_factor when the factor is > 0,
+  more than two window losses are on record and this window's loss is worse than EACH of the last three."""
+  from speecht_b200.speech_model import HostVariable
+  from speecht_b200.training import Training
+
+  class Sess:
+    def run(self, op):
+      return op()
+
+  def run_policy(factor, losses):
+    t = object.__new__(Training)
+    t.flags = types.SimpleNamespace(learning_rate_decay_factor=factor)
+    lr = HostVariable(1e-3, 'learning_rate')
+    model = types.SimpleNamespace(learning_rate=lr, learning_rate_decay_op=lr.assign(lambda: lr.value * factor))
+    history, rates = [], []
+    for loss in losses:
+      t._maybe_decay(Sess(), model, loss, history)
+      history.append(loss)                      # training.py:84 appends AFTER the decision
+      rates.append(lr.value)
+    return rates
+
+  # fewer than three recorded windows: never decays, whatever the loss does
+  assert run_policy(0.5, [1.0, 2.0, 3.0]) == [1e-3] * 3
+  # 4th window worse than each of the last three -> decay once; 5th is better than the 4th -> unchanged
+  np.testing.assert_allclose(run_policy(0.5, [3.0, 2.0, 1.0, 3.5, 3.4]), [1e-3, 1e-3, 1e-3, 5e-4, 5e-4])
+  # worse than two of the last three but not all -> unchanged (strict "> max")
+  assert run_policy(0.5, [3.0, 2.0, 1.0, 2.5]) == [1e-3] * 4
+  assert run_policy(0.5, [1.0, 1.0, 1.0, 1.0]) == [1e-3] * 4       # equal is not worse
+  # keeps decaying while the loss keeps climbing
+  np.testing.assert_allclose(run_policy(0.5, [1.0, 1.0, 1.0, 2.0, 3.0, 4.0])[-3:], [5e-4, 2.5e-4, 1.25e-4])
+  # factor 0 (the CLI default, speecht-cli:69-72) disables the policy
+  assert run_policy(0.0, [1.0, 1.0, 1.0, 9.0]) == [1e-3] * 4
+
+
+def test_sharded_load_samples_partitions_one_commonly_shuffled_list(tmp_path):
+  """Data-parallel reading (new; the reference is single-process): every rank shuffles the file list with the same
+  private generator and keeps every world-th file -- disjoint, complete, and no rank loads what it discards."""
+  import random
+  from speecht_b200.preprocessing import SpeechCorpusReader
+  out = tmp_path / 'preprocessed-power' / 'train'
+  out.mkdir(parents=True)
+  for i in range(10):
+    np.savez(out / ('utt%02d' % i), audio_fragments=np.full((i + 1, 4), i, np.float32), transcript=np.array([i]))
+  reader = SpeechCorpusReader(str(tmp_path))
+  parts = [[int(tr[0]) for _a, tr in reader.load_samples('train', feature_type='power', shard=(r, 3),
+                                                          rng=random.Random(7))] for r in range(3)]
+  assert sorted(sum(parts, [])) == list(range(10))
+  assert [len(p) for p in parts] == [4, 3, 3]
+  whole = [int(tr[0]) for _a, tr in reader.load_samples('train', feature_type='power', rng=random.Random(7))]
+  assert whole[0::3] == parts[0] and whole[1::3] == parts[1] and whole[2::3] == parts[2]
+  assert whole != sorted(whole)                                   # it IS shuffled
+
+
+def test_feeder_thread_failure_surfaces_and_full_queue_does_not_block_shutdown():
+  from speecht_b200 import speech_input
+
+  def broken():
+    yield np.zeros((3, 4), np.float32), [1]
+    raise KeyError('audio_fragments')
+
+  loader = speech_input.InputBatchLoader(4, 1, broken)
+  coord = speech_input.Coordinator()
+  loader.start_threads(None, coord, n_threads=1)
+  with pytest.raises(RuntimeError, match='feeder thread failed'):   # fails fast: at the first or the second dequeue
+    assert loader.dequeue()[0].shape == (1, 3, 4)
+    loader.dequeue()
+  assert coord.should_stop()
+  coord.join()
+
+  # a full queue nobody reads: the last feeder must still terminate once stop is requested
+  def endless():
+    while True:
+      yield np.zeros((2, 4), np.float32), [0]
+
+  loader = speech_input.InputBatchLoader(4, 1, endless, capacity=2)
+  coord = speech_input.Coordinator()
+  (thread,) = loader.start_threads(None, coord, n_threads=1)
+  import time
+  time.sleep(0.3)                                                  # queue fills up
+  coord.request_stop()
+  thread.join(timeout=3.0)
+  assert not thread.is_alive()
+  # at_end() lets data-parallel ranks agree on termination before a step
+  loader = speech_input.InputBatchLoader(4, 1, lambda: iter([(np.zeros((2, 4), np.float32), [0])]))
+  coord = speech_input.Coordinator()
+  loader.start_threads(None, coord, n_threads=1)
+  assert loader.at_end() is False
+  loader.dequeue()
+  assert loader.at_end() is True
+  with pytest.raises(speech_input.OutOfRangeError):
+    loader.dequeue()
+  coord.join()
+
+
+def test_saver_keeps_the_last_five_checkpoints_and_writes_atomically(tmp_path):
+  import torch
+  from speecht_b200.speech_model import HostVariable, Saver, latest_checkpoint
+  eng = types.SimpleNamespace(params=torch.arange(8, dtype=torch.float32), adam_m=torch.zeros(8),
+                              adam_v=torch.ones(8), global_step=0, mark_weights_changed=lambda: None)
+  model = types.SimpleNamespace(engine=eng, learning_rate=HostVariable(1e-3, 'learning_rate'))
+  saver = Saver(model)
+  for step in range(1, 8):
+    eng.global_step = step
+    saver.save(None, str(tmp_path / 'speechT.ckpt'), global_step=step)
+  kept = sorted(f for f in os.listdir(tmp_path) if f.endswith('.npz'))
+  assert kept == ['speechT.ckpt-%d.npz' % s for s in range(3, 8)]      # tf.train.Saver max_to_keep = 5
+  assert not [f for f in os.listdir(tmp_path) if '.tmp' in f]
+  assert latest_checkpoint(str(tmp_path)).endswith('speechT.ckpt-7')
+  eng.params.zero_()
+  saver.restore(None, latest_checkpoint(str(tmp_path)))
+  assert eng.params.tolist() == list(range(8)) and eng.global_step == 7

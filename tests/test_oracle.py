@@ -233,3 +233,55 @@ def test_same_padding_vs_transformers_tf_port():
       out_len, pl, pr = O.same_padding(t, k, s)
       assert (left, right) == (pl, pr), (k, s, t, left, right, pl, pr)
       assert (t + left + right - k) // s + 1 == out_len == -(-t // s)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Known-answer vectors published in TensorFlow's own kernel tests (tests/golden/tf_published_vectors.py): the only
+# third-party golden data for the two CTC ops the reference delegates to TF1.  They pin blank = last class, softmax
+# inside the op, the gradient definition and the greedy decoder's merge / ignore rules.
+# ---------------------------------------------------------------------------------------------------------------
+import os as _os
+import sys as _sys
+_sys.path.insert(0, _os.path.join(_os.path.dirname(_os.path.abspath(__file__)), 'golden'))
+import tf_published_vectors as TFV  # noqa: E402
+
+
+def test_oracle_ctc_loss_matches_tensorflow_published_vectors():
+  logits, targets, seq_len, loss_truth, grad_truth = TFV.ctc_case()
+  loss, grad = O.ctc_loss_and_grad(logits, targets, seq_len)          # blank defaults to the LAST class
+  np.testing.assert_allclose(loss, loss_truth, rtol=0, atol=5e-6)     # literals carry six digits
+  np.testing.assert_allclose(grad, grad_truth, rtol=0, atol=2e-6)
+  # torch's CTC (blank=5, log-softmax applied by hand) is a second independent witness of the same literals ...
+  lp = torch.log_softmax(torch.tensor(logits), dim=-1)
+  lens = torch.tensor([len(r) for r in targets])
+
+  def torch_ctc(label_rows, blank):
+    return F.ctc_loss(lp, torch.tensor([t for row in label_rows for t in row]), torch.tensor(seq_len), lens,
+                      blank=blank, reduction='none').numpy()
+
+  tl = torch_ctc(targets, 5)
+  # ... and the other common convention (blank = class 0, what warp-ctc / torch default to) cannot reproduce them
+  assert np.max(np.abs(torch_ctc([[t + 1 for t in row] for row in targets], 0) - loss_truth)) > 0.1
+  np.testing.assert_allclose(tl, loss_truth, rtol=0, atol=5e-6)
+
+
+def test_oracle_greedy_decoder_matches_tensorflow_published_vectors():
+  logits, seq_len, indices, values, shape, neg = TFV.greedy_case()
+  (ri, rv, rs), rneg = O.ctc_greedy_decoder(logits, seq_len, merge_repeated=True)
+  np.testing.assert_array_equal(ri, indices)
+  np.testing.assert_array_equal(rv, values)
+  np.testing.assert_array_equal(rs, shape)
+  np.testing.assert_allclose(rneg, neg, rtol=1e-6)
+
+
+def test_oracle_adam_is_tensorflows_adam_update_numpy():
+  rng = np.random.default_rng(3)
+  p0 = rng.standard_normal(7); g = rng.standard_normal(7)
+  m0 = rng.standard_normal(7) * 0.1; v0 = rng.random(7) * 0.1
+  for t in (1, 2, 50):
+    p, m, v = [p0.copy()], [m0.copy()], [v0.copy()]
+    O.adam_tf1(p, [g], m, v, lr=1e-4, step=t, eps=1e-3)
+    pt, mt, vt = TFV.adam_update_numpy(p0, g, t, m0, v0, alpha=1e-4, epsilon=1e-3)
+    np.testing.assert_allclose(p[0], pt, rtol=1e-13)
+    np.testing.assert_allclose(m[0], mt, rtol=1e-13)
+    np.testing.assert_allclose(v[0], vt, rtol=1e-13)

@@ -47,7 +47,19 @@ def _worker(rank, world, port, out_dir):
   avg = parallel.mean_scalar(torch.tensor(loss.mean()))
   rows = parallel.gather_decoded([[rank, rank + 1]] * (b - a))
   t = parallel.max_scalar(1.0 + rank)
-  np.savez(os.path.join(out_dir, 'rank%d.npz' % rank), flat=flat.numpy(), avg=avg.numpy(), rows=np.array(rows), t=t)
+  # tensor-based gather of the sparse decode triple (config-5 evaluate at N > 1): rank 0 decodes rows [7,8],[],[9],
+  # rank 1 decodes nothing in its first row and [5] in its second
+  from speecht_b200.ops import SparseTensorValue
+  if rank == 0:
+    sp = SparseTensorValue(np.array([[0, 0], [0, 1], [2, 0]], np.int64), np.array([7, 8, 9], np.int64),
+                           np.array([3, 2], np.int64))
+  else:
+    sp = SparseTensorValue(np.array([[1, 0]], np.int64), np.array([5], np.int64), np.array([2, 1], np.int64))
+  g = parallel.gather_decoded_sparse(sp)
+  same = parallel.identical_across_ranks(flat)                       # the reduced gradient is identical everywhere
+  differs = parallel.identical_across_ranks(torch.full((5,), float(rank)))
+  np.savez(os.path.join(out_dir, 'rank%d.npz' % rank), flat=flat.numpy(), avg=avg.numpy(), rows=np.array(rows), t=t,
+           g_idx=g.indices, g_val=g.values, g_shape=g.dense_shape, same=same, differs=differs)
   dist.destroy_process_group()
 
 
@@ -83,3 +95,7 @@ def test_two_rank_gradient_allreduce_matches_single_process(tmp_path):
   assert abs(float(r0['avg']) - loss.mean()) < 1e-12
   assert r0['rows'].tolist() == [[0, 1], [0, 1], [1, 2], [1, 2]] == r1['rows'].tolist()
   assert float(r0['t']) == 2.0 == float(r1['t'])
+  for r in (r0, r1):
+    assert r['g_idx'].tolist() == [[0, 0], [0, 1], [2, 0], [4, 0]]
+    assert r['g_val'].tolist() == [7, 8, 9, 5] and r['g_shape'].tolist() == [5, 2]
+    assert bool(r['same']) and not bool(r['differs'])

@@ -24,6 +24,7 @@ struct Layer {
   int64_t w_off, b_off;       // float offsets into the flat parameter / gradient buffers
   CUtensorMap tm_fwd_a, tm_fwd_b;     // forward
   CUtensorMap tm_dg_a[2], tm_dg_b;    // data gradient (A = dz ping or pong)
+  CUtensorMap tm_dg_b_n128;           // layer 10 only: filter rows in boxes of 128 (128-wide data-gradient tiles)
   CUtensorMap tm_wg_x, tm_wg_dz[2];   // filter gradient
   CUtensorMap tm_fwd_out;             // store map of this layer's output planes (layers 0..9)
   CUtensorMap tm_dg_out[2];           // store map of the dz buffer the data gradient of this layer writes (1..10)
@@ -53,6 +54,10 @@ struct st_plan {
   int cur_dz;                  // ping/pong buffer holding the gradient wrt the next layer to process
   bool tma_store;              // one / two planes: the epilogues write bf16 planes with TMA stores (store maps needed)
   bool trim;                   // MMAs over channel / time padding are not issued (SPEECHT_B200_TRIM=0 disables)
+  // Layer-10 data gradient (dz9 = dlogits . W10^T, 29-deep contraction, 2000 outputs): an HBM / epilogue kernel, not a
+  // GEMM.  128-wide tiles leave room for TWO accumulator stages in the split modes (2 x 2 x 128 TMEM columns), so the
+  // epilogue of one tile runs under the loads + MMAs of the next (SPEECHT_B200_L10_N128=0 restores 256-wide tiles).
+  bool l10_n128;
   // EXPERIMENTAL, off by default, not yet run on a GPU (SPEECHT_B200_FFA=1): forward of the 32-tap layer 8 as a
   // fast-FIR split -- three half-rate 16-tap convolutions (75 % of the MMAs) + one elementwise combine, DESIGN.md
   // section 8 and tools/ffa_study.py.  Backward is unchanged.
@@ -106,6 +111,8 @@ ST_API int st_plan_create(st_plan** out, int B, int T, int input_size, int num_c
     p->tma_store = n_planes <= 2;
     const char* e = getenv("SPEECHT_B200_TRIM");
     p->trim = !(e && e[0] == '0');
+    e = getenv("SPEECHT_B200_L10_N128");
+    p->l10_n128 = !(e && e[0] == '0') && n_planes == 2;
     e = getenv("SPEECHT_B200_FFA");
     p->ffa = e && e[0] == '1' && n_planes <= 2;
   }
@@ -239,6 +246,10 @@ ST_API int st_plan_bind(st_plan* p, void* arena, size_t arena_bytes, float* para
       rc = tc::make_map_2d(&L.tm_dg_b, bf(p, L.off_wbwd), l == 10 ? 64 : L.Cout, npl * L.K * L.Cin, L.ld_co, 64,
                            wide_n(p));
       if (rc) return rc;
+      if (l == 10 && p->l10_n128) {
+        rc = tc::make_map_2d(&L.tm_dg_b_n128, bf(p, L.off_wbwd), 64, npl * L.K * L.Cin, L.ld_co, 64, 128);
+        if (rc) return rc;
+      }
     }
     // ---- store maps for the epilogues (planes are dense [npl][B][T][ld] inside their buffer)
     if (p->tma_store) {
@@ -475,9 +486,11 @@ ST_API int st_plan_backward_range(st_plan* p, int hi, int lo, st_stream_t stream
       c.b_row_step = L.Cin;
       c.b_col_step = 0;
       c.b_plane_rows = L.K * L.Cin;
+      const bool n128 = l == 10 && p->l10_n128;
+      const int dg_block_n = n128 ? 128 : wide_n(p);
       c.B = p->B; c.To = L.Ti; c.N = L.Cin;
       c.m_tiles_per_utt = (L.Ti + tc::kTileM - 1) / tc::kTileM;
-      c.n_tiles = (L.Cin + wide_n(p) - 1) / wide_n(p);
+      c.n_tiles = (L.Cin + dg_block_n - 1) / dg_block_n;
       c.n_fastest = (size_t)p->npl * p->B * L.To * ld_dz * 2 > (size_t)48 << 20;
       c.bias = nullptr;
       c.relu = 0;
@@ -491,7 +504,8 @@ ST_API int st_plan_backward_range(st_plan* p, int hi, int lo, st_stream_t stream
       c.k_cols = L.Cout;
       c.trim = p->trim;
       ti = timed_begin(p, s);
-      rc = tc::launch_conv(L.tm_dg_a[l == 10 ? 0 : cur], L.tm_dg_b, &L.tm_dg_out[nxt], c, wide_n(p), p->npl, s);
+      rc = tc::launch_conv(L.tm_dg_a[l == 10 ? 0 : cur], n128 ? L.tm_dg_b_n128 : L.tm_dg_b, &L.tm_dg_out[nxt], c,
+                           dg_block_n, p->npl, s);
       if (rc) return rc;
       timed_end(p, ti, 1, l, 2.0 * L.K * L.Cin * L.Cout * (double)L.To * p->B, s);
       p->launches++;

@@ -136,7 +136,8 @@ __device__ __forceinline__ uint32_t positive_bits(const uint4 (&mk)[4]) {
 template <int NPL>
 __device__ __forceinline__ float epilogue_chunk(const ConvParams& p, const CUtensorMap* tmOut, uint8_t* stage,
                                                float (&v)[32], float bias_lane, uint32_t keep, int nc, int lane,
-                                               bool row_ok, int64_t out_row, int t_warp, int b) {
+                                               bool row_ok, int64_t out_row, int t_warp, int b, float* out_f32,
+                                               bool f32_add) {
   // bias_lane: bias[nc + lane] (0 beyond N), fetched with one coalesced load per chunk before the accumulator was
   // ready and broadcast by shuffles here -- 32 dependent uniform loads in the epilogue cost ~30 k cycles per tile.
   // keep: bit i set = column nc+i is a real channel AND (data gradient) the ReLU below it was active.
@@ -172,16 +173,23 @@ __device__ __forceinline__ float epilogue_chunk(const ConvParams& p, const CUten
         if (nc + g * 8 < p.ld_out) store_planes8<NPL>(orow + g * 8, p.out_plane_stride, v + g * 8);
     }
   }
-  if (p.out_f32 && row_ok) {
-    float* frow = p.out_f32 + out_row * p.ld_f32 + nc;
+  if (out_f32 && row_ok) {
+    // f32_add: this work item holds a slice of the taps -- accumulate into the pre-zeroed output (two slices add
+    // commutatively, so the sum does not depend on which one lands first)
+    float* frow = out_f32 + out_row * p.ld_f32 + nc;
     if (nc + 32 <= p.ld_f32 && (p.ld_f32 & 3) == 0) {
 #pragma unroll
-      for (int i = 0; i < 32; i += 4)
-        *reinterpret_cast<float4*>(frow + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+      for (int i = 0; i < 32; i += 4) {
+        if (f32_add) red_add_v4(frow + i, v[i], v[i + 1], v[i + 2], v[i + 3]);
+        else *reinterpret_cast<float4*>(frow + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+      }
     } else {
 #pragma unroll
       for (int i = 0; i < 32; ++i)
-        if (nc + i < p.ld_f32) frow[i] = v[i];
+        if (nc + i < p.ld_f32) {
+          if (f32_add) atomicAdd(frow + i, v[i]);
+          else frow[i] = v[i];
+        }
     }
   }
   if (p.col_sum) {
@@ -240,9 +248,12 @@ template <> struct Products<3> {
 // streaming epilogue (lower register pressure, TMEM loads overlapped with the stores) is used everywhere else.
 // 168 registers is the ceiling for 10 warps: each SM sub-partition holds 16384 registers and gets 3 of the warps
 // (a 200-register build fails to launch), so the two-phase epilogue's 64 live accumulators spill ~450 bytes.
-template <int BLOCK_N, int NPL, bool EARLY>
+// NPROB > 1: several problems of identical shape in one launch (ConvParams::n_problems, k_split): a work item is
+// (problem, tap slice, tile); fp32 outputs only.  NPROB == 1 is the plain single-problem kernel.
+template <int BLOCK_N, int NPL, bool EARLY, int NPROB>
 __global__ void __launch_bounds__(kThreads, 1)
-tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+tc_conv_kernel(const __grid_constant__ std::conditional_t<NPROB == 1, TmSet1, TmSet3> tmAs,
+               const __grid_constant__ std::conditional_t<NPROB == 1, TmSet1, TmSet3> tmBs,
                const __grid_constant__ CUtensorMap tmOut, const ConvParams p) {
   using Cfg = ConvCfg<BLOCK_N, NPL>;
   constexpr int STAGES = Cfg::STAGES;
@@ -264,14 +275,29 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_tiles = p.B * p.m_tiles_per_utt * p.n_tiles;
   const int m_tiles = p.B * p.m_tiles_per_utt;
-  const int nk = p.taps * p.chunks_per_tap;
+  const int ksplit = NPROB > 1 ? max(1, p.k_split) : 1;
+  const int total_work = NPROB > 1 ? num_tiles * ksplit * p.n_problems : num_tiles;
+  // work item -> (problem q, taps [j0, j1), tile); single-problem launches: work item == tile, all taps
+  auto work_coords = [&](int work, int& q, int& j0, int& j1, int& tile) {
+    if constexpr (NPROB > 1) {
+      const int per_prob = num_tiles * ksplit;
+      q = work / per_prob;
+      const int r = work - q * per_prob;
+      const int ks = r / num_tiles;
+      tile = r - ks * num_tiles;
+      j0 = p.taps * ks / ksplit;
+      j1 = p.taps * (ks + 1) / ksplit;
+    } else {
+      q = 0; j0 = 0; j1 = p.taps; tile = work;
+    }
+  };
   // debug stamps of the first tile (streaming-epilogue instantiations only: the two-phase one has no register to spare)
   long long* tl = (!EARLY && p.timeline) ? p.timeline + (int64_t)blockIdx.x * 8 : nullptr;
   if (tl && threadIdx.x == 0) tl[0] = global_ns();                                   // 0: kernel entry
 
   if (warp == 0 && lane == 0) {
-    prefetch_tmap(&tmA);
-    prefetch_tmap(&tmB);
+    prefetch_tmap(&tmAs.m[0]);
+    prefetch_tmap(&tmBs.m[0]);
     if (p.tma_store) prefetch_tmap(&tmOut);
     for (int s = 0; s < STAGES * NG; ++s) {
       mbar_init(full_bar + s, 1);
@@ -300,7 +326,12 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int work = blockIdx.x; work < total_work; work += gridDim.x) {
+        int q, j0, j1, tile;
+        work_coords(work, q, j0, j1, tile);
+        const CUtensorMap* tmA = &tmAs.m[NPROB > 1 ? q : 0];
+        const CUtensorMap* tmB = &tmBs.m[NPROB > 1 ? q : 0];
+        const int pad_left = NPROB > 1 ? p.pad_left_q[q] : p.pad_left;
         // n fastest (A rows read from HBM once, shared through L2 by their n tiles) when A is too big for L2;
         // m fastest (one filter slab hot in L2 for the whole wave) otherwise
         const int nt = p.n_fastest ? tile % p.n_tiles : tile / m_tiles;
@@ -308,11 +339,12 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int b = mt / p.m_tiles_per_utt;
         const int t0 = (mt - b * p.m_tiles_per_utt) * kTileM;
         const int n0 = nt * BLOCK_N;
+        const int jn = j1 - j0, nk = jn * p.chunks_per_tap;
         for (int it = 0; it < nk; ++it) {
           // channel chunk outer, filter tap inner: the taps of one chunk re-read (shifted) the same A rows, which
           // stay in L2, instead of sweeping the whole channel range once per tap
-          const int cc = it / p.taps, j = it - cc * p.taps;
-          const int m = p.a_sign * (j - p.pad_left);
+          const int cc = it / jn, j = j0 + it - cc * jn;
+          const int m = p.a_sign * (j - pad_left);
           const int shift = p.a_stride == 1 ? m : floordiv(m, p.a_stride);
           const int a_col = (m - shift * p.a_stride) * p.a_cin + cc * kChunkK;
           uint8_t* st = smem + stage * Cfg::STAGE_BYTES;
@@ -325,8 +357,8 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               uint64_t* fb = full_bar + stage * NG + g;
               mbar_wait(empty_bar + stage * NG + g, phase ^ 1);
               mbar_expect_tx(fb, Cfg::A_BYTES + Cfg::B_BYTES);
-              tma_load_3d(&tmA, fb, st + pa * Cfg::A_BYTES, a_col, t0 + shift, pa * p.B + b);
-              tma_load_2d(&tmB, fb, st + NPL * Cfg::A_BYTES + pb * Cfg::B_BYTES, b_c0, pb * p.b_plane_rows + b_c1);
+              tma_load_3d(tmA, fb, st + pa * Cfg::A_BYTES, a_col, t0 + shift, pa * p.B + b);
+              tma_load_2d(tmB, fb, st + NPL * Cfg::A_BYTES + pb * Cfg::B_BYTES, b_c0, pb * p.b_plane_rows + b_c1);
             }
           } else {
             uint64_t* fb = full_bar + stage;
@@ -334,10 +366,10 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             mbar_expect_tx(fb, Cfg::STAGE_BYTES);
 #pragma unroll
             for (int pl = 0; pl < NPL; ++pl)
-              tma_load_3d(&tmA, fb, st + pl * Cfg::A_BYTES, a_col, t0 + shift, pl * p.B + b);
+              tma_load_3d(tmA, fb, st + pl * Cfg::A_BYTES, a_col, t0 + shift, pl * p.B + b);
 #pragma unroll
             for (int pl = 0; pl < NPL; ++pl)
-              tma_load_2d(&tmB, fb, st + NPL * Cfg::A_BYTES + pl * Cfg::B_BYTES, b_c0, pl * p.b_plane_rows + b_c1);
+              tma_load_2d(tmB, fb, st + NPL * Cfg::A_BYTES + pl * Cfg::B_BYTES, b_c0, pl * p.b_plane_rows + b_c1);
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
@@ -350,7 +382,9 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       int stage = 0;
       uint32_t phase = 0;
       int local = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
+      for (int work = blockIdx.x; work < total_work; work += gridDim.x, ++local) {
+        int q, j0, j1, tile;
+        work_coords(work, q, j0, j1, tile);
         const int acc = local % Cfg::ACC_STAGES;
         const uint32_t acc_phase = (local / Cfg::ACC_STAGES) & 1;
         // Only real channels are multiplied: the N of the instruction is the tile's channel count rounded up to 16
@@ -407,9 +441,9 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int cc = 0; cc < p.chunks_per_tap; ++cc) {
           const int nkk = p.trim ? min(kChunkK / 16, (p.k_cols - cc * kChunkK + 15) >> 4) : kChunkK / 16;
           if (nkk == kChunkK / 16) {
-            for (int j = 0; j < p.taps; ++j, ++it) iteration(std::true_type{}, it, nkk);
+            for (int j = j0; j < j1; ++j, ++it) iteration(std::true_type{}, it, nkk);
           } else {
-            for (int j = 0; j < p.taps; ++j, ++it) iteration(std::false_type{}, it, nkk);
+            for (int j = j0; j < j1; ++j, ++it) iteration(std::false_type{}, it, nkk);
           }
         }
         umma_commit(tmem_full + acc);                     // accumulator complete -> epilogue
@@ -449,9 +483,11 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
       }
     };
-    prefetch_mask(blockIdx.x);
+    if (NPROB == 1) prefetch_mask(blockIdx.x);
     int local = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
+    for (int work = blockIdx.x; work < total_work; work += gridDim.x, ++local) {
+      int q, j0, j1, tile;
+      work_coords(work, q, j0, j1, tile);
       const int acc = local % Cfg::ACC_STAGES;
       const uint32_t acc_phase = (local / Cfg::ACC_STAGES) & 1;
       int b, t0, n0;
@@ -460,7 +496,9 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int t_warp = t0 + quarter * 32;               // first row of this warp's 32-row slab
       const bool row_ok = t < p.To;
       const int64_t out_row = (int64_t)b * p.To + t;
-      prefetch_mask(tile + gridDim.x);
+      float* out_f32 = NPROB > 1 ? p.out_f32_q[q] : p.out_f32;
+      const bool f32_add = NPROB > 1 && ksplit > 1;
+      if (NPROB == 1) prefetch_mask(tile + gridDim.x);
       // Per chunk of this warp, fetched while the MMAs of the tile are still running: the lane's bias element and
       // the ReLU-mask row segment (data gradient), reduced to one keep-bit per column once it has arrived.
       constexpr int kMine = (kChunks + kChunkStep - 1) / kChunkStep;       // chunks per warp (compile time)
@@ -531,7 +569,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const int c = chunk0 + ci * kChunkStep;
           if (c >= kChunks) continue;
           csum[ci] = epilogue_chunk<NPL>(p, &tmOut, stage, sum[ci], bias_l[ci], keep[ci], n0 + c * 32, lane, row_ok,
-                                         out_row, t_warp, b);
+                                         out_row, t_warp, b, out_f32, f32_add);
         }
       } else {
         // A real loop, not four unrolled copies: one chunk is ~500 instructions, and four copies per tile did not
@@ -556,7 +594,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             if (NPL > 1) v[i] += __uint_as_float(q[i]);        // main + side accumulator, round-to-nearest
           }
           const float cs = epilogue_chunk<NPL>(p, &tmOut, stage, v, bias_c, keep_c, n0 + c * 32, lane, row_ok, out_row,
-                                               t_warp, b);
+                                               t_warp, b, out_f32, f32_add);
 #pragma unroll
           for (int k = 0; k < kMine; ++k)
             if (ci == k) csum[k] = cs;
@@ -611,9 +649,10 @@ struct WgradCfg {
   static constexpr int BOX_BYTES = 64 * 128;                     // one {64 ch, 64 rows} box
 };
 
-template <int BLOCK_N, int NPL>
+template <int BLOCK_N, int NPL, int NPROB>
 __global__ void __launch_bounds__(kThreads, 1)
-tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmDZ,
+tc_wgrad_kernel(const __grid_constant__ std::conditional_t<NPROB == 1, TmSet1, TmSet3> tmXs,
+                const __grid_constant__ std::conditional_t<NPROB == 1, TmSet1, TmSet3> tmDZs,
                 const WgradParams p) {
   using Cfg = WgradCfg<BLOCK_N, NPL>;
   constexpr int STAGES = Cfg::STAGES;
@@ -633,7 +672,8 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
   // R = tiles % gridDim.x tiles are cut into S = gridDim.x / R aligned K slices each so that the last wave also
   // fills the machine.  Sliced tiles accumulate with fp32 atomics into the pre-zeroed gradient, whole tiles store.
   const int tiles_mn = p.m_tiles * p.n_tiles;
-  const int num_tiles = p.taps * tiles_mn;
+  const int tiles_per_problem = p.taps * tiles_mn;
+  const int num_tiles = (NPROB > 1 ? p.n_problems : 1) * tiles_per_problem;
   const int total_iters = p.B * p.t_chunks;
   const int G = gridDim.x;
   const int full_waves = num_tiles / G;
@@ -655,8 +695,8 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
   };
 
   if (warp == 0 && lane == 0) {
-    prefetch_tmap(&tmX);
-    prefetch_tmap(&tmDZ);
+    prefetch_tmap(&tmXs.m[0]);
+    prefetch_tmap(&tmDZs.m[0]);
     for (int s = 0; s < STAGES * NG; ++s) {
       mbar_init(full_bar + s, 1);
       mbar_init(empty_bar + s, 1);
@@ -678,8 +718,10 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   asm volatile("griddepcontrol.wait;" ::: "memory");
 
-  // tile -> (n tile, tap, m tile), n slowest: a wave touches few dZ column slabs
-  auto decode = [&](int tile, int& j, int& mt, int& nt) {
+  // tile -> (problem, n tile, tap, m tile), n slowest within a problem: a wave touches few dZ column slabs
+  auto decode = [&](int tile, int& q, int& j, int& mt, int& nt) {
+    q = NPROB > 1 ? tile / tiles_per_problem : 0;
+    tile -= q * tiles_per_problem;
     const int per_n = p.taps * p.m_tiles;
     nt = tile / per_n;
     const int rem = tile - nt * per_n;
@@ -692,10 +734,12 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
       int stage = 0;
       uint32_t phase = 0;
       for (int i = 0; i < my_items; ++i) {
-        int tile, q0, q1, j, mt, nt;
+        int tile, q0, q1, pq, j, mt, nt;
         item(i, tile, q0, q1);
-        decode(tile, j, mt, nt);
-        const int m = j - p.pad_left;
+        decode(tile, pq, j, mt, nt);
+        const CUtensorMap* tmX = &tmXs.m[NPROB > 1 ? pq : 0];
+        const CUtensorMap* tmDZ = &tmDZs.m[NPROB > 1 ? pq : 0];
+        const int m = j - (NPROB > 1 ? p.pad_left_q[pq] : p.pad_left);
         const int shift = p.a_stride == 1 ? m : floordiv(m, p.a_stride);
         const int a_col = (m - shift * p.a_stride) * p.a_cin + mt * kTileM;
         const int n0 = nt * BLOCK_N;
@@ -714,7 +758,7 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
               if (NG == 2 && pl != g) continue;
 #pragma unroll
               for (int h = 0; h < kTileM / 64; ++h)
-                tma_load_3d(&tmX, fb, st + pl * Cfg::A_BYTES + h * Cfg::BOX_BYTES, a_col + h * 64, t0 + shift,
+                tma_load_3d(tmX, fb, st + pl * Cfg::A_BYTES + h * Cfg::BOX_BYTES, a_col + h * 64, t0 + shift,
                             pl * p.B + b);
             }
 #pragma unroll
@@ -722,7 +766,7 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
               if (NG == 2 && pl != 1 - g) continue;
 #pragma unroll
               for (int h = 0; h < BLOCK_N / 64; ++h)
-                tma_load_3d(&tmDZ, fb, st + NPL * Cfg::A_BYTES + pl * Cfg::B_BYTES + h * Cfg::BOX_BYTES, n0 + h * 64,
+                tma_load_3d(tmDZ, fb, st + NPL * Cfg::A_BYTES + pl * Cfg::B_BYTES + h * Cfg::BOX_BYTES, n0 + h * 64,
                             t0, pl * p.B + b);
             }
           }
@@ -737,9 +781,9 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
       uint32_t phase = 0;
       int local = 0;
       for (; local < my_items; ++local) {
-        int tile, q0, q1, tj, tmt, tnt;
+        int tile, q0, q1, tq, tj, tmt, tnt;
         item(local, tile, q0, q1);
-        decode(tile, tj, tmt, tnt);
+        decode(tile, tq, tj, tmt, tnt);
         // both operands MN-major; N trimmed to the real output channels of this n tile (rounded up to 16)
         const int n_valid = min(BLOCK_N, p.Cout - tnt * BLOCK_N);
         const uint32_t idesc = make_idesc_bf16(kTileM, p.trim ? max(16, (n_valid + 15) & ~15) : BLOCK_N, 1, 1);
@@ -803,9 +847,9 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
     const int row = quarter * 32 + lane;
     int local = 0;
     for (; local < my_items; ++local) {
-      int tile, q0, q1, j, mt, nt;
+      int tile, q0, q1, pq, j, mt, nt;
       item(local, tile, q0, q1);
-      decode(tile, j, mt, nt);
+      decode(tile, pq, j, mt, nt);
       const bool whole_tile = q0 == 0 && q1 == total_iters;
       const int acc = local % Cfg::ACC_STAGES;
       const uint32_t acc_phase = (local / Cfg::ACC_STAGES) & 1;
@@ -814,7 +858,8 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
       mbar_wait(tmem_full + acc, acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * Cfg::ACC_COLS;
-      float* wrow = p.dW + ((int64_t)j * p.Cin + ci) * p.Cout;
+      float* wrow = NPROB > 1 ? p.dW_q[pq] + ((int64_t)j * p.tap_stride_q[pq] * p.Cin + ci) * p.Cout
+                              : p.dW + ((int64_t)j * p.Cin + ci) * p.Cout;
 #pragma unroll 1
       for (int c = chunk0; c < BLOCK_N / 32; c += kChunkStep) {
         uint32_t r[32];
@@ -1100,6 +1145,125 @@ ffa_combine_kernel(const float* __restrict__ a00, const float* __restrict__ a11,
   }
 }
 
+// Backward of the fast-FIR form.  From dy = d(loss)/d(y) of the layer (planes [NPL][B][To][ld]) the gradients of the
+// three partial products: dA00[u] = dy[2u] - dy[2u-1], dA11[u] = dy[2u] - dy[2u+1], dS[u] = dy[2u+1] (dy = 0 outside
+// [0, To)), each as planes [NPL][B][Tu][ld]; one thread per 8 channels of one u
+template <int NPL>
+__global__ void __launch_bounds__(256)
+ffa_dz_prep_kernel(const __nv_bfloat16* __restrict__ dy, __nv_bfloat16* __restrict__ d00,
+                   __nv_bfloat16* __restrict__ d11, __nv_bfloat16* __restrict__ ds, int B, int To, int Tu, int ld) {
+  const int cg = ld / 8;
+  const int64_t groups = (int64_t)B * Tu * cg;
+  const int64_t in_plane = (int64_t)B * To * ld, out_plane = (int64_t)B * Tu * ld;
+  for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < groups; g += (int64_t)gridDim.x * blockDim.x) {
+    const int c8 = (int)(g % cg);
+    const int64_t bu = g / cg;
+    const int u = (int)(bu % Tu);
+    const int b = (int)(bu / Tu);
+    float y[3][8];                                  // rows 2u-1, 2u, 2u+1
+#pragma unroll
+    for (int h = 0; h < 3; ++h) {
+      const int t = 2 * u - 1 + h;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) y[h][i] = 0.f;
+      if (t < 0 || t >= To) continue;
+      for (int pl = NPL - 1; pl >= 0; --pl) {
+        const uint4 q = *reinterpret_cast<const uint4*>(dy + pl * in_plane + ((int64_t)b * To + t) * ld + c8 * 8);
+        const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          y[h][2 * i] += __uint_as_float(w[i] << 16);
+          y[h][2 * i + 1] += __uint_as_float(w[i] & 0xffff0000u);
+        }
+      }
+    }
+    float a[8], c[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { a[i] = y[1][i] - y[0][i]; c[i] = y[1][i] - y[2][i]; }
+    const int64_t o = ((int64_t)b * Tu + u) * ld + c8 * 8;
+    store_planes8<NPL>(d00 + o, out_plane, a);
+    store_planes8<NPL>(d11 + o, out_plane, c);
+    store_planes8<NPL>(ds + o, out_plane, y[2]);
+  }
+}
+
+// dx[2r+1] = d_odd[r] + d_xs[r], dx[2r] = d_even[r] + d_xs[r], times the ReLU mask of the layer below, split to planes
+// [NPL][B][T][ld]; column sums of what is stored go to db (bias gradient of the layer below).  Partials are fp32
+// [B][Tx][ldp].  block (32 channel octets, 8 row lanes); a block owns a contiguous slab of (b, r) rows.
+template <int NPL>
+__global__ void __launch_bounds__(256)
+ffa_dx_combine_kernel(const float* __restrict__ d_odd, const float* __restrict__ d_even, const float* __restrict__ d_xs,
+                      const __nv_bfloat16* __restrict__ mask, __nv_bfloat16* __restrict__ out, float* __restrict__ db,
+                      int B, int T, int Tx, int N, int ldp, int ld, int rows_per_block) {
+  __shared__ float part[8][32 * 8 + 1];
+  const int c8 = threadIdx.x;                                 // channel octet (ld <= 256)
+  const int64_t rows = (int64_t)B * Tx;
+  const int64_t r0 = (int64_t)blockIdx.x * rows_per_block, r1 = min(rows, r0 + rows_per_block);
+  const int64_t out_plane = (int64_t)B * T * ld;
+  float acc[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+  if (c8 * 8 < ld) {
+    for (int64_t br = r0 + threadIdx.y; br < r1; br += 8) {
+      const int b = (int)(br / Tx), r = (int)(br - (int64_t)b * Tx);
+      if (2 * r >= T) continue;
+      const int64_t prow = br * ldp + c8 * 8;
+      float xs[8], ev[8], od[8];
+#pragma unroll
+      for (int i = 0; i < 8; i += 4) {
+        const float4 a = *reinterpret_cast<const float4*>(d_xs + prow + i);
+        const float4 e = *reinterpret_cast<const float4*>(d_even + prow + i);
+        const float4 o = *reinterpret_cast<const float4*>(d_odd + prow + i);
+        xs[i] = a.x; xs[i + 1] = a.y; xs[i + 2] = a.z; xs[i + 3] = a.w;
+        ev[i] = e.x; ev[i + 1] = e.y; ev[i + 2] = e.z; ev[i + 3] = e.w;
+        od[i] = o.x; od[i + 1] = o.y; od[i + 2] = o.z; od[i + 3] = o.w;
+      }
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int t = 2 * r + h;
+        if (t >= T) continue;
+        const int64_t orow = ((int64_t)b * T + t) * ld + c8 * 8;
+        const uint4 mq = *reinterpret_cast<const uint4*>(mask + orow);
+        const uint32_t mw[4] = {mq.x, mq.y, mq.z, mq.w};
+        float v[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const uint32_t hbits = (i & 1) ? (mw[i >> 1] >> 16) : (mw[i >> 1] & 0xffffu);
+          const bool keep = (hbits - 1u) < 0x7fffu && c8 * 8 + i < N;          // mask element > 0 and a real channel
+          v[i] = keep ? (h ? od[i] : ev[i]) + xs[i] : 0.f;
+          acc[i] += v[i];
+        }
+        store_planes8<NPL>(out + orow, out_plane, v);
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) part[threadIdx.y][threadIdx.x * 8 + i] = acc[i];
+  __syncthreads();
+  const int tid = threadIdx.y * 32 + threadIdx.x;
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s += part[i][tid];
+  if (tid < N) atomicAdd(db + tid, s);
+}
+
+// dW[2j] += cs[j], dW[2j+1] += cs[j]  (filter gradient of the fast-FIR form: the pair-sum correlation feeds both taps)
+__global__ void __launch_bounds__(256)
+ffa_dw_combine_kernel(float* __restrict__ dW, const float* __restrict__ cs, int J, int64_t tap_elems4) {
+  const int64_t total = (int64_t)J * tap_elems4;
+  float4* w4 = reinterpret_cast<float4*>(dW);
+  const float4* c4 = reinterpret_cast<const float4*>(cs);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t j = i / tap_elems4, e = i - j * tap_elems4;
+    const float4 c = c4[i];
+    float4 a = w4[(2 * j) * tap_elems4 + e], b = w4[(2 * j + 1) * tap_elems4 + e];
+    a.x += c.x; a.y += c.y; a.z += c.z; a.w += c.w;
+    b.x += c.x; b.y += c.y; b.z += c.z; b.w += c.w;
+    w4[(2 * j) * tap_elems4 + e] = a;
+    w4[(2 * j + 1) * tap_elems4 + e] = b;
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ host side
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -1156,13 +1320,41 @@ int launch_conv_e(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensor
   static bool configured[kMaxDevices] = {};
   const int dev = current_device();
   if (!configured[dev]) {
-    ST_CUDA_CALL(cudaFuncSetAttribute(tc_conv_kernel<BLOCK_N, NPL, EARLY>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      Cfg::SMEM_BYTES));
+    ST_CUDA_CALL(cudaFuncSetAttribute(tc_conv_kernel<BLOCK_N, NPL, EARLY, 1>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     configured[dev] = true;
   }
   const int tiles = p.B * p.m_tiles_per_utt * p.n_tiles;
-  ST_CUDA_CALL(launch_pdl(tc_conv_kernel<BLOCK_N, NPL, EARLY>, grid_for(tiles), Cfg::SMEM_BYTES, stream, tmA, tmB,
+  TmSet1 a, b;
+  a.m[0] = tmA;
+  b.m[0] = tmB;
+  ST_CUDA_CALL(launch_pdl(tc_conv_kernel<BLOCK_N, NPL, EARLY, 1>, grid_for(tiles), Cfg::SMEM_BYTES, stream, a, b,
                           tmOut, p));
+  return ST_OK;
+}
+
+template <int BLOCK_N, int NPL>
+int launch_conv_multi_t(const CUtensorMap* tmA, const CUtensorMap* tmB, const ConvParams& p0, cudaStream_t stream) {
+  using Cfg = ConvCfg<BLOCK_N, NPL>;
+  constexpr bool EARLY = Cfg::ACC_STAGES == 1;      // several work items per CTA, long main loops: release TMEM early
+  static bool configured[kMaxDevices] = {};
+  const int dev = current_device();
+  if (!configured[dev]) {
+    ST_CUDA_CALL(cudaFuncSetAttribute(tc_conv_kernel<BLOCK_N, NPL, EARLY, kMaxProblems>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    configured[dev] = true;
+  }
+  ConvParams p = p0;
+  p.tma_store = 0;
+  p.timeline = nullptr;
+  TmSet3 a, b;
+  for (int q = 0; q < kMaxProblems; ++q) {
+    a.m[q] = tmA[q < p.n_problems ? q : 0];
+    b.m[q] = tmB[q < p.n_problems ? q : 0];
+  }
+  const int work = p.B * p.m_tiles_per_utt * p.n_tiles * (p.k_split > 1 ? p.k_split : 1) * p.n_problems;
+  ST_CUDA_CALL(launch_pdl(tc_conv_kernel<BLOCK_N, NPL, EARLY, kMaxProblems>, grid_for(work), Cfg::SMEM_BYTES, stream, a,
+                          b, a.m[0], p));
   return ST_OK;
 }
 
@@ -1198,11 +1390,33 @@ int launch_wgrad_t(const CUtensorMap& tmX, const CUtensorMap& tmDZ, const WgradP
   static bool configured[kMaxDevices] = {};
   const int dev = current_device();
   if (!configured[dev]) {
-    ST_CUDA_CALL(cudaFuncSetAttribute(tc_wgrad_kernel<BLOCK_N, NPL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    ST_CUDA_CALL(cudaFuncSetAttribute(tc_wgrad_kernel<BLOCK_N, NPL, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       Cfg::SMEM_BYTES));
     configured[dev] = true;
   }
-  ST_CUDA_CALL(launch_pdl(tc_wgrad_kernel<BLOCK_N, NPL>, st_num_sms(), Cfg::SMEM_BYTES, stream, tmX, tmDZ, p));
+  TmSet1 x, dz;
+  x.m[0] = tmX;
+  dz.m[0] = tmDZ;
+  ST_CUDA_CALL(launch_pdl(tc_wgrad_kernel<BLOCK_N, NPL, 1>, st_num_sms(), Cfg::SMEM_BYTES, stream, x, dz, p));
+  return ST_OK;
+}
+
+template <int BLOCK_N, int NPL>
+int launch_wgrad_multi_t(const CUtensorMap* tmX, const CUtensorMap* tmDZ, const WgradParams& p, cudaStream_t stream) {
+  using Cfg = WgradCfg<BLOCK_N, NPL>;
+  static bool configured[kMaxDevices] = {};
+  const int dev = current_device();
+  if (!configured[dev]) {
+    ST_CUDA_CALL(cudaFuncSetAttribute(tc_wgrad_kernel<BLOCK_N, NPL, kMaxProblems>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    configured[dev] = true;
+  }
+  TmSet3 x, dz;
+  for (int q = 0; q < kMaxProblems; ++q) {
+    x.m[q] = tmX[q < p.n_problems ? q : 0];
+    dz.m[q] = tmDZ[q < p.n_problems ? q : 0];
+  }
+  ST_CUDA_CALL(launch_pdl(tc_wgrad_kernel<BLOCK_N, NPL, kMaxProblems>, st_num_sms(), Cfg::SMEM_BYTES, stream, x, dz, p));
   return ST_OK;
 }
 
@@ -1293,6 +1507,19 @@ int launch_conv(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMa
   return ST_ERR_UNSUPPORTED;
 }
 
+int launch_conv_multi(const CUtensorMap* tmA, const CUtensorMap* tmB, const ConvParams& p, int block_n, int n_planes,
+                      cudaStream_t stream) {
+  ST_CHECK_ARG(p.n_problems >= 2 && p.n_problems <= kMaxProblems, "launch_conv_multi: 2..%d problems", kMaxProblems);
+  ST_CHECK_ARG(!p.bias && !p.relu && !p.out_planes && !p.mask_hi && !p.col_sum,
+               "launch_conv_multi: fp32 outputs only (no bias / ReLU / mask / planes / column sums)");
+  ST_CHECK_ARG(p.k_split <= 1 || (p.taps % p.k_split) == 0, "launch_conv_multi: k_split must divide the taps");
+  for (int q = 0; q < p.n_problems; ++q) ST_CHECK_ARG(p.out_f32_q[q] != nullptr, "launch_conv_multi: null output");
+  if (block_n == 256 && n_planes == 2) return launch_conv_multi_t<256, 2>(tmA, tmB, p, stream);
+  if (block_n == 256 && n_planes == 1) return launch_conv_multi_t<256, 1>(tmA, tmB, p, stream);
+  st_set_error("launch_conv_multi: unsupported (block_n=%d, n_planes=%d)", block_n, n_planes);
+  return ST_ERR_UNSUPPORTED;
+}
+
 int launch_wgrad(const CUtensorMap& tmX, const CUtensorMap& tmDZ, const WgradParams& p, int block_n, int n_planes,
                  cudaStream_t stream) {
   if (block_n == 256 && n_planes == 2) return launch_wgrad_t<256, 2>(tmX, tmDZ, p, stream);
@@ -1303,6 +1530,17 @@ int launch_wgrad(const CUtensorMap& tmX, const CUtensorMap& tmDZ, const WgradPar
   if (block_n == 128 && n_planes == 2) return launch_wgrad_t<128, 2>(tmX, tmDZ, p, stream);
   if (block_n == 64 && n_planes == 3) return launch_wgrad_t<64, 3>(tmX, tmDZ, p, stream);
   st_set_error("launch_wgrad: unsupported (block_n=%d, n_planes=%d)", block_n, n_planes);
+  return ST_ERR_UNSUPPORTED;
+}
+
+int launch_wgrad_multi(const CUtensorMap* tmX, const CUtensorMap* tmDZ, const WgradParams& p, int block_n,
+                       int n_planes, cudaStream_t stream) {
+  ST_CHECK_ARG(p.n_problems >= 2 && p.n_problems <= kMaxProblems, "launch_wgrad_multi: 2..%d problems", kMaxProblems);
+  for (int q = 0; q < p.n_problems; ++q)
+    ST_CHECK_ARG(p.dW_q[q] != nullptr && p.tap_stride_q[q] >= 1, "launch_wgrad_multi: bad output of problem %d", q);
+  if (block_n == 256 && n_planes == 2) return launch_wgrad_multi_t<256, 2>(tmX, tmDZ, p, stream);
+  if (block_n == 256 && n_planes == 1) return launch_wgrad_multi_t<256, 1>(tmX, tmDZ, p, stream);
+  st_set_error("launch_wgrad_multi: unsupported (block_n=%d, n_planes=%d)", block_n, n_planes);
   return ST_ERR_UNSUPPORTED;
 }
 
@@ -1357,6 +1595,50 @@ int launch_ffa_combine(const float* a00, const float* a11, const float* sm, cons
   else
     ffa_combine_kernel<1><<<blocks, 256, 0, stream>>>(a00, a11, sm, bias, relu, out, B, To, Tu, N, ld_p, ld_out);
   ST_CUDA_LAUNCH_CHECK("ffa_combine_kernel");
+  return ST_OK;
+}
+
+int launch_ffa_dz_prep(const __nv_bfloat16* dy, __nv_bfloat16* d00, __nv_bfloat16* d11, __nv_bfloat16* ds, int B,
+                       int To, int Tu, int ld, int n_planes, cudaStream_t stream) {
+  ST_CHECK_ARG(ld % 8 == 0 && n_planes >= 1 && n_planes <= 2, "launch_ffa_dz_prep: bad arguments");
+  const int64_t groups = (int64_t)B * Tu * (ld / 8);
+  int blocks = (int)((groups + 255) / 256);
+  const int cap = 16 * st_num_sms();
+  blocks = blocks > cap ? cap : blocks;
+  if (n_planes == 2) ffa_dz_prep_kernel<2><<<blocks, 256, 0, stream>>>(dy, d00, d11, ds, B, To, Tu, ld);
+  else ffa_dz_prep_kernel<1><<<blocks, 256, 0, stream>>>(dy, d00, d11, ds, B, To, Tu, ld);
+  ST_CUDA_LAUNCH_CHECK("ffa_dz_prep_kernel");
+  return ST_OK;
+}
+
+int launch_ffa_dx_combine(const float* d_odd, const float* d_even, const float* d_xs, const __nv_bfloat16* mask,
+                          __nv_bfloat16* out, float* db, int B, int T, int Tx, int N, int ldp, int ld, int n_planes,
+                          cudaStream_t stream) {
+  ST_CHECK_ARG(ld % 8 == 0 && ld <= 256 && ldp % 4 == 0 && ldp >= ld && n_planes >= 1 && n_planes <= 2,
+               "launch_ffa_dx_combine: bad arguments");
+  const int64_t rows = (int64_t)B * Tx;
+  int blocks = (int)((rows + 15) / 16);
+  const int cap = 4 * st_num_sms();
+  blocks = blocks > cap ? cap : (blocks < 1 ? 1 : blocks);
+  const int rows_per_block = (int)((rows + blocks - 1) / blocks);
+  if (n_planes == 2)
+    ffa_dx_combine_kernel<2><<<blocks, dim3(32, 8), 0, stream>>>(d_odd, d_even, d_xs, mask, out, db, B, T, Tx, N, ldp,
+                                                                 ld, rows_per_block);
+  else
+    ffa_dx_combine_kernel<1><<<blocks, dim3(32, 8), 0, stream>>>(d_odd, d_even, d_xs, mask, out, db, B, T, Tx, N, ldp,
+                                                                 ld, rows_per_block);
+  ST_CUDA_LAUNCH_CHECK("ffa_dx_combine_kernel");
+  return ST_OK;
+}
+
+int launch_ffa_dw_combine(float* dW, const float* cs, int J, int64_t tap_elems, cudaStream_t stream) {
+  ST_CHECK_ARG(tap_elems % 4 == 0, "launch_ffa_dw_combine: tap size must be a multiple of 4 floats");
+  const int64_t total = (int64_t)J * (tap_elems / 4);
+  int blocks = (int)((total + 255) / 256);
+  const int cap = 16 * st_num_sms();
+  blocks = blocks > cap ? cap : blocks;
+  ffa_dw_combine_kernel<<<blocks, 256, 0, stream>>>(dW, cs, J, tap_elems / 4);
+  ST_CUDA_LAUNCH_CHECK("ffa_dw_combine_kernel");
   return ST_OK;
 }
 

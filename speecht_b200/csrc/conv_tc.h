@@ -33,7 +33,18 @@ struct ConvParams {
   long long* timeline;           // debug (st_debug_conv_timeline): [grid][8] %globaltimer stamps of the CTA's first tile
   int k_cols;                    // valid contraction columns per tap (A channels): zero-filled K steps are not issued
   int trim;                      // 1: issue only the K steps / N columns that hold real channels (0: full tiles)
+  // ---- several problems of IDENTICAL shape in one persistent launch (launch_conv_multi; fast-FIR split of layer 8):
+  // problem q uses tensor maps A[q] / B[q], its own left padding and fp32 output; the taps of every tile may be cut
+  // into k_split slices that accumulate into the (pre-zeroed) fp32 output with vector reductions.  Multi launches
+  // write fp32 only: no bias, ReLU, mask, bf16 planes or column sums (the combine pass that follows does those).
+  int n_problems;                // 0 / 1: single problem (the fields above); 2..kMaxProblems: use the arrays below
+  int k_split;                   // 0 / 1: whole contraction per tile
+  int pad_left_q[3];
+  float* out_f32_q[3];
 };
+constexpr int kMaxProblems = 3;
+struct TmSet1 { CUtensorMap m[1]; };
+struct TmSet3 { CUtensorMap m[kMaxProblems]; };
 
 // ---- filter-gradient kernel: dW[j, ci, co] += sum_{b,t} X[b, t+shift_j, acol_j + ci] * dZ[b, t, co]
 struct WgradParams {
@@ -43,6 +54,12 @@ struct WgradParams {
   int Cin, Cout;
   float* dW;                     // must be zero on entry (K-sliced tiles accumulate with atomics)
   int trim;                      // 1: N of the last n tile rounded to 16, K steps past the last time row skipped
+  // ---- several problems of identical shape in one launch (launch_wgrad_multi; fast-FIR split of layer 8): problem q
+  // correlates X[q] with dZ[q] using its own left padding and writes tap j to dW_q[q] + j * tap_stride_q[q] * Cin * Cout
+  int n_problems;                // 0 / 1: single problem
+  int pad_left_q[3];
+  float* dW_q[3];
+  int tap_stride_q[3];
 };
 
 int make_map_3d(CUtensorMap* map, const void* base, int C, int T, int Bn, int64_t ld, int64_t batch_stride,
@@ -60,6 +77,12 @@ int launch_conv(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMa
                 int block_n, int n_planes, cudaStream_t stream);
 int launch_wgrad(const CUtensorMap& tmX, const CUtensorMap& tmDZ, const WgradParams& p, int block_n, int n_planes,
                  cudaStream_t stream);
+int launch_wgrad_multi(const CUtensorMap* tmX, const CUtensorMap* tmDZ, const WgradParams& p, int block_n,
+                       int n_planes, cudaStream_t stream);
+// p.n_problems problems (2..3) of identical shape in one launch; fp32 outputs p.out_f32_q[q] (zeroed by the caller
+// when p.k_split > 1), no epilogue extras.  block_n = 256, n_planes 1 or 2.
+int launch_conv_multi(const CUtensorMap* tmA, const CUtensorMap* tmB, const ConvParams& p, int block_n, int n_planes,
+                      cudaStream_t stream);
 
 // fp32 [B][T][F] -> planes [n_planes][B][Tpad][F] (rows t >= T zero)
 int launch_split_input(const float* x, __nv_bfloat16* planes, int B, int T, int Tpad, int F, int n_planes,
@@ -75,7 +98,7 @@ struct PackEntry {
 };
 struct PackTable {
   int n;
-  PackEntry e[12];
+  PackEntry e[16];
 };
 int launch_pack_filters(PackTable& tab, int n_planes, cudaStream_t stream, int* launches);
 // ---- fast-FIR split of a stride-1 layer (experimental, see w2l_plan.cu)
@@ -90,6 +113,15 @@ int launch_ffa_split_taps(const float* w, float* w0, float* w1, float* ws, int J
 int launch_ffa_combine(const float* a00, const float* a11, const float* sm, const float* bias, int relu,
                        __nv_bfloat16* out, int B, int To, int Tu, int N, int ld_p, int ld_out, int n_planes,
                        cudaStream_t stream);
+// backward of the same form: dy planes [n][B][To][ld] -> dA00 / dA11 / dS planes [n][B][Tu][ld]
+int launch_ffa_dz_prep(const __nv_bfloat16* dy, __nv_bfloat16* d00, __nv_bfloat16* d11, __nv_bfloat16* ds, int B,
+                       int To, int Tu, int ld, int n_planes, cudaStream_t stream);
+// fp32 partials d_odd / d_even / d_xs [B][Tx][ldp] -> masked dx planes [n][B][T][ld] + column sums into db
+int launch_ffa_dx_combine(const float* d_odd, const float* d_even, const float* d_xs, const __nv_bfloat16* mask,
+                          __nv_bfloat16* out, float* db, int B, int T, int Tx, int N, int ldp, int ld, int n_planes,
+                          cudaStream_t stream);
+// dW[2j] += cs[j], dW[2j+1] += cs[j] for j < J; tap_elems = Cin*Cout
+int launch_ffa_dw_combine(float* dW, const float* cs, int J, int64_t tap_elems, cudaStream_t stream);
 // db[n] = sum over rows and planes of dz planes [n_planes][rows][ld]
 int launch_bias_grad(const __nv_bfloat16* dz, int64_t rows, int N, int ld, int n_planes, float* db,
                      cudaStream_t stream);

@@ -3,13 +3,12 @@
 // softmax applied internally, frames t >= seq_len get zero gradient.
 //
 // Three kernels:
-//   1. ctc_log_softmax : one warp per (b,t) row, warp-shuffle max / sum over the 29 classes.
-//   2. ctc_alpha_beta  : grid (B,2): CTA (b,0) runs the alpha recursion, CTA (b,1) the beta recursion, both
-//                        500-1500 strictly serial steps with one __syncthreads per step, in the LINEAR domain on
-//                        scaled floats p*2^e (fp32 mantissa, int32 exponent): no transcendental and no fp64 on the
-//                        serial chain, 6e-8 relative error per step.
-//   3. ctc_grad        : one warp per (b,t) row: occupancy per class from alpha+beta-logp, grad = softmax - occ.
-// Algorithmic bytes = read logits + write grad = 2*T*B*C*4; the alpha/beta lattices (T*S doubles each) are
+//   1. ctc_softmax     : one warp per (b,t) row, warp-shuffle max / sum over the 29 classes -> class probabilities.
+//   2. ctc_alpha_beta  : grid (B,2): CTA (b,0) runs the alpha recursion, CTA (b,1) the beta recursion (only alpha
+//                        when no gradient is wanted), 500-1500 strictly serial steps with one __syncthreads per
+//                        step, in the LINEAR domain on scaled floats p*2^e (fp32 mantissa in [1,2), int32 exponent).
+//   3. ctc_grad        : one warp per (b,t) row: occupancy per class from alpha*beta/p(z|x), grad = softmax - occ.
+// Algorithmic bytes = read logits + write grad = 2*T*B*C*4; the alpha/beta lattices (T*S x 8 bytes each) are
 // workspace traffic on top.  The recursion is latency-bound by construction.
 #include "st_common.cuh"
 #include <math.h>
@@ -18,11 +17,11 @@
 
 namespace {
 
-constexpr int kABThreads = 256;
-
+// probs[b][t][c] = max(softmax(logits[t][b][:])[c], FLT_MIN): the emission probabilities the recursions multiply by,
+// kept NORMAL so that products with a mantissa in [1,6) never go denormal.
 __global__ void __launch_bounds__(256)
-ctc_log_softmax_kernel(const float* __restrict__ logits, int64_t stride_t, int64_t stride_b, int T, int B, int C,
-                       const int32_t* __restrict__ seq_len, float* __restrict__ lsm) {
+ctc_softmax_kernel(const float* __restrict__ logits, int64_t stride_t, int64_t stride_b, int T, int B, int C,
+                   const int32_t* __restrict__ seq_len, float* __restrict__ probs) {
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= B * T) return;
@@ -35,56 +34,54 @@ ctc_log_softmax_kernel(const float* __restrict__ logits, int64_t stride_t, int64
   float sum = 0.f;
   for (int c = lane; c < C; c += 32) sum += expf(src[c] - mx);
   sum = warp_sum(sum);
-  const float lse = mx + logf(sum);
-  float* dst = lsm + (int64_t)row * C;
-  for (int c = lane; c < C; c += 32) dst[c] = src[c] - lse;
+  const float inv = 1.f / sum;
+  float* dst = probs + (int64_t)row * C;
+  for (int c = lane; c < C; c += 32) dst[c] = fmaxf(expf(src[c] - mx) * inv, 1.17549435e-38f);
 }
 
 // ---- scaled-float arithmetic for the alpha / beta recursions --------------------------------------------------
-// A lattice value (a probability that reaches 1e-600 and below) is kept in the LINEAR domain as p * 2^e with
-// p in [1,2) (or p == 0) in fp32 and e an int32: one recursion step is two integer max, three exponent-field
-// shifts, two fp32 adds, one fp32 multiply and a renormalisation -- no transcendental and no fp64 on the serial
-// chain (the earlier log-domain / double version spent ~700 cycles per step, this one ~150).  Relative error per
-// step 6e-8, i.e. ~1e-6 after 1500 steps.
+// A lattice value (a probability that reaches 1e-600 and below) is kept in the LINEAR domain as p * 2^e with p in
+// [1,2) in fp32 and e an int32.  ZERO is not special: it is p = 1 with the exponent kZeroExp = -2^28, a number so
+// small that it vanishes in every sum -- no zero tests on the serial chain.  One recursion step is
+//   em  = max(e0, e1, e2)                        (one 3-input integer max)
+//   sum = sum_i p_i * 2^max(e_i - em, -126)      (per term: subtract, clamp, build the power of two, multiply)
+//   x   = sum * y                                (y = emission probability, a normal fp32 in [2^-126, 1])
+//   (p, e) = (x / 2^floor(log2 x), em + floor(log2 x))
+// ~30 instructions, no transcendental and no fp64; relative error 6e-8 per step, ~1e-6 after 1500 steps.  The term
+// with the largest exponent enters with scale 1, so sum is in [1,6) and x is a normal number: no special cases.
 struct SF { float p; int e; };
 constexpr int kZeroExp = -(1 << 28);
 
-__device__ __forceinline__ float sf_shift(float p, int de) {          // p * 2^de for de <= 0
-  return (p == 0.f || de < -60) ? 0.f : __int_as_float(__float_as_int(p) + de * (1 << 23));
+__device__ __forceinline__ float sf_scaled(float p, int de) {          // p * 2^max(de, -126), de <= 0
+  return p * __int_as_float((max(de, -126) + 127) << 23);
 }
-__device__ __forceinline__ SF sf_norm(float x, int ebase) {            // x >= 0 (normal or zero)
-  SF r;
-  if (x == 0.f) { r.p = 0.f; r.e = kZeroExp; return r; }
+__device__ __forceinline__ SF sf_norm(float x, int ebase) {            // x normal and positive
   const int bits = __float_as_int(x);
-  const int ex = ((bits >> 23) & 0xff) - 127;
-  r.p = __int_as_float(bits - ex * (1 << 23));
+  const int ex = (bits >> 23) - 127;
+  SF r;
+  r.p = __int_as_float(bits - (ex << 23));
   r.e = ebase + ex;
   return r;
 }
-__device__ __forceinline__ SF sf_add3_mul(SF a, SF b, SF c, float py, int ey) {   // (a + b + c) * (py * 2^ey)
+__device__ __forceinline__ SF sf_sum3(SF a, SF b, SF c) {              // a + b + c, normalised
   const int em = max(a.e, max(b.e, c.e));
-  const float sum = sf_shift(a.p, a.e - em) + sf_shift(b.p, b.e - em) + sf_shift(c.p, c.e - em);
-  return sf_norm(sum * py, em + ey);
+  return sf_norm(sf_scaled(a.p, a.e - em) + sf_scaled(b.p, b.e - em) + sf_scaled(c.p, c.e - em), em);
 }
-__device__ __forceinline__ void sf_from_log(float l, float& py, int& ey) {        // exp(l) as py * 2^ey, l <= 0
-  const float l2 = l * 1.4426950408889634f;
-  const float fl = floorf(l2);
-  py = exp2f(l2 - fl);
-  ey = (int)fl;
+__device__ __forceinline__ double sf_log(SF v) {                        // natural log; -inf for ZERO
+  return v.e < kZeroExp / 2 ? -INFINITY : ((double)v.e + (double)log2f(v.p)) * 0.6931471805599453;
 }
-__device__ __forceinline__ double sf_log(SF v) {                                   // natural log
-  return v.p == 0.f ? -INFINITY : ((double)v.e + (double)log2f(v.p)) * 0.6931471805599453;
-}
+__device__ __forceinline__ SF sf_zero() { SF r; r.p = 1.f; r.e = kZeroExp; return r; }
 __device__ __forceinline__ SF sf_load(const int2* p) { const int2 v = *p; SF r; r.p = __int_as_float(v.x); r.e = v.y; return r; }
 __device__ __forceinline__ void sf_store(int2* p, SF v) { *p = make_int2(__float_as_int(v.p), v.e); }
 
-// dynamic smem: int2 buf[2][s_pad + 4]; int ext[s_pad]; unsigned char skip[s_pad + 2]; [float lsm_s[len*C]]
+// dynamic smem: int2 buf[2][s_pad + 4]; int ext[s_pad]; unsigned char skip[s_pad + 2]; [float probs_s[len*C]]
 // NS = extended-label positions per thread (S <= NS*blockDim.x; the launcher sizes the block to the longest
-// extended label so that NS == 1 up to 511 characters).  LSM_SMEM: the utterance's log-softmax rows are staged in
+// extended label so that NS == 1 up to 511 characters).  PROBS_SMEM: the utterance's probability rows are staged in
 // shared memory up front (one coalesced pass) so that the serial recursion never waits on an L2 round trip.
-template <int NS, bool LSM_SMEM>
+// STORE: write the lattices for the gradient kernel (off for loss-only calls, which also skip the beta CTAs).
+template <int NS, bool PROBS_SMEM, bool STORE>
 __global__ void __launch_bounds__(1024)
-ctc_alpha_beta_kernel(const float* __restrict__ lsm, int T, int C, const int32_t* __restrict__ labels,
+ctc_alpha_beta_kernel(const float* __restrict__ probs, int T, int C, const int32_t* __restrict__ labels,
                       const int32_t* __restrict__ label_offsets, const int32_t* __restrict__ seq_len, int blank,
                       int s_pad, int2* __restrict__ alpha, int2* __restrict__ beta,
                       double* __restrict__ logp, float* __restrict__ loss, int32_t* __restrict__ status) {
@@ -101,7 +98,7 @@ ctc_alpha_beta_kernel(const float* __restrict__ lsm, int T, int C, const int32_t
   const int bstride = s_pad + 4;
   int* ext = reinterpret_cast<int*>(buf + 2 * bstride);                 // [s_pad]
   unsigned char* skip = reinterpret_cast<unsigned char*>(ext + s_pad);  // [s_pad + 2]
-  float* lsm_s = reinterpret_cast<float*>(smem_raw + (((size_t)2 * bstride * 8 + (size_t)s_pad * 4 + s_pad + 2 + 15) & ~(size_t)15));
+  float* probs_s = reinterpret_cast<float*>(smem_raw + (((size_t)2 * bstride * 8 + (size_t)s_pad * 4 + s_pad + 2 + 15) & ~(size_t)15));
   __shared__ int s_bad;
   if (threadIdx.x == 0) s_bad = 0;
   __syncthreads();
@@ -126,12 +123,12 @@ ctc_alpha_beta_kernel(const float* __restrict__ lsm, int T, int C, const int32_t
     // skip[s]: transition s-2 -> s allowed
     skip[s] = (s >= 2 && s < S && ext[s] != blank && ext[s] != ext[s - 2]) ? 1 : 0;
   }
-  const int2 zero = make_int2(0, kZeroExp);
+  const int2 zero = make_int2(__float_as_int(1.f), kZeroExp);
   for (int i = threadIdx.x; i < 2 * bstride; i += nthr) buf[i] = zero;
-  const float* lrow = lsm + (int64_t)b * T * C;
-  if (LSM_SMEM && !infeasible && len > 0) {
-    for (int i = threadIdx.x; i < len * C; i += nthr) lsm_s[i] = lrow[i];
-    lrow = lsm_s;
+  const float* prow = probs + (int64_t)b * T * C;
+  if (PROBS_SMEM && !infeasible && len > 0) {
+    for (int i = threadIdx.x; i < len * C; i += nthr) probs_s[i] = prow[i];
+    prow = probs_s;
   }
   __syncthreads();
 
@@ -148,15 +145,14 @@ ctc_alpha_beta_kernel(const float* __restrict__ lsm, int T, int C, const int32_t
   int2* lat = (is_beta ? beta : alpha) + (int64_t)b * T * s_pad;
   int my_ext[NS];
   bool my_skip[NS], live[NS];
-  float py[NS];                                     // emission probability of the NEXT step to consume, as py*2^ey
-  int ey[NS];
+  float y[NS];                                      // emission probability of the NEXT step to consume
 #pragma unroll
   for (int j = 0; j < NS; ++j) {
     const int s = threadIdx.x + j * nthr;
     live[j] = s < S;
     my_ext[j] = live[j] ? ext[s] : blank;
     my_skip[j] = false;
-    py[j] = 0.f; ey[j] = 0;
+    y[j] = 1.f;
   }
 
   if (!is_beta) {
@@ -166,11 +162,10 @@ ctc_alpha_beta_kernel(const float* __restrict__ lsm, int T, int C, const int32_t
       const int s = threadIdx.x + j * nthr;
       if (live[j]) {
         my_skip[j] = skip[s] != 0;
-        SF v; v.p = 0.f; v.e = kZeroExp;
-        if (s < 2) { sf_from_log(lrow[my_ext[j]], v.p, v.e); v = sf_norm(v.p, v.e); }
-        sf_store(buf + 2 + s, v);                                       // slot 0, +2 pad so s-1, s-2 read zero
-        sf_store(lat + s, v);
-        if (len > 1) sf_from_log(lrow[(int64_t)C + my_ext[j]], py[j], ey[j]);
+        const SF v = s < 2 ? sf_norm(prow[my_ext[j]], 0) : sf_zero();
+        sf_store(buf + 2 + s, v);                                       // slot 0, +2 pad so s-1, s-2 read ZERO
+        if (STORE) sf_store(lat + s, v);
+        if (len > 1) y[j] = prow[(int64_t)C + my_ext[j]];
       }
     }
     __syncthreads();
@@ -178,15 +173,10 @@ ctc_alpha_beta_kernel(const float* __restrict__ lsm, int T, int C, const int32_t
     for (int t = 1; t < len; ++t, lat_t += s_pad) {
       const int2* prev = buf + ((t - 1) & 1) * bstride;
       int2* cur = buf + (t & 1) * bstride;
-      const float* next_row = lrow + (int64_t)(t + 1) * C;
-      // emission of step t+1 first: independent of the recursion, its MUFU / conversions fill the chain's stalls
-      float pn[NS];
-      int en[NS];
+      const float* next_row = prow + (int64_t)(t + 1) * C;
+      float yn[NS];                                                      // emission of step t+1: off the chain
 #pragma unroll
-      for (int j = 0; j < NS; ++j) {
-        pn[j] = 0.f; en[j] = 0;
-        if (live[j] && t + 1 < len) sf_from_log(next_row[my_ext[j]], pn[j], en[j]);
-      }
+      for (int j = 0; j < NS; ++j) yn[j] = (live[j] && t + 1 < len) ? next_row[my_ext[j]] : 1.f;
       SF v[NS];
 #pragma unroll
       for (int j = 0; j < NS; ++j) {
@@ -194,8 +184,10 @@ ctc_alpha_beta_kernel(const float* __restrict__ lsm, int T, int C, const int32_t
         if (live[j]) {
           const SF a0 = sf_load(prev + 2 + s), a1 = sf_load(prev + 1 + s);
           SF a2 = sf_load(prev + s);
-          if (!my_skip[j]) { a2.p = 0.f; a2.e = kZeroExp; }
-          v[j] = sf_add3_mul(a0, a1, a2, py[j], ey[j]);
+          if (!my_skip[j]) a2.e = kZeroExp;
+          const int em = max(a0.e, max(a1.e, a2.e));
+          const float sum = sf_scaled(a0.p, a0.e - em) + sf_scaled(a1.p, a1.e - em) + sf_scaled(a2.p, a2.e - em);
+          v[j] = sf_norm(sum * y[j], em);
           sf_store(cur + 2 + s, v[j]);
         }
       }
@@ -203,47 +195,41 @@ ctc_alpha_beta_kernel(const float* __restrict__ lsm, int T, int C, const int32_t
 #pragma unroll
       for (int j = 0; j < NS; ++j) {
         const int s = threadIdx.x + j * nthr;
-        if (live[j]) sf_store(lat_t + s, v[j]);                          // global store after the barrier: off the chain
-        py[j] = pn[j]; ey[j] = en[j];
+        if (STORE && live[j]) sf_store(lat_t + s, v[j]);                 // global store after the barrier: off the chain
+        y[j] = yn[j];
       }
     }
     if (threadIdx.x == 0) {
       const int2* fin = buf + ((len - 1) & 1) * bstride;
-      SF zs; zs.p = 0.f; zs.e = kZeroExp;
-      const SF total = sf_add3_mul(sf_load(fin + 2 + S - 1), S > 1 ? sf_load(fin + 2 + S - 2) : zs, zs, 1.f, 0);
+      const SF total = sf_sum3(sf_load(fin + 2 + S - 1), S > 1 ? sf_load(fin + 2 + S - 2) : sf_zero(), sf_zero());
       const double lpz = sf_log(total);
       logp[b] = lpz;
       loss[b] = (float)(-lpz);
-      if (total.p == 0.f) status[b] = 1;
+      if (total.e < kZeroExp / 2) status[b] = 1;
     }
   } else {
     // beta_{len-1}(s) = 1 for the last two positions; smem holds g_t(s) = beta_t(s) * y_t(s) for the step below
-    const float* last = lrow + (int64_t)(len - 1) * C;
+    const float* last = prow + (int64_t)(len - 1) * C;
 #pragma unroll
     for (int j = 0; j < NS; ++j) {
       const int s = threadIdx.x + j * nthr;
       if (live[j]) {
         my_skip[j] = skip[s + 2] != 0;                                  // transition s -> s+2
-        SF v; v.p = (s >= S - 2) ? 1.f : 0.f; v.e = (s >= S - 2) ? 0 : kZeroExp;
-        sf_store(lat + (int64_t)(len - 1) * s_pad + s, v);
-        float p0; int e0;
-        sf_from_log(last[my_ext[j]], p0, e0);
-        sf_store(buf + ((len - 1) & 1) * bstride + s, sf_norm(v.p * p0, v.e + e0));
-        if (len > 1) sf_from_log(lrow[(int64_t)(len - 2) * C + my_ext[j]], py[j], ey[j]);
+        SF v = sf_zero();
+        if (s >= S - 2) v.e = 0;
+        if (STORE) sf_store(lat + (int64_t)(len - 1) * s_pad + s, v);
+        sf_store(buf + ((len - 1) & 1) * bstride + s, sf_norm(v.p * last[my_ext[j]], v.e));
+        if (len > 1) y[j] = prow[(int64_t)(len - 2) * C + my_ext[j]];
       }
     }
     __syncthreads();
     int2* lat_t = lat + (int64_t)(len - 2) * s_pad;
     for (int t = len - 2; t >= 0; --t, lat_t -= s_pad) {
-      const int2* nxt = buf + ((t + 1) & 1) * bstride;                  // entries S..S+3 stay zero
+      const int2* nxt = buf + ((t + 1) & 1) * bstride;                  // entries S..S+3 stay ZERO
       int2* cur = buf + (t & 1) * bstride;
-      float pn[NS];
-      int en[NS];
+      float yn[NS];
 #pragma unroll
-      for (int j = 0; j < NS; ++j) {
-        pn[j] = 0.f; en[j] = 0;
-        if (live[j] && t > 0) sf_from_log(lrow[(int64_t)(t - 1) * C + my_ext[j]], pn[j], en[j]);
-      }
+      for (int j = 0; j < NS; ++j) yn[j] = (live[j] && t > 0) ? prow[(int64_t)(t - 1) * C + my_ext[j]] : 1.f;
       SF v[NS];
 #pragma unroll
       for (int j = 0; j < NS; ++j) {
@@ -251,17 +237,17 @@ ctc_alpha_beta_kernel(const float* __restrict__ lsm, int T, int C, const int32_t
         if (live[j]) {
           const SF b0 = sf_load(nxt + s), b1 = sf_load(nxt + s + 1);
           SF b2 = sf_load(nxt + s + 2);
-          if (!my_skip[j]) { b2.p = 0.f; b2.e = kZeroExp; }
-          v[j] = sf_add3_mul(b0, b1, b2, 1.f, 0);
-          sf_store(cur + s, sf_norm(v[j].p * py[j], v[j].e + ey[j]));
+          if (!my_skip[j]) b2.e = kZeroExp;
+          v[j] = sf_sum3(b0, b1, b2);
+          sf_store(cur + s, sf_norm(v[j].p * y[j], v[j].e));
         }
       }
       __syncthreads();
 #pragma unroll
       for (int j = 0; j < NS; ++j) {
         const int s = threadIdx.x + j * nthr;
-        if (live[j]) sf_store(lat_t + s, v[j]);
-        py[j] = pn[j]; ey[j] = en[j];
+        if (STORE && live[j]) sf_store(lat_t + s, v[j]);
+        y[j] = yn[j];
       }
     }
   }
@@ -269,7 +255,7 @@ ctc_alpha_beta_kernel(const float* __restrict__ lsm, int T, int C, const int32_t
 
 // One warp per (b,t) row.  grad row = grad_scale * (softmax - occupancy); zero for t >= seq_len[b].
 __global__ void __launch_bounds__(256)
-ctc_grad_kernel(const float* __restrict__ lsm, const int2* __restrict__ alpha, const int2* __restrict__ beta,
+ctc_grad_kernel(const float* __restrict__ probs, const int2* __restrict__ alpha, const int2* __restrict__ beta,
                 const double* __restrict__ logp, const int32_t* __restrict__ labels,
                 const int32_t* __restrict__ label_offsets, const int32_t* __restrict__ seq_len,
                 const int32_t* __restrict__ status, int T, int B, int C, int blank, int s_pad,
@@ -294,13 +280,11 @@ ctc_grad_kernel(const float* __restrict__ lsm, const int2* __restrict__ alpha, c
     const int2* be = beta + ((int64_t)b * T + t) * s_pad;
     float blank_sum = 0.f;
     for (int s = lane; s < S; s += 32) {
-      // occupancy = alpha*beta / p(z|x) = 2^(ea+eb-lz2) * pa*pb: integer exponents subtract exactly
+      // occupancy = alpha*beta / p(z|x) = 2^(ea+eb-lz2) * pa*pb: integer exponents subtract exactly; a ZERO factor
+      // (exponent -2^28) drives the power of two to 0
       const SF av = sf_load(a + s), bv = sf_load(be + s);
-      float e = 0.f;
-      if (av.p != 0.f && bv.p != 0.f) {
-        const float v2 = (float)((double)(av.e + bv.e) - lz2);
-        e = v2 > -140.f ? exp2f(v2) * (av.p * bv.p) : 0.f;
-      }
+      const float v2 = (float)((double)(av.e + bv.e) - lz2);
+      const float e = v2 > -140.f ? exp2f(v2) * (av.p * bv.p) : 0.f;
       if (s & 1) {
         atomicAdd(&bins[warp][labels[l0 + (s >> 1)]], e);
       } else {
@@ -309,14 +293,14 @@ ctc_grad_kernel(const float* __restrict__ lsm, const int2* __restrict__ alpha, c
     }
     blank_sum = warp_sum(blank_sum);
     __syncwarp();
-    const float* lr = lsm + (int64_t)row * C;
+    const float* pr = probs + (int64_t)row * C;
     if (lane < C) {
       float occ = bins[warp][lane] + (lane == blank ? blank_sum : 0.f);
-      g0 = grad_scale * (__expf(lr[lane]) - occ);
+      g0 = grad_scale * (pr[lane] - occ);
     }
     if (lane + 32 < C) {
       float occ = bins[warp][lane + 32] + (lane + 32 == blank ? blank_sum : 0.f);
-      g1 = grad_scale * (__expf(lr[lane + 32]) - occ);
+      g1 = grad_scale * (pr[lane + 32] - occ);
     }
   }
   if (grad) {
@@ -416,26 +400,32 @@ ST_API int st_ctc_loss(const float* logits, int64_t stride_t, int64_t stride_b, 
   cudaStream_t s = st_cu(stream);
 
   const int rows = B * T;
-  ctc_log_softmax_kernel<<<(rows + 7) / 8, 256, 0, s>>>(logits, stride_t, stride_b, T, B, C, seq_len, lsm);
-  ST_CUDA_LAUNCH_CHECK("ctc_log_softmax_kernel");
+  ctc_softmax_kernel<<<(rows + 7) / 8, 256, 0, s>>>(logits, stride_t, stride_b, T, B, C, seq_len, lsm);
+  ST_CUDA_LAUNCH_CHECK("ctc_softmax_kernel");
 
+  const bool want_grad = grad || grad_planes;
   const size_t smem_base = (((size_t)2 * (s_pad + 4) * sizeof(double) + (size_t)s_pad * sizeof(int) + (size_t)(s_pad + 2) + 15) &
                             ~(size_t)15);
-  const size_t smem_lsm = (size_t)T * C * sizeof(float);
-  const bool lsm_in_smem = smem_base + smem_lsm + 64 <= 200 * 1024;
-  const size_t smem = smem_base + (lsm_in_smem ? smem_lsm : 0) + 64;
+  const size_t smem_probs = (size_t)T * C * sizeof(float);
+  const bool probs_in_smem = smem_base + smem_probs + 64 <= 200 * 1024;
+  const size_t smem = smem_base + (probs_in_smem ? smem_probs : 0) + 64;
   const int S_max = 2 * max_label_len + 1;
   const int threads = S_max >= 1024 ? 1024 : (S_max + 31) / 32 * 32;
   const int ns = S_max <= threads ? 1 : (S_max <= 2 * threads ? 2 : (S_max <= 4 * threads ? 4 : 8));
-#define ST_CTC_LAUNCH(NS_, SM_)                                                                                      \
+  // loss only: the alpha recursion alone gives p(z|x); no beta CTAs, no lattice stores
+#define ST_CTC_LAUNCH2(NS_, SM_, ST_)                                                                                \
   do {                                                                                                               \
     if (smem > 48 * 1024)                                                                                            \
-      ST_CUDA_CALL(cudaFuncSetAttribute(ctc_alpha_beta_kernel<NS_, SM_>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                        (int)smem));                                                                 \
-    ctc_alpha_beta_kernel<NS_, SM_><<<dim3(B, 2), threads, smem, s>>>(lsm, T, C, labels, label_offsets, seq_len,  \
-                                                                       blank, s_pad, alpha, beta, logp, loss, status); \
+      ST_CUDA_CALL(cudaFuncSetAttribute(ctc_alpha_beta_kernel<NS_, SM_, ST_>,                                        \
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                    \
+    ctc_alpha_beta_kernel<NS_, SM_, ST_><<<dim3(B, ST_ ? 2 : 1), threads, smem, s>>>(                                \
+        lsm, T, C, labels, label_offsets, seq_len, blank, s_pad, alpha, beta, logp, loss, status);                   \
   } while (0)
-  if (lsm_in_smem) {
+#define ST_CTC_LAUNCH(NS_, SM_)                                                                                      \
+  do {                                                                                                               \
+    if (want_grad) ST_CTC_LAUNCH2(NS_, SM_, true); else ST_CTC_LAUNCH2(NS_, SM_, false);                             \
+  } while (0)
+  if (probs_in_smem) {
     if (ns == 1) ST_CTC_LAUNCH(1, true); else if (ns == 2) ST_CTC_LAUNCH(2, true);
     else if (ns == 4) ST_CTC_LAUNCH(4, true); else ST_CTC_LAUNCH(8, true);
   } else {
@@ -443,6 +433,7 @@ ST_API int st_ctc_loss(const float* logits, int64_t stride_t, int64_t stride_b, 
     else if (ns == 4) ST_CTC_LAUNCH(4, false); else ST_CTC_LAUNCH(8, false);
   }
 #undef ST_CTC_LAUNCH
+#undef ST_CTC_LAUNCH2
   ST_CUDA_LAUNCH_CHECK("ctc_alpha_beta_kernel");
   if (grad || grad_planes) {
     ctc_grad_kernel<<<(rows + 7) / 8, 256, 0, s>>>(lsm, alpha, beta, logp, labels, label_offsets, seq_len, status,

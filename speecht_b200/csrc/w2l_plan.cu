@@ -58,13 +58,16 @@ struct st_plan {
   // GEMM.  128-wide tiles leave room for TWO accumulator stages in the split modes (2 x 2 x 128 TMEM columns), so the
   // epilogue of one tile runs under the loads + MMAs of the next (SPEECHT_B200_L10_N128=0 restores 256-wide tiles).
   bool l10_n128;
-  // EXPERIMENTAL, off by default, not yet run on a GPU (SPEECHT_B200_FFA=1): forward of the 32-tap layer 8 as a
-  // fast-FIR split -- three half-rate 16-tap convolutions (75 % of the MMAs) + one elementwise combine, DESIGN.md
-  // section 8 and tools/ffa_study.py.  Backward is unchanged.
+  // Fast-FIR split of the 32-tap layer 8 (65 % of the FLOPs): forward, data gradient and filter gradient each run
+  // THREE half-rate 16-tap problems (75 % of the MMAs) in one persistent launch, plus elementwise prepare / combine
+  // passes (index algebra and backward formulas checked on the CPU by tools/ffa_study.py).
+  // SPEECHT_B200_FFA=0 restores the direct 32-tap kernels; bf16x6 (three planes) always uses them.
   bool ffa;
   int ffa_Tx, ffa_Tu;                            // rows of the pair-sum planes / of the partial products
-  size_t off_ffa_xs, off_ffa_w32[3], off_ffa_w[3], off_ffa_p[3];
-  CUtensorMap tm_ffa_a[3], tm_ffa_b[3];
+  size_t off_ffa_xs, off_ffa_w32[3], off_ffa_w[3], off_ffa_wb[3], off_ffa_p[3], off_ffa_dxp[3], off_ffa_cs;
+  CUtensorMap tm_ffa_a[3], tm_ffa_b[3];          // forward: A = odd / even row views of x, pair sums; B = w0, w1, ws
+  CUtensorMap tm_ffa_dg_a[3], tm_ffa_dg_b[3];    // data gradient: A = dA00 / dA11 / dS planes; B = backward layouts
+  CUtensorMap tm_ffa_wg_x[3], tm_ffa_wg_dz[3];   // filter gradient: the same operands in 64-row boxes
 };
 
 namespace {
@@ -114,7 +117,7 @@ ST_API int st_plan_create(st_plan** out, int B, int T, int input_size, int num_c
     e = getenv("SPEECHT_B200_L10_N128");
     p->l10_n128 = !(e && e[0] == '0') && n_planes == 2;
     e = getenv("SPEECHT_B200_FFA");
-    p->ffa = e && e[0] == '1' && n_planes <= 2;
+    p->ffa = !(e && e[0] == '0') && n_planes <= 2;
   }
   // reference speech_model.py:275-292
   const int table[11][5] = {{48, 2, input_size, 250, 1}, {7, 1, 250, 250, 1}, {7, 1, 250, 250, 1}, {7, 1, 250, 250, 1},
@@ -157,6 +160,7 @@ ST_API int st_plan_create(st_plan** out, int B, int T, int input_size, int num_c
   p->dz_elems = (size_t)B * p->To * 2000;
   p->off_dz[0] = take((size_t)n_planes * p->dz_elems * 2);
   p->off_dz[1] = take((size_t)n_planes * p->dz_elems * 2);
+  if (p->To < 8) p->ffa = false;              // nothing to gain on a handful of frames (and the odd-row view may be empty)
   if (p->ffa) {
     const Layer& L8 = p->layers[8];
     p->ffa_Tx = (L8.Ti + 1) / 2;
@@ -165,8 +169,15 @@ ST_API int st_plan_create(st_plan** out, int B, int T, int input_size, int num_c
     for (int i = 0; i < 3; ++i) {
       p->off_ffa_w32[i] = take((size_t)(L8.K / 2) * L8.Cin * L8.Cout * sizeof(float));
       p->off_ffa_w[i] = take((size_t)n_planes * L8.Cout * (L8.K / 2) * L8.cin_p * 2);
-      p->off_ffa_p[i] = take((size_t)B * p->ffa_Tu * L8.Cout * sizeof(float));
+      p->off_ffa_wb[i] = take((size_t)n_planes * (L8.K / 2) * L8.Cin * L8.ld_co * 2);
+      // forward: fp32 partial product [B][Tu][Cout]; backward: the planes of dA00 / dA11 / dS [npl][B][Tu][Cout] live
+      // in the same bytes (the partial products are dead once the forward combine has run)
+      const size_t fwd_bytes = (size_t)B * p->ffa_Tu * L8.Cout * sizeof(float);
+      const size_t bwd_bytes = (size_t)n_planes * B * p->ffa_Tu * L8.ld_out * 2;
+      p->off_ffa_p[i] = take(fwd_bytes > bwd_bytes ? fwd_bytes : bwd_bytes);
+      p->off_ffa_dxp[i] = take((size_t)B * p->ffa_Tx * 256 * sizeof(float));
     }
+    p->off_ffa_cs = take((size_t)(L8.K / 2) * L8.Cin * L8.Cout * sizeof(float));
   }
   p->arena_bytes = off;
   *out = p;
@@ -282,9 +293,30 @@ ST_API int st_plan_bind(st_plan* p, void* arena, size_t arena_bytes, float* para
     rc = tc::make_map_3d(&p->tm_ffa_a[2], bf(p, p->off_ffa_xs), L8.Cin, p->ffa_Tx, npl * B, L8.ld_in,
                          (int64_t)p->ffa_Tx * L8.ld_in, 64, 128);
     if (rc) return rc;
+    // the same three A operands in 64-row boxes for the filter gradient
+    rc = tc::make_map_3d(&p->tm_ffa_wg_x[0], x + L8.ld_in, L8.Cin, L8.Ti / 2, npl * B, 2 * L8.ld_in,
+                         (int64_t)L8.Ti * L8.ld_in, 64, 64);
+    if (rc) return rc;
+    rc = tc::make_map_3d(&p->tm_ffa_wg_x[1], x, L8.Cin, (L8.Ti + 1) / 2, npl * B, 2 * L8.ld_in,
+                         (int64_t)L8.Ti * L8.ld_in, 64, 64);
+    if (rc) return rc;
+    rc = tc::make_map_3d(&p->tm_ffa_wg_x[2], bf(p, p->off_ffa_xs), L8.Cin, p->ffa_Tx, npl * B, L8.ld_in,
+                         (int64_t)p->ffa_Tx * L8.ld_in, 64, 64);
+    if (rc) return rc;
     for (int i = 0; i < 3; ++i) {
       rc = tc::make_map_2d(&p->tm_ffa_b[i], bf(p, p->off_ffa_w[i]), (L8.K / 2) * L8.cin_p, npl * L8.Cout,
                            (int64_t)(L8.K / 2) * L8.cin_p, 64, wide_n(p));
+      if (rc) return rc;
+      // backward: gradients of the partial products as planes [npl*B][Tu][Cout]
+      const __nv_bfloat16* dA = bf(p, p->off_ffa_p[i]);
+      rc = tc::make_map_3d(&p->tm_ffa_dg_a[i], dA, L8.Cout, p->ffa_Tu, npl * B, L8.ld_out,
+                           (int64_t)p->ffa_Tu * L8.ld_out, 64, 128);
+      if (rc) return rc;
+      rc = tc::make_map_3d(&p->tm_ffa_wg_dz[i], dA, L8.Cout, p->ffa_Tu, npl * B, L8.ld_out,
+                           (int64_t)p->ffa_Tu * L8.ld_out, 64, 64);
+      if (rc) return rc;
+      rc = tc::make_map_2d(&p->tm_ffa_dg_b[i], bf(p, p->off_ffa_wb[i]), L8.Cout, npl * (L8.K / 2) * L8.Cin, L8.ld_co, 64,
+                           wide_n(p));
       if (rc) return rc;
     }
   }
@@ -295,13 +327,29 @@ ST_API int st_plan_bind(st_plan* p, void* arena, size_t arena_bytes, float* para
 // fp32 parameters -> bf16 operand planes (forward K-major layout for every layer, backward layout for layers 1..10)
 namespace {
 
-int pack_layers(st_plan* p, int l0, int l1, cudaStream_t s) {
+int pack_layers(st_plan* p, cudaStream_t s) {
   tc::PackTable tab{};
-  tab.n = l1 - l0;
-  for (int l = l0; l < l1; ++l) {
+  Layer& L8 = p->layers[8];
+  float* w32[3] = {nullptr, nullptr, nullptr};
+  if (p->ffa) {
+    // fast-FIR filters of layer 8: even taps, odd taps and their sum, each packed like a 16-tap filter in both
+    // operand layouts; the direct 32-tap layouts of layer 8 are then not needed
+    for (int i = 0; i < 3; ++i) w32[i] = reinterpret_cast<float*>(p->arena + p->off_ffa_w32[i]);
+    const int rc = tc::launch_ffa_split_taps(p->params + L8.w_off, w32[0], w32[1], w32[2], L8.K / 2,
+                                             (int64_t)L8.Cin * L8.Cout, s);
+    if (rc) return rc;
+    p->launches++;
+  }
+  for (int l = 0; l < 11; ++l) {
     Layer& L = p->layers[l];
-    tab.e[l - l0] = tc::PackEntry{p->params + L.w_off, bf(p, L.off_wfwd), l > 0 ? bf(p, L.off_wbwd) : nullptr,
-                                  L.K, L.Cin, L.Cout, L.cin_p, L.ld_co, 0};
+    if (l == 8 && p->ffa) {
+      for (int i = 0; i < 3; ++i)
+        tab.e[tab.n++] = tc::PackEntry{w32[i], bf(p, p->off_ffa_w[i]), bf(p, p->off_ffa_wb[i]), L8.K / 2, L8.Cin,
+                                       L8.Cout, L8.cin_p, L8.ld_co, 0};
+      continue;
+    }
+    tab.e[tab.n++] = tc::PackEntry{p->params + L.w_off, bf(p, L.off_wfwd), l > 0 ? bf(p, L.off_wbwd) : nullptr,
+                                   L.K, L.Cin, L.Cout, L.cin_p, L.ld_co, 0};
   }
   int n = 0;
   const int rc = tc::launch_pack_filters(tab, p->npl, s, &n);
@@ -314,67 +362,127 @@ int pack_layers(st_plan* p, int l0, int l1, cudaStream_t s) {
 
 ST_API int st_plan_pack_weights(st_plan* p, st_stream_t stream) {
   ST_CHECK_ARG(p && p->bound, "st_plan_pack_weights: plan is not bound");
-  int rc = pack_layers(p, 0, 11, st_cu(stream));
-  if (rc || !p->ffa) return rc;
-  // fast-FIR filters of layer 8: even taps, odd taps and their sum, each packed like a 16-tap forward filter
-  Layer& L8 = p->layers[8];
-  float* w32[3];
-  for (int i = 0; i < 3; ++i) w32[i] = reinterpret_cast<float*>(p->arena + p->off_ffa_w32[i]);
-  rc = tc::launch_ffa_split_taps(p->params + L8.w_off, w32[0], w32[1], w32[2], L8.K / 2, (int64_t)L8.Cin * L8.Cout,
-                                 st_cu(stream));
-  if (rc) return rc;
-  tc::PackTable tab{};
-  tab.n = 3;
-  for (int i = 0; i < 3; ++i)
-    tab.e[i] = tc::PackEntry{w32[i], bf(p, p->off_ffa_w[i]), nullptr, L8.K / 2, L8.Cin, L8.Cout, L8.cin_p, L8.ld_co, 0};
-  int n = 0;
-  rc = tc::launch_pack_filters(tab, p->npl, st_cu(stream), &n);
-  if (rc) return rc;
-  p->launches += n + 1;
-  return ST_OK;
+  return pack_layers(p, st_cu(stream));
 }
 
 namespace {
 
-// EXPERIMENTAL (SPEECHT_B200_FFA=1): y = x (*) w over 32 taps as
+// Fast-FIR form of layer 8: y = x (*) w over 32 taps as
 //   A00[u] = sum_j odd [u+j-8] w[2j],  A11[u] = sum_j even[u+j-7] w[2j+1],  S[u] = sum_j xs[u+j-7] (w[2j]+w[2j+1])
 //   y[2u] = A00[u] + A11[u],           y[2u+1] = S[u] - A11[u] - A00[u+1]            (tools/ffa_study.py)
-// with odd[r] = x[2r+1], even[r] = x[2r], xs[r] = x[2r] + x[2r+1]: three 16-tap launches of tc_conv_kernel writing
-// fp32 partial products, then bias + ReLU + plane split in ffa_combine_kernel.
+// with odd[r] = x[2r+1], even[r] = x[2r], xs[r] = x[2r] + x[2r+1]: three 16-tap problems in ONE launch of
+// tc_conv_kernel writing fp32 partial products, then bias + ReLU + plane split in ffa_combine_kernel.
 int forward_layer8_ffa(st_plan* p, cudaStream_t s) {
   Layer& L = p->layers[8];
   int rc = tc::launch_pair_sum_planes(act_in(p, 8), bf(p, p->off_ffa_xs), p->B, L.Ti, p->ffa_Tx, L.ld_in, p->npl, s);
   if (rc) return rc;
   p->launches++;
   float* part[3];
+  tc::ConvParams c{};
+  c.taps = L.K / 2;
+  c.chunks_per_tap = L.cin_p / 64;
+  c.a_sign = 1;
+  c.a_stride = 1;
+  c.a_cin = 0;
+  c.b_row_step = 0;
+  c.b_col_step = L.cin_p;
+  c.b_plane_rows = L.Cout;
+  c.B = p->B; c.To = p->ffa_Tu; c.N = L.Cout;
+  c.m_tiles_per_utt = (p->ffa_Tu + tc::kTileM - 1) / tc::kTileM;
+  c.n_tiles = (L.Cout + wide_n(p) - 1) / wide_n(p);
+  c.n_fastest = 0;
+  c.ld_f32 = L.Cout;
+  c.k_cols = L.Cin;
+  c.trim = p->trim;
+  c.n_problems = 3;
+  c.k_split = 1;
   for (int i = 0; i < 3; ++i) {
     part[i] = reinterpret_cast<float*>(p->arena + p->off_ffa_p[i]);
-    tc::ConvParams c{};
-    c.taps = L.K / 2;
-    c.chunks_per_tap = L.cin_p / 64;
-    c.pad_left = i == 0 ? 8 : 7;
-    c.a_sign = 1;
-    c.a_stride = 1;
-    c.a_cin = 0;
-    c.b_row_step = 0;
-    c.b_col_step = L.cin_p;
-    c.b_plane_rows = L.Cout;
-    c.B = p->B; c.To = p->ffa_Tu; c.N = L.Cout;
-    c.m_tiles_per_utt = (p->ffa_Tu + tc::kTileM - 1) / tc::kTileM;
-    c.n_tiles = (L.Cout + wide_n(p) - 1) / wide_n(p);
-    c.n_fastest = 0;
-    c.out_f32 = part[i];
-    c.ld_f32 = L.Cout;
-    c.k_cols = L.Cin;
-    c.trim = p->trim;
-    const int ti = timed_begin(p, s);
-    rc = tc::launch_conv(p->tm_ffa_a[i], p->tm_ffa_b[i], nullptr, c, wide_n(p), p->npl, s);
-    if (rc) return rc;
-    timed_end(p, ti, 0, 8, 2.0 * L.K * L.Cin * L.Cout * (double)L.To * p->B / 3.0, s);
-    p->launches++;
+    c.pad_left_q[i] = i == 0 ? 8 : 7;
+    c.out_f32_q[i] = part[i];
   }
+  const int ti = timed_begin(p, s);
+  rc = tc::launch_conv_multi(p->tm_ffa_a, p->tm_ffa_b, c, wide_n(p), p->npl, s);
+  if (rc) return rc;
+  timed_end(p, ti, 0, 8, 2.0 * L.K * L.Cin * L.Cout * (double)L.To * p->B, s);
+  p->launches++;
   rc = tc::launch_ffa_combine(part[0], part[1], part[2], p->params + L.b_off, L.relu, bf(p, L.off_out), p->B, L.To,
                               p->ffa_Tu, L.Cout, L.Cout, L.ld_out, p->npl, s);
+  if (rc) return rc;
+  p->launches++;
+  return ST_OK;
+}
+
+// Backward of the fast-FIR form (formulas: tools/ffa_study.py, checked against autograd).  dz = planes of
+// d(loss)/d(y8); writes the filter gradient of layer 8, the planes of d(loss)/d(x) (masked by layer 7's ReLU) into
+// dz_out and layer 7's bias gradient.
+int backward_layer8_ffa(st_plan* p, const __nv_bfloat16* dz, __nv_bfloat16* dz_out, cudaStream_t s) {
+  Layer& L = p->layers[8];
+  Layer& Lb = p->layers[7];
+  const int J = L.K / 2;
+  __nv_bfloat16* dA[3];
+  for (int i = 0; i < 3; ++i) dA[i] = bf(p, p->off_ffa_p[i]);
+  int rc = tc::launch_ffa_dz_prep(dz, dA[0], dA[1], dA[2], p->B, L.To, p->ffa_Tu, L.ld_out, p->npl, s);
+  if (rc) return rc;
+  p->launches++;
+  // ---- filter gradient: dw[2j] = <odd, dA00>_j + <xs, dS>_j, dw[2j+1] = <even, dA11>_j + <xs, dS>_j
+  float* cs = reinterpret_cast<float*>(p->arena + p->off_ffa_cs);
+  ST_CUDA_CALL(cudaMemsetAsync(cs, 0, (size_t)J * L.Cin * L.Cout * sizeof(float), s));
+  tc::WgradParams w{};
+  w.B = p->B; w.To = p->ffa_Tu; w.t_chunks = (p->ffa_Tu + 63) / 64;
+  w.taps = J; w.a_stride = 1; w.a_cin = 0;
+  w.m_tiles = (L.Cin + 127) / 128;
+  w.n_tiles = (L.Cout + wide_n(p) - 1) / wide_n(p);
+  w.Cin = L.Cin; w.Cout = L.Cout;
+  w.trim = p->trim;
+  w.n_problems = 3;
+  float* dW = p->grads + L.w_off;
+  w.pad_left_q[0] = 8; w.dW_q[0] = dW;                              w.tap_stride_q[0] = 2;   // even taps
+  w.pad_left_q[1] = 7; w.dW_q[1] = dW + (int64_t)L.Cin * L.Cout;    w.tap_stride_q[1] = 2;   // odd taps
+  w.pad_left_q[2] = 7; w.dW_q[2] = cs;                              w.tap_stride_q[2] = 1;
+  int ti = timed_begin(p, s);
+  rc = tc::launch_wgrad_multi(p->tm_ffa_wg_x, p->tm_ffa_wg_dz, w, wide_n(p), p->npl, s);
+  if (rc) return rc;
+  timed_end(p, ti, 2, 8, 2.0 * L.K * L.Cin * L.Cout * (double)L.To * p->B, s);
+  p->launches++;
+  rc = tc::launch_ffa_dw_combine(dW, cs, J, (int64_t)L.Cin * L.Cout, s);
+  if (rc) return rc;
+  p->launches++;
+  // ---- data gradient: d_odd = dA00 (*)^T w0, d_even = dA11 (*)^T w1, d_xs = dS (*)^T ws as fp32 [B][Tx][256],
+  // each tile's taps in two slices so that 384 work items fill 148 SMs
+  float* dxp[3];
+  for (int i = 0; i < 3; ++i) dxp[i] = reinterpret_cast<float*>(p->arena + p->off_ffa_dxp[i]);
+  const size_t dxp_bytes = (size_t)p->B * p->ffa_Tx * 256 * sizeof(float);
+  for (int i = 0; i < 3; ++i) ST_CUDA_CALL(cudaMemsetAsync(dxp[i], 0, dxp_bytes, s));
+  tc::ConvParams c{};
+  c.taps = J;
+  c.chunks_per_tap = (L.Cout + 63) / 64;
+  c.a_sign = -1;
+  c.a_stride = 1;
+  c.a_cin = 0;
+  c.b_row_step = L.Cin;
+  c.b_col_step = 0;
+  c.b_plane_rows = J * L.Cin;
+  c.B = p->B; c.To = p->ffa_Tx; c.N = L.Cin;
+  c.m_tiles_per_utt = (p->ffa_Tx + tc::kTileM - 1) / tc::kTileM;
+  c.n_tiles = (L.Cin + wide_n(p) - 1) / wide_n(p);
+  c.n_fastest = 1;
+  c.ld_f32 = 256;
+  c.k_cols = L.Cout;
+  c.trim = p->trim;
+  c.n_problems = 3;
+  c.k_split = 2;
+  for (int i = 0; i < 3; ++i) {
+    c.pad_left_q[i] = i == 0 ? 8 : 7;
+    c.out_f32_q[i] = dxp[i];
+  }
+  ti = timed_begin(p, s);
+  rc = tc::launch_conv_multi(p->tm_ffa_dg_a, p->tm_ffa_dg_b, c, wide_n(p), p->npl, s);
+  if (rc) return rc;
+  timed_end(p, ti, 1, 8, 2.0 * L.K * L.Cin * L.Cout * (double)L.To * p->B, s);
+  p->launches++;
+  rc = tc::launch_ffa_dx_combine(dxp[0], dxp[1], dxp[2], bf(p, Lb.off_out), dz_out, p->grads + Lb.b_off, p->B, L.Ti,
+                                 p->ffa_Tx, L.Cin, 256, Lb.ld_out, p->npl, s);
   if (rc) return rc;
   p->launches++;
   return ST_OK;
@@ -451,6 +559,13 @@ ST_API int st_plan_backward_range(st_plan* p, int hi, int lo, st_stream_t stream
     const int ld_dz = l == 10 ? 64 : L.ld_out;
     const int64_t rows = (int64_t)p->B * L.To;
     int rc = ST_OK;
+    if (l == 8 && p->ffa) {
+      const int nxt = cur ^ 1;
+      rc = backward_layer8_ffa(p, dz, bf(p, p->off_dz[nxt]), s);
+      if (rc) return rc;
+      cur = nxt;
+      continue;
+    }
     if (l == 10) {
       // bias gradient of the last layer from the CTC gradient planes; layers 0..9 get theirs from the epilogue of
       // the data-gradient kernel that produces their dz (ConvParams::col_sum)

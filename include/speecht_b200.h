@@ -135,6 +135,15 @@ int st_plan_launches(const st_plan* plan);
 int st_plan_set_timing(st_plan* plan, int enable);
 int st_plan_read_timings(st_plan* plan, int* kind, int* layer, double* flops, float* ms, int max_records);
 
+/* ---- caller of a1: audio loading                                                 preprocessing.py:169 ----
+ * librosa.load(audio_file) decodes LibriSpeech's .flac files through soundfile / audioread; neither exists in this
+ * image, so the native FLAC decoder is part of the library.  HOST functions (no GPU, no stream): `data` is the whole
+ * file in host memory.  st_flac_info_host: info = {sample_rate, channels, bits_per_sample}, samples per channel
+ * (0 = unknown) and the MD5 of the unencoded PCM (STREAMINFO).  st_flac_decode_host: interleaved int32 samples
+ * out[sample][channel]; *decoded = samples per channel.  Frame CRC-8 / CRC-16 are verified. */
+int st_flac_info_host(const uint8_t* data, size_t nbytes, int32_t* info, int64_t* total_samples, uint8_t* md5);
+int st_flac_decode_host(const uint8_t* data, size_t nbytes, int32_t* out, int64_t capacity, int64_t* decoded);
+
 /* Debug: per-CTA %globaltimer timeline of ONE tensor-core conv launch (the launch_index-th forward / data-gradient
  * launch after this call): buf[grid][8] int64 device memory -- 0 entry, 1 previous grid complete, 2 first operands
  * landed, 3 last MMA issued, 4 accumulator complete, 5 epilogue issued, 6 staging tiles drained, 7 exit.

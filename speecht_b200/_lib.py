@@ -66,6 +66,8 @@ _SIGNATURES = {
   'st_plan_set_timing': (c_int, [P, c_int]),
   'st_plan_read_timings': (c_int, [P, P, P, P, P, c_int]),
   'st_debug_conv_timeline': (c_int, [P, c_int]),
+  'st_flac_info_host': (c_int, [P, c_size_t, P, P, P]),
+  'st_flac_decode_host': (c_int, [P, c_size_t, P, c_int64, P]),
 }
 
 _lib = None

@@ -17,7 +17,8 @@ OBJ_DIR = os.path.join(HERE, 'build')
 LIB_PATH = os.path.join(HERE, 'libspeecht_b200.so')
 HEADER = os.path.join(os.path.dirname(HERE), 'include', 'speecht_b200.h')
 
-SOURCES = ['st_api.cu', 'decode.cu', 'ctc.cu', 'conv_f32.cu', 'optim.cu', 'melspec.cu', 'conv_tc.cu', 'w2l_plan.cu']
+SOURCES = ['st_api.cu', 'decode.cu', 'ctc.cu', 'conv_f32.cu', 'optim.cu', 'melspec.cu', 'conv_tc.cu', 'w2l_plan.cu',
+           'flac_host.cu']
 
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17',
               '-Xcompiler', '-fPIC', '-Xcompiler', '-fvisibility=hidden', '--expt-relaxed-constexpr']

@@ -51,10 +51,13 @@ constexpr int kSmemBudget = 227 * 1024;
 constexpr int kBarrierBytes = 1024;                // mbarriers + TMEM slot, after the pipeline stages
 constexpr int kStageTileBytes = 2 * 32 * 32 * 2;   // per epilogue warp: 2 planes x 32 rows x 32 bf16 columns
 
-template <int BLOCK_N, int NPL>
+// PAIR: two CTAs of one cluster share a 256-row tile (cta_group::2): each holds its own 128 rows of A and HALF of
+// the B tile, so a stage is a third smaller and the B operand crosses L2 -> shared memory once per pair.
+template <int BLOCK_N, int NPL, bool PAIR = false>
 struct ConvCfg {
   static constexpr int A_BYTES = kTileM * kChunkK * 2;           // 16 KB: 128 rows x 128 B
-  static constexpr int B_BYTES = BLOCK_N * kChunkK * 2;
+  static constexpr int B_ROWS = PAIR ? BLOCK_N / 2 : BLOCK_N;    // B rows (output channels) held by one CTA
+  static constexpr int B_BYTES = B_ROWS * kChunkK * 2;
   static constexpr int STAGE_BYTES = NPL * (A_BYTES + B_BYTES);
   // epilogue staging tiles for the TMA stores (one [2 planes][32][32] bf16 tile per epilogue warp); the three-plane
   // mode has no shared memory left for them and keeps the direct stores
@@ -250,12 +253,14 @@ template <> struct Products<3> {
 // (a 200-register build fails to launch), so the two-phase epilogue's 64 live accumulators spill ~450 bytes.
 // NPROB > 1: several problems of identical shape in one launch (ConvParams::n_problems, k_split): a work item is
 // (problem, tap slice, tile); fp32 outputs only.  NPROB == 1 is the plain single-problem kernel.
-template <int BLOCK_N, int NPL, bool EARLY, int NPROB>
+// PAIR: launched as clusters of two CTAs; a work item is a PAIR of m tiles (rank r of the cluster owns m tile
+// 2*pair + r), the leader (rank 0) issues tcgen05.mma.cta_group::2 with M = 256 for both.
+template <int BLOCK_N, int NPL, bool EARLY, int NPROB, bool PAIR>
 __global__ void __launch_bounds__(kThreads, 1)
 tc_conv_kernel(const __grid_constant__ std::conditional_t<NPROB == 1, TmSet1, TmSet3> tmAs,
                const __grid_constant__ std::conditional_t<NPROB == 1, TmSet1, TmSet3> tmBs,
                const __grid_constant__ CUtensorMap tmOut, const ConvParams p) {
-  using Cfg = ConvCfg<BLOCK_N, NPL>;
+  using Cfg = ConvCfg<BLOCK_N, NPL, PAIR>;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
   // SWIZZLE_128B tiles need 1024-byte alignment in the shared window
@@ -273,8 +278,12 @@ tc_conv_kernel(const __grid_constant__ std::conditional_t<NPROB == 1, TmSet1, Tm
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int num_tiles = p.B * p.m_tiles_per_utt * p.n_tiles;
-  const int m_tiles = p.B * p.m_tiles_per_utt;
+  const uint32_t rank = PAIR ? cluster_ctarank() : 0u;           // position in the CTA pair; rank 0 leads
+  const int cta_id = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;        // work-loop start
+  const int cta_step = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;        // work-loop stride
+  const int m_tiles_real = p.B * p.m_tiles_per_utt;
+  const int m_tiles = PAIR ? (m_tiles_real + 1) >> 1 : m_tiles_real;         // PAIR: pairs of m tiles
+  const int num_tiles = m_tiles * p.n_tiles;
   const int ksplit = NPROB > 1 ? max(1, p.k_split) : 1;
   const int total_work = NPROB > 1 ? num_tiles * ksplit * p.n_problems : num_tiles;
   // work item -> (problem q, taps [j0, j1), tile); single-problem launches: work item == tile, all taps
@@ -305,13 +314,18 @@ tc_conv_kernel(const __grid_constant__ std::conditional_t<NPROB == 1, TmSet1, Tm
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tmem_full + a, 1);
-      mbar_init(tmem_empty + a, kEpilogueWarps);
+      // PAIR: the leader's MMA thread waits for the epilogue warps of BOTH CTAs (the peer's arrive remotely)
+      mbar_init(tmem_empty + a, kEpilogueWarps * (PAIR ? 2 : 1));
     }
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
+  if (warp == 1) {
+    if constexpr (PAIR) tmem_alloc_pair<Cfg::TMEM_COLS>(tmem_slot);
+    else tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
+  }
   tc_fence_before();
-  __syncthreads();
+  if constexpr (PAIR) cluster_sync_all();         // barriers of both CTAs initialised before any remote arrive / TMA
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   // Programmatic dependent launch: everything above (barrier init, TMEM allocation, descriptor prefetch) touched no
@@ -320,13 +334,25 @@ tc_conv_kernel(const __grid_constant__ std::conditional_t<NPROB == 1, TmSet1, Tm
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   asm volatile("griddepcontrol.wait;" ::: "memory");
   if (tl && threadIdx.x == 0) tl[1] = global_ns();                                   // 1: previous grid complete
+  // tile -> (b, t0, n0) of THIS CTA; PAIR: rank r owns m tile 2*pair + r, which may not exist when the count is odd:
+  // its loads then aim at rows far outside the tensor (TMA zero fill) and its epilogue stores nothing
+  constexpr int kNoRow = 1 << 20;
+  auto cta_tile = [&](int tile, int& b, int& t0, int& n0) {
+    const int nt = p.n_fastest ? tile % p.n_tiles : tile / m_tiles;
+    int mt = p.n_fastest ? tile / p.n_tiles : tile % m_tiles;
+    if constexpr (PAIR) mt = 2 * mt + (int)rank;
+    b = mt / p.m_tiles_per_utt;
+    t0 = (mt - b * p.m_tiles_per_utt) * kTileM;
+    n0 = nt * BLOCK_N;
+    if (PAIR && mt >= m_tiles_real) { b = 0; t0 = kNoRow; }
+  };
 
   if (warp == 0) {
     // ===================================================== TMA producer
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int work = blockIdx.x; work < total_work; work += gridDim.x) {
+      for (int work = cta_id; work < total_work; work += cta_step) {
         int q, j0, j1, tile;
         work_coords(work, q, j0, j1, tile);
         const CUtensorMap* tmA = &tmAs.m[NPROB > 1 ? q : 0];
@@ -334,11 +360,15 @@ tc_conv_kernel(const __grid_constant__ std::conditional_t<NPROB == 1, TmSet1, Tm
         const int pad_left = NPROB > 1 ? p.pad_left_q[q] : p.pad_left;
         // n fastest (A rows read from HBM once, shared through L2 by their n tiles) when A is too big for L2;
         // m fastest (one filter slab hot in L2 for the whole wave) otherwise
-        const int nt = p.n_fastest ? tile % p.n_tiles : tile / m_tiles;
-        const int mt = p.n_fastest ? tile / p.n_tiles : tile % m_tiles;
-        const int b = mt / p.m_tiles_per_utt;
-        const int t0 = (mt - b * p.m_tiles_per_utt) * kTileM;
-        const int n0 = nt * BLOCK_N;
+        int b, t0, n0;
+        cta_tile(tile, b, t0, n0);
+        // PAIR: this CTA holds B rows [n0 + rank * n_mma / 2, ...): the halves of the N the instruction multiplies
+        int b_half = 0;
+        if constexpr (PAIR) {
+          const int n_valid = min(BLOCK_N, p.N - n0);
+          const int n_mma = p.trim ? max(16, (n_valid + 15) & ~15) : BLOCK_N;
+          b_half = (int)rank * (n_mma >> 1);
+        }
         const int jn = j1 - j0, nk = jn * p.chunks_per_tap;
         for (int it = 0; it < nk; ++it) {
           // channel chunk outer, filter tap inner: the taps of one chunk re-read (shifted) the same A rows, which
@@ -348,7 +378,7 @@ tc_conv_kernel(const __grid_constant__ std::conditional_t<NPROB == 1, TmSet1, Tm
           const int shift = p.a_stride == 1 ? m : floordiv(m, p.a_stride);
           const int a_col = (m - shift * p.a_stride) * p.a_cin + cc * kChunkK;
           uint8_t* st = smem + stage * Cfg::STAGE_BYTES;
-          const int b_c0 = j * p.b_col_step + cc * kChunkK, b_c1 = n0 + j * p.b_row_step;
+          const int b_c0 = j * p.b_col_step + cc * kChunkK, b_c1 = n0 + j * p.b_row_step + b_half;
           if (NG == 2) {
 #pragma unroll
             for (int g = 0; g < NG; ++g) {
@@ -356,20 +386,41 @@ tc_conv_kernel(const __grid_constant__ std::conditional_t<NPROB == 1, TmSet1, Tm
               const int pa = g, pb = 1 - g;
               uint64_t* fb = full_bar + stage * NG + g;
               mbar_wait(empty_bar + stage * NG + g, phase ^ 1);
-              mbar_expect_tx(fb, Cfg::A_BYTES + Cfg::B_BYTES);
-              tma_load_3d(tmA, fb, st + pa * Cfg::A_BYTES, a_col, t0 + shift, pa * p.B + b);
-              tma_load_2d(tmB, fb, st + NPL * Cfg::A_BYTES + pb * Cfg::B_BYTES, b_c0, pb * p.b_plane_rows + b_c1);
+              if constexpr (PAIR) {
+                // both CTAs' bytes complete on the LEADER's barrier; the leader alone arms it
+                if (rank == 0) mbar_expect_tx(fb, 2 * (Cfg::A_BYTES + Cfg::B_BYTES));
+                const uint32_t fbc = mapa_u32(smem_u32(fb), 0);
+                tma_load_3d_pair(tmA, fbc, st + pa * Cfg::A_BYTES, a_col, t0 + shift, pa * p.B + b);
+                tma_load_2d_pair(tmB, fbc, st + NPL * Cfg::A_BYTES + pb * Cfg::B_BYTES, b_c0,
+                                 pb * p.b_plane_rows + b_c1);
+              } else {
+                mbar_expect_tx(fb, Cfg::A_BYTES + Cfg::B_BYTES);
+                tma_load_3d(tmA, fb, st + pa * Cfg::A_BYTES, a_col, t0 + shift, pa * p.B + b);
+                tma_load_2d(tmB, fb, st + NPL * Cfg::A_BYTES + pb * Cfg::B_BYTES, b_c0, pb * p.b_plane_rows + b_c1);
+              }
             }
           } else {
             uint64_t* fb = full_bar + stage;
             mbar_wait(empty_bar + stage, phase ^ 1);
-            mbar_expect_tx(fb, Cfg::STAGE_BYTES);
+            if constexpr (PAIR) {
+              if (rank == 0) mbar_expect_tx(fb, 2 * Cfg::STAGE_BYTES);
+              const uint32_t fbc = mapa_u32(smem_u32(fb), 0);
 #pragma unroll
-            for (int pl = 0; pl < NPL; ++pl)
-              tma_load_3d(tmA, fb, st + pl * Cfg::A_BYTES, a_col, t0 + shift, pl * p.B + b);
+              for (int pl = 0; pl < NPL; ++pl)
+                tma_load_3d_pair(tmA, fbc, st + pl * Cfg::A_BYTES, a_col, t0 + shift, pl * p.B + b);
 #pragma unroll
-            for (int pl = 0; pl < NPL; ++pl)
-              tma_load_2d(tmB, fb, st + NPL * Cfg::A_BYTES + pl * Cfg::B_BYTES, b_c0, pl * p.b_plane_rows + b_c1);
+              for (int pl = 0; pl < NPL; ++pl)
+                tma_load_2d_pair(tmB, fbc, st + NPL * Cfg::A_BYTES + pl * Cfg::B_BYTES, b_c0,
+                                 pl * p.b_plane_rows + b_c1);
+            } else {
+              mbar_expect_tx(fb, Cfg::STAGE_BYTES);
+#pragma unroll
+              for (int pl = 0; pl < NPL; ++pl)
+                tma_load_3d(tmA, fb, st + pl * Cfg::A_BYTES, a_col, t0 + shift, pl * p.B + b);
+#pragma unroll
+              for (int pl = 0; pl < NPL; ++pl)
+                tma_load_2d(tmB, fb, st + NPL * Cfg::A_BYTES + pl * Cfg::B_BYTES, b_c0, pl * p.b_plane_rows + b_c1);
+            }
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
@@ -377,12 +428,12 @@ tc_conv_kernel(const __grid_constant__ std::conditional_t<NPROB == 1, TmSet1, Tm
     }
     __syncwarp();
   } else if (warp == 1) {
-    // ===================================================== MMA issuer (one thread)
-    if (lane == 0) {
+    // ===================================================== MMA issuer (one thread; PAIR: of the leader CTA only)
+    if (lane == 0 && rank == 0) {
       int stage = 0;
       uint32_t phase = 0;
       int local = 0;
-      for (int work = blockIdx.x; work < total_work; work += gridDim.x, ++local) {
+      for (int work = cta_id; work < total_work; work += cta_step, ++local) {
         int q, j0, j1, tile;
         work_coords(work, q, j0, j1, tile);
         const int acc = local % Cfg::ACC_STAGES;
@@ -393,7 +444,8 @@ tc_conv_kernel(const __grid_constant__ std::conditional_t<NPROB == 1, TmSet1, Tm
         // are power-bound, so every MMA that is not executed is time.
         const int nt = p.n_fastest ? tile % p.n_tiles : tile / m_tiles;
         const int n_valid = min(BLOCK_N, p.N - nt * BLOCK_N);
-        const uint32_t idesc = make_idesc_bf16(kTileM, p.trim ? max(16, (n_valid + 15) & ~15) : BLOCK_N, 0, 0);
+        const uint32_t idesc = make_idesc_bf16(PAIR ? 2 * kTileM : kTileM,
+                                               p.trim ? max(16, (n_valid + 15) & ~15) : BLOCK_N, 0, 0);
         mbar_wait(tmem_empty + acc, acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_main = tmem_base + acc * Cfg::ACC_COLS;
@@ -416,13 +468,11 @@ tc_conv_kernel(const __grid_constant__ std::conditional_t<NPROB == 1, TmSet1, Tm
             const uint64_t db = make_smem_desc_sw128(b_addr + pb * Cfg::B_BYTES, 16, 1024);
             auto step = [&](int kk) {
               // advancing 16 bf16 along K = 32 bytes inside the 128-byte swizzled row = +2 in the address field
-              if (pa == 0 && pb == 0) {
-                umma_bf16(d_main, da + (uint64_t)(kk * 2), db + (uint64_t)(kk * 2), idesc, acc_main);
-                acc_main = 1u;
-              } else {
-                umma_bf16(d_side, da + (uint64_t)(kk * 2), db + (uint64_t)(kk * 2), idesc, acc_side);
-                acc_side = 1u;
-              }
+              const uint32_t d = (pa == 0 && pb == 0) ? d_main : d_side;
+              uint32_t& accf = (pa == 0 && pb == 0) ? acc_main : acc_side;
+              if constexpr (PAIR) umma_bf16_pair(d, da + (uint64_t)(kk * 2), db + (uint64_t)(kk * 2), idesc, accf);
+              else umma_bf16(d, da + (uint64_t)(kk * 2), db + (uint64_t)(kk * 2), idesc, accf);
+              accf = 1u;
             };
             if constexpr (FULL) {
 #pragma unroll
@@ -431,8 +481,11 @@ tc_conv_kernel(const __grid_constant__ std::conditional_t<NPROB == 1, TmSet1, Tm
 #pragma unroll 1
               for (int kk = 0; kk < nkk; ++kk) step(kk);
             }
-            // a group's smem is reusable once the MMAs issued so far have read it
-            if (PR::release(pr) >= 0) umma_commit(empty_bar + stage * NG + PR::release(pr));
+            // a group's smem is reusable once the MMAs issued so far have read it (PAIR: in both CTAs)
+            if (PR::release(pr) >= 0) {
+              if constexpr (PAIR) umma_commit_pair(empty_bar + stage * NG + PR::release(pr), 3);
+              else umma_commit(empty_bar + stage * NG + PR::release(pr));
+            }
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         };
@@ -446,7 +499,8 @@ tc_conv_kernel(const __grid_constant__ std::conditional_t<NPROB == 1, TmSet1, Tm
             for (int j = j0; j < j1; ++j, ++it) iteration(std::false_type{}, it, nkk);
           }
         }
-        umma_commit(tmem_full + acc);                     // accumulator complete -> epilogue
+        if constexpr (PAIR) umma_commit_pair(tmem_full + acc, 3);   // accumulators complete -> both epilogues
+        else umma_commit(tmem_full + acc);                // accumulator complete -> epilogue
         if (tl && local == 0) tl[3] = global_ns();                                   // 3: last MMA of the tile issued
       }
     }
@@ -459,12 +513,11 @@ tc_conv_kernel(const __grid_constant__ std::conditional_t<NPROB == 1, TmSet1, Tm
     constexpr int kChunks = BLOCK_N / 32;
     const int row = quarter * 32 + lane;
     uint8_t* stage = smem + STAGES * Cfg::STAGE_BYTES + kBarrierBytes + (warp - 2) * kStageTileBytes;
-    auto tile_coords = [&](int tile, int& b, int& t0, int& n0) {
-      const int nt = p.n_fastest ? tile % p.n_tiles : tile / m_tiles;
-      const int mt = p.n_fastest ? tile / p.n_tiles : tile % m_tiles;
-      b = mt / p.m_tiles_per_utt;
-      t0 = (mt - b * p.m_tiles_per_utt) * kTileM;
-      n0 = nt * BLOCK_N;
+    auto tile_coords = [&](int tile, int& b, int& t0, int& n0) { cta_tile(tile, b, t0, n0); };
+    // accumulator stage drained: PAIR arrives on the LEADER's barrier (its MMA thread feeds both TMEMs)
+    auto release_acc = [&](int acc) {
+      if constexpr (PAIR) mbar_arrive_cluster(mapa_u32(smem_u32(tmem_empty + acc), 0));
+      else mbar_arrive(tmem_empty + acc);
     };
     // ReLU-mask rows of a tile (data gradient only) are pulled into L2 one tile ahead: the forward activations they
     // come from were written a whole forward+loss ago and would otherwise be an HBM round trip in the epilogue
@@ -483,9 +536,9 @@ tc_conv_kernel(const __grid_constant__ std::conditional_t<NPROB == 1, TmSet1, Tm
         }
       }
     };
-    if (NPROB == 1) prefetch_mask(blockIdx.x);
+    if (NPROB == 1) prefetch_mask(cta_id);
     int local = 0;
-    for (int work = blockIdx.x; work < total_work; work += gridDim.x, ++local) {
+    for (int work = cta_id; work < total_work; work += cta_step, ++local) {
       int q, j0, j1, tile;
       work_coords(work, q, j0, j1, tile);
       const int acc = local % Cfg::ACC_STAGES;
@@ -498,7 +551,7 @@ tc_conv_kernel(const __grid_constant__ std::conditional_t<NPROB == 1, TmSet1, Tm
       const int64_t out_row = (int64_t)b * p.To + t;
       float* out_f32 = NPROB > 1 ? p.out_f32_q[q] : p.out_f32;
       const bool f32_add = NPROB > 1 && ksplit > 1;
-      if (NPROB == 1) prefetch_mask(tile + gridDim.x);
+      if (NPROB == 1) prefetch_mask(tile + cta_step);
       // Per chunk of this warp, fetched while the MMAs of the tile are still running: the lane's bias element and
       // the ReLU-mask row segment (data gradient), reduced to one keep-bit per column once it has arrived.
       constexpr int kMine = (kChunks + kChunkStep - 1) / kChunkStep;       // chunks per warp (compile time)
@@ -561,7 +614,7 @@ tc_conv_kernel(const __grid_constant__ std::conditional_t<NPROB == 1, TmSet1, Tm
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(tmem_empty + acc);
+        if (lane == 0) release_acc(acc);
 
         // Phase 2: bias / ReLU / ReLU-mask / plane split / stores / bias-gradient column sums, from registers
 #pragma unroll
@@ -601,7 +654,7 @@ tc_conv_kernel(const __grid_constant__ std::conditional_t<NPROB == 1, TmSet1, Tm
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(tmem_empty + acc);
+        if (lane == 0) release_acc(acc);
       }
       if (p.col_sum) {
 #pragma unroll
@@ -620,10 +673,12 @@ tc_conv_kernel(const __grid_constant__ std::conditional_t<NPROB == 1, TmSet1, Tm
   }
 
   tc_fence_before();
-  __syncthreads();
+  if constexpr (PAIR) cluster_sync_all();         // neither CTA leaves (or frees TMEM) while its peer still works
+  else __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+    if constexpr (PAIR) tmem_dealloc_pair<Cfg::TMEM_COLS>(tmem_base);
+    else tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
   }
   if (tl && threadIdx.x == 0) tl[7] = global_ns();                                   // 7: exit
 }
@@ -960,11 +1015,19 @@ pack_filter_both_kernel(const PackTable tab) {
 #pragma unroll
   for (int r = 0; r < 64; r += 8) {
     const int ci = ci0 + r + ty;
-    const float* src = e.w + ((int64_t)k * e.Cin + ci) * e.Cout + co0;
+    // tap_mode: 0 = tap k of the source; 1 / 2 = its even / odd taps (2k, 2k+1); 3 = their sum (fast-FIR filters)
+    const int ksrc = e.tap_mode == 0 ? k : (e.tap_mode == 2 ? 2 * k + 1 : 2 * k);
+    const float* src = e.w + ((int64_t)ksrc * e.Cin + ci) * e.Cout + co0;
+    const int64_t tap = (int64_t)e.Cin * e.Cout;
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
       const int c = tx + 32 * h;
-      tile[r + ty][c] = (ci < e.Cin && co0 + c < e.Cout) ? __ldg(src + c) : 0.f;
+      float v = 0.f;
+      if (ci < e.Cin && co0 + c < e.Cout) {
+        v = __ldg(src + c);
+        if (e.tap_mode == 3) v += __ldg(src + tap + c);
+      }
+      tile[r + ty][c] = v;
     }
   }
   __syncthreads();
@@ -1091,20 +1154,6 @@ pair_sum_planes_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __res
       }
     }
     store_planes8<NPL>(xs + ((int64_t)b * Tx + r) * ld + c8 * 8, out_plane, v);
-  }
-}
-
-// w [2J][Cin][Cout] fp32 -> w0 = even taps, w1 = odd taps, ws = w0 + w1, each [J][Cin][Cout] fp32
-__global__ void __launch_bounds__(256)
-ffa_split_taps_kernel(const float* __restrict__ w, float* __restrict__ w0, float* __restrict__ w1,
-                      float* __restrict__ ws, int J, int64_t tap_elems) {
-  const int64_t total = (int64_t)J * tap_elems;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t j = i / tap_elems, e = i - j * tap_elems;
-    const float a = __ldg(w + (2 * j) * tap_elems + e), c = __ldg(w + (2 * j + 1) * tap_elems + e);
-    w0[i] = a;
-    w1[i] = c;
-    ws[i] = a + c;
   }
 }
 
@@ -1297,50 +1346,79 @@ int grid_for(int work_items) {
 // Launch with the programmatic-stream-serialization attribute (PDL): the kernel may begin while the previous kernel
 // of the stream drains; it synchronises with `griddepcontrol.wait` before touching global memory.
 template <class Kernel, class... Args>
-cudaError_t launch_pdl(Kernel kernel, int grid, int smem, cudaStream_t stream, const Args&... args) {
+cudaError_t launch_pdl_cluster(Kernel kernel, int grid, int cluster, int smem, cudaStream_t stream, const Args&... args) {
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(grid);
   cfg.blockDim = dim3(kThreads);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = stream;
   static const bool pdl = []() { const char* e = getenv("SPEECHT_B200_PDL"); return !(e && e[0] == '0'); }();
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = pdl ? 1 : 0;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
+  if (cluster > 1) {                       // CTA pairs: consecutive blocks form a cluster on the SMs of one TPC
+    attr[1].id = cudaLaunchAttributeClusterDimension;
+    attr[1].val.clusterDim.x = cluster;
+    attr[1].val.clusterDim.y = 1;
+    attr[1].val.clusterDim.z = 1;
+    cfg.numAttrs = 2;
+  }
   return cudaLaunchKernelEx(&cfg, kernel, args...);
 }
 
-template <int BLOCK_N, int NPL, bool EARLY>
+template <class Kernel, class... Args>
+cudaError_t launch_pdl(Kernel kernel, int grid, int smem, cudaStream_t stream, const Args&... args) {
+  return launch_pdl_cluster(kernel, grid, 1, smem, stream, args...);
+}
+
+// CTA-pair (cta_group::2) tiles for the 256-wide forward / data-gradient launches: SPEECHT_B200_PAIR=1 enables them
+bool pair_enabled() {
+  static const bool on = []() { const char* e = getenv("SPEECHT_B200_PAIR"); return e && e[0] == '1'; }();
+  return on;
+}
+
+// grid of a CTA-pair launch: one cluster of two CTAs per work item, at most one cluster per TPC
+int pair_grid(int pair_work) {
+  const int clusters = st_num_sms() / 2;
+  return 2 * (pair_work < clusters ? pair_work : clusters);
+}
+
+template <int BLOCK_N, int NPL, bool EARLY, bool PAIR>
 int launch_conv_e(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmOut, const ConvParams& p,
                   cudaStream_t stream) {
-  using Cfg = ConvCfg<BLOCK_N, NPL>;
+  using Cfg = ConvCfg<BLOCK_N, NPL, PAIR>;
   // the opt-in for > 48 KB of dynamic shared memory is a per-DEVICE function attribute
   static bool configured[kMaxDevices] = {};
   const int dev = current_device();
   if (!configured[dev]) {
-    ST_CUDA_CALL(cudaFuncSetAttribute(tc_conv_kernel<BLOCK_N, NPL, EARLY, 1>,
+    ST_CUDA_CALL(cudaFuncSetAttribute(tc_conv_kernel<BLOCK_N, NPL, EARLY, 1, PAIR>,
                                       cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     configured[dev] = true;
   }
-  const int tiles = p.B * p.m_tiles_per_utt * p.n_tiles;
+  const int m_tiles = p.B * p.m_tiles_per_utt;
   TmSet1 a, b;
   a.m[0] = tmA;
   b.m[0] = tmB;
-  ST_CUDA_CALL(launch_pdl(tc_conv_kernel<BLOCK_N, NPL, EARLY, 1>, grid_for(tiles), Cfg::SMEM_BYTES, stream, a, b,
-                          tmOut, p));
+  if constexpr (PAIR) {
+    ST_CUDA_CALL(launch_pdl_cluster(tc_conv_kernel<BLOCK_N, NPL, EARLY, 1, true>, pair_grid(((m_tiles + 1) / 2) * p.n_tiles),
+                                    2, Cfg::SMEM_BYTES, stream, a, b, tmOut, p));
+  } else {
+    ST_CUDA_CALL(launch_pdl(tc_conv_kernel<BLOCK_N, NPL, EARLY, 1, false>, grid_for(m_tiles * p.n_tiles), Cfg::SMEM_BYTES,
+                            stream, a, b, tmOut, p));
+  }
   return ST_OK;
 }
 
-template <int BLOCK_N, int NPL>
+template <int BLOCK_N, int NPL, bool PAIR>
 int launch_conv_multi_t(const CUtensorMap* tmA, const CUtensorMap* tmB, const ConvParams& p0, cudaStream_t stream) {
-  using Cfg = ConvCfg<BLOCK_N, NPL>;
+  using Cfg = ConvCfg<BLOCK_N, NPL, PAIR>;
   constexpr bool EARLY = Cfg::ACC_STAGES == 1;      // several work items per CTA, long main loops: release TMEM early
   static bool configured[kMaxDevices] = {};
   const int dev = current_device();
   if (!configured[dev]) {
-    ST_CUDA_CALL(cudaFuncSetAttribute(tc_conv_kernel<BLOCK_N, NPL, EARLY, kMaxProblems>,
+    ST_CUDA_CALL(cudaFuncSetAttribute(tc_conv_kernel<BLOCK_N, NPL, EARLY, kMaxProblems, PAIR>,
                                       cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     configured[dev] = true;
   }
@@ -1352,9 +1430,16 @@ int launch_conv_multi_t(const CUtensorMap* tmA, const CUtensorMap* tmB, const Co
     a.m[q] = tmA[q < p.n_problems ? q : 0];
     b.m[q] = tmB[q < p.n_problems ? q : 0];
   }
-  const int work = p.B * p.m_tiles_per_utt * p.n_tiles * (p.k_split > 1 ? p.k_split : 1) * p.n_problems;
-  ST_CUDA_CALL(launch_pdl(tc_conv_kernel<BLOCK_N, NPL, EARLY, kMaxProblems>, grid_for(work), Cfg::SMEM_BYTES, stream, a,
-                          b, a.m[0], p));
+  const int m_tiles = p.B * p.m_tiles_per_utt;
+  const int per_tile = (p.k_split > 1 ? p.k_split : 1) * p.n_problems;
+  if constexpr (PAIR) {
+    ST_CUDA_CALL(launch_pdl_cluster(tc_conv_kernel<BLOCK_N, NPL, EARLY, kMaxProblems, true>,
+                                    pair_grid(((m_tiles + 1) / 2) * p.n_tiles * per_tile), 2, Cfg::SMEM_BYTES, stream, a, b,
+                                    a.m[0], p));
+  } else {
+    ST_CUDA_CALL(launch_pdl(tc_conv_kernel<BLOCK_N, NPL, EARLY, kMaxProblems, false>,
+                            grid_for(m_tiles * p.n_tiles * per_tile), Cfg::SMEM_BYTES, stream, a, b, a.m[0], p));
+  }
   return ST_OK;
 }
 
@@ -1376,12 +1461,26 @@ int launch_conv_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensor
   const CUtensorMap& tmO = p.tma_store ? *tmOut : tmA;          // placeholder when unused
   // early TMEM release pays when a CTA has several tiles, no second accumulator stage, and a main loop long enough
   // to hide the register-resident epilogue behind it
-  const int tiles = p.B * p.m_tiles_per_utt * p.n_tiles;
-  const bool early = ConvCfg<BLOCK_N, NPL>::ACC_STAGES == 1 && tiles > st_num_sms() && p.taps * p.chunks_per_tap >= 16;
-  if constexpr (ConvCfg<BLOCK_N, NPL>::ACC_STAGES == 1) {
-    if (early) return launch_conv_e<BLOCK_N, NPL, true>(tmA, tmB, tmO, p, stream);
+  const int m_tiles = p.B * p.m_tiles_per_utt;
+  // CTA pairs for the wide launches with enough m tiles to pair up (the 250-channel layers have one tile per SM and
+  // nothing to share; they stay on single CTAs)
+  constexpr bool kCanPair = BLOCK_N == 256 && NPL <= 2;
+  const bool pair = kCanPair && p.pair;
+  const int work = pair ? ((m_tiles + 1) / 2) * p.n_tiles : m_tiles * p.n_tiles;
+  const int ctas = pair ? st_num_sms() / 2 : st_num_sms();
+  const bool early = ConvCfg<BLOCK_N, NPL>::ACC_STAGES == 1 && work > ctas && p.taps * p.chunks_per_tap >= 16;
+  if constexpr (kCanPair) {
+    if (pair) {
+      if constexpr (ConvCfg<BLOCK_N, NPL>::ACC_STAGES == 1) {
+        if (early) return launch_conv_e<BLOCK_N, NPL, true, true>(tmA, tmB, tmO, p, stream);
+      }
+      return launch_conv_e<BLOCK_N, NPL, false, true>(tmA, tmB, tmO, p, stream);
+    }
   }
-  return launch_conv_e<BLOCK_N, NPL, false>(tmA, tmB, tmO, p, stream);
+  if constexpr (ConvCfg<BLOCK_N, NPL>::ACC_STAGES == 1) {
+    if (early) return launch_conv_e<BLOCK_N, NPL, true, false>(tmA, tmB, tmO, p, stream);
+  }
+  return launch_conv_e<BLOCK_N, NPL, false, false>(tmA, tmB, tmO, p, stream);
 }
 
 template <int BLOCK_N, int NPL>
@@ -1421,6 +1520,11 @@ int launch_wgrad_multi_t(const CUtensorMap* tmX, const CUtensorMap* tmDZ, const 
 }
 
 }  // namespace
+
+bool want_pair(int m_tiles, int n_tiles, int block_n, int n_planes, bool multi) {
+  if (!pair_enabled() || block_n != 256 || n_planes > 2 || m_tiles < 2) return false;
+  return multi || m_tiles * n_tiles > st_num_sms();
+}
 
 void set_conv_timeline(long long* buf, int launch_index) {
   g_timeline_buf = buf;
@@ -1514,8 +1618,11 @@ int launch_conv_multi(const CUtensorMap* tmA, const CUtensorMap* tmB, const Conv
                "launch_conv_multi: fp32 outputs only (no bias / ReLU / mask / planes / column sums)");
   ST_CHECK_ARG(p.k_split <= 1 || (p.taps % p.k_split) == 0, "launch_conv_multi: k_split must divide the taps");
   for (int q = 0; q < p.n_problems; ++q) ST_CHECK_ARG(p.out_f32_q[q] != nullptr, "launch_conv_multi: null output");
-  if (block_n == 256 && n_planes == 2) return launch_conv_multi_t<256, 2>(tmA, tmB, p, stream);
-  if (block_n == 256 && n_planes == 1) return launch_conv_multi_t<256, 1>(tmA, tmB, p, stream);
+  const bool pair = p.pair != 0;
+  if (block_n == 256 && n_planes == 2)
+    return pair ? launch_conv_multi_t<256, 2, true>(tmA, tmB, p, stream) : launch_conv_multi_t<256, 2, false>(tmA, tmB, p, stream);
+  if (block_n == 256 && n_planes == 1)
+    return pair ? launch_conv_multi_t<256, 1, true>(tmA, tmB, p, stream) : launch_conv_multi_t<256, 1, false>(tmA, tmB, p, stream);
   st_set_error("launch_conv_multi: unsupported (block_n=%d, n_planes=%d)", block_n, n_planes);
   return ST_ERR_UNSUPPORTED;
 }
@@ -1568,17 +1675,6 @@ int launch_pair_sum_planes(const __nv_bfloat16* x, __nv_bfloat16* xs, int B, int
   if (n_planes == 2) pair_sum_planes_kernel<2><<<blocks, 256, 0, stream>>>(x, xs, B, T, Tx, ld);
   else pair_sum_planes_kernel<1><<<blocks, 256, 0, stream>>>(x, xs, B, T, Tx, ld);
   ST_CUDA_LAUNCH_CHECK("pair_sum_planes_kernel");
-  return ST_OK;
-}
-
-int launch_ffa_split_taps(const float* w, float* w0, float* w1, float* ws, int J, int64_t tap_elems,
-                          cudaStream_t stream) {
-  const int64_t total = (int64_t)J * tap_elems;
-  int blocks = (int)((total + 255) / 256);
-  const int cap = 16 * st_num_sms();
-  blocks = blocks > cap ? cap : blocks;
-  ffa_split_taps_kernel<<<blocks, 256, 0, stream>>>(w, w0, w1, ws, J, tap_elems);
-  ST_CUDA_LAUNCH_CHECK("ffa_split_taps_kernel");
   return ST_OK;
 }
 

@@ -37,6 +37,9 @@ struct ConvParams {
   // problem q uses tensor maps A[q] / B[q], its own left padding and fp32 output; the taps of every tile may be cut
   // into k_split slices that accumulate into the (pre-zeroed) fp32 output with vector reductions.  Multi launches
   // write fp32 only: no bias, ReLU, mask, bf16 planes or column sums (the combine pass that follows does those).
+  // CTA pairs (cta_group::2): 1 = launch as clusters of two CTAs sharing 256-row tiles.  The B tensor map must then
+  // have boxes of block_n / 2 rows (each CTA loads half of the B tile).  Decide with want_pair().
+  int pair;
   int n_problems;                // 0 / 1: single problem (the fields above); 2..kMaxProblems: use the arrays below
   int k_split;                   // 0 / 1: whole contraction per tile
   int pad_left_q[3];
@@ -75,6 +78,10 @@ void set_conv_timeline(long long* buf, int launch_index);
 // tmOut: store map of p.out_planes, required when p.out_planes is set and n_planes <= 2 (see make_map_3d_store)
 int launch_conv(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap* tmOut, const ConvParams& p,
                 int block_n, int n_planes, cudaStream_t stream);
+// Should a forward / data-gradient launch of m_tiles x n_tiles tiles (256 wide, 1-2 planes) run on CTA pairs?
+// SPEECHT_B200_PAIR=1 enables them; single launches need more tiles than SMs (the 250-channel layers have one tile
+// per SM and nothing to share), multi-problem launches at least two m tiles.
+bool want_pair(int m_tiles, int n_tiles, int block_n, int n_planes, bool multi);
 int launch_wgrad(const CUtensorMap& tmX, const CUtensorMap& tmDZ, const WgradParams& p, int block_n, int n_planes,
                  cudaStream_t stream);
 int launch_wgrad_multi(const CUtensorMap* tmX, const CUtensorMap* tmDZ, const WgradParams& p, int block_n,
@@ -95,6 +102,7 @@ struct PackEntry {
   __nv_bfloat16* bwd;
   int K, Cin, Cout, cin_p, ld_co;
   int blk0;                      // first block of this layer, filled by launch_pack_filters
+  int tap_mode;                  // 0: pack tap k of w; 1 / 2: its even / odd taps; 3: even + odd (w then holds 2K taps)
 };
 struct PackTable {
   int n;
@@ -105,9 +113,6 @@ int launch_pack_filters(PackTable& tab, int n_planes, cudaStream_t stream, int* 
 // xs planes [n][B][Tx][ld] of x[b][2r] + x[b][2r+1] from x planes [n][B][T][ld]
 int launch_pair_sum_planes(const __nv_bfloat16* x, __nv_bfloat16* xs, int B, int T, int Tx, int ld, int n_planes,
                            cudaStream_t stream);
-// w [2J][tap_elems] fp32 -> even taps, odd taps, their sum, each [J][tap_elems]
-int launch_ffa_split_taps(const float* w, float* w0, float* w1, float* ws, int J, int64_t tap_elems,
-                          cudaStream_t stream);
 // y[2u] = act(A00[u] + A11[u] + bias), y[2u+1] = act(S[u] - A11[u] - A00[u+1] + bias): fp32 [B][Tu][ld_p] partial
 // products -> bf16 planes [n][B][To][ld_out]
 int launch_ffa_combine(const float* a00, const float* a11, const float* sm, const float* bias, int relu,

@@ -125,12 +125,16 @@ ctc_alpha_beta_kernel(const float* __restrict__ probs, int T, int C, const int32
   }
   const int2 zero = make_int2(__float_as_int(1.f), kZeroExp);
   for (int i = threadIdx.x; i < 2 * bstride; i += nthr) buf[i] = zero;
-  const float* prow = probs + (int64_t)b * T * C;
+  const float* grow = probs + (int64_t)b * T * C;
   if (PROBS_SMEM && !infeasible && len > 0) {
-    for (int i = threadIdx.x; i < len * C; i += nthr) probs_s[i] = prow[i];
-    prow = probs_s;
+    for (int i = threadIdx.x; i < len * C; i += nthr) probs_s[i] = grow[i];
   }
   __syncthreads();
+  // emission probability y_t(c): a shared-memory load when the rows are staged (never a generic-address load)
+  auto emis = [&](int t, int c) -> float {
+    if constexpr (PROBS_SMEM) return probs_s[t * C + c];
+    else return __ldg(grow + (int64_t)t * C + c);
+  };
 
   if (infeasible || len <= 0) {
     if (!is_beta && threadIdx.x == 0) {
@@ -162,10 +166,10 @@ ctc_alpha_beta_kernel(const float* __restrict__ probs, int T, int C, const int32
       const int s = threadIdx.x + j * nthr;
       if (live[j]) {
         my_skip[j] = skip[s] != 0;
-        const SF v = s < 2 ? sf_norm(prow[my_ext[j]], 0) : sf_zero();
+        const SF v = s < 2 ? sf_norm(emis(0, my_ext[j]), 0) : sf_zero();
         sf_store(buf + 2 + s, v);                                       // slot 0, +2 pad so s-1, s-2 read ZERO
         if (STORE) sf_store(lat + s, v);
-        if (len > 1) y[j] = prow[(int64_t)C + my_ext[j]];
+        if (len > 1) y[j] = emis(1, my_ext[j]);
       }
     }
     __syncthreads();
@@ -173,10 +177,9 @@ ctc_alpha_beta_kernel(const float* __restrict__ probs, int T, int C, const int32
     for (int t = 1; t < len; ++t, lat_t += s_pad) {
       const int2* prev = buf + ((t - 1) & 1) * bstride;
       int2* cur = buf + (t & 1) * bstride;
-      const float* next_row = prow + (int64_t)(t + 1) * C;
       float yn[NS];                                                      // emission of step t+1: off the chain
 #pragma unroll
-      for (int j = 0; j < NS; ++j) yn[j] = (live[j] && t + 1 < len) ? next_row[my_ext[j]] : 1.f;
+      for (int j = 0; j < NS; ++j) yn[j] = (live[j] && t + 1 < len) ? emis(t + 1, my_ext[j]) : 1.f;
       SF v[NS];
 #pragma unroll
       for (int j = 0; j < NS; ++j) {
@@ -209,7 +212,6 @@ ctc_alpha_beta_kernel(const float* __restrict__ probs, int T, int C, const int32
     }
   } else {
     // beta_{len-1}(s) = 1 for the last two positions; smem holds g_t(s) = beta_t(s) * y_t(s) for the step below
-    const float* last = prow + (int64_t)(len - 1) * C;
 #pragma unroll
     for (int j = 0; j < NS; ++j) {
       const int s = threadIdx.x + j * nthr;
@@ -218,8 +220,8 @@ ctc_alpha_beta_kernel(const float* __restrict__ probs, int T, int C, const int32
         SF v = sf_zero();
         if (s >= S - 2) v.e = 0;
         if (STORE) sf_store(lat + (int64_t)(len - 1) * s_pad + s, v);
-        sf_store(buf + ((len - 1) & 1) * bstride + s, sf_norm(v.p * last[my_ext[j]], v.e));
-        if (len > 1) y[j] = prow[(int64_t)(len - 2) * C + my_ext[j]];
+        sf_store(buf + ((len - 1) & 1) * bstride + s, sf_norm(v.p * emis(len - 1, my_ext[j]), v.e));
+        if (len > 1) y[j] = emis(len - 2, my_ext[j]);
       }
     }
     __syncthreads();
@@ -229,7 +231,7 @@ ctc_alpha_beta_kernel(const float* __restrict__ probs, int T, int C, const int32
       int2* cur = buf + (t & 1) * bstride;
       float yn[NS];
 #pragma unroll
-      for (int j = 0; j < NS; ++j) yn[j] = (live[j] && t > 0) ? prow[(int64_t)(t - 1) * C + my_ext[j]] : 1.f;
+      for (int j = 0; j < NS; ++j) yn[j] = (live[j] && t > 0) ? emis(t - 1, my_ext[j]) : 1.f;
       SF v[NS];
 #pragma unroll
       for (int j = 0; j < NS; ++j) {
@@ -253,7 +255,17 @@ ctc_alpha_beta_kernel(const float* __restrict__ probs, int T, int C, const int32
   }
 }
 
+__device__ __forceinline__ float fast_exp2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 // One warp per (b,t) row.  grad row = grad_scale * (softmax - occupancy); zero for t >= seq_len[b].
+// occupancy(s) = alpha*beta / p(z|x) = pa*pb * 2^(ea + eb - log2 p(z|x)): log2 p(z|x) is split ONCE per row into an
+// integer and a fraction in [0,1), so the exponents subtract exactly in integers and nothing on the per-state path is
+// double precision.  Label states accumulate into a PRIVATE row of bins per lane (no shared-memory atomics, whose
+// same-class collisions serialise); the 32 rows are summed per class at the end.
 __global__ void __launch_bounds__(256)
 ctc_grad_kernel(const float* __restrict__ probs, const int2* __restrict__ alpha, const int2* __restrict__ beta,
                 const double* __restrict__ logp, const int32_t* __restrict__ labels,
@@ -261,7 +273,7 @@ ctc_grad_kernel(const float* __restrict__ probs, const int2* __restrict__ alpha,
                 const int32_t* __restrict__ status, int T, int B, int C, int blank, int s_pad,
                 float grad_scale, float* __restrict__ grad, int64_t stride_t, int64_t stride_b,
                 __nv_bfloat16* __restrict__ planes, int n_planes, int c_pad) {
-  __shared__ float bins[8][64];
+  extern __shared__ float bins_all[];                       // [8 warps][32 lanes][C + 1]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int row = blockIdx.x * 8 + warp;
   if (row >= B * T) return;
@@ -270,36 +282,37 @@ ctc_grad_kernel(const float* __restrict__ probs, const int2* __restrict__ alpha,
   const bool live = t < len && status[b] == 0;
   float g0 = 0.f, g1 = 0.f;                     // classes lane and lane+32 (C <= 64)
   if (live) {
-    bins[warp][lane] = 0.f;
-    bins[warp][lane + 32] = 0.f;
-    __syncwarp();
+    const int cw = C + 1;                       // odd row pitch for 29 classes: lanes land in different banks
+    float* mine = bins_all + ((size_t)warp * 32 + lane) * cw;
+    for (int c = 0; c < C; ++c) mine[c] = 0.f;
     const int l0 = label_offsets[b];
     const int S = 2 * (label_offsets[b + 1] - l0) + 1;
     const double lz2 = logp[b] * 1.4426950408889634;                      // log2 p(z|x)
+    const double lzi = floor(lz2);
+    const int li = (int)lzi;
+    const float lf = (float)(lz2 - lzi);
     const int2* a = alpha + ((int64_t)b * T + t) * s_pad;
     const int2* be = beta + ((int64_t)b * T + t) * s_pad;
     float blank_sum = 0.f;
     for (int s = lane; s < S; s += 32) {
-      // occupancy = alpha*beta / p(z|x) = 2^(ea+eb-lz2) * pa*pb: integer exponents subtract exactly; a ZERO factor
-      // (exponent -2^28) drives the power of two to 0
       const SF av = sf_load(a + s), bv = sf_load(be + s);
-      const float v2 = (float)((double)(av.e + bv.e) - lz2);
-      const float e = v2 > -140.f ? exp2f(v2) * (av.p * bv.p) : 0.f;
-      if (s & 1) {
-        atomicAdd(&bins[warp][labels[l0 + (s >> 1)]], e);
-      } else {
-        blank_sum += e;
-      }
+      const int de = max(av.e + bv.e - li, -200);                          // a ZERO factor (exponent -2^28) -> 0
+      const float e = fast_exp2((float)de - lf) * (av.p * bv.p);
+      if (s & 1) mine[labels[l0 + (s >> 1)]] += e;
+      else blank_sum += e;
     }
     blank_sum = warp_sum(blank_sum);
     __syncwarp();
     const float* pr = probs + (int64_t)row * C;
+    const float* wbins = bins_all + (size_t)warp * 32 * cw;
     if (lane < C) {
-      float occ = bins[warp][lane] + (lane == blank ? blank_sum : 0.f);
+      float occ = lane == blank ? blank_sum : 0.f;
+      for (int l = 0; l < 32; ++l) occ += wbins[((l + lane) & 31) * cw + lane];
       g0 = grad_scale * (pr[lane] - occ);
     }
     if (lane + 32 < C) {
-      float occ = bins[warp][lane + 32] + (lane + 32 == blank ? blank_sum : 0.f);
+      float occ = lane + 32 == blank ? blank_sum : 0.f;
+      for (int l = 0; l < 32; ++l) occ += wbins[((l + lane) & 31) * cw + lane + 32];
       g1 = grad_scale * (pr[lane + 32] - occ);
     }
   }
@@ -393,14 +406,14 @@ ST_API int st_ctc_loss(const float* logits, int64_t stride_t, int64_t stride_b, 
   const size_t need = ctc_offsets(T, B, C, max_label_len, &off_a, &off_b, &off_l, &s_pad);
   ST_CHECK_ARG(workspace_bytes >= need, "st_ctc_loss: workspace %zu < required %zu bytes", workspace_bytes, need);
   char* ws = static_cast<char*>(workspace);
-  float* lsm = reinterpret_cast<float*>(ws);
+  float* probs = reinterpret_cast<float*>(ws);      // class probabilities [B][T][C]
   int2* alpha = reinterpret_cast<int2*>(ws + off_a);          // scaled-float lattices, 8 bytes per entry
   int2* beta = reinterpret_cast<int2*>(ws + off_b);
   double* logp = reinterpret_cast<double*>(ws + off_l);
   cudaStream_t s = st_cu(stream);
 
   const int rows = B * T;
-  ctc_softmax_kernel<<<(rows + 7) / 8, 256, 0, s>>>(logits, stride_t, stride_b, T, B, C, seq_len, lsm);
+  ctc_softmax_kernel<<<(rows + 7) / 8, 256, 0, s>>>(logits, stride_t, stride_b, T, B, C, seq_len, probs);
   ST_CUDA_LAUNCH_CHECK("ctc_softmax_kernel");
 
   const bool want_grad = grad || grad_planes;
@@ -419,7 +432,7 @@ ST_API int st_ctc_loss(const float* logits, int64_t stride_t, int64_t stride_b, 
       ST_CUDA_CALL(cudaFuncSetAttribute(ctc_alpha_beta_kernel<NS_, SM_, ST_>,                                        \
                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                    \
     ctc_alpha_beta_kernel<NS_, SM_, ST_><<<dim3(B, ST_ ? 2 : 1), threads, smem, s>>>(                                \
-        lsm, T, C, labels, label_offsets, seq_len, blank, s_pad, alpha, beta, logp, loss, status);                   \
+        probs, T, C, labels, label_offsets, seq_len, blank, s_pad, alpha, beta, logp, loss, status);                  \
   } while (0)
 #define ST_CTC_LAUNCH(NS_, SM_)                                                                                      \
   do {                                                                                                               \
@@ -436,7 +449,10 @@ ST_API int st_ctc_loss(const float* logits, int64_t stride_t, int64_t stride_b, 
 #undef ST_CTC_LAUNCH2
   ST_CUDA_LAUNCH_CHECK("ctc_alpha_beta_kernel");
   if (grad || grad_planes) {
-    ctc_grad_kernel<<<(rows + 7) / 8, 256, 0, s>>>(lsm, alpha, beta, logp, labels, label_offsets, seq_len, status,
+    const size_t grad_smem = (size_t)8 * 32 * (C + 1) * sizeof(float);
+    if (grad_smem > 48 * 1024)
+      ST_CUDA_CALL(cudaFuncSetAttribute(ctc_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)grad_smem));
+    ctc_grad_kernel<<<(rows + 7) / 8, 256, grad_smem, s>>>(probs, alpha, beta, logp, labels, label_offsets, seq_len, status,
                                                    T, B, C, blank, s_pad, grad_scale, grad, stride_t, stride_b,
                                                    static_cast<__nv_bfloat16*>(grad_planes), n_planes, c_pad);
     ST_CUDA_LAUNCH_CHECK("ctc_grad_kernel");

@@ -26,6 +26,7 @@ struct Layer {
   CUtensorMap tm_dg_a[2], tm_dg_b;    // data gradient (A = dz ping or pong)
   CUtensorMap tm_dg_b_n128;           // layer 10 only: filter rows in boxes of 128 (128-wide data-gradient tiles)
   CUtensorMap tm_wg_x, tm_wg_dz[2];   // filter gradient
+  bool pair_fwd, pair_dg;             // forward / data gradient on CTA pairs: their B maps hold half-height boxes
   CUtensorMap tm_fwd_out;             // store map of this layer's output planes (layers 0..9)
   CUtensorMap tm_dg_out[2];           // store map of the dz buffer the data gradient of this layer writes (1..10)
 };
@@ -64,7 +65,8 @@ struct st_plan {
   // SPEECHT_B200_FFA=0 restores the direct 32-tap kernels; bf16x6 (three planes) always uses them.
   bool ffa;
   int ffa_Tx, ffa_Tu;                            // rows of the pair-sum planes / of the partial products
-  size_t off_ffa_xs, off_ffa_w32[3], off_ffa_w[3], off_ffa_wb[3], off_ffa_p[3], off_ffa_dxp[3], off_ffa_cs;
+  size_t off_ffa_xs, off_ffa_w[3], off_ffa_wb[3], off_ffa_p[3], off_ffa_dxp[3], off_ffa_cs;
+  bool ffa_pair_fwd, ffa_pair_dg;                // the multi-problem launches run on CTA pairs
   CUtensorMap tm_ffa_a[3], tm_ffa_b[3];          // forward: A = odd / even row views of x, pair sums; B = w0, w1, ws
   CUtensorMap tm_ffa_dg_a[3], tm_ffa_dg_b[3];    // data gradient: A = dA00 / dA11 / dS planes; B = backward layouts
   CUtensorMap tm_ffa_wg_x[3], tm_ffa_wg_dz[3];   // filter gradient: the same operands in 64-row boxes
@@ -167,7 +169,6 @@ ST_API int st_plan_create(st_plan** out, int B, int T, int input_size, int num_c
     p->ffa_Tu = (L8.To + 1) / 2 + 1;
     p->off_ffa_xs = take((size_t)n_planes * B * p->ffa_Tx * L8.ld_in * 2);
     for (int i = 0; i < 3; ++i) {
-      p->off_ffa_w32[i] = take((size_t)(L8.K / 2) * L8.Cin * L8.Cout * sizeof(float));
       p->off_ffa_w[i] = take((size_t)n_planes * L8.Cout * (L8.K / 2) * L8.cin_p * 2);
       p->off_ffa_wb[i] = take((size_t)n_planes * (L8.K / 2) * L8.Cin * L8.ld_co * 2);
       // forward: fp32 partial product [B][Tu][Cout]; backward: the planes of dA00 / dA11 / dS [npl][B][Tu][Cout] live
@@ -227,8 +228,10 @@ ST_API int st_plan_bind(st_plan* p, void* arena, size_t arena_bytes, float* para
                            64, 128);
     }
     if (rc) return rc;
+    L.pair_fwd = tc::want_pair(B * ((L.To + tc::kTileM - 1) / tc::kTileM), (L.Cout + block_n - 1) / block_n, block_n,
+                               npl, false);
     rc = tc::make_map_2d(&L.tm_fwd_b, bf(p, L.off_wfwd), L.K * L.cin_p, npl * L.Cout, (int64_t)L.K * L.cin_p, 64,
-                         block_n);
+                         L.pair_fwd ? block_n / 2 : block_n);
     if (rc) return rc;
     // ---- filter gradient: X = input activation planes (boxes of 64 rows), dZ = gradient wrt this layer's output
     if (L.stride == 1) {
@@ -254,8 +257,11 @@ ST_API int st_plan_bind(st_plan* p, void* arena, size_t arena_bytes, float* para
       }
     }
     if (l > 0) {
+      L.pair_dg = !(l == 10 && p->l10_n128) &&
+                  tc::want_pair(B * ((L.Ti + tc::kTileM - 1) / tc::kTileM), (L.Cin + wide_n(p) - 1) / wide_n(p),
+                                wide_n(p), npl, false);
       rc = tc::make_map_2d(&L.tm_dg_b, bf(p, L.off_wbwd), l == 10 ? 64 : L.Cout, npl * L.K * L.Cin, L.ld_co, 64,
-                           wide_n(p));
+                           L.pair_dg ? wide_n(p) / 2 : wide_n(p));
       if (rc) return rc;
       if (l == 10 && p->l10_n128) {
         rc = tc::make_map_2d(&L.tm_dg_b_n128, bf(p, L.off_wbwd), 64, npl * L.K * L.Cin, L.ld_co, 64, 128);
@@ -284,6 +290,8 @@ ST_API int st_plan_bind(st_plan* p, void* arena, size_t arena_bytes, float* para
     // the pair-sum planes; B operands: the packed even-tap, odd-tap and summed filters (forward layout, 16 taps)
     Layer& L8 = p->layers[8];
     const __nv_bfloat16* x = act_in(p, 8);
+    p->ffa_pair_fwd = tc::want_pair(B * ((p->ffa_Tu + tc::kTileM - 1) / tc::kTileM), 1, wide_n(p), npl, true);
+    p->ffa_pair_dg = tc::want_pair(B * ((p->ffa_Tx + tc::kTileM - 1) / tc::kTileM), 1, wide_n(p), npl, true);
     rc = tc::make_map_3d(&p->tm_ffa_a[0], x + L8.ld_in, L8.Cin, L8.Ti / 2, npl * B, 2 * L8.ld_in,
                          (int64_t)L8.Ti * L8.ld_in, 64, 128);
     if (rc) return rc;
@@ -305,7 +313,7 @@ ST_API int st_plan_bind(st_plan* p, void* arena, size_t arena_bytes, float* para
     if (rc) return rc;
     for (int i = 0; i < 3; ++i) {
       rc = tc::make_map_2d(&p->tm_ffa_b[i], bf(p, p->off_ffa_w[i]), (L8.K / 2) * L8.cin_p, npl * L8.Cout,
-                           (int64_t)(L8.K / 2) * L8.cin_p, 64, wide_n(p));
+                           (int64_t)(L8.K / 2) * L8.cin_p, 64, p->ffa_pair_fwd ? wide_n(p) / 2 : wide_n(p));
       if (rc) return rc;
       // backward: gradients of the partial products as planes [npl*B][Tu][Cout]
       const __nv_bfloat16* dA = bf(p, p->off_ffa_p[i]);
@@ -316,7 +324,7 @@ ST_API int st_plan_bind(st_plan* p, void* arena, size_t arena_bytes, float* para
                            (int64_t)p->ffa_Tu * L8.ld_out, 64, 64);
       if (rc) return rc;
       rc = tc::make_map_2d(&p->tm_ffa_dg_b[i], bf(p, p->off_ffa_wb[i]), L8.Cout, npl * (L8.K / 2) * L8.Cin, L8.ld_co, 64,
-                           wide_n(p));
+                           p->ffa_pair_dg ? wide_n(p) / 2 : wide_n(p));
       if (rc) return rc;
     }
   }
@@ -330,26 +338,18 @@ namespace {
 int pack_layers(st_plan* p, cudaStream_t s) {
   tc::PackTable tab{};
   Layer& L8 = p->layers[8];
-  float* w32[3] = {nullptr, nullptr, nullptr};
-  if (p->ffa) {
-    // fast-FIR filters of layer 8: even taps, odd taps and their sum, each packed like a 16-tap filter in both
-    // operand layouts; the direct 32-tap layouts of layer 8 are then not needed
-    for (int i = 0; i < 3; ++i) w32[i] = reinterpret_cast<float*>(p->arena + p->off_ffa_w32[i]);
-    const int rc = tc::launch_ffa_split_taps(p->params + L8.w_off, w32[0], w32[1], w32[2], L8.K / 2,
-                                             (int64_t)L8.Cin * L8.Cout, s);
-    if (rc) return rc;
-    p->launches++;
-  }
   for (int l = 0; l < 11; ++l) {
     Layer& L = p->layers[l];
     if (l == 8 && p->ffa) {
+      // fast-FIR filters of layer 8: even taps, odd taps and their sum, each packed like a 16-tap filter in both
+      // operand layouts straight from the 32-tap fp32 tensor; the direct 32-tap layouts are then not needed
       for (int i = 0; i < 3; ++i)
-        tab.e[tab.n++] = tc::PackEntry{w32[i], bf(p, p->off_ffa_w[i]), bf(p, p->off_ffa_wb[i]), L8.K / 2, L8.Cin,
-                                       L8.Cout, L8.cin_p, L8.ld_co, 0};
+        tab.e[tab.n++] = tc::PackEntry{p->params + L8.w_off, bf(p, p->off_ffa_w[i]), bf(p, p->off_ffa_wb[i]), L8.K / 2,
+                                       L8.Cin, L8.Cout, L8.cin_p, L8.ld_co, 0, i + 1};
       continue;
     }
     tab.e[tab.n++] = tc::PackEntry{p->params + L.w_off, bf(p, L.off_wfwd), l > 0 ? bf(p, L.off_wbwd) : nullptr,
-                                   L.K, L.Cin, L.Cout, L.cin_p, L.ld_co, 0};
+                                   L.K, L.Cin, L.Cout, L.cin_p, L.ld_co, 0, 0};
   }
   int n = 0;
   const int rc = tc::launch_pack_filters(tab, p->npl, s, &n);
@@ -396,6 +396,7 @@ int forward_layer8_ffa(st_plan* p, cudaStream_t s) {
   c.trim = p->trim;
   c.n_problems = 3;
   c.k_split = 1;
+  c.pair = p->ffa_pair_fwd;
   for (int i = 0; i < 3; ++i) {
     part[i] = reinterpret_cast<float*>(p->arena + p->off_ffa_p[i]);
     c.pad_left_q[i] = i == 0 ? 8 : 7;
@@ -472,6 +473,7 @@ int backward_layer8_ffa(st_plan* p, const __nv_bfloat16* dz, __nv_bfloat16* dz_o
   c.trim = p->trim;
   c.n_problems = 3;
   c.k_split = 2;
+  c.pair = p->ffa_pair_dg;
   for (int i = 0; i < 3; ++i) {
     c.pad_left_q[i] = i == 0 ? 8 : 7;
     c.out_f32_q[i] = dxp[i];
@@ -531,6 +533,7 @@ ST_API int st_plan_forward(st_plan* p, const float* inputs, st_stream_t stream) 
     c.tma_store = p->tma_store && l < 10;
     c.k_cols = L.Cin;
     c.trim = p->trim;
+    c.pair = L.pair_fwd;
     const int ti = timed_begin(p, s);
     rc = tc::launch_conv(L.tm_fwd_a, L.tm_fwd_b, l < 10 ? &L.tm_fwd_out : nullptr, c, block_n, p->npl, s);
     if (rc) return rc;
@@ -618,6 +621,7 @@ ST_API int st_plan_backward_range(st_plan* p, int hi, int lo, st_stream_t stream
       c.tma_store = p->tma_store;
       c.k_cols = L.Cout;
       c.trim = p->trim;
+      c.pair = L.pair_dg;
       ti = timed_begin(p, s);
       rc = tc::launch_conv(L.tm_dg_a[l == 10 ? 0 : cur], n128 ? L.tm_dg_b_n128 : L.tm_dg_b, &L.tm_dg_out[nxt], c,
                            dg_block_n, p->npl, s);

@@ -5,8 +5,9 @@ signature (preprocessing.py:36) and runs on the GPU (csrc/melspec.cu).  `SpeechC
 contract between `preprocess` and `train/evaluate`: `<data>/preprocessed-power/<split>/<audio_id>.npz` with keys
 `audio_fragments [T, n_mels]` and `transcript [L]` (preprocessing.py:178,199-206,243-279).
 
-Decoding FLAC needs an audio decoder the image does not have (no soundfile / audioread / ffmpeg): audio loading is
-delegated to an injectable `load_audio(path) -> (samples, samplerate)`; WAV files are read with the stdlib.
+Audio loading follows `librosa.load(audio_file)` (preprocessing.py:169): mono float32 resampled to 22050 Hz.  The
+image has no soundfile / audioread / ffmpeg, so .flac files go through the library's own FLAC decoder
+(csrc/flac_host.cu, MD5-verified) and .wav files through the stdlib; resampling is a polyphase Kaiser FIR (scipy).
 The MFCC feature type (preprocessing.py:61-84) is out of scope (not the default, not on the hot path).
 """
 import fnmatch
@@ -50,9 +51,25 @@ def calc_power_spectrogram_batch(audio_list, samplerate, n_mels=128, n_fft=512, 
   return [feat[i, :frames[i]].copy() for i in range(len(audio_list))]
 
 
-def load_wav(path):
-  """Minimal PCM16 WAV reader (the reference uses librosa.load, preprocessing.py:169, which resamples to 22050 Hz;
-  no resampler is available here, so the native rate is returned)."""
+LOAD_SAMPLERATE = 22050          # librosa.load's default `sr`: the reference resamples EVERY file to it
+
+
+def resample(audio, orig_sr, target_sr=LOAD_SAMPLERATE):
+  """Band-limited polyphase resampling (Kaiser-windowed FIR, scipy.signal.resample_poly) in place of librosa's
+  'kaiser_best' windowed-sinc interpolation (resampy): same output length ceil(n * target / orig), the same kind
+  of filter; sample values agree to the filters' stop-band level, not bit for bit."""
+  if int(orig_sr) == int(target_sr):
+    return np.ascontiguousarray(audio, dtype=np.float32)
+  from math import gcd
+  from scipy.signal import resample_poly
+  g = gcd(int(orig_sr), int(target_sr))
+  out = resample_poly(np.asarray(audio, dtype=np.float64), int(target_sr) // g, int(orig_sr) // g)
+  n_out = -(-len(audio) * int(target_sr) // int(orig_sr))          # ceil, librosa's n_samples
+  return np.ascontiguousarray(out[:n_out], dtype=np.float32)
+
+
+def read_wav(path):
+  """Minimal PCM16 WAV reader -> (mono float32 in [-1, 1), native sample rate)."""
   with wave.open(path, 'rb') as f:
     if f.getsampwidth() != 2:
       raise ValueError('only 16-bit PCM WAV is supported')
@@ -60,6 +77,51 @@ def load_wav(path):
     if f.getnchannels() > 1:
       data = data.reshape(-1, f.getnchannels()).mean(axis=1)
     return data, f.getframerate()
+
+
+def read_flac(path, verify_md5=True):
+  """FLAC file -> (mono float32 in [-1, 1), native sample rate) through the library's native decoder
+  (csrc/flac_host.cu); the decoded PCM is checked against the MD5 signature in STREAMINFO."""
+  import ctypes
+  import hashlib
+  from ._lib import check, lib
+  raw = np.fromfile(path, dtype=np.uint8)
+  info = (ctypes.c_int32 * 3)()
+  total = ctypes.c_int64()
+  md5 = (ctypes.c_uint8 * 16)()
+  check(lib().st_flac_info_host(raw.ctypes.data, raw.size, info, ctypes.byref(total), md5))
+  rate, channels, bits = info[0], info[1], info[2]
+  # unknown length (streamed encodes): a frame holds at most 65535 samples and at least ~10 bytes
+  capacity = total.value if total.value > 0 else raw.size * 65535 // 10
+  pcm = np.empty((max(capacity, 1), channels), dtype=np.int32)
+  decoded = ctypes.c_int64()
+  check(lib().st_flac_decode_host(raw.ctypes.data, raw.size, pcm.ctypes.data, capacity, ctypes.byref(decoded)))
+  pcm = pcm[:decoded.value]
+  if verify_md5 and any(md5):
+    width = (bits + 7) // 8
+    le = pcm.astype('<i4').view(np.uint8).reshape(-1, channels, 4)[:, :, :width]
+    if hashlib.md5(np.ascontiguousarray(le).tobytes()).digest() != bytes(md5):
+      raise ValueError('FLAC MD5 mismatch: %s does not decode to the audio it was encoded from' % path)
+  audio = pcm.astype(np.float32).mean(axis=1) / float(1 << (bits - 1))
+  return audio, rate
+
+
+def load_audio(path, sr=LOAD_SAMPLERATE):
+  """librosa.load(path) as the reference calls it (preprocessing.py:169): mono float32 RESAMPLED to 22050 Hz.
+  -> (audio, sr).  .flac through the native decoder, .wav through the stdlib."""
+  ext = os.path.splitext(path)[1].lower()
+  if ext == '.flac':
+    audio, rate = read_flac(path)
+  elif ext == '.wav':
+    audio, rate = read_wav(path)
+  else:
+    raise ValueError('unsupported audio file type: %s' % path)
+  return resample(audio, rate, sr), sr
+
+
+def load_wav(path):
+  """Kept for callers of the first version: a WAV file loaded like load_audio (resampled to 22050 Hz)."""
+  return load_audio(path)
 
 
 def iglob_recursive(directory, file_pattern):
@@ -76,7 +138,7 @@ class SpeechCorpusReader:
   def __init__(self, data_directory, load_audio=None):
     self._data_directory = data_directory
     self._transcript_dict_cache = None
-    self._load_audio = load_audio or load_wav
+    self._load_audio = load_audio or globals()['load_audio']
 
   @property
   def _transcript_dict(self):

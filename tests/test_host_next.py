@@ -74,7 +74,7 @@ def test_npz_store_layout_and_load_samples(tmp_path):
 
 def test_wav_loader_roundtrip(tmp_path):
   import wave
-  from speecht_b200.preprocessing import load_wav
+  from speecht_b200.preprocessing import read_wav as load_wav
   x = (np.sin(np.arange(1600) * 0.1) * 12000).astype(np.int16)
   with wave.open(str(tmp_path / 'a.wav'), 'wb') as f:
     f.setnchannels(1); f.setsampwidth(2); f.setframerate(16000); f.writeframes(x.tobytes())

@@ -435,7 +435,7 @@ def run_ours(args, rank, local_rank, world):
   feed = HostFeed()
   model = speech_model.create_default_model(flags, 128, feed)
   sess = speech_model.Session(dev)
-  d2h_bytes = [4]
+  d2h_bytes = [4 * B]                                       # the [B] per-utterance losses, averaged on the host
   if mode == 'train':
     def step_e2e(i):
       model.step(sess)
@@ -443,7 +443,7 @@ def run_ours(args, rank, local_rank, world):
     def step_e2e(i):
       _loss, decoded, _labels = model.step(sess, update=False, decode=True, return_label=True)
       rows = decoded[0]
-      d2h_bytes[0] = 4 + 4 * B + 4 * int(rows.values.shape[0])
+      d2h_bytes[0] = 4 * B + 4 * B + 4 * int(rows.values.shape[0])
       if world > 1:
         parallel.gather_decoded_sparse(rows, group, device=dev)
   for i in range(args.warmup):
@@ -549,7 +549,7 @@ def aux_kernels(eng, dev, B, seconds, host_set, peaks_path):
     'melspec (a1-a3)': (lambda: ops.power_spectrogram(wav, [n_samp] * B, 16000), B * (4 * n_samp + 4 * T * 128)),
     'ctc_loss+grad (a8-a9)': (lambda: ops.ctc_loss(batch, logits, want_grad=True), 2 * To * B * 29 * 4),
     'ctc_greedy_decode (a12)': (lambda: lib_decode(ops, logits, batch), To * B * 29 * 4),
-    'sumsq+clip_adam (a10-a11)': (lambda: (ops.global_norm_sq(scratch[1], nsq),
+    'sumsq+clip_adam (a10-a11)': (lambda: (ops.global_norm_sq(scratch[1], nsq, zero=True),
                                            ops.clip_adam(scratch[0], scratch[1], scratch[2], scratch[3], 1, 1e-4,
                                                          normsq=nsq)), 8 * n * 4),
   }

@@ -87,7 +87,7 @@ int st_conv1d_bwd_filter_f32(const float* x, const float* dy, const float* y_act
  * sum(g^2) into *accum (double, device; the caller zeroes it -- several calls may add into it).
  * st_clip_adam: g' = g * grad_prescale * clip*min(1/norm, 1/clip), norm = sqrt(*normsq)*grad_prescale;
  * TF1 Adam: lr_t = lr*sqrt(1-b2^step)/(1-b1^step); p -= lr_t*m/(sqrt(v)+eps).  step counts from 1. */
-int st_sumsq(const float* g, int64_t n, double* accum, st_stream_t stream);
+int st_sumsq(const float* g, int64_t n, double* accum, int zero_first, st_stream_t stream);
 int st_clip_adam(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
                  float eps, int64_t step, float max_norm, const double* normsq, float grad_prescale,
                  st_stream_t stream);

@@ -45,7 +45,7 @@ _SIGNATURES = {
   'st_conv1d_fwd_f32': (c_int, [P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P]),
   'st_conv1d_bwd_data_f32': (c_int, [P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, P]),
   'st_conv1d_bwd_filter_f32': (c_int, [P, P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, P]),
-  'st_sumsq': (c_int, [P, c_int64, P, P]),
+  'st_sumsq': (c_int, [P, c_int64, P, c_int, P]),
   'st_clip_adam': (c_int, [P, P, P, P, c_int64, c_float, c_float, c_float, c_float, c_int64, c_float, P, c_float, P]),
   'st_melspec_workspace_bytes': (c_size_t, [c_int, c_int, c_int, c_int, c_int]),
   'st_melspec': (c_int, [P, c_int64, P, c_int, c_int, P, c_int, c_int, c_int, P, c_int, P, P, c_size_t, P]),

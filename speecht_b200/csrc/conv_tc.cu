@@ -257,8 +257,8 @@ template <> struct Products<3> {
 // 2*pair + r), the leader (rank 0) issues tcgen05.mma.cta_group::2 with M = 256 for both.
 template <int BLOCK_N, int NPL, bool EARLY, int NPROB, bool PAIR>
 __global__ void __launch_bounds__(kThreads, 1)
-tc_conv_kernel(const __grid_constant__ std::conditional_t<NPROB == 1, TmSet1, TmSet3> tmAs,
-               const __grid_constant__ std::conditional_t<NPROB == 1, TmSet1, TmSet3> tmBs,
+tc_conv_kernel(const __grid_constant__ std::conditional_t<NPROB == 1, TmSet1, TmSetN> tmAs,
+               const __grid_constant__ std::conditional_t<NPROB == 1, TmSet1, TmSetN> tmBs,
                const __grid_constant__ CUtensorMap tmOut, const ConvParams p) {
   using Cfg = ConvCfg<BLOCK_N, NPL, PAIR>;
   constexpr int STAGES = Cfg::STAGES;
@@ -706,8 +706,8 @@ struct WgradCfg {
 
 template <int BLOCK_N, int NPL, int NPROB>
 __global__ void __launch_bounds__(kThreads, 1)
-tc_wgrad_kernel(const __grid_constant__ std::conditional_t<NPROB == 1, TmSet1, TmSet3> tmXs,
-                const __grid_constant__ std::conditional_t<NPROB == 1, TmSet1, TmSet3> tmDZs,
+tc_wgrad_kernel(const __grid_constant__ std::conditional_t<NPROB == 1, TmSet1, TmSetN> tmXs,
+                const __grid_constant__ std::conditional_t<NPROB == 1, TmSet1, TmSetN> tmDZs,
                 const WgradParams p) {
   using Cfg = WgradCfg<BLOCK_N, NPL>;
   constexpr int STAGES = Cfg::STAGES;
@@ -1015,17 +1015,16 @@ pack_filter_both_kernel(const PackTable tab) {
 #pragma unroll
   for (int r = 0; r < 64; r += 8) {
     const int ci = ci0 + r + ty;
-    // tap_mode: 0 = tap k of the source; 1 / 2 = its even / odd taps (2k, 2k+1); 3 = their sum (fast-FIR filters)
-    const int ksrc = e.tap_mode == 0 ? k : (e.tap_mode == 2 ? 2 * k + 1 : 2 * k);
-    const float* src = e.w + ((int64_t)ksrc * e.Cin + ci) * e.Cout + co0;
+    // packed tap k = sum of the source taps tap_group * k + c over the set bits c of tap_mask (fast-FIR filters)
     const int64_t tap = (int64_t)e.Cin * e.Cout;
+    const float* src = e.w + ((int64_t)(e.tap_group * k) * e.Cin + ci) * e.Cout + co0;
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
       const int c = tx + 32 * h;
       float v = 0.f;
       if (ci < e.Cin && co0 + c < e.Cout) {
-        v = __ldg(src + c);
-        if (e.tap_mode == 3) v += __ldg(src + tap + c);
+        for (int g = 0; g < e.tap_group; ++g)
+          if (e.tap_mask & (1 << g)) v += __ldg(src + g * tap + c);
       }
       tile[r + ty][c] = v;
     }
@@ -1313,6 +1312,262 @@ ffa_dw_combine_kernel(float* __restrict__ dW, const float* __restrict__ cs, int 
   }
 }
 
+// ---- two levels of the fast-FIR split (nine quarter-rate 8-tap problems; algebra: tools/ffa2_study.py) --------------
+// Leaf order everywhere: 0 XX, 1 XY, 2 XZ, 3 YX, 4 YY, 5 YZ, 6 ZX, 7 ZY, 8 ZZ (first letter: level-1 product X1 = odd
+// rows (*) even taps, Y1 = even rows (*) odd taps, Z1 = pair sums (*) tap sums; second letter: the same split inside it).
+struct Ptr9f { float* p[9]; };
+struct Ptr9c { const float* p[9]; };
+struct Ptr9h { __nv_bfloat16* p[9]; };
+
+__device__ __forceinline__ void load_merged8(const __nv_bfloat16* base, int64_t plane, int npl, float* v) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = 0.f;
+  for (int pl = npl - 1; pl >= 0; --pl) {
+    const uint4 q = *reinterpret_cast<const uint4*>(base + pl * plane);
+    const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      v[2 * i] += __uint_as_float(w[i] << 16);
+      v[2 * i + 1] += __uint_as_float(w[i] & 0xffff0000u);
+    }
+  }
+}
+
+// The five quarter-rate input sequences that are sums (the other four leaves read row views x[4r+c] directly):
+//   s[0][r] = x[4r-1] + x[4r+1]   (leaf XZ)      s[1][r] = x[4r] + x[4r+2]     (leaf YZ)
+//   s[2][r] = x[4r+2] + x[4r+3]   (leaf ZX)      s[3][r] = x[4r] + x[4r+1]     (leaf ZY)
+//   s[4][r] = s[3][r] + s[2][r]   (leaf ZZ)      x = 0 outside [0, T); planes [NPL][B][Tq][ld]
+template <int NPL>
+__global__ void __launch_bounds__(256)
+ffa2_inputs_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* s0, __nv_bfloat16* s1, __nv_bfloat16* s2,
+                   __nv_bfloat16* s3, __nv_bfloat16* s4, int B, int T, int Tq, int ld) {
+  const int cg = ld / 8;
+  const int64_t groups = (int64_t)B * Tq * cg;
+  const int64_t in_plane = (int64_t)B * T * ld, out_plane = (int64_t)B * Tq * ld;
+  for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < groups; g += (int64_t)gridDim.x * blockDim.x) {
+    const int c8 = (int)(g % cg);
+    const int64_t br = g / cg;
+    const int r = (int)(br % Tq);
+    const int b = (int)(br / Tq);
+    float v[5][8];                                   // rows 4r-1 .. 4r+3
+#pragma unroll
+    for (int h = 0; h < 5; ++h) {
+      const int t = 4 * r - 1 + h;
+      if (t >= 0 && t < T) load_merged8(x + ((int64_t)b * T + t) * ld + c8 * 8, in_plane, NPL, v[h]);
+      else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[h][i] = 0.f;
+      }
+    }
+    float o[5][8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      o[0][i] = v[0][i] + v[2][i];
+      o[1][i] = v[1][i] + v[3][i];
+      o[2][i] = v[3][i] + v[4][i];
+      o[3][i] = v[1][i] + v[2][i];
+      o[4][i] = o[3][i] + o[2][i];
+    }
+    const int64_t off = ((int64_t)b * Tq + r) * ld + c8 * 8;
+    store_planes8<NPL>(s0 + off, out_plane, o[0]);
+    store_planes8<NPL>(s1 + off, out_plane, o[1]);
+    store_planes8<NPL>(s2 + off, out_plane, o[2]);
+    store_planes8<NPL>(s3 + off, out_plane, o[3]);
+    store_planes8<NPL>(s4 + off, out_plane, o[4]);
+  }
+}
+
+// Forward combine: X1[2q] = XX[q] + XY[q], X1[2q+1] = XZ[q] - XY[q] - XX[q+1] (likewise Y1, Z1), then
+// y[2u] = X1[u] + Y1[u], y[2u+1] = Z1[u] - Y1[u] - X1[u+1]; + bias, ReLU, plane split.  Partials fp32 [B][Tq][ld_p];
+// one thread per 8 channels of one q (four output rows 4q .. 4q+3).
+template <int NPL>
+__global__ void __launch_bounds__(256)
+ffa2_combine_kernel(const Ptr9c part, const float* __restrict__ bias, int relu, __nv_bfloat16* __restrict__ out, int B,
+                    int To, int Tq, int N, int ld_p, int ld_out) {
+  const int cg = ld_out / 8;
+  const int64_t groups = (int64_t)B * Tq * cg;
+  const int64_t out_plane = (int64_t)B * To * ld_out;
+  for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < groups; g += (int64_t)gridDim.x * blockDim.x) {
+    const int c8 = (int)(g % cg);
+    const int64_t bq = g / cg;
+    const int q = (int)(bq % Tq);
+    const int b = (int)(bq / Tq);
+    if (4 * q >= To) continue;
+    const int64_t row = ((int64_t)b * Tq + q) * ld_p + c8 * 8;
+    const bool nxt = q + 1 < Tq;
+    float y[4][8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const bool ok = c8 * 8 + i < N;
+      float a[9], an[9];
+#pragma unroll
+      for (int l = 0; l < 9; ++l) a[l] = ok ? part.p[l][row + i] : 0.f;
+      // rows q+1 of the leaves that enter shifted: XX, XY (for X1[2q+2]), YX, ZX
+      an[0] = (ok && nxt) ? part.p[0][row + ld_p + i] : 0.f;
+      an[1] = (ok && nxt) ? part.p[1][row + ld_p + i] : 0.f;
+      an[3] = (ok && nxt) ? part.p[3][row + ld_p + i] : 0.f;
+      an[6] = (ok && nxt) ? part.p[6][row + ld_p + i] : 0.f;
+      const float x1e = a[0] + a[1], x1o = a[2] - a[1] - an[0], x1n = an[0] + an[1];
+      const float y1e = a[3] + a[4], y1o = a[5] - a[4] - an[3];
+      const float z1e = a[6] + a[7], z1o = a[8] - a[7] - an[6];
+      const float bv = (ok && bias) ? __ldg(bias + c8 * 8 + i) : 0.f;
+      y[0][i] = x1e + y1e + bv;
+      y[1][i] = z1e - y1e - x1o + bv;
+      y[2][i] = x1o + y1o + bv;
+      y[3][i] = z1o - y1o - x1n + bv;
+#pragma unroll
+      for (int h = 0; h < 4; ++h) {
+        if (relu) y[h][i] = fmaxf(y[h][i], 0.f);
+        if (!ok) y[h][i] = 0.f;
+      }
+    }
+    __nv_bfloat16* o = out + ((int64_t)b * To + 4 * q) * ld_out + c8 * 8;
+#pragma unroll
+    for (int h = 0; h < 4; ++h)
+      if (4 * q + h < To) store_planes8<NPL>(o + h * ld_out, out_plane, y[h]);
+  }
+}
+
+// Backward prepare: gradients of the nine leaf products from dy (planes [NPL][B][To][ld]), planes [NPL][B][Tq][ld]:
+// level 1: GX[u] = dy[2u] - dy[2u-1], GY[u] = dy[2u] - dy[2u+1], GZ[u] = dy[2u+1]; level 2 of each G:
+// d?X[q] = G[2q] - G[2q-1], d?Y[q] = G[2q] - G[2q+1], d?Z[q] = G[2q+1]  (dy = 0 outside [0, To)).
+template <int NPL>
+__global__ void __launch_bounds__(256)
+ffa2_dz_prep_kernel(const __nv_bfloat16* __restrict__ dy, const Ptr9h out, int B, int To, int Tq, int ld) {
+  const int cg = ld / 8;
+  const int64_t groups = (int64_t)B * Tq * cg;
+  const int64_t in_plane = (int64_t)B * To * ld, out_plane = (int64_t)B * Tq * ld;
+  for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < groups; g += (int64_t)gridDim.x * blockDim.x) {
+    const int c8 = (int)(g % cg);
+    const int64_t bq = g / cg;
+    const int q = (int)(bq % Tq);
+    const int b = (int)(bq / Tq);
+    float d[7][8];                                   // dy rows 4q-3 .. 4q+3
+#pragma unroll
+    for (int h = 0; h < 7; ++h) {
+      const int t = 4 * q - 3 + h;
+      if (t >= 0 && t < To) load_merged8(dy + ((int64_t)b * To + t) * ld + c8 * 8, in_plane, NPL, d[h]);
+      else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) d[h][i] = 0.f;
+      }
+    }
+    const int64_t off = ((int64_t)b * Tq + q) * ld + c8 * 8;
+    float o[8];
+    // G(2q-1), G(2q), G(2q+1) of the three level-1 gradients, from rows d[k+3] = dy[4q+k]
+#pragma unroll
+    for (int lvl = 0; lvl < 3; ++lvl) {
+      float gm[8], g0[8], gp[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        if (lvl == 0) { gm[i] = d[1][i] - d[0][i]; g0[i] = d[3][i] - d[2][i]; gp[i] = d[5][i] - d[4][i]; }
+        else if (lvl == 1) { gm[i] = d[1][i] - d[2][i]; g0[i] = d[3][i] - d[4][i]; gp[i] = d[5][i] - d[6][i]; }
+        else { gm[i] = d[2][i]; g0[i] = d[4][i]; gp[i] = d[6][i]; }
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) o[i] = g0[i] - gm[i];
+      store_planes8<NPL>(out.p[3 * lvl + 0] + off, out_plane, o);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) o[i] = g0[i] - gp[i];
+      store_planes8<NPL>(out.p[3 * lvl + 1] + off, out_plane, o);
+      store_planes8<NPL>(out.p[3 * lvl + 2] + off, out_plane, gp);
+    }
+  }
+}
+
+// Data-gradient combine of the nine leaf partials g[l] (fp32 [B][Tqx][ldp]):
+//   dx[4r]   = gYY[r] + gYZ[r] + gZY[r] + gZZ[r]        dx[4r+1] = gXX[r] + gXZ[r]   + gZY[r] + gZZ[r]
+//   dx[4r+2] = gYX[r] + gYZ[r] + gZX[r] + gZZ[r]        dx[4r+3] = gXY[r] + gXZ[r+1] + gZX[r] + gZZ[r]
+// times the ReLU mask of the layer below, split to planes [NPL][B][T][ld]; column sums into db.
+template <int NPL>
+__global__ void __launch_bounds__(256)
+ffa2_dx_combine_kernel(const Ptr9c gp, const __nv_bfloat16* __restrict__ mask, __nv_bfloat16* __restrict__ out,
+                       float* __restrict__ db, int B, int T, int Tqx, int N, int ldp, int ld, int rows_per_block) {
+  __shared__ float part[8][32 * 8 + 1];
+  const int c8 = threadIdx.x;
+  const int64_t rows = (int64_t)B * Tqx;
+  const int64_t r0 = (int64_t)blockIdx.x * rows_per_block, r1 = min(rows, r0 + rows_per_block);
+  const int64_t out_plane = (int64_t)B * T * ld;
+  float acc[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+  if (c8 * 8 < ld) {
+    for (int64_t br = r0 + threadIdx.y; br < r1; br += 8) {
+      const int b = (int)(br / Tqx), r = (int)(br - (int64_t)b * Tqx);
+      if (4 * r >= T) continue;
+      const int64_t prow = br * ldp + c8 * 8;
+      float g[9][8], gxz_n[8];
+#pragma unroll
+      for (int l = 0; l < 9; ++l) {
+#pragma unroll
+        for (int i = 0; i < 8; i += 4) {
+          const float4 a = *reinterpret_cast<const float4*>(gp.p[l] + prow + i);
+          g[l][i] = a.x; g[l][i + 1] = a.y; g[l][i + 2] = a.z; g[l][i + 3] = a.w;
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 8; i += 4) {
+        float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (r + 1 < Tqx) a = *reinterpret_cast<const float4*>(gp.p[2] + prow + ldp + i);
+        gxz_n[i] = a.x; gxz_n[i + 1] = a.y; gxz_n[i + 2] = a.z; gxz_n[i + 3] = a.w;
+      }
+#pragma unroll
+      for (int h = 0; h < 4; ++h) {
+        const int t = 4 * r + h;
+        if (t >= T) continue;
+        const int64_t orow = ((int64_t)b * T + t) * ld + c8 * 8;
+        const uint4 mq = *reinterpret_cast<const uint4*>(mask + orow);
+        const uint32_t mw[4] = {mq.x, mq.y, mq.z, mq.w};
+        float v[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const uint32_t hbits = (i & 1) ? (mw[i >> 1] >> 16) : (mw[i >> 1] & 0xffffu);
+          const bool keep = (hbits - 1u) < 0x7fffu && c8 * 8 + i < N;
+          float s;
+          if (h == 0) s = (g[4][i] + g[5][i]) + (g[7][i] + g[8][i]);
+          else if (h == 1) s = (g[0][i] + g[2][i]) + (g[7][i] + g[8][i]);
+          else if (h == 2) s = (g[3][i] + g[5][i]) + (g[6][i] + g[8][i]);
+          else s = (g[1][i] + gxz_n[i]) + (g[6][i] + g[8][i]);
+          v[i] = keep ? s : 0.f;
+          acc[i] += v[i];
+        }
+        store_planes8<NPL>(out + orow, out_plane, v);
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) part[threadIdx.y][threadIdx.x * 8 + i] = acc[i];
+  __syncthreads();
+  const int tid = threadIdx.y * 32 + threadIdx.x;
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s += part[i][tid];
+  if (tid < N) atomicAdd(db + tid, s);
+}
+
+// Filter-gradient combine of the nine leaf correlations c[l] ([J][tap] fp32, J = taps / 4):
+//   dW[4i]   = cXX + cXZ + cZX + cZZ      dW[4i+1] = cYX + cYZ + cZX + cZZ
+//   dW[4i+2] = cXY + cXZ + cZY + cZZ      dW[4i+3] = cYY + cYZ + cZY + cZZ
+__global__ void __launch_bounds__(256)
+ffa2_dw_combine_kernel(float* __restrict__ dW, const Ptr9c c, int J, int64_t tap_elems4) {
+  const int64_t total = (int64_t)J * tap_elems4;
+  float4* w4 = reinterpret_cast<float4*>(dW);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t j = i / tap_elems4, e = i - j * tap_elems4;
+    float4 v[9];
+#pragma unroll
+    for (int l = 0; l < 9; ++l) v[l] = reinterpret_cast<const float4*>(c.p[l])[i];
+    auto add4 = [](float4 a, float4 b, float4 cc, float4 d) {
+      return make_float4((a.x + b.x) + (cc.x + d.x), (a.y + b.y) + (cc.y + d.y), (a.z + b.z) + (cc.z + d.z),
+                         (a.w + b.w) + (cc.w + d.w));
+    };
+    w4[(4 * j + 0) * tap_elems4 + e] = add4(v[0], v[2], v[6], v[8]);
+    w4[(4 * j + 1) * tap_elems4 + e] = add4(v[3], v[5], v[6], v[8]);
+    w4[(4 * j + 2) * tap_elems4 + e] = add4(v[1], v[2], v[7], v[8]);
+    w4[(4 * j + 3) * tap_elems4 + e] = add4(v[4], v[5], v[7], v[8]);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ host side
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -1373,9 +1628,9 @@ cudaError_t launch_pdl(Kernel kernel, int grid, int smem, cudaStream_t stream, c
   return launch_pdl_cluster(kernel, grid, 1, smem, stream, args...);
 }
 
-// CTA-pair (cta_group::2) tiles for the 256-wide forward / data-gradient launches: SPEECHT_B200_PAIR=1 enables them
+// CTA-pair (cta_group::2) tiles for the 256-wide forward / data-gradient launches (SPEECHT_B200_PAIR=0 disables them)
 bool pair_enabled() {
-  static const bool on = []() { const char* e = getenv("SPEECHT_B200_PAIR"); return e && e[0] == '1'; }();
+  static const bool on = []() { const char* e = getenv("SPEECHT_B200_PAIR"); return !(e && e[0] == '0'); }();
   return on;
 }
 
@@ -1425,7 +1680,7 @@ int launch_conv_multi_t(const CUtensorMap* tmA, const CUtensorMap* tmB, const Co
   ConvParams p = p0;
   p.tma_store = 0;
   p.timeline = nullptr;
-  TmSet3 a, b;
+  TmSetN a, b;
   for (int q = 0; q < kMaxProblems; ++q) {
     a.m[q] = tmA[q < p.n_problems ? q : 0];
     b.m[q] = tmB[q < p.n_problems ? q : 0];
@@ -1510,7 +1765,7 @@ int launch_wgrad_multi_t(const CUtensorMap* tmX, const CUtensorMap* tmDZ, const 
                                       cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     configured[dev] = true;
   }
-  TmSet3 x, dz;
+  TmSetN x, dz;
   for (int q = 0; q < kMaxProblems; ++q) {
     x.m[q] = tmX[q < p.n_problems ? q : 0];
     dz.m[q] = tmDZ[q < p.n_problems ? q : 0];
@@ -1521,8 +1776,12 @@ int launch_wgrad_multi_t(const CUtensorMap* tmX, const CUtensorMap* tmDZ, const 
 
 }  // namespace
 
-bool want_pair(int m_tiles, int n_tiles, int block_n, int n_planes, bool multi) {
+bool want_pair(int m_tiles, int n_tiles, int block_n, int n_planes, bool multi, int k_iters) {
   if (!pair_enabled() || block_n != 256 || n_planes > 2 || m_tiles < 2) return false;
+  // Measured same-box (profiles/r02_pair_ab_session7.txt): split modes gain on every eligible launch (layer-8 / layer-9
+  // data gradients -5 %, forward neutral); in plain bf16 a pair tile's hand-offs between the two CTAs only pay off on
+  // long contractions -- layer 8 gains 3-10 %, the 32-iteration layer-9 tiles lose 5-9 % and stay on single CTAs.
+  if (n_planes == 1 && k_iters < 64) return false;
   return multi || m_tiles * n_tiles > st_num_sms();
 }
 

@@ -42,12 +42,12 @@ struct ConvParams {
   int pair;
   int n_problems;                // 0 / 1: single problem (the fields above); 2..kMaxProblems: use the arrays below
   int k_split;                   // 0 / 1: whole contraction per tile
-  int pad_left_q[3];
-  float* out_f32_q[3];
+  int pad_left_q[9];
+  float* out_f32_q[9];
 };
-constexpr int kMaxProblems = 3;
+constexpr int kMaxProblems = 9;   // three for one level of the fast-FIR split, nine for two
 struct TmSet1 { CUtensorMap m[1]; };
-struct TmSet3 { CUtensorMap m[kMaxProblems]; };
+struct TmSetN { CUtensorMap m[kMaxProblems]; };
 
 // ---- filter-gradient kernel: dW[j, ci, co] += sum_{b,t} X[b, t+shift_j, acol_j + ci] * dZ[b, t, co]
 struct WgradParams {
@@ -60,9 +60,9 @@ struct WgradParams {
   // ---- several problems of identical shape in one launch (launch_wgrad_multi; fast-FIR split of layer 8): problem q
   // correlates X[q] with dZ[q] using its own left padding and writes tap j to dW_q[q] + j * tap_stride_q[q] * Cin * Cout
   int n_problems;                // 0 / 1: single problem
-  int pad_left_q[3];
-  float* dW_q[3];
-  int tap_stride_q[3];
+  int pad_left_q[9];
+  float* dW_q[9];
+  int tap_stride_q[9];
 };
 
 int make_map_3d(CUtensorMap* map, const void* base, int C, int T, int Bn, int64_t ld, int64_t batch_stride,
@@ -79,9 +79,10 @@ void set_conv_timeline(long long* buf, int launch_index);
 int launch_conv(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap* tmOut, const ConvParams& p,
                 int block_n, int n_planes, cudaStream_t stream);
 // Should a forward / data-gradient launch of m_tiles x n_tiles tiles (256 wide, 1-2 planes) run on CTA pairs?
-// SPEECHT_B200_PAIR=1 enables them; single launches need more tiles than SMs (the 250-channel layers have one tile
-// per SM and nothing to share), multi-problem launches at least two m tiles.
-bool want_pair(int m_tiles, int n_tiles, int block_n, int n_planes, bool multi);
+// On by default (SPEECHT_B200_PAIR=0 disables them); single launches need more tiles than SMs (the 250-channel layers
+// have one tile per SM and nothing to share), multi-problem launches at least two m tiles; k_iters = pipeline
+// iterations (64-deep K chunks) per tile.
+bool want_pair(int m_tiles, int n_tiles, int block_n, int n_planes, bool multi, int k_iters);
 int launch_wgrad(const CUtensorMap& tmX, const CUtensorMap& tmDZ, const WgradParams& p, int block_n, int n_planes,
                  cudaStream_t stream);
 int launch_wgrad_multi(const CUtensorMap* tmX, const CUtensorMap* tmDZ, const WgradParams& p, int block_n,
@@ -102,11 +103,13 @@ struct PackEntry {
   __nv_bfloat16* bwd;
   int K, Cin, Cout, cin_p, ld_co;
   int blk0;                      // first block of this layer, filled by launch_pack_filters
-  int tap_mode;                  // 0: pack tap k of w; 1 / 2: its even / odd taps; 3: even + odd (w then holds 2K taps)
+  // packed tap k = sum over the set bits c of tap_mask of source tap (tap_group * k + c): plain packing is group 1,
+  // mask 1; the fast-FIR filters are group 2 (masks 1, 2, 3 = even taps, odd taps, their sum) or group 4
+  int tap_group, tap_mask;
 };
 struct PackTable {
   int n;
-  PackEntry e[16];
+  PackEntry e[20];
 };
 int launch_pack_filters(PackTable& tab, int n_planes, cudaStream_t stream, int* launches);
 // ---- fast-FIR split of a stride-1 layer (experimental, see w2l_plan.cu)

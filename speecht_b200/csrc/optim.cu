@@ -69,9 +69,11 @@ clip_adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __re
 
 }  // namespace
 
-ST_API int st_sumsq(const float* g, int64_t n, double* accum, st_stream_t stream) {
+ST_API int st_sumsq(const float* g, int64_t n, double* accum, int zero_first, st_stream_t stream) {
   ST_CHECK_ARG(g && accum && n >= 0, "st_sumsq: bad argument");
   ST_CHECK_ARG((reinterpret_cast<uintptr_t>(g) & 15) == 0, "st_sumsq: buffer must be 16-byte aligned");
+  // zero_first: *accum = 0 on the stream before the blocks add into it (a memset node, not a separate kernel)
+  if (zero_first) ST_CUDA_CALL(cudaMemsetAsync(accum, 0, sizeof(double), st_cu(stream)));
   if (n == 0) return ST_OK;
   int blocks = (int)((n / 4 + 255) / 256);
   const int cap = 8 * st_num_sms();

@@ -229,7 +229,7 @@ ST_API int st_plan_bind(st_plan* p, void* arena, size_t arena_bytes, float* para
     }
     if (rc) return rc;
     L.pair_fwd = tc::want_pair(B * ((L.To + tc::kTileM - 1) / tc::kTileM), (L.Cout + block_n - 1) / block_n, block_n,
-                               npl, false);
+                               npl, false, L.K * (L.cin_p / 64));
     rc = tc::make_map_2d(&L.tm_fwd_b, bf(p, L.off_wfwd), L.K * L.cin_p, npl * L.Cout, (int64_t)L.K * L.cin_p, 64,
                          L.pair_fwd ? block_n / 2 : block_n);
     if (rc) return rc;
@@ -259,7 +259,7 @@ ST_API int st_plan_bind(st_plan* p, void* arena, size_t arena_bytes, float* para
     if (l > 0) {
       L.pair_dg = !(l == 10 && p->l10_n128) &&
                   tc::want_pair(B * ((L.Ti + tc::kTileM - 1) / tc::kTileM), (L.Cin + wide_n(p) - 1) / wide_n(p),
-                                wide_n(p), npl, false);
+                                wide_n(p), npl, false, L.K * (l == 10 ? 1 : (L.Cout + 63) / 64));
       rc = tc::make_map_2d(&L.tm_dg_b, bf(p, L.off_wbwd), l == 10 ? 64 : L.Cout, npl * L.K * L.Cin, L.ld_co, 64,
                            L.pair_dg ? wide_n(p) / 2 : wide_n(p));
       if (rc) return rc;
@@ -290,8 +290,10 @@ ST_API int st_plan_bind(st_plan* p, void* arena, size_t arena_bytes, float* para
     // the pair-sum planes; B operands: the packed even-tap, odd-tap and summed filters (forward layout, 16 taps)
     Layer& L8 = p->layers[8];
     const __nv_bfloat16* x = act_in(p, 8);
-    p->ffa_pair_fwd = tc::want_pair(B * ((p->ffa_Tu + tc::kTileM - 1) / tc::kTileM), 1, wide_n(p), npl, true);
-    p->ffa_pair_dg = tc::want_pair(B * ((p->ffa_Tx + tc::kTileM - 1) / tc::kTileM), 1, wide_n(p), npl, true);
+    p->ffa_pair_fwd = tc::want_pair(B * ((p->ffa_Tu + tc::kTileM - 1) / tc::kTileM), 1, wide_n(p), npl, true,
+                                    (L8.K / 2) * (L8.cin_p / 64));
+    p->ffa_pair_dg = tc::want_pair(B * ((p->ffa_Tx + tc::kTileM - 1) / tc::kTileM), 1, wide_n(p), npl, true,
+                                   (L8.K / 4) * ((L8.Cout + 63) / 64));
     rc = tc::make_map_3d(&p->tm_ffa_a[0], x + L8.ld_in, L8.Cin, L8.Ti / 2, npl * B, 2 * L8.ld_in,
                          (int64_t)L8.Ti * L8.ld_in, 64, 128);
     if (rc) return rc;
@@ -345,11 +347,11 @@ int pack_layers(st_plan* p, cudaStream_t s) {
       // operand layouts straight from the 32-tap fp32 tensor; the direct 32-tap layouts are then not needed
       for (int i = 0; i < 3; ++i)
         tab.e[tab.n++] = tc::PackEntry{p->params + L8.w_off, bf(p, p->off_ffa_w[i]), bf(p, p->off_ffa_wb[i]), L8.K / 2,
-                                       L8.Cin, L8.Cout, L8.cin_p, L8.ld_co, 0, i + 1};
+                                       L8.Cin, L8.Cout, L8.cin_p, L8.ld_co, 0, 2, i + 1};
       continue;
     }
     tab.e[tab.n++] = tc::PackEntry{p->params + L.w_off, bf(p, L.off_wfwd), l > 0 ? bf(p, L.off_wbwd) : nullptr,
-                                   L.K, L.Cin, L.Cout, L.cin_p, L.ld_co, 0, 0};
+                                   L.K, L.Cin, L.Cout, L.cin_p, L.ld_co, 0, 1, 1};
   }
   int n = 0;
   const int rc = tc::launch_pack_filters(tab, p->npl, s, &n);

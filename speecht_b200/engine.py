@@ -29,6 +29,24 @@ from ._lib import check, lib, ptr, stream_ptr
 PRECISIONS = ('fp32', 'bf16x6', 'bf16x3', 'bf16')
 
 
+class BatchMean:
+  """tf.reduce_mean(cost) (speech_model.py:75) of the per-utterance losses, evaluated WHEN READ: the step itself
+  launches no reduction kernel; .item() copies the [B] losses to the host (4*B bytes) and averages them in float32."""
+
+  def __init__(self, loss):
+    self.loss = loss
+
+  def item(self):
+    return float(self.loss.detach().cpu().numpy().mean(dtype=np.float32))
+
+  def __float__(self):
+    return self.item()
+
+  def tensor(self):
+    """Device scalar (for collectives such as parallel.mean_scalar)."""
+    return self.loss.mean()
+
+
 def _on_engine_device(fn):
   """The native calls launch on torch's CURRENT device and stream: run the method with the engine's own device
   current, so an engine created for cuda:1 works while cuda:0 is the process default."""
@@ -321,7 +339,7 @@ class W2LEngine:
       loss, _ = ops.ctc_loss(labels, logits, ctc_len, want_grad=False)
       self.launches += 2
       out['loss'] = loss
-      out['avg_loss'] = loss.mean()
+      out['avg_loss'] = BatchMean(loss)
     if decode:
       out['decoded'], out['neg_sum_logits'] = ops.ctc_greedy_decoder(logits, ctc_len)
       self.launches += 1
@@ -351,7 +369,7 @@ class W2LEngine:
     scale = 1.0 / (B * self.world_size)                                # tf.reduce_mean folded into the gradient
     loss, dlogits = ops.ctc_loss(batch, logits, want_grad=True, grad_scale=scale)
     self.launches += 3
-    out = {'loss': loss, 'avg_loss': loss.mean(), 'decoded': None, 'logits': logits}
+    out = {'loss': loss, 'avg_loss': BatchMean(loss), 'decoded': None, 'logits': logits}
     if decode:
       out['decoded'], out['neg_sum_logits'] = ops.ctc_greedy_decoder(logits, ctc_len)
       self.launches += 1
@@ -378,8 +396,7 @@ class W2LEngine:
     if not reduced:
       self.allreduce_gradients()
     self.global_step += 1
-    self._normsq.zero_()
-    ops.global_norm_sq(self.grads, self._normsq)
+    ops.global_norm_sq(self.grads, self._normsq, zero=True)
     ops.clip_adam(self.params, self.grads, self.adam_m, self.adam_v, self.global_step, learning_rate,
                   max_norm=max_gradient_norm, normsq=self._normsq)
     self.launches += 2

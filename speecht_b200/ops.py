@@ -228,12 +228,13 @@ def sparse_from_rows(values, counts):
 # ------------------------------------------------------------------------------------------------
 # optimiser
 # ------------------------------------------------------------------------------------------------
-def global_norm_sq(flat_grads, accum=None):
-  """sum(g^2) over the flat gradient buffer (first half of tf.clip_by_global_norm, speech_model.py:80)."""
+def global_norm_sq(flat_grads, accum=None, zero=False):
+  """sum(g^2) over the flat gradient buffer (first half of tf.clip_by_global_norm, speech_model.py:80).
+  accum: device double that the sum is ADDED to (zero=True clears it first, on the stream); None: a fresh one."""
   _require_cuda(flat_grads)
   if accum is None:
-    accum = torch.zeros((1,), dtype=torch.float64, device=flat_grads.device)
-  check(lib().st_sumsq(ptr(flat_grads), flat_grads.numel(), ptr(accum), stream_ptr()))
+    accum, zero = torch.empty((1,), dtype=torch.float64, device=flat_grads.device), True
+  check(lib().st_sumsq(ptr(flat_grads), flat_grads.numel(), ptr(accum), int(bool(zero)), stream_ptr()))
   return accum
 
 

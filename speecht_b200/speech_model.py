@@ -303,7 +303,7 @@ class SpeechModel:
       self._prefetch_next()                     # next batch's H2D overlaps this step's kernels
     output = []
     if loss:
-      output.append(np.float32(res['avg_loss'].item()))       # the device->host read of the step's result
+      output.append(np.float32(res['avg_loss'].item()))       # the device->host read of the step's result ([B] losses)
     if decode:
       output.append(res['decoded'])
     if return_label:

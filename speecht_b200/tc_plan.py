@@ -155,7 +155,8 @@ class TCPlan:
     scale = 1.0 / (B * eng.world_size)
     loss, _ = ops.ctc_loss(batch, logits, want_grad=False, grad_scale=scale, grad_planes=sh.dlogits_planes)
     eng.launches += 3
-    out = {'loss': loss, 'avg_loss': loss.mean(), 'decoded': None, 'logits': logits}
+    from .engine import BatchMean
+    out = {'loss': loss, 'avg_loss': BatchMean(loss), 'decoded': None, 'logits': logits}
     if decode:
       out['decoded'], out['neg_sum_logits'] = ops.ctc_greedy_decoder(logits, ctc_len)
       eng.launches += 1

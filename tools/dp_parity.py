@@ -30,7 +30,7 @@ def main():
   losses = []
   for _ in range(2):
     res = eng.train_step(torch.from_numpy(inputs[a:b]).cuda(), lengths[a:b], labels[a:b], 1e-3)
-    losses.append(parallel.mean_scalar(res['avg_loss']).item())
+    losses.append(parallel.mean_scalar(res['avg_loss'].tensor()).item())
   flat = eng.params.clone()
   # every rank must hold bit-identical parameters (same reduced gradient, same update)
   gathered = [torch.empty_like(flat) for _ in range(world)]

@@ -1997,6 +1997,87 @@ int launch_ffa_dw_combine(float* dW, const float* cs, int J, int64_t tap_elems, 
   return ST_OK;
 }
 
+namespace {
+int ew_blocks(int64_t groups) {
+  int blocks = (int)((groups + 255) / 256);
+  const int cap = 16 * st_num_sms();
+  return blocks > cap ? cap : (blocks < 1 ? 1 : blocks);
+}
+}  // namespace
+
+int launch_ffa2_inputs(const __nv_bfloat16* x, __nv_bfloat16* const* s5, int B, int T, int Tq, int ld, int n_planes,
+                       cudaStream_t stream) {
+  ST_CHECK_ARG(ld % 8 == 0 && n_planes >= 1 && n_planes <= 2, "launch_ffa2_inputs: bad arguments");
+  const int blocks = ew_blocks((int64_t)B * Tq * (ld / 8));
+  if (n_planes == 2) ffa2_inputs_kernel<2><<<blocks, 256, 0, stream>>>(x, s5[0], s5[1], s5[2], s5[3], s5[4], B, T, Tq, ld);
+  else ffa2_inputs_kernel<1><<<blocks, 256, 0, stream>>>(x, s5[0], s5[1], s5[2], s5[3], s5[4], B, T, Tq, ld);
+  ST_CUDA_LAUNCH_CHECK("ffa2_inputs_kernel");
+  return ST_OK;
+}
+
+int launch_ffa2_combine(float* const* part9, const float* bias, int relu, __nv_bfloat16* out, int B, int To, int Tq,
+                        int N, int ld_p, int ld_out, int n_planes, cudaStream_t stream) {
+  ST_CHECK_ARG(ld_out % 8 == 0 && n_planes >= 1 && n_planes <= 2, "launch_ffa2_combine: bad arguments");
+  Ptr9c pp;
+  for (int l = 0; l < 9; ++l) pp.p[l] = part9[l];
+  const int blocks = ew_blocks((int64_t)B * Tq * (ld_out / 8));
+  if (n_planes == 2) ffa2_combine_kernel<2><<<blocks, 256, 0, stream>>>(pp, bias, relu, out, B, To, Tq, N, ld_p, ld_out);
+  else ffa2_combine_kernel<1><<<blocks, 256, 0, stream>>>(pp, bias, relu, out, B, To, Tq, N, ld_p, ld_out);
+  ST_CUDA_LAUNCH_CHECK("ffa2_combine_kernel");
+  return ST_OK;
+}
+
+int launch_ffa2_dz_prep(const __nv_bfloat16* dy, __nv_bfloat16* const* out9, int B, int To, int Tq, int ld, int n_planes,
+                        cudaStream_t stream) {
+  ST_CHECK_ARG(ld % 8 == 0 && n_planes >= 1 && n_planes <= 2, "launch_ffa2_dz_prep: bad arguments");
+  Ptr9h pp;
+  for (int l = 0; l < 9; ++l) pp.p[l] = out9[l];
+  const int blocks = ew_blocks((int64_t)B * Tq * (ld / 8));
+  if (n_planes == 2) ffa2_dz_prep_kernel<2><<<blocks, 256, 0, stream>>>(dy, pp, B, To, Tq, ld);
+  else ffa2_dz_prep_kernel<1><<<blocks, 256, 0, stream>>>(dy, pp, B, To, Tq, ld);
+  ST_CUDA_LAUNCH_CHECK("ffa2_dz_prep_kernel");
+  return ST_OK;
+}
+
+int launch_ffa2_dx_combine(float* const* g9, const __nv_bfloat16* mask, __nv_bfloat16* out, float* db, int B, int T,
+                           int Tqx, int N, int ldp, int ld, int n_planes, cudaStream_t stream) {
+  ST_CHECK_ARG(ld % 8 == 0 && ld <= 256 && ldp % 4 == 0 && ldp >= ld && n_planes >= 1 && n_planes <= 2,
+               "launch_ffa2_dx_combine: bad arguments");
+  Ptr9c pp;
+  for (int l = 0; l < 9; ++l) pp.p[l] = g9[l];
+  const int64_t rows = (int64_t)B * Tqx;
+  int blocks = (int)((rows + 7) / 8);
+  const int cap = 4 * st_num_sms();
+  blocks = blocks > cap ? cap : (blocks < 1 ? 1 : blocks);
+  const int rows_per_block = (int)((rows + blocks - 1) / blocks);
+  if (n_planes == 2)
+    ffa2_dx_combine_kernel<2><<<blocks, dim3(32, 8), 0, stream>>>(pp, mask, out, db, B, T, Tqx, N, ldp, ld, rows_per_block);
+  else
+    ffa2_dx_combine_kernel<1><<<blocks, dim3(32, 8), 0, stream>>>(pp, mask, out, db, B, T, Tqx, N, ldp, ld, rows_per_block);
+  ST_CUDA_LAUNCH_CHECK("ffa2_dx_combine_kernel");
+  return ST_OK;
+}
+
+int launch_ffa2_dw_combine(float* dW, float* const* c9, int J, int64_t tap_elems, cudaStream_t stream) {
+  ST_CHECK_ARG(tap_elems % 4 == 0, "launch_ffa2_dw_combine: tap size must be a multiple of 4 floats");
+  Ptr9c pp;
+  for (int l = 0; l < 9; ++l) pp.p[l] = c9[l];
+  ffa2_dw_combine_kernel<<<ew_blocks((int64_t)J * (tap_elems / 4)), 256, 0, stream>>>(dW, pp, J, tap_elems / 4);
+  ST_CUDA_LAUNCH_CHECK("ffa2_dw_combine_kernel");
+  return ST_OK;
+}
+
+// Does a filter-gradient launch of `num_tiles` tiles cut its last wave into K slices (which ACCUMULATE into dW, so the
+// outputs must be zero on entry)?  Mirrors the wave-aligned split of tc_wgrad_kernel.
+bool wgrad_accumulates(int num_tiles, int total_iters) {
+  const int G = st_num_sms();
+  const int tail_tiles = num_tiles % G;
+  if (tail_tiles == 0) return false;
+  const int cap = total_iters / 4 > 0 ? total_iters / 4 : 1;
+  const int split = G / tail_tiles < cap ? G / tail_tiles : cap;
+  return split > 1;
+}
+
 int launch_pack_filters(PackTable& tab, int n_planes, cudaStream_t stream, int* launches) {
   *launches = 0;
   int blocks = 0;

@@ -130,6 +130,23 @@ int launch_ffa_dx_combine(const float* d_odd, const float* d_even, const float* 
                           cudaStream_t stream);
 // dW[2j] += cs[j], dW[2j+1] += cs[j] for j < J; tap_elems = Cin*Cout
 int launch_ffa_dw_combine(float* dW, const float* cs, int J, int64_t tap_elems, cudaStream_t stream);
+// ---- two levels of the split: nine quarter-rate 8-tap problems (leaf order XX XY XZ YX YY YZ ZX ZY ZZ, conv_tc.cu)
+// the five summed input sequences s5[i] planes [n][B][Tq][ld] from x planes [n][B][T][ld]
+int launch_ffa2_inputs(const __nv_bfloat16* x, __nv_bfloat16* const* s5, int B, int T, int Tq, int ld, int n_planes,
+                       cudaStream_t stream);
+// nine fp32 partial products [B][Tq][ld_p] -> act(y + bias) planes [n][B][To][ld_out]
+int launch_ffa2_combine(float* const* part9, const float* bias, int relu, __nv_bfloat16* out, int B, int To, int Tq,
+                        int N, int ld_p, int ld_out, int n_planes, cudaStream_t stream);
+// dy planes [n][B][To][ld] -> gradients of the nine leaf products, planes [n][B][Tq][ld]
+int launch_ffa2_dz_prep(const __nv_bfloat16* dy, __nv_bfloat16* const* out9, int B, int To, int Tq, int ld, int n_planes,
+                        cudaStream_t stream);
+// nine fp32 input-gradient partials [B][Tqx][ldp] -> masked dx planes [n][B][T][ld] + column sums into db
+int launch_ffa2_dx_combine(float* const* g9, const __nv_bfloat16* mask, __nv_bfloat16* out, float* db, int B, int T,
+                           int Tqx, int N, int ldp, int ld, int n_planes, cudaStream_t stream);
+// nine fp32 leaf correlations [J][tap_elems] -> dW [4J][tap_elems]
+int launch_ffa2_dw_combine(float* dW, float* const* c9, int J, int64_t tap_elems, cudaStream_t stream);
+// true when a filter-gradient launch of num_tiles tiles accumulates into its outputs (they must then be zeroed)
+bool wgrad_accumulates(int num_tiles, int total_iters);
 // db[n] = sum over rows and planes of dz planes [n_planes][rows][ld]
 int launch_bias_grad(const __nv_bfloat16* dz, int64_t rows, int N, int ld, int n_planes, float* db,
                      cudaStream_t stream);

@@ -62,8 +62,14 @@ struct st_plan {
   // Fast-FIR split of the 32-tap layer 8 (65 % of the FLOPs): forward, data gradient and filter gradient each run
   // THREE half-rate 16-tap problems (75 % of the MMAs) in one persistent launch, plus elementwise prepare / combine
   // passes (index algebra and backward formulas checked on the CPU by tools/ffa_study.py).
-  // SPEECHT_B200_FFA=0 restores the direct 32-tap kernels; bf16x6 (three planes) always uses them.
-  bool ffa;
+  // TWO levels (the default): each of the three half-rate problems is split again -- nine quarter-rate 8-tap
+  // problems, 56 % of the MMAs (tools/ffa2_study.py).  `ffa` is the level in use: SPEECHT_B200_FFA=1 keeps one level,
+  // =0 restores the direct 32-tap kernels; bf16x6 (three planes) always uses the direct kernels.
+  int ffa;
+  int ffa2_Tq, ffa2_Tqi;                         // rows of the leaf products / of the quarter-rate input sequences
+  size_t off_ffa2_s[5], off_ffa2_w[9], off_ffa2_wb[9], off_ffa2_p[9], off_ffa2_dxp[9], off_ffa2_c[9];
+  bool ffa2_pair_fwd, ffa2_pair_dg;
+  CUtensorMap tm_ffa2_a[9], tm_ffa2_b[9], tm_ffa2_dg_a[9], tm_ffa2_dg_b[9], tm_ffa2_wg_x[9], tm_ffa2_wg_dz[9];
   int ffa_Tx, ffa_Tu;                            // rows of the pair-sum planes / of the partial products
   size_t off_ffa_xs, off_ffa_w[3], off_ffa_wb[3], off_ffa_p[3], off_ffa_dxp[3], off_ffa_cs;
   bool ffa_pair_fwd, ffa_pair_dg;                // the multi-problem launches run on CTA pairs
@@ -119,7 +125,7 @@ ST_API int st_plan_create(st_plan** out, int B, int T, int input_size, int num_c
     e = getenv("SPEECHT_B200_L10_N128");
     p->l10_n128 = !(e && e[0] == '0') && n_planes == 2;
     e = getenv("SPEECHT_B200_FFA");
-    p->ffa = !(e && e[0] == '0') && n_planes <= 2;
+    p->ffa = n_planes > 2 ? 0 : (e && e[0] >= '0' && e[0] <= '2' ? e[0] - '0' : 2);
   }
   // reference speech_model.py:275-292
   const int table[11][5] = {{48, 2, input_size, 250, 1}, {7, 1, 250, 250, 1}, {7, 1, 250, 250, 1}, {7, 1, 250, 250, 1},
@@ -162,8 +168,26 @@ ST_API int st_plan_create(st_plan** out, int B, int T, int input_size, int num_c
   p->dz_elems = (size_t)B * p->To * 2000;
   p->off_dz[0] = take((size_t)n_planes * p->dz_elems * 2);
   p->off_dz[1] = take((size_t)n_planes * p->dz_elems * 2);
-  if (p->To < 8) p->ffa = false;              // nothing to gain on a handful of frames (and the odd-row view may be empty)
-  if (p->ffa) {
+  if (p->To < 8) p->ffa = 0;                  // nothing to gain on a handful of frames (and the odd-row view may be empty)
+  if (p->ffa == 2 && p->To < 16) p->ffa = 1;
+  if (p->ffa == 2) {
+    const Layer& L8 = p->layers[8];
+    const int Tu = (L8.To + 1) / 2 + 1;
+    p->ffa2_Tq = (Tu + 1) / 2 + 1;
+    p->ffa2_Tqi = (L8.Ti + 3) / 4 + 1;
+    for (int i = 0; i < 5; ++i) p->off_ffa2_s[i] = take((size_t)n_planes * B * p->ffa2_Tqi * L8.ld_in * 2);
+    for (int i = 0; i < 9; ++i) {
+      p->off_ffa2_w[i] = take((size_t)n_planes * L8.Cout * (L8.K / 4) * L8.cin_p * 2);
+      p->off_ffa2_wb[i] = take((size_t)n_planes * (L8.K / 4) * L8.Cin * L8.ld_co * 2);
+      // forward: fp32 leaf product [B][Tq][Cout]; backward: the planes of its gradient live in the same bytes
+      const size_t fwd_bytes = (size_t)B * p->ffa2_Tq * L8.Cout * sizeof(float);
+      const size_t bwd_bytes = (size_t)n_planes * B * p->ffa2_Tq * L8.ld_out * 2;
+      p->off_ffa2_p[i] = take(fwd_bytes > bwd_bytes ? fwd_bytes : bwd_bytes);
+      p->off_ffa2_dxp[i] = take((size_t)B * p->ffa2_Tqi * 256 * sizeof(float));
+      p->off_ffa2_c[i] = take((size_t)(L8.K / 4) * L8.Cin * L8.Cout * sizeof(float));
+    }
+  }
+  if (p->ffa == 1) {
     const Layer& L8 = p->layers[8];
     p->ffa_Tx = (L8.Ti + 1) / 2;
     p->ffa_Tu = (L8.To + 1) / 2 + 1;
@@ -203,6 +227,60 @@ ST_API int st_plan_logit_frames(const st_plan* p) { return p ? p->To : 0; }
 ST_API float* st_plan_logits(st_plan* p) { return p && p->arena ? reinterpret_cast<float*>(p->arena + p->off_logits) : nullptr; }
 ST_API void* st_plan_dlogits_planes(st_plan* p) { return p && p->arena ? p->arena + p->off_dlogits : nullptr; }
 ST_API int st_plan_launches(const st_plan* p) { return p ? p->launches : 0; }
+
+namespace {
+
+// Leaves of the two-level fast-FIR split of layer 8 (order XX XY XZ YX YY YZ ZX ZY ZZ; tools/ffa2_study.py): the
+// quarter-rate input sequence (a row view x[4r + view_c] of the layer's input, or the summed sequence s[seq]), the
+// left padding of its 8-tap correlation and which of the source taps w[4i + c] its filter sums (bit c of tap_mask).
+struct Leaf { int view_c, seq, pad, tap_mask; };
+const Leaf kLeaves[9] = {{1, -1, 4, 0x1}, {3, -1, 4, 0x4}, {-1, 0, 3, 0x5},
+                         {2, -1, 4, 0x2}, {0, -1, 3, 0x8}, {-1, 1, 3, 0xa},
+                         {-1, 2, 4, 0x3}, {-1, 3, 3, 0xc}, {-1, 4, 3, 0xf}};
+
+int bind_ffa2(st_plan* p) {
+  Layer& L8 = p->layers[8];
+  const int B = p->B, npl = p->npl, J = L8.K / 4;
+  const __nv_bfloat16* x = act_in(p, 8);
+  p->ffa2_pair_fwd = tc::want_pair(B * ((p->ffa2_Tq + tc::kTileM - 1) / tc::kTileM), 1, wide_n(p), npl, true,
+                                   J * (L8.cin_p / 64));
+  p->ffa2_pair_dg = tc::want_pair(B * ((p->ffa2_Tqi + tc::kTileM - 1) / tc::kTileM), 1, wide_n(p), npl, true,
+                                  J * ((L8.Cout + 63) / 64));
+  int rc;
+  for (int l = 0; l < 9; ++l) {
+    const Leaf& lf = kLeaves[l];
+    // A operand (forward) / X operand (filter gradient): the leaf's quarter-rate input sequence
+    for (int box_t = 128; box_t >= 64; box_t -= 64) {
+      CUtensorMap* m = box_t == 128 ? &p->tm_ffa2_a[l] : &p->tm_ffa2_wg_x[l];
+      if (lf.view_c >= 0) {
+        const int rows = (L8.Ti - lf.view_c + 3) / 4;
+        rc = tc::make_map_3d(m, x + (int64_t)lf.view_c * L8.ld_in, L8.Cin, rows, npl * B, 4 * L8.ld_in,
+                             (int64_t)L8.Ti * L8.ld_in, 64, box_t);
+      } else {
+        rc = tc::make_map_3d(m, bf(p, p->off_ffa2_s[lf.seq]), L8.Cin, p->ffa2_Tqi, npl * B, L8.ld_in,
+                             (int64_t)p->ffa2_Tqi * L8.ld_in, 64, box_t);
+      }
+      if (rc) return rc;
+    }
+    rc = tc::make_map_2d(&p->tm_ffa2_b[l], bf(p, p->off_ffa2_w[l]), J * L8.cin_p, npl * L8.Cout, (int64_t)J * L8.cin_p,
+                         64, p->ffa2_pair_fwd ? wide_n(p) / 2 : wide_n(p));
+    if (rc) return rc;
+    // backward: the gradient of the leaf product as planes [npl*B][Tq][Cout]
+    const __nv_bfloat16* dA = bf(p, p->off_ffa2_p[l]);
+    rc = tc::make_map_3d(&p->tm_ffa2_dg_a[l], dA, L8.Cout, p->ffa2_Tq, npl * B, L8.ld_out,
+                         (int64_t)p->ffa2_Tq * L8.ld_out, 64, 128);
+    if (rc) return rc;
+    rc = tc::make_map_3d(&p->tm_ffa2_wg_dz[l], dA, L8.Cout, p->ffa2_Tq, npl * B, L8.ld_out,
+                         (int64_t)p->ffa2_Tq * L8.ld_out, 64, 64);
+    if (rc) return rc;
+    rc = tc::make_map_2d(&p->tm_ffa2_dg_b[l], bf(p, p->off_ffa2_wb[l]), L8.Cout, npl * J * L8.Cin, L8.ld_co, 64,
+                         p->ffa2_pair_dg ? wide_n(p) / 2 : wide_n(p));
+    if (rc) return rc;
+  }
+  return ST_OK;
+}
+
+}  // namespace
 
 ST_API int st_plan_bind(st_plan* p, void* arena, size_t arena_bytes, float* params, float* grads) {
   ST_CHECK_ARG(p && arena && params && grads, "st_plan_bind: null pointer");
@@ -285,7 +363,11 @@ ST_API int st_plan_bind(st_plan* p, void* arena, size_t arena_bytes, float* para
       }
     }
   }
-  if (p->ffa) {
+  if (p->ffa == 2) {
+    rc = bind_ffa2(p);
+    if (rc) return rc;
+  }
+  if (p->ffa == 1) {
     // A operands of the three half-rate convolutions: row views of the layer-7 output x (odd rows, even rows) and
     // the pair-sum planes; B operands: the packed even-tap, odd-tap and summed filters (forward layout, 16 taps)
     Layer& L8 = p->layers[8];
@@ -342,7 +424,13 @@ int pack_layers(st_plan* p, cudaStream_t s) {
   Layer& L8 = p->layers[8];
   for (int l = 0; l < 11; ++l) {
     Layer& L = p->layers[l];
-    if (l == 8 && p->ffa) {
+    if (l == 8 && p->ffa == 2) {
+      for (int i = 0; i < 9; ++i)
+        tab.e[tab.n++] = tc::PackEntry{p->params + L8.w_off, bf(p, p->off_ffa2_w[i]), bf(p, p->off_ffa2_wb[i]), L8.K / 4,
+                                       L8.Cin, L8.Cout, L8.cin_p, L8.ld_co, 0, 4, kLeaves[i].tap_mask};
+      continue;
+    }
+    if (l == 8 && p->ffa == 1) {
       // fast-FIR filters of layer 8: even taps, odd taps and their sum, each packed like a 16-tap filter in both
       // operand layouts straight from the 32-tap fp32 tensor; the direct 32-tap layouts are then not needed
       for (int i = 0; i < 3; ++i)
@@ -492,6 +580,121 @@ int backward_layer8_ffa(st_plan* p, const __nv_bfloat16* dz, __nv_bfloat16* dz_o
   return ST_OK;
 }
 
+// ---- two levels: nine quarter-rate 8-tap problems per pass (leaf table kLeaves, algebra in tools/ffa2_study.py)
+int forward_layer8_ffa2(st_plan* p, cudaStream_t s) {
+  Layer& L = p->layers[8];
+  __nv_bfloat16* seq[5];
+  for (int i = 0; i < 5; ++i) seq[i] = bf(p, p->off_ffa2_s[i]);
+  int rc = tc::launch_ffa2_inputs(act_in(p, 8), seq, p->B, L.Ti, p->ffa2_Tqi, L.ld_in, p->npl, s);
+  if (rc) return rc;
+  p->launches++;
+  float* part[9];
+  tc::ConvParams c{};
+  c.taps = L.K / 4;
+  c.chunks_per_tap = L.cin_p / 64;
+  c.a_sign = 1;
+  c.a_stride = 1;
+  c.a_cin = 0;
+  c.b_row_step = 0;
+  c.b_col_step = L.cin_p;
+  c.b_plane_rows = L.Cout;
+  c.B = p->B; c.To = p->ffa2_Tq; c.N = L.Cout;
+  c.m_tiles_per_utt = (p->ffa2_Tq + tc::kTileM - 1) / tc::kTileM;
+  c.n_tiles = (L.Cout + wide_n(p) - 1) / wide_n(p);
+  c.n_fastest = 0;
+  c.ld_f32 = L.Cout;
+  c.k_cols = L.Cin;
+  c.trim = p->trim;
+  c.n_problems = 9;
+  c.k_split = 1;
+  c.pair = p->ffa2_pair_fwd;
+  for (int i = 0; i < 9; ++i) {
+    part[i] = reinterpret_cast<float*>(p->arena + p->off_ffa2_p[i]);
+    c.pad_left_q[i] = kLeaves[i].pad;
+    c.out_f32_q[i] = part[i];
+  }
+  const int ti = timed_begin(p, s);
+  rc = tc::launch_conv_multi(p->tm_ffa2_a, p->tm_ffa2_b, c, wide_n(p), p->npl, s);
+  if (rc) return rc;
+  timed_end(p, ti, 0, 8, 2.0 * L.K * L.Cin * L.Cout * (double)L.To * p->B, s);
+  p->launches++;
+  rc = tc::launch_ffa2_combine(part, p->params + L.b_off, L.relu, bf(p, L.off_out), p->B, L.To, p->ffa2_Tq, L.Cout,
+                               L.Cout, L.ld_out, p->npl, s);
+  if (rc) return rc;
+  p->launches++;
+  return ST_OK;
+}
+
+int backward_layer8_ffa2(st_plan* p, const __nv_bfloat16* dz, __nv_bfloat16* dz_out, cudaStream_t s) {
+  Layer& L = p->layers[8];
+  Layer& Lb = p->layers[7];
+  const int J = L.K / 4;
+  __nv_bfloat16* dA[9];
+  float* cw[9];
+  float* dxp[9];
+  for (int i = 0; i < 9; ++i) {
+    dA[i] = bf(p, p->off_ffa2_p[i]);
+    cw[i] = reinterpret_cast<float*>(p->arena + p->off_ffa2_c[i]);
+    dxp[i] = reinterpret_cast<float*>(p->arena + p->off_ffa2_dxp[i]);
+  }
+  int rc = tc::launch_ffa2_dz_prep(dz, dA, p->B, L.To, p->ffa2_Tq, L.ld_out, p->npl, s);
+  if (rc) return rc;
+  p->launches++;
+  // ---- filter gradient: nine leaf correlations into their own [J][Cin][Cout] buffers, then one combine into dW
+  tc::WgradParams w{};
+  w.B = p->B; w.To = p->ffa2_Tq; w.t_chunks = (p->ffa2_Tq + 63) / 64;
+  w.taps = J; w.a_stride = 1; w.a_cin = 0;
+  w.m_tiles = (L.Cin + 127) / 128;
+  w.n_tiles = (L.Cout + wide_n(p) - 1) / wide_n(p);
+  w.Cin = L.Cin; w.Cout = L.Cout;
+  w.trim = p->trim;
+  w.n_problems = 9;
+  for (int i = 0; i < 9; ++i) { w.pad_left_q[i] = kLeaves[i].pad; w.dW_q[i] = cw[i]; w.tap_stride_q[i] = 1; }
+  if (tc::wgrad_accumulates(9 * J * w.m_tiles * w.n_tiles, p->B * w.t_chunks)) {
+    const size_t bytes = (size_t)J * L.Cin * L.Cout * sizeof(float);
+    for (int i = 0; i < 9; ++i) ST_CUDA_CALL(cudaMemsetAsync(cw[i], 0, bytes, s));
+  }
+  int ti = timed_begin(p, s);
+  rc = tc::launch_wgrad_multi(p->tm_ffa2_wg_x, p->tm_ffa2_wg_dz, w, wide_n(p), p->npl, s);
+  if (rc) return rc;
+  timed_end(p, ti, 2, 8, 2.0 * L.K * L.Cin * L.Cout * (double)L.To * p->B, s);
+  p->launches++;
+  rc = tc::launch_ffa2_dw_combine(p->grads + L.w_off, cw, J, (int64_t)L.Cin * L.Cout, s);
+  if (rc) return rc;
+  p->launches++;
+  // ---- data gradient: nine transposed 8-tap correlations -> fp32 [B][Tqi][256], whole contraction per tile
+  tc::ConvParams c{};
+  c.taps = J;
+  c.chunks_per_tap = (L.Cout + 63) / 64;
+  c.a_sign = -1;
+  c.a_stride = 1;
+  c.a_cin = 0;
+  c.b_row_step = L.Cin;
+  c.b_col_step = 0;
+  c.b_plane_rows = J * L.Cin;
+  c.B = p->B; c.To = p->ffa2_Tqi; c.N = L.Cin;
+  c.m_tiles_per_utt = (p->ffa2_Tqi + tc::kTileM - 1) / tc::kTileM;
+  c.n_tiles = (L.Cin + wide_n(p) - 1) / wide_n(p);
+  c.n_fastest = 1;
+  c.ld_f32 = 256;
+  c.k_cols = L.Cout;
+  c.trim = p->trim;
+  c.n_problems = 9;
+  c.k_split = 1;
+  c.pair = p->ffa2_pair_dg;
+  for (int i = 0; i < 9; ++i) { c.pad_left_q[i] = kLeaves[i].pad; c.out_f32_q[i] = dxp[i]; }
+  ti = timed_begin(p, s);
+  rc = tc::launch_conv_multi(p->tm_ffa2_dg_a, p->tm_ffa2_dg_b, c, wide_n(p), p->npl, s);
+  if (rc) return rc;
+  timed_end(p, ti, 1, 8, 2.0 * L.K * L.Cin * L.Cout * (double)L.To * p->B, s);
+  p->launches++;
+  rc = tc::launch_ffa2_dx_combine(dxp, bf(p, Lb.off_out), dz_out, p->grads + Lb.b_off, p->B, L.Ti, p->ffa2_Tqi, L.Cin,
+                                  256, Lb.ld_out, p->npl, s);
+  if (rc) return rc;
+  p->launches++;
+  return ST_OK;
+}
+
 }  // namespace
 
 ST_API int st_plan_forward(st_plan* p, const float* inputs, st_stream_t stream) {
@@ -504,7 +707,7 @@ ST_API int st_plan_forward(st_plan* p, const float* inputs, st_stream_t stream) 
     Layer& L = p->layers[l];
     const int block_n = l == 10 ? 32 : wide_n(p);
     if (l == 8 && p->ffa) {
-      rc = forward_layer8_ffa(p, s);
+      rc = p->ffa == 2 ? forward_layer8_ffa2(p, s) : forward_layer8_ffa(p, s);
       if (rc) return rc;
       continue;
     }
@@ -566,7 +769,8 @@ ST_API int st_plan_backward_range(st_plan* p, int hi, int lo, st_stream_t stream
     int rc = ST_OK;
     if (l == 8 && p->ffa) {
       const int nxt = cur ^ 1;
-      rc = backward_layer8_ffa(p, dz, bf(p, p->off_dz[nxt]), s);
+      rc = p->ffa == 2 ? backward_layer8_ffa2(p, dz, bf(p, p->off_dz[nxt]), s)
+                       : backward_layer8_ffa(p, dz, bf(p, p->off_dz[nxt]), s);
       if (rc) return rc;
       cur = nxt;
       continue;

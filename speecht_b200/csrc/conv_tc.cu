@@ -1395,21 +1395,32 @@ ffa2_combine_kernel(const Ptr9c part, const float* __restrict__ bias, int relu, 
     if (4 * q >= To) continue;
     const int64_t row = ((int64_t)b * Tq + q) * ld_p + c8 * 8;
     const bool nxt = q + 1 < Tq;
+    // 16-byte loads: the partial products are read once, 8 channels per thread (ld_p and N are multiples of 8 for
+    // every layer this is used on; a ragged last octet falls back to scalars)
+    const bool full8 = c8 * 8 + 8 <= N && (ld_p & 3) == 0;
+    float a[9][8], an[4][8];                         // an: rows q+1 of XX, XY, YX, ZX
+    auto load8 = [&](const float* src, bool on, float* dst) {
+      if (on && full8) {
+        const float4 u = *reinterpret_cast<const float4*>(src), w = *reinterpret_cast<const float4*>(src + 4);
+        dst[0] = u.x; dst[1] = u.y; dst[2] = u.z; dst[3] = u.w; dst[4] = w.x; dst[5] = w.y; dst[6] = w.z; dst[7] = w.w;
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) dst[i] = (on && c8 * 8 + i < N) ? src[i] : 0.f;
+      }
+    };
+#pragma unroll
+    for (int l = 0; l < 9; ++l) load8(part.p[l] + row, true, a[l]);
+    load8(part.p[0] + row + ld_p, nxt, an[0]);
+    load8(part.p[1] + row + ld_p, nxt, an[1]);
+    load8(part.p[3] + row + ld_p, nxt, an[2]);
+    load8(part.p[6] + row + ld_p, nxt, an[3]);
     float y[4][8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       const bool ok = c8 * 8 + i < N;
-      float a[9], an[9];
-#pragma unroll
-      for (int l = 0; l < 9; ++l) a[l] = ok ? part.p[l][row + i] : 0.f;
-      // rows q+1 of the leaves that enter shifted: XX, XY (for X1[2q+2]), YX, ZX
-      an[0] = (ok && nxt) ? part.p[0][row + ld_p + i] : 0.f;
-      an[1] = (ok && nxt) ? part.p[1][row + ld_p + i] : 0.f;
-      an[3] = (ok && nxt) ? part.p[3][row + ld_p + i] : 0.f;
-      an[6] = (ok && nxt) ? part.p[6][row + ld_p + i] : 0.f;
-      const float x1e = a[0] + a[1], x1o = a[2] - a[1] - an[0], x1n = an[0] + an[1];
-      const float y1e = a[3] + a[4], y1o = a[5] - a[4] - an[3];
-      const float z1e = a[6] + a[7], z1o = a[8] - a[7] - an[6];
+      const float x1e = a[0][i] + a[1][i], x1o = a[2][i] - a[1][i] - an[0][i], x1n = an[0][i] + an[1][i];
+      const float y1e = a[3][i] + a[4][i], y1o = a[5][i] - a[4][i] - an[2][i];
+      const float z1e = a[6][i] + a[7][i], z1o = a[8][i] - a[7][i] - an[3][i];
       const float bv = (ok && bias) ? __ldg(bias + c8 * 8 + i) : 0.f;
       y[0][i] = x1e + y1e + bv;
       y[1][i] = z1e - y1e - x1o + bv;
@@ -1629,9 +1640,9 @@ cudaError_t launch_pdl(Kernel kernel, int grid, int smem, cudaStream_t stream, c
 }
 
 // CTA-pair (cta_group::2) tiles for the 256-wide forward / data-gradient launches (SPEECHT_B200_PAIR=0 disables them)
-bool pair_enabled() {
-  static const bool on = []() { const char* e = getenv("SPEECHT_B200_PAIR"); return !(e && e[0] == '0'); }();
-  return on;
+bool pair_enabled() {                        // read when a plan is bound (want_pair), not cached
+  const char* e = getenv("SPEECHT_B200_PAIR");
+  return !(e && e[0] == '0');
 }
 
 // grid of a CTA-pair launch: one cluster of two CTAs per work item, at most one cluster per TPC
@@ -1778,7 +1789,7 @@ int launch_wgrad_multi_t(const CUtensorMap* tmX, const CUtensorMap* tmDZ, const 
 
 bool want_pair(int m_tiles, int n_tiles, int block_n, int n_planes, bool multi, int k_iters) {
   if (!pair_enabled() || block_n != 256 || n_planes > 2 || m_tiles < 2) return false;
-  // Measured same-box (profiles/r02_pair_ab_session7.txt): split modes gain on every eligible launch (layer-8 / layer-9
+  // Measured same-box (profiles/r02_pair_ab_session7.txt, r02_pair_default_ab_session8.txt): split modes gain on every eligible launch (layer-8 / layer-9
   // data gradients -5 %, forward neutral); in plain bf16 a pair tile's hand-offs between the two CTAs only pay off on
   // long contractions -- layer 8 gains 3-10 %, the 32-iteration layer-9 tiles lose 5-9 % and stay on single CTAs.
   if (n_planes == 1 && k_iters < 64) return false;

@@ -107,6 +107,29 @@ def _workspace(key, nbytes, device):
   return buf
 
 
+class _PinnedPool:
+  """Page-locked staging buffers for the per-step label upload.  cudaHostAlloc costs ~0.1 ms, so buffers are
+  recycled -- but only once the asynchronous copy that last read them has finished (its event has fired), because
+  a caller that does not synchronise every step would otherwise overwrite labels still on their way to the device."""
+
+  def __init__(self):
+    self.items = []                                   # [buffer, event or None]
+
+  def acquire(self, n):
+    for item in self.items:
+      buf, ev = item
+      if buf.numel() >= n and (ev is None or ev.query()):
+        item[1] = None
+        return item
+    item = [torch.empty((max(n, 1024),), dtype=torch.int32).pin_memory(), None]
+    if len(self.items) < 64:
+      self.items.append(item)
+    return item
+
+
+_pinned_pool = _PinnedPool()
+
+
 class CTCBatch:
   """Device-side label / length tensors of one batch, uploaded asynchronously from pinned memory so that no host
   synchronisation sits between the forward pass and the loss kernels."""
@@ -121,13 +144,19 @@ class CTCBatch:
                                               C - 1))
     self.max_len = int(np.max(np.diff(offsets))) if self.B else 0
     n_lab = max(int(flat.size), 1)
+    n = n_lab + 2 * self.B + 1
     # one pinned staging buffer, one async copy: [labels | offsets | seq_len]
-    host = torch.empty((n_lab + 2 * self.B + 1,), dtype=torch.int32).pin_memory()
-    host[:flat.size] = torch.from_numpy(flat) if flat.size else host[:0]
-    host[n_lab:n_lab + self.B + 1] = torch.from_numpy(offsets)
-    host[n_lab + self.B + 1:] = torch.from_numpy(seq_host)
+    item = _pinned_pool.acquire(n)
+    host = item[0][:n]
+    view = host.numpy()
+    view[:flat.size] = flat
+    view[n_lab:n_lab + self.B + 1] = offsets
+    view[n_lab + self.B + 1:] = seq_host
     self._host = host
     dev = host.to(device, non_blocking=True)
+    ev = torch.cuda.Event()
+    ev.record()
+    item[1] = ev
     self.labels = dev[:n_lab]
     self.offsets = dev[n_lab:n_lab + self.B + 1]
     self.seq_len = dev[n_lab + self.B + 1:]

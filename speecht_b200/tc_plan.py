@@ -148,9 +148,10 @@ class TCPlan:
     eng = self.engine
     B, T, _ = inputs.shape
     ctc_len = np.asarray(sequence_lengths, dtype=np.int32) // 2
-    # labels go up first (pinned, async) so that nothing synchronises the host between forward and loss
-    batch = ops.CTCBatch(labels, ctc_len, -(-T // 2), eng.num_classes, eng.device)
+    # the forward kernels are enqueued FIRST: flattening / validating the labels and their (pinned, asynchronous)
+    # upload are host work that then runs underneath them instead of in front of the step
     logits = self.forward(inputs.contiguous(), keep_activations=True)
+    batch = ops.CTCBatch(labels, ctc_len, -(-T // 2), eng.num_classes, eng.device)
     sh = self._last
     scale = 1.0 / (B * eng.world_size)
     loss, _ = ops.ctc_loss(batch, logits, want_grad=False, grad_scale=scale, grad_planes=sh.dlogits_planes)

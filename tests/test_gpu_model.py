@@ -253,7 +253,7 @@ def test_shape_changes_share_one_arena_and_stay_correct():
   assert len(eng._tc().shapes) == 3 and eng._tc().arena is not None
 
 
-@pytest.mark.parametrize('T', [100, 37, 6, 2])
+@pytest.mark.parametrize('T', [100, 37, 24, 6, 2])
 def test_tensor_path_even_short_and_tiny_time_axes(T):
   """Even T (pad 23/23 on the stride-2 layer instead of 23/24), T not a multiple of anything, and time axes far
   shorter than a 128-row tile / the 48-tap first filter: TMA zero fill must reproduce TF 'SAME' everywhere."""
@@ -307,21 +307,29 @@ def test_training_reduces_the_loss_on_a_fixed_batch(precision):
   assert np.mean(losses[-10:]) < np.mean(losses[:10])
 
 
-@pytest.mark.skipif(os.environ.get('SPEECHT_B200_TEST_EXPERIMENTAL') != '1',
-                    reason='experimental fast-FIR forward of layer 8 (SPEECHT_B200_FFA=1): opt-in until it has been '
-                           'validated on a GPU (DESIGN.md section 8)')
-@pytest.mark.parametrize('seconds', [1, 3])
-def test_experimental_fast_fir_layer8_forward_parity(seconds, monkeypatch):
-  """The three-convolution form of layer 8 must give the same activations (1e-4 gate; expected ~4e-5 on the odd rows
-  of layer 8) and the same greedy labels as the oracle.  The switch is read when a plan is created."""
-  monkeypatch.setenv('SPEECHT_B200_FFA', '1')
-  inputs, lengths, labels = O.synthetic_batch(seed=4, batch=3, seconds=seconds)
+@pytest.mark.parametrize('level,pair', [(0, '1'), (1, '1'), (2, '1'), (2, '0')])
+def test_fast_fir_levels_and_cta_pairs_give_the_same_step(level, pair, monkeypatch):
+  """Layer 8 as the direct 32-tap kernels (level 0), one fast-FIR level (three half-rate problems) or two (nine
+  quarter-rate problems, the default), on CTA pairs or single CTAs: activations of every layer against the float64
+  oracle (1e-4 gate) and the gradients of one train step "same-mask" against the oracle backward (3e-4).  The
+  switches are read when a plan is created / the library first launches."""
+  monkeypatch.setenv('SPEECHT_B200_FFA', str(level))
+  monkeypatch.setenv('SPEECHT_B200_PAIR', pair)
+  inputs, lengths, labels = O.synthetic_batch(seed=4, batch=3, seconds=[3, 2, 3])
   weights = O.xavier_weights(np.random.default_rng(98), dtype=np.float32)
   w64 = [(w.astype(np.float64), b.astype(np.float64)) for w, b in weights]
   logits, acts = O.wav2letter_forward(inputs.astype(np.float64), w64, keep_activations=True)
+  loss, dlog = O.ctc_loss_and_grad(logits, labels, lengths // 2)
   eng = _engine('bf16x3', weights)
-  out = eng.forward(torch.from_numpy(inputs).cuda(), keep_activations=True)
-  errs = [rel(a, acts[l + 1]) for l, a in enumerate(_gpu_activations(eng))]
-  print('fast-FIR layer 8: per-layer rel err vs float64 oracle', ' '.join('%.2e' % e for e in errs))
+  res = eng.train_step(torch.from_numpy(inputs).cuda(), lengths, labels, 1e-4)
+  gpu_acts = _gpu_activations(eng)
+  errs = [rel(a, acts[l + 1]) for l, a in enumerate(gpu_acts)]
+  print('fast-FIR level %d pair %s: per-layer rel err vs float64 oracle %s' % (level, pair, ' '.join('%.2e' % e for e in errs)))
   assert max(errs) < 1e-4, errs
-  assert rel(out.cpu().numpy(), logits) < 1e-4
+  assert rel(res['loss'].cpu().numpy(), loss) < 1e-4
+  acts_h = [acts[0]] + [np.where(g > 0, np.maximum(acts[l + 1], 1e-30), 0.0) for l, g in enumerate(gpu_acts)]
+  acts_h.append(acts[11])
+  ref_grads = O.wav2letter_backward(acts_h, w64, dlog / 3)
+  for li, ((dw, db), (rdw, rdb)) in enumerate(zip(eng.weight_grads, ref_grads)):
+    assert rel(dw.cpu().numpy(), rdw) < 3e-4, (li, rel(dw.cpu().numpy(), rdw))
+    assert rel(db.cpu().numpy(), rdb) < 3e-4, (li, rel(db.cpu().numpy(), rdb))

@@ -73,6 +73,9 @@ def parse_args():
   p.add_argument('--no-cpu-baseline', action='store_true')
   p.add_argument('--no-sustained', action='store_true', help='skip the >= 2 s sustained pass')
   p.add_argument('--sustained-seconds', type=float, default=2.5)
+  p.add_argument('--eval-buckets', type=int, default=1,
+                 help='config 5 only: evaluate each batch as this many length-sorted groups padded to their own maximum '
+                      '(default 1 = the reference behaviour: the whole batch padded to its longest utterance)')
   args = p.parse_args()
   cfg = dict(CONFIGS[args.config])
   if args.batch is not None:
@@ -355,13 +358,22 @@ def run_ours(args, rank, local_rank, world):
       eng.train_step(dev_inputs[i % n_sets], h[1], h[2], lr)
   else:
     from speecht_b200 import ops
-    ctc_batches = [ops.CTCBatch(h[2], h[1] // 2, (h[0].shape[1] + 1) // 2, eng.num_classes, dev) for h in host_sets]
+    # one (inputs, CTC batch) pair per length bucket of every set (a single bucket = the reference's padded batch)
+    groups = []
+    for h, x in zip(host_sets, dev_inputs):
+      per_set = []
+      for g in W2LEngine.length_buckets(h[1], args.eval_buckets):
+        t_max = max(int(h[1][g].max()), 2)
+        xg = x if args.eval_buckets <= 1 else x[torch.from_numpy(g.astype(np.int64)).to(dev)][:, :t_max].contiguous()
+        per_set.append((xg, ops.CTCBatch([h[2][b] for b in g], h[1][g] // 2, (xg.shape[1] + 1) // 2, eng.num_classes,
+                                         dev)))
+      groups.append(per_set)
 
     def step_resident(i):
       # forward + CTC loss + greedy-decode kernels; the compacted label rows stay on the device (the host-side
       # SparseTensor assembly and, at N > 1, the gather of the rows belong to the e2e number below)
-      k = i % n_sets
-      eng.evaluate_step_device(dev_inputs[k], ctc_batches[k])
+      for xg, batch in groups[i % n_sets]:
+        eng.evaluate_step_device(xg, batch)
 
   sampler = ClockSampler(local_rank)
   if rank == 0:
@@ -431,7 +443,7 @@ def run_ours(args, rank, local_rank, world):
   flags = types.SimpleNamespace(command='train' if mode == 'train' else 'evaluate', learning_rate=lr,
                                 learning_rate_decay_factor=0.0, max_gradient_norm=5.0, momentum=0.9, log_dir='log',
                                 run_name='bench', run_type='train', precision=precision, process_group=group,
-                                engine=eng, language_model=None)
+                                engine=eng, language_model=None, eval_buckets=args.eval_buckets)
   feed = HostFeed()
   model = speech_model.create_default_model(flags, 128, feed)
   sess = speech_model.Session(dev)
@@ -468,7 +480,11 @@ def run_ours(args, rank, local_rank, world):
 
   mean_frames = float(np.mean([h[1].mean() for h in host_sets]))
   fwd_flops = conv_flops_forward(B, T)
-  h2d = int(pinned[0].numel() * 4 + sum(len(l) for l in host_sets[0][2]) * 4 + 8 * B + 4)
+  # inputs: SpeechModel uploads only the valid frames of a batch that is more than a quarter padding (the zeros are
+  # written on the device), the whole padded tensor otherwise
+  full_bytes, valid_bytes = int(pinned[0].numel() * 4), int(host_sets[0][1].sum()) * 128 * 4
+  h2d_inputs = valid_bytes if valid_bytes < 0.75 * full_bytes else full_bytes
+  h2d = int(h2d_inputs + sum(len(l) for l in host_sets[0][2]) * 4 + 8 * B + 4)
   line = {
     'metric': metric_name(cfg), 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
     'warmup': args.warmup, 'ms_per_step': ms_step, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
@@ -478,7 +494,7 @@ def run_ours(args, rank, local_rank, world):
     'data': 'synthetic',
     'config': {'workload': cfg['name'] + ' (T=%d mel frames -> T\'=%d logit frames)' % (T, (T + 1) // 2),
                'bench_config': args.config, 'mode': mode, 'global_batch': world * B, 'precision': precision,
-               'parallelism': 'dp%d' % world, 'mean_frames': mean_frames,
+               'parallelism': 'dp%d' % world, 'mean_frames': mean_frames, 'eval_buckets': args.eval_buckets,
                'l2': 'no explicit flush: per-step working set (activations+params+grads+Adam > 1 GB) exceeds the '
                      '126 MB L2 and %d distinct input batches rotate' % n_sets,
                'conv_tflop_per_step_per_gpu': (3 if mode == 'train' else 1) * fwd_flops / 1e12},
@@ -508,7 +524,7 @@ def lookup_traffic(precision, B, T, kernel):
   tr = json.load(open(TRAFFIC_PATH)).get('%s/B%d/T%d' % (precision, B, T))
   if not tr or (kernel and kernel not in tr.get('kernel', '')):
     return None, None
-  return tr.get('bytes_per_launch'), tr.get('source')
+  return tr.get('bytes_per_launch'), '%s; launch: %s' % (tr.get('source'), tr.get('launch', 'n/a'))
 
 
 def aux_kernels(eng, dev, B, seconds, host_set, peaks_path):

@@ -130,6 +130,10 @@ float* st_plan_logits(st_plan* plan);
 void* st_plan_dlogits_planes(st_plan* plan);
 int st_plan_get_activation(st_plan* plan, int layer, float* dst, st_stream_t stream);
 int st_plan_launches(const st_plan* plan);
+/* Packed filters live in a leading arena region whose offsets do not depend on (B, T): plans bound into the SAME arena
+ * share them, and a plan needs st_plan_pack_weights again only after the parameters changed or when no plan of its
+ * filter set (0 / 1 / 2 = fast-FIR level of layer 8) has packed since. */
+int st_plan_filter_set(const st_plan* plan);
 /* bench support: CUDA-event pair around every tensor-core launch (kind 0 = forward conv, 1 = data gradient,
  * 2 = filter gradient); st_plan_read_timings is host-synchronous and returns the number of records written. */
 int st_plan_set_timing(st_plan* plan, int enable);

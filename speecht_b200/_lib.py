@@ -63,6 +63,7 @@ _SIGNATURES = {
   'st_plan_dlogits_planes': (c_void_p, [P]),
   'st_plan_get_activation': (c_int, [P, c_int, P, P]),
   'st_plan_launches': (c_int, [P]),
+  'st_plan_filter_set': (c_int, [P]),
   'st_plan_set_timing': (c_int, [P, c_int]),
   'st_plan_read_timings': (c_int, [P, P, P, P, P, c_int]),
   'st_debug_conv_timeline': (c_int, [P, c_int]),

@@ -113,6 +113,10 @@ __device__ __forceinline__ void store_planes8(__nv_bfloat16* dst, int64_t plane_
   }
 }
 
+struct Ptr9f { float* p[9]; };
+struct Ptr9c { const float* p[9]; };
+struct Ptr9h { __nv_bfloat16* p[9]; };
+
 // One 32-column chunk of the epilogue for this lane's output row, from the summed accumulators v[32]:
 // + bias, ReLU or ReLU-mask, then
 //   * bf16 planes: staged [plane][32 rows][32 cols] in the warp's shared-memory tile and written with ONE TMA store
@@ -1069,6 +1073,84 @@ pack_filter_both_kernel(const PackTable tab) {
   }
 }
 
+// The nine filters of the two-level fast-FIR split of a 4J-tap layer in ONE pass over its fp32 tensor: a block loads
+// the four source taps w[4i + c] of a 64(ci) x 64(co) tile once and writes, for every leaf l, the tap sum selected by
+// the bits of masks[l] in both operand layouts (leaf order and masks: w2l_plan.cu kLeaves).  Packing the leaves as
+// nine independent table entries read the tensor four times over.
+struct LeafMasks { int m[9]; };
+template <int NPL>
+__global__ void __launch_bounds__(256)
+pack_ffa2_kernel(const float* __restrict__ w, const Ptr9h fwd, const Ptr9h bwd, const LeafMasks masks, int J, int Cin,
+                 int Cout, int cin_p, int ld_co) {
+  extern __shared__ float tiles[];                    // [4][64][65]
+  int lb = blockIdx.x;
+  const int co_tiles = (ld_co + 63) / 64, ci_tiles = cin_p / 64;
+  const int co0 = (lb % co_tiles) * 64;
+  lb /= co_tiles;
+  const int ci0 = (lb % ci_tiles) * 64;
+  const int k = lb / ci_tiles;
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  const int64_t tap = (int64_t)Cin * Cout;
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+#pragma unroll
+    for (int r = 0; r < 64; r += 8) {
+      const int ci = ci0 + r + ty;
+      const float* src = w + ((int64_t)(4 * k + g) * Cin + ci) * Cout + co0;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int c = tx + 32 * h;
+        tiles[(g * 64 + r + ty) * 65 + c] = (ci < Cin && co0 + c < Cout) ? __ldg(src + c) : 0.f;
+      }
+    }
+  }
+  __syncthreads();
+  auto leaf_sum = [&](int mask, int row, int col) {
+    float v = 0.f;
+#pragma unroll
+    for (int g = 0; g < 4; ++g)
+      if (mask & (1 << g)) v += tiles[(g * 64 + row) * 65 + col];
+    return v;
+  };
+  const int64_t ld = (int64_t)J * cin_p;
+  const int64_t fwd_plane = (int64_t)Cout * ld, bwd_plane = (int64_t)J * Cin * ld_co;
+  for (int l = 0; l < 9; ++l) {
+    const int mask = masks.m[l];
+#pragma unroll
+    for (int r = 0; r < 64; r += 8) {
+      const int c = r + ty, co = co0 + c;
+      if (co < Cout) {
+        float v0 = leaf_sum(mask, 2 * tx, c), v1 = leaf_sum(mask, 2 * tx + 1, c);
+        __nv_bfloat16* dst = fwd.p[l] + (int64_t)co * ld + (int64_t)k * cin_p + ci0 + 2 * tx;
+#pragma unroll
+        for (int pl = 0; pl < NPL; ++pl) {
+          const __nv_bfloat16 h0 = __float2bfloat16_rn(v0), h1 = __float2bfloat16_rn(v1);
+          *reinterpret_cast<uint32_t*>(dst + pl * fwd_plane) = pack_bf16x2(h0, h1);
+          v0 -= __bfloat162float(h0);
+          v1 -= __bfloat162float(h1);
+        }
+      }
+    }
+    if (co0 + 2 * tx < ld_co) {
+#pragma unroll
+      for (int r = 0; r < 64; r += 8) {
+        const int ci = ci0 + r + ty;
+        if (ci < Cin) {
+          float v0 = leaf_sum(mask, r + ty, 2 * tx), v1 = leaf_sum(mask, r + ty, 2 * tx + 1);
+          __nv_bfloat16* dst = bwd.p[l] + ((int64_t)k * Cin + ci) * ld_co + co0 + 2 * tx;
+#pragma unroll
+          for (int pl = 0; pl < NPL; ++pl) {
+            const __nv_bfloat16 h0 = __float2bfloat16_rn(v0), h1 = __float2bfloat16_rn(v1);
+            *reinterpret_cast<uint32_t*>(dst + pl * bwd_plane) = pack_bf16x2(h0, h1);
+            v0 -= __bfloat162float(h0);
+            v1 -= __bfloat162float(h1);
+          }
+        }
+      }
+    }
+  }
+}
+
 // db[n] += sum_rows sum_planes dz[pl][row][n]; block (32 column octets, 8 row lanes): each thread streams 16-byte
 // vectors (8 bf16 columns) down its rows; grid (ceil(ld/256), row chunks)
 __global__ void __launch_bounds__(256)
@@ -1315,9 +1397,6 @@ ffa_dw_combine_kernel(float* __restrict__ dW, const float* __restrict__ cs, int 
 // ---- two levels of the fast-FIR split (nine quarter-rate 8-tap problems; algebra: tools/ffa2_study.py) --------------
 // Leaf order everywhere: 0 XX, 1 XY, 2 XZ, 3 YX, 4 YY, 5 YZ, 6 ZX, 7 ZY, 8 ZZ (first letter: level-1 product X1 = odd
 // rows (*) even taps, Y1 = even rows (*) odd taps, Z1 = pair sums (*) tap sums; second letter: the same split inside it).
-struct Ptr9f { float* p[9]; };
-struct Ptr9c { const float* p[9]; };
-struct Ptr9h { __nv_bfloat16* p[9]; };
 
 __device__ __forceinline__ void load_merged8(const __nv_bfloat16* base, int64_t plane, int npl, float* v) {
 #pragma unroll
@@ -2103,6 +2182,26 @@ int launch_pack_filters(PackTable& tab, int n_planes, cudaStream_t stream, int* 
   else pack_filter_both_kernel<1><<<blocks, dim3(32, 8), 0, stream>>>(tab);
   ST_CUDA_LAUNCH_CHECK("pack_filter_both_kernel");
   *launches = 1;
+  return ST_OK;
+}
+
+int launch_pack_ffa2(const float* w, __nv_bfloat16* const* fwd9, __nv_bfloat16* const* bwd9, const int* masks9, int J,
+                     int Cin, int Cout, int cin_p, int ld_co, int n_planes, cudaStream_t stream) {
+  ST_CHECK_ARG(cin_p % 64 == 0 && ld_co % 4 == 0 && ld_co >= Cout && n_planes >= 1 && n_planes <= 2,
+               "launch_pack_ffa2: bad arguments");
+  Ptr9h f, b;
+  LeafMasks m;
+  for (int l = 0; l < 9; ++l) { f.p[l] = fwd9[l]; b.p[l] = bwd9[l]; m.m[l] = masks9[l]; }
+  const int blocks = J * (cin_p / 64) * ((ld_co + 63) / 64);
+  const int smem = 4 * 64 * 65 * (int)sizeof(float);
+  if (n_planes == 2) {
+    ST_CUDA_CALL(cudaFuncSetAttribute(pack_ffa2_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    pack_ffa2_kernel<2><<<blocks, dim3(32, 8), smem, stream>>>(w, f, b, m, J, Cin, Cout, cin_p, ld_co);
+  } else {
+    ST_CUDA_CALL(cudaFuncSetAttribute(pack_ffa2_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    pack_ffa2_kernel<1><<<blocks, dim3(32, 8), smem, stream>>>(w, f, b, m, J, Cin, Cout, cin_p, ld_co);
+  }
+  ST_CUDA_LAUNCH_CHECK("pack_ffa2_kernel");
   return ST_OK;
 }
 

@@ -145,6 +145,9 @@ int launch_ffa2_dx_combine(float* const* g9, const __nv_bfloat16* mask, __nv_bfl
                            int Tqx, int N, int ldp, int ld, int n_planes, cudaStream_t stream);
 // nine fp32 leaf correlations [J][tap_elems] -> dW [4J][tap_elems]
 int launch_ffa2_dw_combine(float* dW, float* const* c9, int J, int64_t tap_elems, cudaStream_t stream);
+// the nine leaf filters (tap sums selected by masks9[l] over w[4i + c]) in both operand layouts, one pass over w
+int launch_pack_ffa2(const float* w, __nv_bfloat16* const* fwd9, __nv_bfloat16* const* bwd9, const int* masks9, int J,
+                     int Cin, int Cout, int cin_p, int ld_co, int n_planes, cudaStream_t stream);
 // true when a filter-gradient launch of num_tiles tiles accumulates into its outputs (they must then be zeroed)
 bool wgrad_accumulates(int num_tiles, int total_iters);
 // db[n] = sum over rows and planes of dz planes [n_planes][rows][ld]

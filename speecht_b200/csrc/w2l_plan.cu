@@ -40,6 +40,7 @@ struct st_plan {
   int To;                      // logit frames
   std::vector<Layer> layers;
   size_t off_in, off_logits, off_dlogits, off_dz[2], arena_bytes;
+  size_t filter_bytes;         // leading arena region holding the packed filters (shape independent)
   size_t dz_elems;             // elements per plane of a dz buffer
   char* arena;
   float* params;
@@ -127,13 +128,17 @@ ST_API int st_plan_create(st_plan** out, int B, int T, int input_size, int num_c
     e = getenv("SPEECHT_B200_FFA");
     p->ffa = n_planes > 2 ? 0 : (e && e[0] >= '0' && e[0] <= '2' ? e[0] - '0' : 2);
   }
+  const int ffa_requested = p->ffa;
   // reference speech_model.py:275-292
   const int table[11][5] = {{48, 2, input_size, 250, 1}, {7, 1, 250, 250, 1}, {7, 1, 250, 250, 1}, {7, 1, 250, 250, 1},
                             {7, 1, 250, 250, 1},         {7, 1, 250, 250, 1}, {7, 1, 250, 250, 1}, {7, 1, 250, 250, 1},
                             {32, 1, 250, 2000, 1},       {1, 1, 2000, 2000, 1}, {1, 1, 2000, num_classes, 0}};
   size_t off = 0;
   auto take = [&](size_t bytes) { size_t o = off; off = (off + bytes + 1023) / 1024 * 1024; return o; };
-  p->off_in = take((size_t)n_planes * B * p->Tpad * input_size * 2);
+  // Region 1 -- packed filters.  Their offsets depend on n_planes (and the requested fast-FIR level) only, so every
+  // plan of an engine finds them at the same place in the shared arena: a change of batch shape does not invalidate
+  // them (an evaluate run over ragged batches packs once, not once per shape).  Region 2 -- everything whose size
+  // depends on (B, T) -- follows.
   int t = T, ld_prev = input_size;
   int64_t poff = 0;
   for (int l = 0; l < 11; ++l) {
@@ -152,7 +157,6 @@ ST_API int st_plan_create(st_plan** out, int B, int T, int input_size, int num_c
     if (L.Cout == 250) L.ld_co = 256;
     L.off_wfwd = take((size_t)n_planes * L.Cout * L.K * L.cin_p * 2);
     L.off_wbwd = l > 0 ? take((size_t)n_planes * L.K * L.Cin * L.ld_co * 2) : 0;
-    L.off_out = l < 10 ? take((size_t)n_planes * B * L.To * L.ld_out * 2) : 0;
     // flat parameter layout: must match engine.ParamLayout (64-float alignment)
     L.w_off = poff;
     poff = (poff + (int64_t)L.K * L.Cin * L.Cout + 63) / 64 * 64;
@@ -163,6 +167,27 @@ ST_API int st_plan_create(st_plan** out, int B, int T, int input_size, int num_c
     p->layers.push_back(L);
   }
   p->To = t;
+  {
+    // leaf filters of the fast-FIR levels a plan of this engine may use (small shapes fall back to lower levels)
+    const Layer& L8 = p->layers[8];
+    if (ffa_requested >= 1)
+      for (int i = 0; i < 3; ++i) {
+        p->off_ffa_w[i] = take((size_t)n_planes * L8.Cout * (L8.K / 2) * L8.cin_p * 2);
+        p->off_ffa_wb[i] = take((size_t)n_planes * (L8.K / 2) * L8.Cin * L8.ld_co * 2);
+      }
+    if (ffa_requested >= 2)
+      for (int i = 0; i < 9; ++i) {
+        p->off_ffa2_w[i] = take((size_t)n_planes * L8.Cout * (L8.K / 4) * L8.cin_p * 2);
+        p->off_ffa2_wb[i] = take((size_t)n_planes * (L8.K / 4) * L8.Cin * L8.ld_co * 2);
+      }
+  }
+  p->filter_bytes = off;
+  // ---- region 2: shape dependent
+  p->off_in = take((size_t)n_planes * B * p->Tpad * input_size * 2);
+  for (int l = 0; l < 10; ++l) {
+    Layer& L = p->layers[l];
+    L.off_out = take((size_t)n_planes * B * L.To * L.ld_out * 2);
+  }
   p->off_logits = take((size_t)B * p->To * 32 * sizeof(float));
   p->off_dlogits = take((size_t)n_planes * B * p->To * 64 * 2);
   p->dz_elems = (size_t)B * p->To * 2000;
@@ -177,8 +202,6 @@ ST_API int st_plan_create(st_plan** out, int B, int T, int input_size, int num_c
     p->ffa2_Tqi = (L8.Ti + 3) / 4 + 1;
     for (int i = 0; i < 5; ++i) p->off_ffa2_s[i] = take((size_t)n_planes * B * p->ffa2_Tqi * L8.ld_in * 2);
     for (int i = 0; i < 9; ++i) {
-      p->off_ffa2_w[i] = take((size_t)n_planes * L8.Cout * (L8.K / 4) * L8.cin_p * 2);
-      p->off_ffa2_wb[i] = take((size_t)n_planes * (L8.K / 4) * L8.Cin * L8.ld_co * 2);
       // forward: fp32 leaf product [B][Tq][Cout]; backward: the planes of its gradient live in the same bytes
       const size_t fwd_bytes = (size_t)B * p->ffa2_Tq * L8.Cout * sizeof(float);
       const size_t bwd_bytes = (size_t)n_planes * B * p->ffa2_Tq * L8.ld_out * 2;
@@ -193,8 +216,6 @@ ST_API int st_plan_create(st_plan** out, int B, int T, int input_size, int num_c
     p->ffa_Tu = (L8.To + 1) / 2 + 1;
     p->off_ffa_xs = take((size_t)n_planes * B * p->ffa_Tx * L8.ld_in * 2);
     for (int i = 0; i < 3; ++i) {
-      p->off_ffa_w[i] = take((size_t)n_planes * L8.Cout * (L8.K / 2) * L8.cin_p * 2);
-      p->off_ffa_wb[i] = take((size_t)n_planes * (L8.K / 2) * L8.Cin * L8.ld_co * 2);
       // forward: fp32 partial product [B][Tu][Cout]; backward: the planes of dA00 / dA11 / dS [npl][B][Tu][Cout] live
       // in the same bytes (the partial products are dead once the forward combine has run)
       const size_t fwd_bytes = (size_t)B * p->ffa_Tu * L8.Cout * sizeof(float);
@@ -227,6 +248,9 @@ ST_API int st_plan_logit_frames(const st_plan* p) { return p ? p->To : 0; }
 ST_API float* st_plan_logits(st_plan* p) { return p && p->arena ? reinterpret_cast<float*>(p->arena + p->off_logits) : nullptr; }
 ST_API void* st_plan_dlogits_planes(st_plan* p) { return p && p->arena ? p->arena + p->off_dlogits : nullptr; }
 ST_API int st_plan_launches(const st_plan* p) { return p ? p->launches : 0; }
+// Which packed filters this plan reads: the fast-FIR level of layer 8 it runs (0 = direct 32-tap kernels).  The packed
+// filters sit at shape-independent arena offsets, so plans of one level share them (speecht_b200/tc_plan.py).
+ST_API int st_plan_filter_set(const st_plan* p) { return p ? p->ffa : 0; }
 
 namespace {
 
@@ -425,9 +449,19 @@ int pack_layers(st_plan* p, cudaStream_t s) {
   for (int l = 0; l < 11; ++l) {
     Layer& L = p->layers[l];
     if (l == 8 && p->ffa == 2) {
-      for (int i = 0; i < 9; ++i)
-        tab.e[tab.n++] = tc::PackEntry{p->params + L8.w_off, bf(p, p->off_ffa2_w[i]), bf(p, p->off_ffa2_wb[i]), L8.K / 4,
-                                       L8.Cin, L8.Cout, L8.cin_p, L8.ld_co, 0, 4, kLeaves[i].tap_mask};
+      // the nine leaf filters of the two-level split: their own launch, one pass over the 32-tap tensor
+      __nv_bfloat16* f9[9];
+      __nv_bfloat16* b9[9];
+      int m9[9];
+      for (int i = 0; i < 9; ++i) {
+        f9[i] = bf(p, p->off_ffa2_w[i]);
+        b9[i] = bf(p, p->off_ffa2_wb[i]);
+        m9[i] = kLeaves[i].tap_mask;
+      }
+      const int rc2 = tc::launch_pack_ffa2(p->params + L8.w_off, f9, b9, m9, L8.K / 4, L8.Cin, L8.Cout, L8.cin_p,
+                                           L8.ld_co, p->npl, s);
+      if (rc2) return rc2;
+      p->launches++;
       continue;
     }
     if (l == 8 && p->ffa == 1) {

@@ -329,9 +329,24 @@ class W2LEngine:
       self._plan = TCPlan(self)
     return self._plan
 
+  @staticmethod
+  def length_buckets(sequence_lengths, buckets):
+    """Utterance indices of `buckets` groups of similar length (sorted by length, split evenly): evaluating each
+    group padded to its OWN maximum skips most of the padding frames of a ragged batch."""
+    order = np.argsort(np.asarray(sequence_lengths), kind='stable')
+    return [g for g in np.array_split(order, max(1, min(int(buckets), len(order)))) if len(g)]
+
   @_on_engine_device
-  def evaluate_step(self, inputs, sequence_lengths, labels=None, decode=True):
-    """model.step(update=False, decode=True): returns dict(loss [B] tensor|None, avg_loss, decoded, logits)."""
+  def evaluate_step(self, inputs, sequence_lengths, labels=None, decode=True, buckets=1):
+    """model.step(update=False, decode=True): returns dict(loss [B] tensor|None, avg_loss, decoded, logits).
+
+    buckets > 1 (optional; the reference always pads the whole batch to its longest utterance, speech_input.py:38-43):
+    the batch is evaluated as that many length-sorted groups, each padded to its own maximum.  Results come back in
+    the original utterance order; `logits` is then None.  Because the network does not mask padding
+    (speech_model.py:128-181), the last ~20 logit frames of an utterance depend on how much padding follows it, so a
+    bucketed evaluation is NOT bit-identical to the reference batch -- parity is checked unbucketed."""
+    if buckets > 1 and inputs.shape[0] > 1:
+      return self._evaluate_bucketed(inputs, sequence_lengths, labels, decode, buckets)
     logits = self.forward(inputs, keep_activations=False)
     ctc_len = np.asarray(sequence_lengths, dtype=np.int32) // 2      # speech_model.py:74,114
     out = {'logits': logits, 'loss': None, 'avg_loss': None, 'decoded': None}
@@ -343,6 +358,52 @@ class W2LEngine:
     if decode:
       out['decoded'], out['neg_sum_logits'] = ops.ctc_greedy_decoder(logits, ctc_len)
       self.launches += 1
+    return out
+
+  def _evaluate_bucketed(self, inputs, sequence_lengths, labels, decode, buckets):
+    lengths = np.asarray(sequence_lengths, dtype=np.int32)
+    B = int(lengths.shape[0])
+    rows = None
+    if labels is not None:
+      flat, offsets = ops.flatten_labels(labels)
+      rows = [flat[offsets[b]:offsets[b + 1]] for b in range(B)]
+    loss = torch.zeros((B,), dtype=torch.float32, device=self.device) if labels is not None else None
+    pending = []
+    # every group's kernels are enqueued first (the next group's forward reuses the arena, which stream order makes
+    # safe); results cross to the host once, at the end
+    for group in self.length_buckets(lengths, buckets):
+      idx = torch.from_numpy(group.astype(np.int64)).to(self.device)
+      t_max = max(int(lengths[group].max()), 2)
+      x = inputs.index_select(0, idx)[:, :t_max].contiguous()
+      logits = self.forward(x, keep_activations=False)
+      ctc_len = lengths[group] // 2
+      batch = ops.CTCBatch([rows[b] for b in group] if rows is not None else [[] for _ in group], ctc_len,
+                           logits.shape[0], self.num_classes, self.device, validate=rows is not None)
+      if loss is not None:
+        group_loss, _ = ops.ctc_loss(batch, logits, want_grad=False)
+        loss.index_copy_(0, idx, group_loss)
+        self.launches += 2
+      if decode:
+        pending.append((group,) + ops.ctc_greedy_decode_device(logits, batch.seq_len, fresh=True))
+        self.launches += 1
+    out = {'logits': None, 'loss': loss, 'avg_loss': BatchMean(loss) if loss is not None else None, 'decoded': None}
+    if decode:
+      decoded_rows = [None] * B
+      neg = np.zeros((B, 1), dtype=np.float32)
+      for group, values, counts, group_neg in pending:
+        sp = ops.sparse_from_rows(values, counts)
+        starts = np.searchsorted(sp.indices[:, 0], np.arange(len(group) + 1))
+        for j, b in enumerate(group):
+          decoded_rows[b] = sp.values[starts[j]:starts[j + 1]]
+        neg[group, 0] = group_neg.cpu().numpy()
+      counts = np.array([len(r) for r in decoded_rows], dtype=np.int64)
+      n = int(counts.sum())
+      row_idx = np.repeat(np.arange(B, dtype=np.int64), counts)
+      col_idx = np.arange(n, dtype=np.int64) - np.repeat(np.cumsum(counts) - counts, counts)
+      values = np.concatenate(decoded_rows).astype(np.int64) if n else np.zeros((0,), dtype=np.int64)
+      out['decoded'] = [ops.SparseTensorValue(np.stack([row_idx, col_idx], axis=1).reshape(n, 2), values,
+                                              np.array([B, int(counts.max()) if B else 0], dtype=np.int64))]
+      out['neg_sum_logits'] = neg
     return out
 
   @_on_engine_device

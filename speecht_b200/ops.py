@@ -199,23 +199,24 @@ def ctc_loss(labels, logits, sequence_length=None, want_grad=True, grad_scale=1.
 _decode_bufs = {}
 
 
-def ctc_greedy_decode_device(logits, d_seq, merge_repeated=True):
+def ctc_greedy_decode_device(logits, d_seq, merge_repeated=True, fresh=False):
   """The decode kernel alone: logits [T,B,C] (strided view allowed), d_seq int32 [B] on the device ->
-  (label rows [B, max(T,1)] int32, counts [B] int32, neg_sum_logits [B] f32), all on the device (buffers are reused
-  per shape: copy what must survive the next call)."""
+  (label rows [B, max(T,1)] int32, counts [B] int32, neg_sum_logits [B] f32), all on the device.  The buffers are
+  reused per shape (copy what must survive the next call) unless fresh=True."""
   _require_cuda(logits)
   T, B, C = logits.shape
   if logits.stride(2) != 1 or logits.dtype != torch.float32:
     raise ValueError('logits must be float32 with unit class stride')
   dev = logits.device
   key = (T, B, dev)
-  buf = _decode_bufs.get(key)
+  buf = None if fresh else _decode_bufs.get(key)
   if buf is None:
-    if len(_decode_bufs) > 16:
-      _decode_bufs.clear()
     buf = (torch.empty((B, max(T, 1)), dtype=torch.int32, device=dev),
            torch.empty((B,), dtype=torch.int32, device=dev), torch.empty((B,), dtype=torch.float32, device=dev))
-    _decode_bufs[key] = buf
+    if not fresh:
+      if len(_decode_bufs) > 16:
+        _decode_bufs.clear()
+      _decode_bufs[key] = buf
   values, counts, neg = buf
   check(lib().st_ctc_greedy_decode(ptr(logits), logits.stride(0), logits.stride(1), T, B, C, ptr(d_seq), C - 1,
                                    int(bool(merge_repeated)), ptr(values), ptr(counts), ptr(neg), stream_ptr()))

@@ -47,7 +47,7 @@ class _Shape:
     off = lib().st_plan_dlogits_planes(self.handle) - base
     npl = N_PLANES[engine.precision]
     self.dlogits_planes = self.arena[off:off + npl * B * self.To * 64 * 2].view(torch.bfloat16).view(npl, B, self.To, 64)
-    self.weights_version = -1
+    self.filter_set = lib().st_plan_filter_set(self.handle)
 
   def close(self):
     if self.handle:
@@ -67,7 +67,9 @@ class TCPlan:
     self.engine = engine
     self.shapes = {}
     self.arena = None                 # ONE arena shared by every shape (only one shape is live at a time)
-    self._active = None
+    # engine weights version last packed, per filter set: the packed filters sit at shape-independent offsets at the
+    # head of the arena, so switching the batch shape does not invalidate them
+    self.packed = {}
 
   def _shape(self, B, T):
     """Plan for this batch shape.  Ragged training produces a new (B, T) almost every step: plans (offsets + TMA
@@ -83,15 +85,13 @@ class TCPlan:
         for other in self.shapes.values():
           other.close()
         self.shapes.clear()
+        self.packed = {}
         self.arena = None                                      # release before growing
         self.arena = torch.zeros((int(sh.nbytes * 1.1) + 1024,), dtype=torch.uint8, device=self.engine.device)
       sh.bind(self.engine, self.arena)
       self.shapes[key] = sh
       if getattr(self, 'timing', False):
         check(lib().st_plan_set_timing(sh.handle, 1))
-    if self._active is not key and self._active != key:
-      sh.weights_version = -1                                  # another shape's buffers overlapped the filter planes
-      self._active = key
     return sh
 
   def set_timing(self, enable):
@@ -119,10 +119,13 @@ class TCPlan:
     self.engine.launches += lib().st_plan_launches(sh.handle) - before
 
   def _pack(self, sh):
-    if sh.weights_version != self.engine._weights_version:
+    if self.packed.get(sh.filter_set) != self.engine._weights_version:
       before = lib().st_plan_launches(sh.handle)
       check(lib().st_plan_pack_weights(sh.handle, stream_ptr()))
-      sh.weights_version = self.engine._weights_version
+      # a plan packs the layers common to every set plus its own layer-8 variant
+      if self.packed.get('common') != self.engine._weights_version:
+        self.packed = {'common': self.engine._weights_version}
+      self.packed[sh.filter_set] = self.engine._weights_version
       self._launch_count(sh, before)
 
   def forward(self, inputs, keep_activations=False):

@@ -333,3 +333,73 @@ def test_fast_fir_levels_and_cta_pairs_give_the_same_step(level, pair, monkeypat
   for li, ((dw, db), (rdw, rdb)) in enumerate(zip(eng.weight_grads, ref_grads)):
     assert rel(dw.cpu().numpy(), rdw) < 3e-4, (li, rel(dw.cpu().numpy(), rdw))
     assert rel(db.cpu().numpy(), rdb) < 3e-4, (li, rel(db.cpu().numpy(), rdb))
+
+
+def test_ragged_host_batch_is_uploaded_without_its_padding_and_arrives_identical():
+  """SpeechModel._to_device sends only the valid frames of a mostly-padding batch (zeros are written on the device):
+  the device tensor must equal the host tensor exactly, on the default stream and on the prefetch stream."""
+  import types
+  from speecht_b200 import speech_input, speech_model
+  rng = np.random.default_rng(0)
+  lengths = np.array([40, 7, 0, 19], dtype=np.int32)
+  host = np.zeros((4, 40, 128), dtype=np.float32)
+  for b, n in enumerate(lengths):
+    host[b, :n] = rng.standard_normal((n, 128)).astype(np.float32)
+  loader = speech_input.SingleInputLoader(128)
+  flags = types.SimpleNamespace(command='evaluate', learning_rate=1e-4, learning_rate_decay_factor=0.0,
+                                max_gradient_norm=5.0, momentum=0.9, log_dir='log', run_name='t', run_type='test',
+                                language_model=None)
+  model = speech_model.create_default_model(flags, 128, loader)
+  dev, ev = model._to_device(torch.from_numpy(host).pin_memory(), None, lengths)
+  torch.cuda.synchronize()
+  np.testing.assert_array_equal(dev.cpu().numpy(), host)
+  stream = torch.cuda.Stream()
+  dev2, ev2 = model._to_device(torch.from_numpy(host).pin_memory(), stream, lengths)
+  ev2.synchronize()
+  np.testing.assert_array_equal(dev2.cpu().numpy(), host)
+  full = np.ones((2, 5, 128), dtype=np.float32)                    # no padding: one plain copy
+  dev3, _ = model._to_device(full, None, np.array([5, 5]))
+  np.testing.assert_array_equal(dev3.cpu().numpy(), full)
+
+
+def test_bucketed_evaluate_restores_order_and_equals_per_group_evaluation():
+  """evaluate_step(buckets=G): optional length-sorted groups padded to their own maximum.  (1) Equal-length batch:
+  grouping changes nothing, bit for bit.  (2) Ragged batch: results come back in the original utterance order and
+  equal evaluating every group by hand; utterances that keep the batch maximum as their padding (the longest group)
+  also equal the unbucketed reference-style evaluation."""
+  from speecht_b200.engine import W2LEngine
+  eng = W2LEngine(precision='bf16x3')
+  eng.init_xavier(seed=6)
+  inputs, lengths, labels = O.synthetic_batch(seed=9, batch=6, seconds=1)
+  x = torch.from_numpy(inputs).cuda()
+  a = eng.evaluate_step(x, lengths, labels)
+  a_loss, a_vals, a_idx = a['loss'].cpu().numpy(), a['decoded'][0].values.copy(), a['decoded'][0].indices.copy()
+  b = eng.evaluate_step(x, lengths, labels, buckets=3)
+  np.testing.assert_array_equal(b['loss'].cpu().numpy(), a_loss)
+  np.testing.assert_array_equal(b['decoded'][0].values, a_vals)
+  np.testing.assert_array_equal(b['decoded'][0].indices, a_idx)
+  assert b['logits'] is None
+
+  secs = [3, 1, 2, 1, 3, 2, 1]
+  inputs, lengths, labels = O.synthetic_batch(seed=10, batch=len(secs), seconds=secs)
+  x = torch.from_numpy(inputs).cuda()
+  full = eng.evaluate_step(x, lengths, labels)
+  full_loss = full['loss'].cpu().numpy()
+  full_rows = [full['decoded'][0].values[full['decoded'][0].indices[:, 0] == u] for u in range(len(secs))]
+  res = eng.evaluate_step(x, lengths, labels, buckets=3)
+  loss = res['loss'].cpu().numpy()
+  rows = [res['decoded'][0].values[res['decoded'][0].indices[:, 0] == u] for u in range(len(secs))]
+  assert res['decoded'][0].dense_shape[0] == len(secs)
+  for group in W2LEngine.length_buckets(lengths, 3):
+    t_max = int(lengths[group].max())
+    one = eng.evaluate_step(x[torch.from_numpy(group).cuda()][:, :t_max].contiguous(), lengths[group],
+                            [labels[u] for u in group])
+    np.testing.assert_array_equal(loss[group], one['loss'].cpu().numpy())
+    for j, u in enumerate(group):
+      np.testing.assert_array_equal(rows[u], one['decoded'][0].values[one['decoded'][0].indices[:, 0] == j])
+  longest = [u for u, s in enumerate(secs) if s == 3]
+  np.testing.assert_array_equal(loss[longest], full_loss[longest])
+  for u in longest:
+    np.testing.assert_array_equal(rows[u], full_rows[u])
+  # shorter utterances see other padding than in the reference batch: close, not identical
+  assert np.max(np.abs(loss - full_loss) / full_loss) < 0.05

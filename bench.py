@@ -126,6 +126,36 @@ def conv_flops_forward(batch, T):
   return total
 
 
+def n_input_sets(cfg):
+  return 4 if cfg['mode'] == 'train' else 2              # distinct batches rotated so that inputs never sit in L2
+
+
+def batch_lengths(seed, batch, seconds):
+  """The frame counts make_batch(seed, batch, seconds) draws (its first use of the generator)."""
+  rng = np.random.default_rng(seed)
+  if isinstance(seconds, (tuple, list)):
+    secs = rng.integers(int(seconds[0]), int(seconds[1]) + 1, size=batch).astype(np.float64)
+  else:
+    secs = np.full((batch,), float(seconds))
+  return np.array([frames_for(s) for s in secs], dtype=np.int32)
+
+
+def workload_config(args, world):
+  """`config` of the JSON line: a function of the command line only, so that the GPU arm and the reference arm
+  (which times a bounded SAMPLE of the same workload, described in its cpu_baseline.sample) print the same dict."""
+  cfg = args.cfg
+  B = cfg['batch']
+  lens = [batch_lengths(100 * 0 + i, B, cfg['seconds']) for i in range(n_input_sets(cfg))]   # rank 0's batches
+  T = int(max(l.max() for l in lens))
+  return {'workload': cfg['name'] + ' (T=%d mel frames -> T\'=%d logit frames)' % (T, (T + 1) // 2),
+          'bench_config': args.config, 'mode': cfg['mode'], 'global_batch': world * B, 'precision': cfg['precision'],
+          'parallelism': 'dp%d' % world, 'mean_frames': float(np.mean([l.mean() for l in lens])),
+          'eval_buckets': args.eval_buckets,
+          'l2': 'no explicit flush: per-step working set (activations+params+grads+Adam > 1 GB) exceeds the '
+                '126 MB L2 and %d distinct input batches rotate' % n_input_sets(cfg),
+          'conv_tflop_per_step_per_gpu': (3 if cfg['mode'] == 'train' else 1) * conv_flops_forward(B, T) / 1e12}
+
+
 def metric_name(cfg):
   if cfg['mode'] == 'eval':
     return 'utterances/sec (1-30s@16kHz, 128-mel) evaluate-step: forward + CTC loss + greedy decode'
@@ -256,17 +286,17 @@ def run_reference(args, rank, world):
   cfg = args.cfg
   threads = cpu_threads(args.cpu_threads)
   secs = cpu_sample_seconds(cfg)
-  # bounded: about a second per train step at 8 x 10 s on 16 threads; cap the whole run near a minute
-  per_step_guess = 1.2 * (args.cpu_sample / 8.0) * (secs / 10.0) * (0.4 if cfg['mode'] == 'eval' else 1.0)
-  steps = int(max(1, min(args.steps, 60.0 / max(per_step_guess, 1e-3))))
-  warmup = int(max(0, min(args.warmup, 1)))
+  # bounded: about 1.2 s per train step at 8 x 10 s on 16 threads (slower boxes: 3 s); K and W are honoured as long as
+  # the whole run stays near two minutes
+  per_step_guess = 1.5 * (args.cpu_sample / 8.0) * (secs / 10.0) * (0.4 if cfg['mode'] == 'eval' else 1.0)
+  warmup = int(max(0, min(args.warmup, 5)))
+  steps = int(max(1, min(args.steps, 120.0 / max(per_step_guess, 1e-3) - warmup)))
   rec, sec = cpu_baseline_record(cfg, args.cpu_sample, steps, warmup, threads)
   line = {
     'impl': 'reference', 'metric': metric_name(cfg), 'value': rec['value'], 'unit': UNIT, 'n_gpus': args.gpus,
     'steps': steps, 'warmup': warmup, 'ms_per_step': sec * 1e3, 'higher_is_better': True, 'scaling': 'weak',
     'vs_baseline': None, 'dtype': 'fp32', 'data': 'synthetic',
-    'config': {'workload': cfg['name'] + '; CPU sample of %d x %gs utterances/step' % (args.cpu_sample, secs),
-               'global_batch': args.cpu_sample, 'seconds': secs, 'bench_config': args.config},
+    'config': workload_config(args, max(1, args.gpus)),
     'cpu_baseline': rec,
     'e2e': {'value': rec['value'], 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
     'gpu_launches': 0,
@@ -322,7 +352,7 @@ def run_ours(args, rank, local_rank, world):
     group = dist.group.WORLD
 
   B = cfg['batch']
-  n_sets = 4 if mode == 'train' else 2                      # rotate distinct batches so inputs never sit in L2
+  n_sets = n_input_sets(cfg)
   host_sets = [make_batch(100 * rank + i, B, cfg['seconds']) for i in range(n_sets)]
   pinned = [torch.from_numpy(h[0]).pin_memory() for h in host_sets]
   dev_inputs = [p.to(dev) for p in pinned]
@@ -478,8 +508,6 @@ def run_ours(args, rank, local_rank, world):
   if rank != 0:
     return
 
-  mean_frames = float(np.mean([h[1].mean() for h in host_sets]))
-  fwd_flops = conv_flops_forward(B, T)
   # inputs: SpeechModel uploads only the valid frames of a batch that is more than a quarter padding (the zeros are
   # written on the device), the whole padded tensor otherwise
   full_bytes, valid_bytes = int(pinned[0].numel() * 4), int(host_sets[0][1].sum()) * 128 * 4
@@ -492,12 +520,7 @@ def run_ours(args, rank, local_rank, world):
               'bf16x6': 'fp32 (bf16x6: three bf16 planes per operand, 6 products on tcgen05, fp32 accumulate)',
               'bf16': 'bf16 conv operands, fp32 accumulate; CTC/Adam fp32'}[precision],
     'data': 'synthetic',
-    'config': {'workload': cfg['name'] + ' (T=%d mel frames -> T\'=%d logit frames)' % (T, (T + 1) // 2),
-               'bench_config': args.config, 'mode': mode, 'global_batch': world * B, 'precision': precision,
-               'parallelism': 'dp%d' % world, 'mean_frames': mean_frames, 'eval_buckets': args.eval_buckets,
-               'l2': 'no explicit flush: per-step working set (activations+params+grads+Adam > 1 GB) exceeds the '
-                     '126 MB L2 and %d distinct input batches rotate' % n_sets,
-               'conv_tflop_per_step_per_gpu': (3 if mode == 'train' else 1) * fwd_flops / 1e12},
+    'config': workload_config(args, world),
     'clocks': clocks,
     'e2e': {'value': e2e_value, 'unit': UNIT, 'ms_per_step': e2e_ms, 'h2d_bytes_per_step': h2d,
             'd2h_bytes_per_step': int(d2h_bytes[0])},

@@ -738,10 +738,19 @@ tc_wgrad_kernel(const __grid_constant__ std::conditional_t<NPROB == 1, TmSet1, T
   const int full_waves = num_tiles / G;
   const int tail_tiles = num_tiles - full_waves * G;
   const int tail_split = tail_tiles > 0 ? max(1, min(G / tail_tiles, total_iters / 4 > 0 ? total_iters / 4 : 1)) : 1;
-  const int my_items = full_waves + ((int)blockIdx.x < tail_tiles * tail_split ? 1 : 0);
+  const int fsplit = p.force_split > 1 ? p.force_split : 0;
+  const int forced_items = fsplit * num_tiles;
+  const int my_items = fsplit ? ((int)blockIdx.x < forced_items ? (forced_items - (int)blockIdx.x + G - 1) / G : 0)
+                              : full_waves + ((int)blockIdx.x < tail_tiles * tail_split ? 1 : 0);
   // item i of this CTA -> (tile, q0, q1)
   auto item = [&](int i, int& tile, int& q0, int& q1) {
-    if (i < full_waves) {
+    if (fsplit) {
+      const int g = i * G + (int)blockIdx.x;               // slice-major: a wave sweeps one K range in phase
+      const int slice = g / num_tiles;
+      tile = g - slice * num_tiles;
+      q0 = (int)((int64_t)total_iters * slice / fsplit);
+      q1 = (int)((int64_t)total_iters * (slice + 1) / fsplit);
+    } else if (i < full_waves) {
       tile = i * G + blockIdx.x;
       q0 = 0;
       q1 = total_iters;
@@ -2159,6 +2168,19 @@ int launch_ffa2_dw_combine(float* dW, float* const* c9, int J, int64_t tap_elems
 
 // Does a filter-gradient launch of `num_tiles` tiles cut its last wave into K slices (which ACCUMULATE into dW, so the
 // outputs must be zero on entry)?  Mirrors the wave-aligned split of tc_wgrad_kernel.
+int wgrad_best_split(int num_tiles, int total_iters) {
+  const int G = st_num_sms();
+  if (num_tiles >= G) return 1;
+  int best = 1;
+  int64_t best_cost = (int64_t)((num_tiles + G - 1) / G) * total_iters;
+  for (int s = 2; s <= 8 && s * 4 <= total_iters; ++s) {
+    // makespan in iterations + a charge for the extra accumulation epilogues
+    const int64_t cost = (int64_t)((num_tiles * s + G - 1) / G) * ((total_iters + s - 1) / s + 4);
+    if (cost < best_cost) { best_cost = cost; best = s; }
+  }
+  return best;
+}
+
 bool wgrad_accumulates(int num_tiles, int total_iters) {
   const int G = st_num_sms();
   const int tail_tiles = num_tiles % G;

@@ -63,7 +63,14 @@ struct WgradParams {
   int pad_left_q[9];
   float* dW_q[9];
   int tap_stride_q[9];
+  // > 1: EVERY tile's contraction is cut into this many slices (work items = tiles x slices, slice-major so that a
+  // wave works on one K range in phase); all slices accumulate into the pre-zeroed dW.  For launches with fewer tiles
+  // than SMs (the merged filter gradients of the 250-channel layers); 0 / 1 = the wave-aligned split.
+  int force_split;
 };
+// slices per tile that balance `num_tiles` tiles of `total_iters` iterations over the SMs (1 = leave the wave-aligned
+// split in charge)
+int wgrad_best_split(int num_tiles, int total_iters);
 
 int make_map_3d(CUtensorMap* map, const void* base, int C, int T, int Bn, int64_t ld, int64_t batch_stride,
                 int box_c, int box_t);

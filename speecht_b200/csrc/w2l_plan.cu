@@ -40,6 +40,11 @@ struct st_plan {
   int To;                      // logit frames
   std::vector<Layer> layers;
   size_t off_in, off_logits, off_dlogits, off_dz[2], arena_bytes;
+  // gradients wrt the outputs of layers 0..7 each keep their OWN buffer (the 2000-channel ones of layers 8, 9 share the
+  // ping / pong pair): the filter gradients of the seven 250-channel layers are deferred to ONE multi-problem launch
+  // at the end of the backward pass and need all of them alive (SPEECHT_B200_MERGE_WGRAD=0: one launch per layer)
+  size_t off_dzs[8];
+  bool merge_wgrad;
   size_t filter_bytes;         // leading arena region holding the packed filters (shape independent)
   size_t dz_elems;             // elements per plane of a dz buffer
   char* arena;
@@ -125,6 +130,8 @@ ST_API int st_plan_create(st_plan** out, int B, int T, int input_size, int num_c
     p->trim = !(e && e[0] == '0');
     e = getenv("SPEECHT_B200_L10_N128");
     p->l10_n128 = !(e && e[0] == '0') && n_planes == 2;
+    e = getenv("SPEECHT_B200_MERGE_WGRAD");
+    p->merge_wgrad = !(e && e[0] == '0') && n_planes <= 2;
     e = getenv("SPEECHT_B200_FFA");
     p->ffa = n_planes > 2 ? 0 : (e && e[0] >= '0' && e[0] <= '2' ? e[0] - '0' : 2);
   }
@@ -193,6 +200,10 @@ ST_API int st_plan_create(st_plan** out, int B, int T, int input_size, int num_c
   p->dz_elems = (size_t)B * p->To * 2000;
   p->off_dz[0] = take((size_t)n_planes * p->dz_elems * 2);
   p->off_dz[1] = take((size_t)n_planes * p->dz_elems * 2);
+  for (int l = 0; l < 8; ++l) {
+    const Layer& L = p->layers[l];
+    p->off_dzs[l] = take((size_t)n_planes * B * L.To * L.ld_out * 2);
+  }
   if (p->To < 8) p->ffa = 0;                  // nothing to gain on a handful of frames (and the odd-row view may be empty)
   if (p->ffa == 2 && p->To < 16) p->ffa = 1;
   if (p->ffa == 2) {
@@ -344,7 +355,7 @@ ST_API int st_plan_bind(st_plan* p, void* arena, size_t arena_bytes, float* para
     }
     if (rc) return rc;
     for (int s = 0; s < 2; ++s) {
-      const __nv_bfloat16* dz = l == 10 ? bf(p, p->off_dlogits) : bf(p, p->off_dz[s]);
+      const __nv_bfloat16* dz = l == 10 ? bf(p, p->off_dlogits) : (l <= 7 ? bf(p, p->off_dzs[l]) : bf(p, p->off_dz[s]));
       const int ld_dz = l == 10 ? 64 : L.ld_out;
       const int64_t plane_rows = (int64_t)L.To * ld_dz;
       // NOTE: planes of a dz buffer are p->dz_elems apart only for the shared ping/pong buffers; expressing the
@@ -380,8 +391,8 @@ ST_API int st_plan_bind(st_plan* p, void* arena, size_t arena_bytes, float* para
       if (l > 0) {
         const Layer& Lb = p->layers[l - 1];
         for (int s = 0; s < 2; ++s) {
-          rc = tc::make_map_3d_store(&L.tm_dg_out[s], bf(p, p->off_dz[s]), Lb.ld_out, Lb.To, npl * B, Lb.ld_out,
-                                     (int64_t)Lb.To * Lb.ld_out);
+          rc = tc::make_map_3d_store(&L.tm_dg_out[s], l - 1 <= 7 ? bf(p, p->off_dzs[l - 1]) : bf(p, p->off_dz[s]),
+                                     Lb.ld_out, Lb.To, npl * B, Lb.ld_out, (int64_t)Lb.To * Lb.ld_out);
           if (rc) return rc;
         }
       }
@@ -794,17 +805,18 @@ ST_API int st_plan_backward_range(st_plan* p, int hi, int lo, st_stream_t stream
     // filter gradients of K-sliced tiles accumulate with atomics: zero the whole flat buffer once per backward
     ST_CUDA_CALL(cudaMemsetAsync(p->grads, 0, (size_t)st_plan_param_floats(p) * sizeof(float), s));
   }
-  int cur = p->cur_dz;                          // dz buffer holding the gradient wrt layer l's output (l < 10)
+  int cur = p->cur_dz;                          // ping / pong buffer holding the gradient wrt layer 8's / 9's output
+  int deferred[8], n_deferred = 0;              // 250-channel layers whose filter gradient waits for the merged launch
   for (int l = hi; l >= lo; --l) {
     Layer& L = p->layers[l];
-    const __nv_bfloat16* dz = l == 10 ? bf(p, p->off_dlogits) : bf(p, p->off_dz[cur]);
+    const __nv_bfloat16* dz = l == 10 ? bf(p, p->off_dlogits) : (l <= 7 ? bf(p, p->off_dzs[l]) : bf(p, p->off_dz[cur]));
     const int ld_dz = l == 10 ? 64 : L.ld_out;
     const int64_t rows = (int64_t)p->B * L.To;
     int rc = ST_OK;
     if (l == 8 && p->ffa) {
       const int nxt = cur ^ 1;
-      rc = p->ffa == 2 ? backward_layer8_ffa2(p, dz, bf(p, p->off_dz[nxt]), s)
-                       : backward_layer8_ffa(p, dz, bf(p, p->off_dz[nxt]), s);
+      rc = p->ffa == 2 ? backward_layer8_ffa2(p, dz, bf(p, p->off_dzs[7]), s)
+                       : backward_layer8_ffa(p, dz, bf(p, p->off_dzs[7]), s);
       if (rc) return rc;
       cur = nxt;
       continue;
@@ -816,7 +828,9 @@ ST_API int st_plan_backward_range(st_plan* p, int hi, int lo, st_stream_t stream
       if (rc) return rc;
       p->launches++;
     }
-    // ---- filter gradient
+    // ---- filter gradient (the seven 250-channel layers: deferred to one multi-problem launch after the loop)
+    const bool defer = p->merge_wgrad && l >= 1 && l <= 7;
+    if (defer) deferred[n_deferred++] = l;
     tc::WgradParams w{};
     w.B = p->B; w.To = L.To; w.t_chunks = (L.To + 63) / 64;
     w.taps = L.K; w.pad_left = L.pad_left; w.a_stride = L.stride; w.a_cin = L.Cin;
@@ -825,11 +839,14 @@ ST_API int st_plan_backward_range(st_plan* p, int hi, int lo, st_stream_t stream
     w.Cin = L.Cin; w.Cout = L.Cout;
     w.dW = p->grads + L.w_off;
     w.trim = p->trim;
-    int ti = timed_begin(p, s);
-    rc = tc::launch_wgrad(L.tm_wg_x, L.tm_wg_dz[l == 10 ? 0 : cur], w, l == 10 ? 64 : wide_n(p), p->npl, s);
-    if (rc) return rc;
-    timed_end(p, ti, 2, l, 2.0 * L.K * L.Cin * L.Cout * (double)L.To * p->B, s);
-    p->launches++;
+    int ti = -1;
+    if (!defer) {
+      ti = timed_begin(p, s);
+      rc = tc::launch_wgrad(L.tm_wg_x, L.tm_wg_dz[l == 10 ? 0 : cur], w, l == 10 ? 64 : wide_n(p), p->npl, s);
+      if (rc) return rc;
+      timed_end(p, ti, 2, l, 2.0 * L.K * L.Cin * L.Cout * (double)L.To * p->B, s);
+      p->launches++;
+    }
     // ---- data gradient, ReLU mask of the layer below fused
     if (l > 0) {
       Layer& Lb = p->layers[l - 1];
@@ -852,7 +869,7 @@ ST_API int st_plan_backward_range(st_plan* p, int hi, int lo, st_stream_t stream
       c.n_fastest = (size_t)p->npl * p->B * L.To * ld_dz * 2 > (size_t)48 << 20;
       c.bias = nullptr;
       c.relu = 0;
-      c.out_planes = bf(p, p->off_dz[nxt]);
+      c.out_planes = l - 1 <= 7 ? bf(p, p->off_dzs[l - 1]) : bf(p, p->off_dz[nxt]);
       c.out_plane_stride = (int64_t)p->B * Lb.To * Lb.ld_out;
       c.ld_out = Lb.ld_out;
       c.mask_hi = bf(p, Lb.off_out);
@@ -872,6 +889,44 @@ ST_API int st_plan_backward_range(st_plan* p, int hi, int lo, st_stream_t stream
     }
   }
   p->cur_dz = cur;
+  if (n_deferred > 0) {
+    // ONE launch for the filter gradients of the deferred layers (identical shapes: 250 -> 250 channels, 7 taps): 14
+    // tiles per layer are far fewer than SMs, so every tile's time contraction is cut into slices (force_split) --
+    // seven separate launches each paid their own prologue, pipeline fill and accumulation epilogue for ~26 us of MMAs
+    const Layer& L = p->layers[deferred[0]];
+    CUtensorMap tx[tc::kMaxProblems], tz[tc::kMaxProblems];
+    tc::WgradParams w{};
+    w.B = p->B; w.To = L.To; w.t_chunks = (L.To + 63) / 64;
+    w.taps = L.K; w.pad_left = L.pad_left; w.a_stride = L.stride; w.a_cin = L.Cin;
+    w.m_tiles = (L.Cin + 127) / 128;
+    w.n_tiles = (L.Cout + wide_n(p) - 1) / wide_n(p);
+    w.Cin = L.Cin; w.Cout = L.Cout;
+    w.trim = p->trim;
+    w.n_problems = n_deferred;
+    double flops = 0;
+    for (int i = 0; i < n_deferred; ++i) {
+      const Layer& Li = p->layers[deferred[i]];
+      tx[i] = Li.tm_wg_x;
+      tz[i] = Li.tm_wg_dz[0];
+      w.pad_left_q[i] = Li.pad_left;
+      w.dW_q[i] = p->grads + Li.w_off;
+      w.tap_stride_q[i] = 1;
+      flops += 2.0 * Li.K * Li.Cin * Li.Cout * (double)Li.To * p->B;
+    }
+    int rc;
+    const int ti = timed_begin(p, s);
+    if (n_deferred == 1) {
+      w.dW = w.dW_q[0];
+      w.n_problems = 0;
+      rc = tc::launch_wgrad(tx[0], tz[0], w, wide_n(p), p->npl, s);
+    } else {
+      w.force_split = tc::wgrad_best_split(n_deferred * w.taps * w.m_tiles * w.n_tiles, p->B * w.t_chunks);
+      rc = tc::launch_wgrad_multi(tx, tz, w, wide_n(p), p->npl, s);
+    }
+    if (rc) return rc;
+    timed_end(p, ti, 2, deferred[n_deferred - 1], flops, s);
+    p->launches++;
+  }
   return ST_OK;
 }
 

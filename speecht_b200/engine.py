@@ -31,12 +31,33 @@ PRECISIONS = ('fp32', 'bf16x6', 'bf16x3', 'bf16')
 
 class BatchMean:
   """tf.reduce_mean(cost) (speech_model.py:75) of the per-utterance losses, evaluated WHEN READ: the step itself
-  launches no reduction kernel; .item() copies the [B] losses to the host (4*B bytes) and averages them in float32."""
+  launches no reduction kernel; .item() averages the [B] losses on the host in float32.
 
-  def __init__(self, loss):
+  early=True (train steps): the losses are copied to pinned host memory right after the CTC kernels and an event is
+  recorded THERE, so .item() returns as soon as the loss exists -- while backward and Adam of the same step are still
+  running -- and the caller's next step is enqueued without the GPU ever waiting for the host."""
+
+  _free = []                                        # pinned [>= B] float32 buffers not owned by a live BatchMean
+
+  def __init__(self, loss, early=False):
     self.loss = loss
+    self._host = self._event = None
+    if early and loss.is_cuda:
+      n = loss.numel()
+      for i, buf in enumerate(BatchMean._free):
+        if buf.numel() >= n:
+          self._host = BatchMean._free.pop(i)
+          break
+      if self._host is None:
+        self._host = torch.empty((max(n, 64),), dtype=torch.float32).pin_memory()
+      self._host[:n].copy_(loss.detach(), non_blocking=True)
+      self._event = torch.cuda.Event()
+      self._event.record()
 
   def item(self):
+    if self._event is not None:
+      self._event.synchronize()
+      return float(self._host[:self.loss.numel()].numpy().mean(dtype=np.float32))
     return float(self.loss.detach().cpu().numpy().mean(dtype=np.float32))
 
   def __float__(self):
@@ -45,6 +66,13 @@ class BatchMean:
   def tensor(self):
     """Device scalar (for collectives such as parallel.mean_scalar)."""
     return self.loss.mean()
+
+  def __del__(self):
+    try:
+      if self._host is not None and self._event is not None and self._event.query() and len(BatchMean._free) < 16:
+        BatchMean._free.append(self._host)
+    except Exception:
+      pass
 
 
 def _on_engine_device(fn):
@@ -430,7 +458,7 @@ class W2LEngine:
     scale = 1.0 / (B * self.world_size)                                # tf.reduce_mean folded into the gradient
     loss, dlogits = ops.ctc_loss(batch, logits, want_grad=True, grad_scale=scale)
     self.launches += 3
-    out = {'loss': loss, 'avg_loss': BatchMean(loss), 'decoded': None, 'logits': logits}
+    out = {'loss': loss, 'avg_loss': BatchMean(loss, early=True), 'decoded': None, 'logits': logits}
     if decode:
       out['decoded'], out['neg_sum_logits'] = ops.ctc_greedy_decoder(logits, ctc_len)
       self.launches += 1

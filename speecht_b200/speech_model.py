@@ -311,12 +311,16 @@ class SpeechModel:
     if update:
       res = self.engine.train_step(d_inputs, lengths, labels, self.learning_rate.value, self.max_gradient_norm,
                                    decode=decode)
+      if feed_dict is None:
+        self._prefetch_next()                   # next batch's H2D overlaps this step's kernels
     else:
+      # an evaluate step ends with a blocking read of the decoded labels: the next batch's upload must be under way
+      # BEFORE it, or it would start only once this step has finished
+      if feed_dict is None:
+        self._prefetch_next()
       res = self.engine.evaluate_step(d_inputs, lengths, labels if loss else None, decode=decode,
                                       buckets=getattr(self, 'eval_buckets', 1))
     self.last_result = res
-    if feed_dict is None:
-      self._prefetch_next()                     # next batch's H2D overlaps this step's kernels
     output = []
     if loss:
       output.append(np.float32(res['avg_loss'].item()))       # the device->host read of the step's result ([B] losses)

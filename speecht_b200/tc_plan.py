@@ -160,7 +160,7 @@ class TCPlan:
     loss, _ = ops.ctc_loss(batch, logits, want_grad=False, grad_scale=scale, grad_planes=sh.dlogits_planes)
     eng.launches += 3
     from .engine import BatchMean
-    out = {'loss': loss, 'avg_loss': BatchMean(loss), 'decoded': None, 'logits': logits}
+    out = {'loss': loss, 'avg_loss': BatchMean(loss, early=True), 'decoded': None, 'logits': logits}
     if decode:
       out['decoded'], out['neg_sum_logits'] = ops.ctc_greedy_decoder(logits, ctc_len)
       eng.launches += 1

@@ -6,18 +6,29 @@ only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl refere
 import it.  Nothing under speecht_b200/ imports it; the product path fails loudly without the
 CUDA library.
 
-PARITY UNPINNED.  The reference's own test-suite (speecht/tests/test_speechCorpusReader.py)
-holds no golden vector for any function on this path, and neither TensorFlow 1.x nor librosa
-can be imported in the build container or on the GPU box (no wheels, no network).  Library
-semantics below are restated from the published behaviour of
+PARITY: PINNED TO PUBLISHED KNOWN-ANSWER VECTORS ONLY, NOT TO A RUN OF THE REFERENCE ("parity
+unpinned" in the strict sense of the build rules).  The reference's own test-suite
+(speecht/tests/test_speechCorpusReader.py) holds one value on this path -- the 114 881 samples its
+LibriSpeech FLAC fixture loads to, reproduced by the native FLAC decoder + resampler -- and neither
+TensorFlow 1.x nor librosa can be imported in the build container or on the GPU box (no wheels, no
+network).  Library semantics below are restated from the published behaviour of
   * tensorflow 1.x (requirements.txt:2, unpinned ">=1.0.1"): tf.nn.conv1d 'SAME',
     tf.nn.ctc_loss, tf.nn.ctc_greedy_decoder, tf.clip_by_global_norm, tf.train.AdamOptimizer
   * librosa 0.5-0.7 (requirements.txt:5, unpinned ">=0.5.0"): feature.melspectrogram,
     power_to_db, filters.mel
-and are cross-checked in tests/ against independent implementations available here
-(torch.nn.functional.conv1d / ctc_loss, brute-force CTC path enumeration, scipy FFT).
-Agreement with those is not agreement with TF1; every claim made with this oracle reads
-"vs CPU restatement of the reference".
+and are checked in tests/test_oracle.py against
+  * the literals TensorFlow's own kernel tests publish (tests/golden/tf_published_vectors.py, typed in
+    from the published test sources): ctc_loss_op_test testBasic (loss + gradient, six digits),
+    ctc_decoder_ops_test testCTCGreedyDecoder, conv_ops_test (1x1, stride-2 SAME, kernel smaller than
+    stride, stride-2 data / filter gradients -- integer valued, exact), clip_ops_test
+    testClipByGlobalNormClipped, adam_test's adam_update_numpy;
+  * the mel-scale examples printed in librosa's docstrings (mel_frequencies(n_mels=40), hz_to_mel,
+    mel_to_hz);
+  * independent implementations available here: torch conv1d / ctc_loss + autograd, brute-force CTC
+    path enumeration, torchaudio's librosa-compatible mel pipeline, transformers' TF-port padding.
+What stays unpinned: the 11-layer stack end to end, exact-tie behaviour of the greedy arg-max, librosa's
+triangle construction / Slaney normalisation / power_to_db beyond the torchaudio cross-check.  Claims
+about those read "vs CPU restatement of the reference".
 
 Every function cites the reference file:line whose behaviour it follows.
 """

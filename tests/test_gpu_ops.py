@@ -254,3 +254,24 @@ def test_ctc_kernels_reproduce_tensorflow_published_test_vectors(ops):
   np.testing.assert_array_equal(dec[0].values, values)
   np.testing.assert_array_equal(dec[0].dense_shape, shape)
   np.testing.assert_allclose(gneg, neg, rtol=1e-6)
+
+
+def test_conv_kernels_reproduce_tensorflow_published_test_vectors(ops):
+  """conv_ops_test.py literals (tests/golden/tf_published_vectors.py) through the C ABI: SAME with a stride (padding
+  column on the right), the [width, in, out] filter layout, stride-2 data and filter gradients.  Integer valued and
+  small: fp32 is exact."""
+  import sys
+  sys.path.insert(0, GOLDEN)
+  import tf_published_vectors as TFV
+  for name, x, w, stride, expected in TFV.conv_forward_cases():
+    y = ops.conv1d(dev(x), dev(w), None, stride=stride, relu=False).cpu().numpy()
+    assert y.shape == expected.shape, name
+    np.testing.assert_array_equal(y, expected, err_msg=name)
+  for name, x, w, stride, dy, fold, dx_lit, dw_lit in TFV.conv_backward_cases():
+    dx = ops.conv1d_backprop_input(dev(dy), dev(w), x.shape, stride=stride).cpu().numpy()
+    dw, db = ops.conv1d_backprop_filter(dev(x), dev(dy), w.shape[0], stride=stride)
+    np.testing.assert_array_equal(fold(dx), dx_lit, err_msg=name)
+    np.testing.assert_array_equal(dw.cpu().numpy(), dw_lit, err_msg=name)
+  # clip_ops_test.py::testClipByGlobalNormClipped: global norm 5
+  flat = dev(np.concatenate([a.ravel() for a in TFV.CLIP_INPUTS]))
+  assert ops.global_norm_sq(flat).item() == TFV.CLIP_GLOBAL_NORM ** 2

@@ -285,3 +285,36 @@ def test_oracle_adam_is_tensorflows_adam_update_numpy():
     np.testing.assert_allclose(p[0], pt, rtol=1e-13)
     np.testing.assert_allclose(m[0], mt, rtol=1e-13)
     np.testing.assert_allclose(v[0], vt, rtol=1e-13)
+
+
+def test_oracle_conv_matches_tensorflow_published_vectors():
+  """conv_ops_test.py literals restated as the 1-D problems they contain: SAME with a stride (padding column on the
+  right), filter layout, stride-2 data and filter gradients -- integer valued, so exact."""
+  for name, x, w, stride, expected in TFV.conv_forward_cases():
+    y = O.conv1d_same(x, w, np.zeros(w.shape[2]), stride, False)
+    assert y.shape == expected.shape, name
+    np.testing.assert_array_equal(y, expected, err_msg=name)
+  for name, x, w, stride, dy, fold, dx_lit, dw_lit in TFV.conv_backward_cases():
+    dx, dw, db = O.conv1d_same_backward(x, w, stride, dy)
+    np.testing.assert_array_equal(fold(dx), dx_lit, err_msg=name)
+    np.testing.assert_array_equal(dw, dw_lit, err_msg=name)
+  # the padding column on the LEFT (the other way to make SAME) cannot produce the stride-2 literals
+  name, x, w, stride, expected = TFV.conv_forward_cases()[1]
+  flipped = O.conv1d_same(x[:, ::-1], w[::-1], np.zeros(3), stride, False)[:, ::-1]
+  assert np.max(np.abs(flipped - expected)) > 100
+
+
+def test_oracle_clip_matches_tensorflow_published_vector():
+  clipped, norm = O.clip_by_global_norm(TFV.CLIP_INPUTS, TFV.CLIP_NORM)
+  assert norm == TFV.CLIP_GLOBAL_NORM
+  for c, e in zip(clipped, TFV.CLIP_OUTPUTS):
+    np.testing.assert_allclose(c, e, rtol=1e-15)
+
+
+def test_oracle_mel_scale_matches_librosa_published_docstring_values():
+  hz, mel = TFV.LIBROSA_HZ_TO_MEL
+  np.testing.assert_allclose(O._hz_to_mel_slaney(np.array(hz)), mel, rtol=0, atol=1e-12)
+  mel, hz = TFV.LIBROSA_MEL_TO_HZ
+  np.testing.assert_allclose(O._mel_to_hz_slaney(np.array(mel)), hz, rtol=0, atol=5e-4)
+  edges = O._mel_to_hz_slaney(np.linspace(O._hz_to_mel_slaney(0.0), O._hz_to_mel_slaney(11025.0), 40))
+  np.testing.assert_allclose(edges, TFV.LIBROSA_MEL_FREQUENCIES_40, rtol=0, atol=5e-4)   # three printed decimals

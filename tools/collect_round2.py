@@ -21,8 +21,9 @@ CAPTURES = {
   'l9_dgrad': ('l9_dgrad_bf16x3', None, 'layer-9 data gradient on CTA pairs'),
   'l1_fwd': ('l1_fwd_bf16x3', None, 'layer-1 forward (250 channels, one tile per CTA)'),
   'l8_wgrad': ('l8_wgrad_bf16x3', None, 'layer-8 filter gradient (nine-problem launch)'),
+  'l1_7_wgrad': ('l1_7_wgrad_bf16x3', None, 'filter gradients of the seven 250-channel layers, one launch, forced K slices'),
   'ctc_alpha_beta': ('ctc_alpha_beta', None, 'CTC alpha/beta recursion'),
-  'pack': ('pack_filters', None, 'filter packing'),
+  'pack': ('pack_ffa2', None, 'one-pass packing of the nine leaf filters of layer 8'),
   'l8_fwd_cfg3': ('l8_fwd_bf16_cfg3', 'bf16/B64/T1001', 'layer-8 forward at config 3 (plain bf16, batch 64)'),
 }
 

@@ -42,6 +42,8 @@ timeout 600 python bench.py --config 5 --impl reference > $O/bench_cfg5_referenc
 stamp "bench cfg5 reference rc=$?"
 timeout 600 python bench.py --config 5 --precision bf16 --no-cpu-baseline > $O/bench_cfg5_bf16.json 2> $O/bench_cfg5_bf16.err
 stamp "bench cfg5 bf16 rc=$?: $(line $O/bench_cfg5_bf16.json)"
+timeout 600 python bench.py --config 5 --eval-buckets 8 --no-cpu-baseline > $O/bench_cfg5_buckets8.json 2> $O/bench_cfg5_buckets8.err
+stamp "bench cfg5 buckets 8 rc=$?: $(line $O/bench_cfg5_buckets8.json)"
 timeout 900 python tools/accuracy_sweep.py 32 1001 8 > $O/accuracy_sweep.txt 2>&1
 stamp "accuracy sweep rc=$?: $(tail -1 $O/accuracy_sweep.txt)"
 B="python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-sustained"
@@ -54,13 +56,14 @@ full() {  # name, kernel regex, skip, extra bench args
   stamp "ncu full $name rc=$?"
 }
 # tc_conv launches: 11 (loss-delta forward) + 21 (warm-up step) + 21 (first timed step), then forward L0..L10, data
-# gradients L10, L9, L8, L7..L1; tc_wgrad launches: 11 per step in the order L10, L9, L8, L7..L0
+# gradients L10, L9, L8, L7..L1; tc_wgrad launches: 5 per step in the order L10, L9, L8 (nine leaves), L0, L1-7 (merged)
 full l8_fwd tc_conv_kernel 61
 full l8_dgrad tc_conv_kernel 66
 full l9_dgrad tc_conv_kernel 65
 full l1_fwd tc_conv_kernel 54
-full l8_wgrad tc_wgrad_kernel 24
+full l8_wgrad tc_wgrad_kernel 12
+full l1_7_wgrad tc_wgrad_kernel 14
 full ctc_alpha_beta ctc_alpha_beta 3
-full pack pack_filter_both 3
+full pack pack_ffa2 3
 full l8_fwd_cfg3 tc_conv_kernel 61 --config 3
 cat $S

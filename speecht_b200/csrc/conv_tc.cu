@@ -113,6 +113,18 @@ __device__ __forceinline__ void store_planes8(__nv_bfloat16* dst, int64_t plane_
   }
 }
 
+// ReLU-mask bits (ConvParams::mask_out layout: word [c / 32][row], bit c % 32) seen from a thread that owns the eight
+// channels c8 * 8 .. + 7 of one row: they are byte (c8 & 3) of word c8 >> 2.
+__device__ __forceinline__ void store_mask_byte(uint32_t* mask, int64_t rows, int64_t row, int c8, const float* v) {
+  uint32_t bits = 0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) bits |= (uint32_t)(v[i] > 0.f) << i;
+  reinterpret_cast<uint8_t*>(mask + (int64_t)(c8 >> 2) * rows + row)[c8 & 3] = (uint8_t)bits;
+}
+__device__ __forceinline__ uint32_t load_mask_byte(const uint32_t* mask, int64_t rows, int64_t row, int c8) {
+  return reinterpret_cast<const uint8_t*>(mask + (int64_t)(c8 >> 2) * rows + row)[c8 & 3];
+}
+
 struct Ptr9f { float* p[9]; };
 struct Ptr9c { const float* p[9]; };
 struct Ptr9h { __nv_bfloat16* p[9]; };
@@ -123,23 +135,8 @@ struct Ptr9h { __nv_bfloat16* p[9]; };
 //     per plane (box {32 ch, 32 t, 1}; rows t >= T' and channel padding beyond ld are clipped by the tensor map), or
 //     -- bf16x6 only: no shared memory left -- direct 16-byte stores from the lane that owns the row;
 //   * fp32 logits (last layer): direct stores;
-//   * bias gradient of the layer below (data gradient): column sums by a 32x32 transpose-reduce.
-// Bit i of the result = mask element i > 0 (bf16: sign clear and magnitude non-zero), for this lane's 32 columns.
-__device__ __forceinline__ uint32_t positive_bits(const uint4 (&mk)[4]) {
-  uint32_t bits = 0;
-#pragma unroll
-  for (int g = 0; g < 4; ++g) {
-    const uint32_t w[4] = {mk[g].x, mk[g].y, mk[g].z, mk[g].w};
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      // h > 0  <=>  1 <= h <= 0x7fff  <=>  (h - 1) < 0x7fff (unsigned)
-      bits |= (uint32_t)(((w[i] & 0xffffu) - 1u) < 0x7fffu) << (g * 8 + 2 * i);
-      bits |= (uint32_t)(((w[i] >> 16) - 1u) < 0x7fffu) << (g * 8 + 2 * i + 1);
-    }
-  }
-  return bits;
-}
-
+//   * bias gradient of the layer below (data gradient): column sums by a 32x32 transpose-reduce;
+//   * forward of a ReLU layer: the lane's 32 activity bits for the data gradient (ConvParams::mask_out).
 template <int NPL>
 __device__ __forceinline__ float epilogue_chunk(const ConvParams& p, const CUtensorMap* tmOut, uint8_t* stage,
                                                float (&v)[32], float bias_lane, uint32_t keep, int nc, int lane,
@@ -158,6 +155,13 @@ __device__ __forceinline__ float epilogue_chunk(const ConvParams& p, const CUten
   }
 #pragma unroll
   for (int i = 0; i < 32; ++i) v[i] = (keep & (1u << i)) ? v[i] : 0.f;
+  if (p.mask_out && row_ok && nc < p.N) {
+    // ReLU mask of this lane's row for the data gradient: bit i = channel nc + i is active (one coalesced store per warp)
+    uint32_t bits = 0;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) bits |= (uint32_t)(v[i] > 0.f) << i;
+    p.mask_out[(int64_t)(nc >> 5) * p.mask_rows + out_row] = bits;
+  }
   if (p.out_planes) {
     if constexpr (NPL <= 2) {
       // the previous TMA store out of this warp's tile must have finished reading it
@@ -259,7 +263,10 @@ template <> struct Products<3> {
 // (problem, tap slice, tile); fp32 outputs only.  NPROB == 1 is the plain single-problem kernel.
 // PAIR: launched as clusters of two CTAs; a work item is a PAIR of m tiles (rank r of the cluster owns m tile
 // 2*pair + r), the leader (rank 0) issues tcgen05.mma.cta_group::2 with M = 256 for both.
-template <int BLOCK_N, int NPL, bool EARLY, int NPROB, bool PAIR>
+// BMN: the B operand is MN-major -- the filter is read from its BACKWARD layout [K * Cin rows][ld_co] (output channels
+// contiguous, boxes of 64 rows x 64 channels like the filter-gradient operands), so a forward launch needs no packed
+// layout of its own (ConvParams::b_row_step = rows per tap; K rows past Cin meet zero channels of A).
+template <int BLOCK_N, int NPL, bool EARLY, int NPROB, bool PAIR, bool BMN = false>
 __global__ void __launch_bounds__(kThreads, 1)
 tc_conv_kernel(const __grid_constant__ std::conditional_t<NPROB == 1, TmSet1, TmSetN> tmAs,
                const __grid_constant__ std::conditional_t<NPROB == 1, TmSet1, TmSetN> tmBs,
@@ -382,7 +389,22 @@ tc_conv_kernel(const __grid_constant__ std::conditional_t<NPROB == 1, TmSet1, Tm
           const int shift = p.a_stride == 1 ? m : floordiv(m, p.a_stride);
           const int a_col = (m - shift * p.a_stride) * p.a_cin + cc * kChunkK;
           uint8_t* st = smem + stage * Cfg::STAGE_BYTES;
-          const int b_c0 = j * p.b_col_step + cc * kChunkK, b_c1 = n0 + j * p.b_row_step + b_half;
+          // K-major B: box {64 K columns, B_ROWS rows};  MN-major B: B_ROWS / 64 boxes {64 N columns, 64 K rows}
+          const int b_c0 = BMN ? n0 + b_half : j * p.b_col_step + cc * kChunkK;
+          const int b_c1 = BMN ? j * p.b_row_step + cc * kChunkK : n0 + j * p.b_row_step + b_half;
+          auto load_b = [&](uint64_t* fb, uint32_t fbc, int pb) {
+            uint8_t* dst = st + NPL * Cfg::A_BYTES + pb * Cfg::B_BYTES;
+            if constexpr (BMN) {
+#pragma unroll
+              for (int h = 0; h < Cfg::B_ROWS / 64; ++h) {
+                if constexpr (PAIR) tma_load_2d_pair(tmB, fbc, dst + h * 8192, b_c0 + h * 64, pb * p.b_plane_rows + b_c1);
+                else tma_load_2d(tmB, fb, dst + h * 8192, b_c0 + h * 64, pb * p.b_plane_rows + b_c1);
+              }
+            } else {
+              if constexpr (PAIR) tma_load_2d_pair(tmB, fbc, dst, b_c0, pb * p.b_plane_rows + b_c1);
+              else tma_load_2d(tmB, fb, dst, b_c0, pb * p.b_plane_rows + b_c1);
+            }
+          };
           if (NG == 2) {
 #pragma unroll
             for (int g = 0; g < NG; ++g) {
@@ -395,12 +417,11 @@ tc_conv_kernel(const __grid_constant__ std::conditional_t<NPROB == 1, TmSet1, Tm
                 if (rank == 0) mbar_expect_tx(fb, 2 * (Cfg::A_BYTES + Cfg::B_BYTES));
                 const uint32_t fbc = mapa_u32(smem_u32(fb), 0);
                 tma_load_3d_pair(tmA, fbc, st + pa * Cfg::A_BYTES, a_col, t0 + shift, pa * p.B + b);
-                tma_load_2d_pair(tmB, fbc, st + NPL * Cfg::A_BYTES + pb * Cfg::B_BYTES, b_c0,
-                                 pb * p.b_plane_rows + b_c1);
+                load_b(fb, fbc, pb);
               } else {
                 mbar_expect_tx(fb, Cfg::A_BYTES + Cfg::B_BYTES);
                 tma_load_3d(tmA, fb, st + pa * Cfg::A_BYTES, a_col, t0 + shift, pa * p.B + b);
-                tma_load_2d(tmB, fb, st + NPL * Cfg::A_BYTES + pb * Cfg::B_BYTES, b_c0, pb * p.b_plane_rows + b_c1);
+                load_b(fb, 0u, pb);
               }
             }
           } else {
@@ -413,17 +434,14 @@ tc_conv_kernel(const __grid_constant__ std::conditional_t<NPROB == 1, TmSet1, Tm
               for (int pl = 0; pl < NPL; ++pl)
                 tma_load_3d_pair(tmA, fbc, st + pl * Cfg::A_BYTES, a_col, t0 + shift, pl * p.B + b);
 #pragma unroll
-              for (int pl = 0; pl < NPL; ++pl)
-                tma_load_2d_pair(tmB, fbc, st + NPL * Cfg::A_BYTES + pl * Cfg::B_BYTES, b_c0,
-                                 pl * p.b_plane_rows + b_c1);
+              for (int pl = 0; pl < NPL; ++pl) load_b(fb, fbc, pl);
             } else {
               mbar_expect_tx(fb, Cfg::STAGE_BYTES);
 #pragma unroll
               for (int pl = 0; pl < NPL; ++pl)
                 tma_load_3d(tmA, fb, st + pl * Cfg::A_BYTES, a_col, t0 + shift, pl * p.B + b);
 #pragma unroll
-              for (int pl = 0; pl < NPL; ++pl)
-                tma_load_2d(tmB, fb, st + NPL * Cfg::A_BYTES + pl * Cfg::B_BYTES, b_c0, pl * p.b_plane_rows + b_c1);
+              for (int pl = 0; pl < NPL; ++pl) load_b(fb, 0u, pl);
             }
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -449,7 +467,7 @@ tc_conv_kernel(const __grid_constant__ std::conditional_t<NPROB == 1, TmSet1, Tm
         const int nt = p.n_fastest ? tile % p.n_tiles : tile / m_tiles;
         const int n_valid = min(BLOCK_N, p.N - nt * BLOCK_N);
         const uint32_t idesc = make_idesc_bf16(PAIR ? 2 * kTileM : kTileM,
-                                               p.trim ? max(16, (n_valid + 15) & ~15) : BLOCK_N, 0, 0);
+                                               p.trim ? max(16, (n_valid + 15) & ~15) : BLOCK_N, 0, BMN ? 1 : 0);
         mbar_wait(tmem_empty + acc, acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_main = tmem_base + acc * Cfg::ACC_COLS;
@@ -469,13 +487,17 @@ tc_conv_kernel(const __grid_constant__ std::conditional_t<NPROB == 1, TmSet1, Tm
             if (PR::wait(pr) >= 0) { mbar_wait(full_bar + stage * NG + PR::wait(pr), phase); tc_fence_after(); }
             if (tl && local == 0 && it == 0 && pr == 0) tl[2] = global_ns();         // 2: first operands landed
             const uint64_t da = make_smem_desc_sw128(a_addr + pa * Cfg::A_BYTES, 16, 1024);
-            const uint64_t db = make_smem_desc_sw128(b_addr + pb * Cfg::B_BYTES, 16, 1024);
+            // MN-major B (see tc_wgrad_kernel): LBO = distance between the 64-channel boxes, a K step of 16 rows = two
+            // swizzle atoms of 8 rows x 128 B = 2048 bytes = +128 in the address field
+            const uint64_t db = BMN ? make_smem_desc_sw128(b_addr + pb * Cfg::B_BYTES, 8192, 1024)
+                                    : make_smem_desc_sw128(b_addr + pb * Cfg::B_BYTES, 16, 1024);
+            constexpr int kBStep = BMN ? 128 : 2;
             auto step = [&](int kk) {
               // advancing 16 bf16 along K = 32 bytes inside the 128-byte swizzled row = +2 in the address field
               const uint32_t d = (pa == 0 && pb == 0) ? d_main : d_side;
               uint32_t& accf = (pa == 0 && pb == 0) ? acc_main : acc_side;
-              if constexpr (PAIR) umma_bf16_pair(d, da + (uint64_t)(kk * 2), db + (uint64_t)(kk * 2), idesc, accf);
-              else umma_bf16(d, da + (uint64_t)(kk * 2), db + (uint64_t)(kk * 2), idesc, accf);
+              if constexpr (PAIR) umma_bf16_pair(d, da + (uint64_t)(kk * 2), db + (uint64_t)(kk * kBStep), idesc, accf);
+              else umma_bf16(d, da + (uint64_t)(kk * 2), db + (uint64_t)(kk * kBStep), idesc, accf);
               accf = 1u;
             };
             if constexpr (FULL) {
@@ -523,24 +545,6 @@ tc_conv_kernel(const __grid_constant__ std::conditional_t<NPROB == 1, TmSet1, Tm
       if constexpr (PAIR) mbar_arrive_cluster(mapa_u32(smem_u32(tmem_empty + acc), 0));
       else mbar_arrive(tmem_empty + acc);
     };
-    // ReLU-mask rows of a tile (data gradient only) are pulled into L2 one tile ahead: the forward activations they
-    // come from were written a whole forward+loss ago and would otherwise be an HBM round trip in the epilogue
-    auto prefetch_mask = [&](int tile) {
-      if (!p.mask_hi || tile >= num_tiles) return;
-      int b, t0, n0;
-      tile_coords(tile, b, t0, n0);
-      if (t0 + row >= p.To) return;
-      const __nv_bfloat16* mrow = p.mask_hi + ((int64_t)b * p.To + t0 + row) * p.ld_mask;
-#pragma unroll
-      for (int q = chunk0; q < (BLOCK_N + 63) / 64; q += kChunkStep) {
-        const int c = n0 + q * 64;
-        if (c < p.ld_mask) {
-          prefetch_l2(mrow + c);
-          prefetch_l2(mrow + min(c + 63, p.ld_mask - 1));     // rows are not 128-byte aligned when ld % 64 != 0
-        }
-      }
-    };
-    if (NPROB == 1) prefetch_mask(cta_id);
     int local = 0;
     for (int work = cta_id; work < total_work; work += cta_step, ++local) {
       int q, j0, j1, tile;
@@ -555,35 +559,19 @@ tc_conv_kernel(const __grid_constant__ std::conditional_t<NPROB == 1, TmSet1, Tm
       const int64_t out_row = (int64_t)b * p.To + t;
       float* out_f32 = NPROB > 1 ? p.out_f32_q[q] : p.out_f32;
       const bool f32_add = NPROB > 1 && ksplit > 1;
-      if (NPROB == 1) prefetch_mask(tile + cta_step);
       // Per chunk of this warp, fetched while the MMAs of the tile are still running: the lane's bias element and
-      // the ReLU-mask row segment (data gradient), reduced to one keep-bit per column once it has arrived.
+      // (data gradient) the row's word of ReLU-mask bits -- one keep-bit per column.
       constexpr int kMine = (kChunks + kChunkStep - 1) / kChunkStep;       // chunks per warp (compile time)
       float bias_l[kMine];
       uint32_t keep[kMine];
-      {
-        uint4 mk[kMine][4];
 #pragma unroll
-        for (int ci = 0; ci < kMine; ++ci) {
-          const int nc = n0 + (chunk0 + ci * kChunkStep) * 32;
-          bias_l[ci] = (p.bias && nc + lane < p.N) ? __ldg(p.bias + nc + lane) : 0.f;
-          if (p.mask_hi) {
-#pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              mk[ci][g] = make_uint4(0x3f803f80u, 0x3f803f80u, 0x3f803f80u, 0x3f803f80u);    // bf16 1.0 pairs: pass
-              if (row_ok && nc + g * 8 < p.ld_mask)
-                mk[ci][g] = *reinterpret_cast<const uint4*>(p.mask_hi + out_row * p.ld_mask + nc + g * 8);
-            }
-          }
-        }
-        // (the epilogue warps have nothing else to do until the accumulator is complete: the load latency overlaps
-        // the tile's MMAs either way, and the 16 mask vectors are dead before the accumulator registers are needed)
-#pragma unroll
-        for (int ci = 0; ci < kMine; ++ci) {
-          const int nvalid = p.N - (n0 + (chunk0 + ci * kChunkStep) * 32);
-          keep[ci] = nvalid >= 32 ? 0xffffffffu : (nvalid <= 0 ? 0u : ((1u << nvalid) - 1u));
-          if (p.mask_hi) keep[ci] &= positive_bits(mk[ci]);
-        }
+      for (int ci = 0; ci < kMine; ++ci) {
+        const int nc = n0 + (chunk0 + ci * kChunkStep) * 32;
+        bias_l[ci] = (p.bias && nc + lane < p.N) ? __ldg(p.bias + nc + lane) : 0.f;
+        const int nvalid = p.N - nc;
+        keep[ci] = nvalid >= 32 ? 0xffffffffu : (nvalid <= 0 ? 0u : ((1u << nvalid) - 1u));
+        if (p.mask_bits && nvalid > 0)
+          keep[ci] &= row_ok ? __ldg(p.mask_bits + (int64_t)(nc >> 5) * p.mask_rows + out_row) : 0u;
       }
       mbar_wait(tmem_full + acc, acc_phase);
       tc_fence_after();
@@ -688,10 +676,15 @@ tc_conv_kernel(const __grid_constant__ std::conditional_t<NPROB == 1, TmSet1, Tm
 }
 
 // ------------------------------------------------------------------------------------------------ filter gradient
-template <int BLOCK_N, int NPL>
+// PAIR: two CTAs of one cluster work on two tiles that share their dZ (B) tile -- consecutive tiles differ in the
+// filter tap or the Cin tile only -- as ONE tcgen05.mma.cta_group::2 of M = 256: each CTA holds its own X tile and
+// HALF of the dZ columns, so a stage is a third smaller (three stages instead of two in bf16x3) and dZ crosses
+// L2 -> shared memory once per pair.  These launches sit at the L2 -> SM bandwidth cap (96 KB per 12 MMAs and SM).
+template <int BLOCK_N, int NPL, bool PAIR = false>
 struct WgradCfg {
   static constexpr int A_BYTES = kTileM * kChunkK * 2;           // 2 boxes of [64 rows][64 ch]
-  static constexpr int B_BYTES = BLOCK_N * kChunkK * 2;          // BLOCK_N/64 boxes
+  static constexpr int B_COLS = PAIR ? BLOCK_N / 2 : BLOCK_N;    // dZ columns (output channels) held by one CTA
+  static constexpr int B_BYTES = B_COLS * kChunkK * 2;           // B_COLS/64 boxes
   static constexpr int STAGE_BYTES = NPL * (A_BYTES + B_BYTES);
   static constexpr int STAGES_RAW = (kSmemBudget - 2048) / STAGE_BYTES;
   static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
@@ -708,12 +701,12 @@ struct WgradCfg {
   static constexpr int BOX_BYTES = 64 * 128;                     // one {64 ch, 64 rows} box
 };
 
-template <int BLOCK_N, int NPL, int NPROB>
+template <int BLOCK_N, int NPL, int NPROB, bool PAIR>
 __global__ void __launch_bounds__(kThreads, 1)
 tc_wgrad_kernel(const __grid_constant__ std::conditional_t<NPROB == 1, TmSet1, TmSetN> tmXs,
                 const __grid_constant__ std::conditional_t<NPROB == 1, TmSet1, TmSetN> tmDZs,
                 const WgradParams p) {
-  using Cfg = WgradCfg<BLOCK_N, NPL>;
+  using Cfg = WgradCfg<BLOCK_N, NPL, PAIR>;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
@@ -730,36 +723,41 @@ tc_wgrad_kernel(const __grid_constant__ std::conditional_t<NPROB == 1, TmSet1, T
   // contraction index in phase, so tiles that share an operand slab hit it in L2 at the same time); the remaining
   // R = tiles % gridDim.x tiles are cut into S = gridDim.x / R aligned K slices each so that the last wave also
   // fills the machine.  Sliced tiles accumulate with fp32 atomics into the pre-zeroed gradient, whole tiles store.
+  // PAIR: the scheduling unit is a pair of consecutive tiles (2u, 2u + 1) -- same problem and n tile, the host checks
+  // that taps * m_tiles is even -- handled by one cluster; rank r of the cluster owns tile 2u + r.
+  const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
+  const int unit_id = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
   const int tiles_mn = p.m_tiles * p.n_tiles;
   const int tiles_per_problem = p.taps * tiles_mn;
-  const int num_tiles = (NPROB > 1 ? p.n_problems : 1) * tiles_per_problem;
+  const int num_tiles = ((NPROB > 1 ? p.n_problems : 1) * tiles_per_problem) >> (PAIR ? 1 : 0);    // scheduling units
   const int total_iters = p.B * p.t_chunks;
-  const int G = gridDim.x;
+  const int G = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
   const int full_waves = num_tiles / G;
   const int tail_tiles = num_tiles - full_waves * G;
   const int tail_split = tail_tiles > 0 ? max(1, min(G / tail_tiles, total_iters / 4 > 0 ? total_iters / 4 : 1)) : 1;
   const int fsplit = p.force_split > 1 ? p.force_split : 0;
   const int forced_items = fsplit * num_tiles;
-  const int my_items = fsplit ? ((int)blockIdx.x < forced_items ? (forced_items - (int)blockIdx.x + G - 1) / G : 0)
-                              : full_waves + ((int)blockIdx.x < tail_tiles * tail_split ? 1 : 0);
-  // item i of this CTA -> (tile, q0, q1)
+  const int my_items = fsplit ? (unit_id < forced_items ? (forced_items - unit_id + G - 1) / G : 0)
+                              : full_waves + (unit_id < tail_tiles * tail_split ? 1 : 0);
+  // item i of this CTA -> (tile of THIS CTA, q0, q1)
   auto item = [&](int i, int& tile, int& q0, int& q1) {
     if (fsplit) {
-      const int g = i * G + (int)blockIdx.x;               // slice-major: a wave sweeps one K range in phase
+      const int g = i * G + unit_id;                       // slice-major: a wave sweeps one K range in phase
       const int slice = g / num_tiles;
       tile = g - slice * num_tiles;
       q0 = (int)((int64_t)total_iters * slice / fsplit);
       q1 = (int)((int64_t)total_iters * (slice + 1) / fsplit);
     } else if (i < full_waves) {
-      tile = i * G + blockIdx.x;
+      tile = i * G + unit_id;
       q0 = 0;
       q1 = total_iters;
     } else {
-      const int slice = blockIdx.x / tail_tiles;          // CTAs of one slice are consecutive: same K range in phase
-      tile = full_waves * G + blockIdx.x % tail_tiles;
+      const int slice = unit_id / tail_tiles;             // CTAs of one slice are consecutive: same K range in phase
+      tile = full_waves * G + unit_id % tail_tiles;
       q0 = (int)((int64_t)total_iters * slice / tail_split);
       q1 = (int)((int64_t)total_iters * (slice + 1) / tail_split);
     }
+    if constexpr (PAIR) tile = 2 * tile + (int)rank;
   };
 
   if (warp == 0 && lane == 0) {
@@ -771,13 +769,18 @@ tc_wgrad_kernel(const __grid_constant__ std::conditional_t<NPROB == 1, TmSet1, T
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tmem_full + a, 1);
-      mbar_init(tmem_empty + a, kEpilogueWarps);
+      // PAIR: the leader's MMA thread waits for the epilogue warps of BOTH CTAs (the peer's arrive remotely)
+      mbar_init(tmem_empty + a, kEpilogueWarps * (PAIR ? 2 : 1));
     }
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
+  if (warp == 1) {
+    if constexpr (PAIR) tmem_alloc_pair<Cfg::TMEM_COLS>(tmem_slot);
+    else tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
+  }
   tc_fence_before();
-  __syncthreads();
+  if constexpr (PAIR) cluster_sync_all();         // barriers of both CTAs initialised before any remote arrive / TMA
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   // Programmatic dependent launch: everything above (barrier init, TMEM allocation, descriptor prefetch) touched no
@@ -810,7 +813,13 @@ tc_wgrad_kernel(const __grid_constant__ std::conditional_t<NPROB == 1, TmSet1, T
         const int m = j - (NPROB > 1 ? p.pad_left_q[pq] : p.pad_left);
         const int shift = p.a_stride == 1 ? m : floordiv(m, p.a_stride);
         const int a_col = (m - shift * p.a_stride) * p.a_cin + mt * kTileM;
-        const int n0 = nt * BLOCK_N;
+        int n0 = nt * BLOCK_N;
+        if constexpr (PAIR) {
+          // this CTA holds dZ columns [n0 + rank * n_mma / 2, ...): the halves of the N the instruction multiplies
+          const int n_valid = min(BLOCK_N, p.Cout - n0);
+          const int n_mma = p.trim ? max(16, (n_valid + 15) & ~15) : BLOCK_N;
+          n0 += (int)rank * (n_mma >> 1);
+        }
         for (int q = q0; q < q1; ++q) {
           const int b = q / p.t_chunks;
           const int t0 = (q - b * p.t_chunks) * kChunkK;
@@ -820,22 +829,34 @@ tc_wgrad_kernel(const __grid_constant__ std::conditional_t<NPROB == 1, TmSet1, T
             // NG == 2: group X = {X_hi, dZ_lo}, group Y = {X_lo, dZ_hi};  NG == 1: every plane in one group
             uint64_t* fb = full_bar + stage * NG + g;
             mbar_wait(empty_bar + stage * NG + g, phase ^ 1);
-            mbar_expect_tx(fb, NG == 2 ? Cfg::A_BYTES + Cfg::B_BYTES : Cfg::STAGE_BYTES);
+            constexpr uint32_t kBytes = NG == 2 ? Cfg::A_BYTES + Cfg::B_BYTES : Cfg::STAGE_BYTES;
+            uint32_t fbc = 0;
+            if constexpr (PAIR) {
+              // both CTAs' bytes complete on the LEADER's barrier; the leader alone arms it
+              if (rank == 0) mbar_expect_tx(fb, 2 * kBytes);
+              fbc = mapa_u32(smem_u32(fb), 0);
+            } else {
+              mbar_expect_tx(fb, kBytes);
+            }
 #pragma unroll
             for (int pl = 0; pl < NPL; ++pl) {
               if (NG == 2 && pl != g) continue;
 #pragma unroll
-              for (int h = 0; h < kTileM / 64; ++h)
-                tma_load_3d(tmX, fb, st + pl * Cfg::A_BYTES + h * Cfg::BOX_BYTES, a_col + h * 64, t0 + shift,
-                            pl * p.B + b);
+              for (int h = 0; h < kTileM / 64; ++h) {
+                uint8_t* dst = st + pl * Cfg::A_BYTES + h * Cfg::BOX_BYTES;
+                if constexpr (PAIR) tma_load_3d_pair(tmX, fbc, dst, a_col + h * 64, t0 + shift, pl * p.B + b);
+                else tma_load_3d(tmX, fb, dst, a_col + h * 64, t0 + shift, pl * p.B + b);
+              }
             }
 #pragma unroll
             for (int pl = 0; pl < NPL; ++pl) {
               if (NG == 2 && pl != 1 - g) continue;
 #pragma unroll
-              for (int h = 0; h < BLOCK_N / 64; ++h)
-                tma_load_3d(tmDZ, fb, st + NPL * Cfg::A_BYTES + pl * Cfg::B_BYTES + h * Cfg::BOX_BYTES, n0 + h * 64,
-                            t0, pl * p.B + b);
+              for (int h = 0; h < Cfg::B_COLS / 64; ++h) {
+                uint8_t* dst = st + NPL * Cfg::A_BYTES + pl * Cfg::B_BYTES + h * Cfg::BOX_BYTES;
+                if constexpr (PAIR) tma_load_3d_pair(tmDZ, fbc, dst, n0 + h * 64, t0, pl * p.B + b);
+                else tma_load_3d(tmDZ, fb, dst, n0 + h * 64, t0, pl * p.B + b);
+              }
             }
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -844,7 +865,7 @@ tc_wgrad_kernel(const __grid_constant__ std::conditional_t<NPROB == 1, TmSet1, T
     }
     __syncwarp();
   } else if (warp == 1) {
-    if (lane == 0) {
+    if (lane == 0 && rank == 0) {                    // PAIR: the leader issues for both CTAs
       int stage = 0;
       uint32_t phase = 0;
       int local = 0;
@@ -854,7 +875,8 @@ tc_wgrad_kernel(const __grid_constant__ std::conditional_t<NPROB == 1, TmSet1, T
         decode(tile, tq, tj, tmt, tnt);
         // both operands MN-major; N trimmed to the real output channels of this n tile (rounded up to 16)
         const int n_valid = min(BLOCK_N, p.Cout - tnt * BLOCK_N);
-        const uint32_t idesc = make_idesc_bf16(kTileM, p.trim ? max(16, (n_valid + 15) & ~15) : BLOCK_N, 1, 1);
+        const uint32_t idesc = make_idesc_bf16(PAIR ? 2 * kTileM : kTileM,
+                                               p.trim ? max(16, (n_valid + 15) & ~15) : BLOCK_N, 1, 1);
         const int acc = local % Cfg::ACC_STAGES;
         const uint32_t acc_phase = (local / Cfg::ACC_STAGES) & 1;
         mbar_wait(tmem_empty + acc, acc_phase ^ 1);
@@ -877,10 +899,12 @@ tc_wgrad_kernel(const __grid_constant__ std::conditional_t<NPROB == 1, TmSet1, T
               const uint64_t da = make_smem_desc_sw128(a_addr + pa * Cfg::A_BYTES + kk * 2048, Cfg::BOX_BYTES, 1024);
               const uint64_t db = make_smem_desc_sw128(b_addr + pb * Cfg::B_BYTES + kk * 2048, Cfg::BOX_BYTES, 1024);
               if (pa == 0 && pb == 0) {
-                umma_bf16(d_main, da, db, idesc, acc_main);
+                if constexpr (PAIR) umma_bf16_pair(d_main, da, db, idesc, acc_main);
+                else umma_bf16(d_main, da, db, idesc, acc_main);
                 acc_main = 1u;
               } else {
-                umma_bf16(d_side, da, db, idesc, acc_side);
+                if constexpr (PAIR) umma_bf16_pair(d_side, da, db, idesc, acc_side);
+                else umma_bf16(d_side, da, db, idesc, acc_side);
                 acc_side = 1u;
               }
             };
@@ -891,7 +915,10 @@ tc_wgrad_kernel(const __grid_constant__ std::conditional_t<NPROB == 1, TmSet1, T
 #pragma unroll 1
               for (int kk = 0; kk < nkk; ++kk) step(kk);
             }
-            if (PR::release(pr) >= 0) umma_commit(empty_bar + stage * NG + PR::release(pr));
+            if (PR::release(pr) >= 0) {
+              if constexpr (PAIR) umma_commit_pair(empty_bar + stage * NG + PR::release(pr), 3);
+              else umma_commit(empty_bar + stage * NG + PR::release(pr));
+            }
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         };
@@ -904,7 +931,8 @@ tc_wgrad_kernel(const __grid_constant__ std::conditional_t<NPROB == 1, TmSet1, T
           else iteration(std::true_type{}, kChunkK / 16);
           if (++tc == p.t_chunks) tc = 0;
         }
-        umma_commit(tmem_full + acc);
+        if constexpr (PAIR) umma_commit_pair(tmem_full + acc, 3);   // accumulators complete -> both epilogues
+        else umma_commit(tmem_full + acc);
       }
     }
     __syncwarp();
@@ -969,15 +997,21 @@ tc_wgrad_kernel(const __grid_constant__ std::conditional_t<NPROB == 1, TmSet1, T
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(tmem_empty + acc);
+      if (lane == 0) {
+        // accumulator stage drained: PAIR arrives on the LEADER's barrier (its MMA thread feeds both TMEMs)
+        if constexpr (PAIR) mbar_arrive_cluster(mapa_u32(smem_u32(tmem_empty + acc), 0));
+        else mbar_arrive(tmem_empty + acc);
+      }
     }
   }
 
   tc_fence_before();
-  __syncthreads();
+  if constexpr (PAIR) cluster_sync_all();         // neither CTA leaves (or frees TMEM) while its peer still works
+  else __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+    if constexpr (PAIR) tmem_dealloc_pair<Cfg::TMEM_COLS>(tmem_base);
+    else tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
   }
 }
 
@@ -1160,6 +1194,53 @@ pack_ffa2_kernel(const float* __restrict__ w, const Ptr9h fwd, const Ptr9h bwd, 
   }
 }
 
+// Backward-layout planes ONLY, for layers whose forward kernel reads the filter MN-major (ConvParams::b_mn): no
+// transposed copy, so this is a pure streaming pass -- one thread per 8 output channels of one (packed tap, ci) row,
+// 16-byte loads and stores.  Leaf l = sum of the source taps group * k + c over the set bits c of masks.m[l] (plain
+// layers: one leaf, group 1, mask 1; the two-level fast-FIR split of layer 8: nine leaves, group 4).
+template <int NPL>
+__global__ void __launch_bounds__(256)
+pack_bwd_kernel(const float* __restrict__ w, const Ptr9h bwd, const LeafMasks masks, int n_leaves, int group, int J,
+                int Cin, int Cout, int ld_co) {
+  const int cg = ld_co / 8;
+  const int64_t rows = (int64_t)J * Cin;
+  const int64_t groups = rows * cg;
+  const int64_t tap = (int64_t)Cin * Cout;
+  const int64_t plane = rows * ld_co;
+  for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < groups; g += (int64_t)gridDim.x * blockDim.x) {
+    const int c8 = (int)(g % cg);
+    const int64_t row = g / cg;
+    const int ci = (int)(row % Cin);
+    const int k = (int)(row / Cin);
+    float t[4][8];
+#pragma unroll
+    for (int gg = 0; gg < 4; ++gg) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) t[gg][i] = 0.f;
+      if (gg < group && c8 * 8 < Cout) {
+        const float4* src = reinterpret_cast<const float4*>(w + (int64_t)(group * k + gg) * tap + (int64_t)ci * Cout + c8 * 8);
+        const float4 a = __ldg(src), b = __ldg(src + 1);
+        t[gg][0] = a.x; t[gg][1] = a.y; t[gg][2] = a.z; t[gg][3] = a.w;
+        t[gg][4] = b.x; t[gg][5] = b.y; t[gg][6] = b.z; t[gg][7] = b.w;
+      }
+    }
+#pragma unroll 1
+    for (int l = 0; l < n_leaves; ++l) {
+      const int mask = masks.m[l];
+      float v[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        float acc = 0.f;                       // same order of additions as pack_ffa2_kernel (taps ascending)
+#pragma unroll
+        for (int gg = 0; gg < 4; ++gg)
+          if (mask & (1 << gg)) acc += t[gg][i];
+        v[i] = acc;
+      }
+      store_planes8<NPL>(bwd.p[l] + row * ld_co + c8 * 8, plane, v);
+    }
+  }
+}
+
 // db[n] += sum_rows sum_planes dz[pl][row][n]; block (32 column octets, 8 row lanes): each thread streams 16-byte
 // vectors (8 bf16 columns) down its rows; grid (ceil(ld/256), row chunks)
 __global__ void __launch_bounds__(256)
@@ -1252,8 +1333,8 @@ pair_sum_planes_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __res
 template <int NPL>
 __global__ void __launch_bounds__(256)
 ffa_combine_kernel(const float* __restrict__ a00, const float* __restrict__ a11, const float* __restrict__ sm,
-                   const float* __restrict__ bias, int relu, __nv_bfloat16* __restrict__ out, int B, int To, int Tu,
-                   int N, int ld_p, int ld_out) {
+                   const float* __restrict__ bias, int relu, __nv_bfloat16* __restrict__ out,
+                   uint32_t* __restrict__ mask_out, int B, int To, int Tu, int N, int ld_p, int ld_out) {
   const int cg = ld_out / 8;
   const int64_t groups = (int64_t)B * Tu * cg;
   const int64_t out_plane = (int64_t)B * To * ld_out;
@@ -1281,6 +1362,11 @@ ffa_combine_kernel(const float* __restrict__ a00, const float* __restrict__ a11,
     __nv_bfloat16* o = out + ((int64_t)b * To + 2 * u) * ld_out + c8 * 8;
     store_planes8<NPL>(o, out_plane, ye);
     if (2 * u + 1 < To) store_planes8<NPL>(o + ld_out, out_plane, yo);
+    if (mask_out && c8 * 8 < N) {
+      const int64_t row = (int64_t)b * To + 2 * u;
+      store_mask_byte(mask_out, (int64_t)B * To, row, c8, ye);
+      if (2 * u + 1 < To) store_mask_byte(mask_out, (int64_t)B * To, row + 1, c8, yo);
+    }
   }
 }
 
@@ -1332,7 +1418,7 @@ ffa_dz_prep_kernel(const __nv_bfloat16* __restrict__ dy, __nv_bfloat16* __restri
 template <int NPL>
 __global__ void __launch_bounds__(256)
 ffa_dx_combine_kernel(const float* __restrict__ d_odd, const float* __restrict__ d_even, const float* __restrict__ d_xs,
-                      const __nv_bfloat16* __restrict__ mask, __nv_bfloat16* __restrict__ out, float* __restrict__ db,
+                      const uint32_t* __restrict__ mask, __nv_bfloat16* __restrict__ out, float* __restrict__ db,
                       int B, int T, int Tx, int N, int ldp, int ld, int rows_per_block) {
   __shared__ float part[8][32 * 8 + 1];
   const int c8 = threadIdx.x;                                 // channel octet (ld <= 256)
@@ -1362,13 +1448,11 @@ ffa_dx_combine_kernel(const float* __restrict__ d_odd, const float* __restrict__
         const int t = 2 * r + h;
         if (t >= T) continue;
         const int64_t orow = ((int64_t)b * T + t) * ld + c8 * 8;
-        const uint4 mq = *reinterpret_cast<const uint4*>(mask + orow);
-        const uint32_t mw[4] = {mq.x, mq.y, mq.z, mq.w};
+        const uint32_t mbits = c8 * 8 < N ? load_mask_byte(mask, (int64_t)B * T, (int64_t)b * T + t, c8) : 0u;
         float v[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          const uint32_t hbits = (i & 1) ? (mw[i >> 1] >> 16) : (mw[i >> 1] & 0xffffu);
-          const bool keep = (hbits - 1u) < 0x7fffu && c8 * 8 + i < N;          // mask element > 0 and a real channel
+          const bool keep = (mbits >> i) & 1u;                                  // ReLU below was active (real channel)
           v[i] = keep ? (h ? od[i] : ev[i]) + xs[i] : 0.f;
           acc[i] += v[i];
         }
@@ -1470,8 +1554,8 @@ ffa2_inputs_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* s0, __nv_
 // one thread per 8 channels of one q (four output rows 4q .. 4q+3).
 template <int NPL>
 __global__ void __launch_bounds__(256)
-ffa2_combine_kernel(const Ptr9c part, const float* __restrict__ bias, int relu, __nv_bfloat16* __restrict__ out, int B,
-                    int To, int Tq, int N, int ld_p, int ld_out) {
+ffa2_combine_kernel(const Ptr9c part, const float* __restrict__ bias, int relu, __nv_bfloat16* __restrict__ out,
+                    uint32_t* __restrict__ mask_out, int B, int To, int Tq, int N, int ld_p, int ld_out) {
   const int cg = ld_out / 8;
   const int64_t groups = (int64_t)B * Tq * cg;
   const int64_t out_plane = (int64_t)B * To * ld_out;
@@ -1523,7 +1607,10 @@ ffa2_combine_kernel(const Ptr9c part, const float* __restrict__ bias, int relu, 
     __nv_bfloat16* o = out + ((int64_t)b * To + 4 * q) * ld_out + c8 * 8;
 #pragma unroll
     for (int h = 0; h < 4; ++h)
-      if (4 * q + h < To) store_planes8<NPL>(o + h * ld_out, out_plane, y[h]);
+      if (4 * q + h < To) {
+        store_planes8<NPL>(o + h * ld_out, out_plane, y[h]);
+        if (mask_out && c8 * 8 < N) store_mask_byte(mask_out, (int64_t)B * To, (int64_t)b * To + 4 * q + h, c8, y[h]);
+      }
   }
 }
 
@@ -1580,7 +1667,7 @@ ffa2_dz_prep_kernel(const __nv_bfloat16* __restrict__ dy, const Ptr9h out, int B
 // times the ReLU mask of the layer below, split to planes [NPL][B][T][ld]; column sums into db.
 template <int NPL>
 __global__ void __launch_bounds__(256)
-ffa2_dx_combine_kernel(const Ptr9c gp, const __nv_bfloat16* __restrict__ mask, __nv_bfloat16* __restrict__ out,
+ffa2_dx_combine_kernel(const Ptr9c gp, const uint32_t* __restrict__ mask, __nv_bfloat16* __restrict__ out,
                        float* __restrict__ db, int B, int T, int Tqx, int N, int ldp, int ld, int rows_per_block) {
   __shared__ float part[8][32 * 8 + 1];
   const int c8 = threadIdx.x;
@@ -1615,13 +1702,11 @@ ffa2_dx_combine_kernel(const Ptr9c gp, const __nv_bfloat16* __restrict__ mask, _
         const int t = 4 * r + h;
         if (t >= T) continue;
         const int64_t orow = ((int64_t)b * T + t) * ld + c8 * 8;
-        const uint4 mq = *reinterpret_cast<const uint4*>(mask + orow);
-        const uint32_t mw[4] = {mq.x, mq.y, mq.z, mq.w};
+        const uint32_t mbits = c8 * 8 < N ? load_mask_byte(mask, (int64_t)B * T, (int64_t)b * T + t, c8) : 0u;
         float v[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          const uint32_t hbits = (i & 1) ? (mw[i >> 1] >> 16) : (mw[i >> 1] & 0xffffu);
-          const bool keep = (hbits - 1u) < 0x7fffu && c8 * 8 + i < N;
+          const bool keep = (mbits >> i) & 1u;
           float s;
           if (h == 0) s = (g[4][i] + g[5][i]) + (g[7][i] + g[8][i]);
           else if (h == 1) s = (g[0][i] + g[2][i]) + (g[7][i] + g[8][i]);
@@ -1739,15 +1824,18 @@ int pair_grid(int pair_work) {
   return 2 * (pair_work < clusters ? pair_work : clusters);
 }
 
-template <int BLOCK_N, int NPL, bool EARLY, bool PAIR>
+template <int BLOCK_N, int NPL, bool EARLY, bool PAIR, bool BMN = false>
 int launch_conv_e(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmOut, const ConvParams& p,
                   cudaStream_t stream) {
   using Cfg = ConvCfg<BLOCK_N, NPL, PAIR>;
+  if constexpr (!BMN && BLOCK_N == 256 && NPL <= 2) {
+    if (p.b_mn) return launch_conv_e<BLOCK_N, NPL, EARLY, PAIR, true>(tmA, tmB, tmOut, p, stream);
+  }
   // the opt-in for > 48 KB of dynamic shared memory is a per-DEVICE function attribute
   static bool configured[kMaxDevices] = {};
   const int dev = current_device();
   if (!configured[dev]) {
-    ST_CUDA_CALL(cudaFuncSetAttribute(tc_conv_kernel<BLOCK_N, NPL, EARLY, 1, PAIR>,
+    ST_CUDA_CALL(cudaFuncSetAttribute(tc_conv_kernel<BLOCK_N, NPL, EARLY, 1, PAIR, BMN>,
                                       cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     configured[dev] = true;
   }
@@ -1756,23 +1844,26 @@ int launch_conv_e(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensor
   a.m[0] = tmA;
   b.m[0] = tmB;
   if constexpr (PAIR) {
-    ST_CUDA_CALL(launch_pdl_cluster(tc_conv_kernel<BLOCK_N, NPL, EARLY, 1, true>, pair_grid(((m_tiles + 1) / 2) * p.n_tiles),
-                                    2, Cfg::SMEM_BYTES, stream, a, b, tmOut, p));
+    ST_CUDA_CALL(launch_pdl_cluster(tc_conv_kernel<BLOCK_N, NPL, EARLY, 1, true, BMN>,
+                                    pair_grid(((m_tiles + 1) / 2) * p.n_tiles), 2, Cfg::SMEM_BYTES, stream, a, b, tmOut, p));
   } else {
-    ST_CUDA_CALL(launch_pdl(tc_conv_kernel<BLOCK_N, NPL, EARLY, 1, false>, grid_for(m_tiles * p.n_tiles), Cfg::SMEM_BYTES,
-                            stream, a, b, tmOut, p));
+    ST_CUDA_CALL(launch_pdl(tc_conv_kernel<BLOCK_N, NPL, EARLY, 1, false, BMN>, grid_for(m_tiles * p.n_tiles),
+                            Cfg::SMEM_BYTES, stream, a, b, tmOut, p));
   }
   return ST_OK;
 }
 
-template <int BLOCK_N, int NPL, bool PAIR>
+template <int BLOCK_N, int NPL, bool PAIR, bool BMN = false>
 int launch_conv_multi_t(const CUtensorMap* tmA, const CUtensorMap* tmB, const ConvParams& p0, cudaStream_t stream) {
   using Cfg = ConvCfg<BLOCK_N, NPL, PAIR>;
   constexpr bool EARLY = Cfg::ACC_STAGES == 1;      // several work items per CTA, long main loops: release TMEM early
+  if constexpr (!BMN) {
+    if (p0.b_mn) return launch_conv_multi_t<BLOCK_N, NPL, PAIR, true>(tmA, tmB, p0, stream);
+  }
   static bool configured[kMaxDevices] = {};
   const int dev = current_device();
   if (!configured[dev]) {
-    ST_CUDA_CALL(cudaFuncSetAttribute(tc_conv_kernel<BLOCK_N, NPL, EARLY, kMaxProblems, PAIR>,
+    ST_CUDA_CALL(cudaFuncSetAttribute(tc_conv_kernel<BLOCK_N, NPL, EARLY, kMaxProblems, PAIR, BMN>,
                                       cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     configured[dev] = true;
   }
@@ -1787,11 +1878,11 @@ int launch_conv_multi_t(const CUtensorMap* tmA, const CUtensorMap* tmB, const Co
   const int m_tiles = p.B * p.m_tiles_per_utt;
   const int per_tile = (p.k_split > 1 ? p.k_split : 1) * p.n_problems;
   if constexpr (PAIR) {
-    ST_CUDA_CALL(launch_pdl_cluster(tc_conv_kernel<BLOCK_N, NPL, EARLY, kMaxProblems, true>,
+    ST_CUDA_CALL(launch_pdl_cluster(tc_conv_kernel<BLOCK_N, NPL, EARLY, kMaxProblems, true, BMN>,
                                     pair_grid(((m_tiles + 1) / 2) * p.n_tiles * per_tile), 2, Cfg::SMEM_BYTES, stream, a, b,
                                     a.m[0], p));
   } else {
-    ST_CUDA_CALL(launch_pdl(tc_conv_kernel<BLOCK_N, NPL, EARLY, kMaxProblems, false>,
+    ST_CUDA_CALL(launch_pdl(tc_conv_kernel<BLOCK_N, NPL, EARLY, kMaxProblems, false, BMN>,
                             grid_for(m_tiles * p.n_tiles * per_tile), Cfg::SMEM_BYTES, stream, a, b, a.m[0], p));
   }
   return ST_OK;
@@ -1837,40 +1928,47 @@ int launch_conv_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensor
   return launch_conv_e<BLOCK_N, NPL, false, false>(tmA, tmB, tmO, p, stream);
 }
 
-template <int BLOCK_N, int NPL>
-int launch_wgrad_t(const CUtensorMap& tmX, const CUtensorMap& tmDZ, const WgradParams& p, cudaStream_t stream) {
-  using Cfg = WgradCfg<BLOCK_N, NPL>;
+// persistent filter-gradient grid: one CTA per SM, or one cluster of two CTAs per TPC
+template <int BLOCK_N, int NPL, int NPROB, bool PAIR, class Tm>
+int launch_wgrad_k(const Tm& x, const Tm& dz, const WgradParams& p, cudaStream_t stream) {
+  using Cfg = WgradCfg<BLOCK_N, NPL, PAIR>;
   static bool configured[kMaxDevices] = {};
   const int dev = current_device();
   if (!configured[dev]) {
-    ST_CUDA_CALL(cudaFuncSetAttribute(tc_wgrad_kernel<BLOCK_N, NPL, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      Cfg::SMEM_BYTES));
+    ST_CUDA_CALL(cudaFuncSetAttribute(tc_wgrad_kernel<BLOCK_N, NPL, NPROB, PAIR>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     configured[dev] = true;
   }
-  TmSet1 x, dz;
-  x.m[0] = tmX;
-  dz.m[0] = tmDZ;
-  ST_CUDA_CALL(launch_pdl(tc_wgrad_kernel<BLOCK_N, NPL, 1>, st_num_sms(), Cfg::SMEM_BYTES, stream, x, dz, p));
+  if constexpr (PAIR) {
+    ST_CUDA_CALL(launch_pdl_cluster(tc_wgrad_kernel<BLOCK_N, NPL, NPROB, true>, 2 * (st_num_sms() / 2), 2, Cfg::SMEM_BYTES,
+                                    stream, x, dz, p));
+  } else {
+    ST_CUDA_CALL(launch_pdl(tc_wgrad_kernel<BLOCK_N, NPL, NPROB, false>, st_num_sms(), Cfg::SMEM_BYTES, stream, x, dz, p));
+  }
   return ST_OK;
 }
 
 template <int BLOCK_N, int NPL>
-int launch_wgrad_multi_t(const CUtensorMap* tmX, const CUtensorMap* tmDZ, const WgradParams& p, cudaStream_t stream) {
-  using Cfg = WgradCfg<BLOCK_N, NPL>;
-  static bool configured[kMaxDevices] = {};
-  const int dev = current_device();
-  if (!configured[dev]) {
-    ST_CUDA_CALL(cudaFuncSetAttribute(tc_wgrad_kernel<BLOCK_N, NPL, kMaxProblems>,
-                                      cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-    configured[dev] = true;
+int launch_wgrad_t(const CUtensorMap& tmX, const CUtensorMap& tmDZ, const WgradParams& p, cudaStream_t stream) {
+  TmSet1 x, dz;
+  x.m[0] = tmX;
+  dz.m[0] = tmDZ;
+  if constexpr (BLOCK_N == 256 && NPL <= 2) {
+    if (wgrad_pair(p.taps, p.m_tiles, BLOCK_N, NPL)) return launch_wgrad_k<BLOCK_N, NPL, 1, true>(x, dz, p, stream);
   }
+  return launch_wgrad_k<BLOCK_N, NPL, 1, false>(x, dz, p, stream);
+}
+
+template <int BLOCK_N, int NPL>
+int launch_wgrad_multi_t(const CUtensorMap* tmX, const CUtensorMap* tmDZ, const WgradParams& p, cudaStream_t stream) {
   TmSetN x, dz;
   for (int q = 0; q < kMaxProblems; ++q) {
     x.m[q] = tmX[q < p.n_problems ? q : 0];
     dz.m[q] = tmDZ[q < p.n_problems ? q : 0];
   }
-  ST_CUDA_CALL(launch_pdl(tc_wgrad_kernel<BLOCK_N, NPL, kMaxProblems>, st_num_sms(), Cfg::SMEM_BYTES, stream, x, dz, p));
-  return ST_OK;
+  if (wgrad_pair(p.taps, p.m_tiles, BLOCK_N, NPL))
+    return launch_wgrad_k<BLOCK_N, NPL, kMaxProblems, true>(x, dz, p, stream);
+  return launch_wgrad_k<BLOCK_N, NPL, kMaxProblems, false>(x, dz, p, stream);
 }
 
 }  // namespace
@@ -1881,7 +1979,24 @@ bool want_pair(int m_tiles, int n_tiles, int block_n, int n_planes, bool multi, 
   // data gradients -5 %, forward neutral); in plain bf16 a pair tile's hand-offs between the two CTAs only pay off on
   // long contractions -- layer 8 gains 3-10 %, the 32-iteration layer-9 tiles lose 5-9 % and stay on single CTAs.
   if (n_planes == 1 && k_iters < 64) return false;
-  return multi || m_tiles * n_tiles > st_num_sms();
+  // One-wave launches (the 250-channel layers and layer 0: 128 tiles, every one with the SAME filter tile) are bound by
+  // L2 -> shared-memory bandwidth, two thirds of it the B operand: a pair fetches B once (SPEECHT_B200_PAIR_SMALL=0:
+  // only launches of more than one wave pair up)
+  const char* e = getenv("SPEECHT_B200_PAIR_SMALL");
+  const bool small_ok = e && e[0] == '1';
+  return multi || small_ok || m_tiles * n_tiles > st_num_sms();
+}
+
+// Filter-gradient launches on CTA pairs: 256-wide tiles, at most two planes, and an even number of (tap, Cin tile)
+// combinations per n tile so that tiles 2u and 2u + 1 always share their dZ tile.  Measured same-box
+// (profiles/r02_wgrad_pair_ab_session17.txt): plain bf16 gains on every layer (layer 8 -16 %, layer 9 -11 %, the
+// 250-channel layers -12 %; step -3.8 % at config 3); in bf16x3 only the one-tap layer 9 gains (-6 %), the others are
+// neutral to +2 % and stay on single CTAs.  SPEECHT_B200_WGRAD_PAIR=0 / 1 forces none / all eligible launches.
+bool wgrad_pair(int taps, int m_tiles, int block_n, int n_planes) {
+  if (block_n != 256 || n_planes > 2 || ((taps * m_tiles) & 1) != 0) return false;
+  const char* e = getenv("SPEECHT_B200_WGRAD_PAIR");
+  if (e && (e[0] == '0' || e[0] == '1')) return e[0] == '1';
+  return n_planes == 1 || taps == 1;
 }
 
 void set_conv_timeline(long long* buf, int launch_index) {
@@ -1972,7 +2087,7 @@ int launch_conv(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMa
 int launch_conv_multi(const CUtensorMap* tmA, const CUtensorMap* tmB, const ConvParams& p, int block_n, int n_planes,
                       cudaStream_t stream) {
   ST_CHECK_ARG(p.n_problems >= 2 && p.n_problems <= kMaxProblems, "launch_conv_multi: 2..%d problems", kMaxProblems);
-  ST_CHECK_ARG(!p.bias && !p.relu && !p.out_planes && !p.mask_hi && !p.col_sum,
+  ST_CHECK_ARG(!p.bias && !p.relu && !p.out_planes && !p.mask_bits && !p.mask_out && !p.col_sum,
                "launch_conv_multi: fp32 outputs only (no bias / ReLU / mask / planes / column sums)");
   ST_CHECK_ARG(p.k_split <= 1 || (p.taps % p.k_split) == 0, "launch_conv_multi: k_split must divide the taps");
   for (int q = 0; q < p.n_problems; ++q) ST_CHECK_ARG(p.out_f32_q[q] != nullptr, "launch_conv_multi: null output");
@@ -2037,17 +2152,17 @@ int launch_pair_sum_planes(const __nv_bfloat16* x, __nv_bfloat16* xs, int B, int
 }
 
 int launch_ffa_combine(const float* a00, const float* a11, const float* sm, const float* bias, int relu,
-                       __nv_bfloat16* out, int B, int To, int Tu, int N, int ld_p, int ld_out, int n_planes,
-                       cudaStream_t stream) {
+                       __nv_bfloat16* out, uint32_t* mask_out, int B, int To, int Tu, int N, int ld_p, int ld_out,
+                       int n_planes, cudaStream_t stream) {
   ST_CHECK_ARG(ld_out % 8 == 0 && n_planes >= 1 && n_planes <= 2, "launch_ffa_combine: bad arguments");
   const int64_t groups = (int64_t)B * Tu * (ld_out / 8);
   int blocks = (int)((groups + 255) / 256);
   const int cap = 16 * st_num_sms();
   blocks = blocks > cap ? cap : blocks;
   if (n_planes == 2)
-    ffa_combine_kernel<2><<<blocks, 256, 0, stream>>>(a00, a11, sm, bias, relu, out, B, To, Tu, N, ld_p, ld_out);
+    ffa_combine_kernel<2><<<blocks, 256, 0, stream>>>(a00, a11, sm, bias, relu, out, mask_out, B, To, Tu, N, ld_p, ld_out);
   else
-    ffa_combine_kernel<1><<<blocks, 256, 0, stream>>>(a00, a11, sm, bias, relu, out, B, To, Tu, N, ld_p, ld_out);
+    ffa_combine_kernel<1><<<blocks, 256, 0, stream>>>(a00, a11, sm, bias, relu, out, mask_out, B, To, Tu, N, ld_p, ld_out);
   ST_CUDA_LAUNCH_CHECK("ffa_combine_kernel");
   return ST_OK;
 }
@@ -2065,7 +2180,7 @@ int launch_ffa_dz_prep(const __nv_bfloat16* dy, __nv_bfloat16* d00, __nv_bfloat1
   return ST_OK;
 }
 
-int launch_ffa_dx_combine(const float* d_odd, const float* d_even, const float* d_xs, const __nv_bfloat16* mask,
+int launch_ffa_dx_combine(const float* d_odd, const float* d_even, const float* d_xs, const uint32_t* mask,
                           __nv_bfloat16* out, float* db, int B, int T, int Tx, int N, int ldp, int ld, int n_planes,
                           cudaStream_t stream) {
   ST_CHECK_ARG(ld % 8 == 0 && ld <= 256 && ldp % 4 == 0 && ldp >= ld && n_planes >= 1 && n_planes <= 2,
@@ -2114,14 +2229,14 @@ int launch_ffa2_inputs(const __nv_bfloat16* x, __nv_bfloat16* const* s5, int B, 
   return ST_OK;
 }
 
-int launch_ffa2_combine(float* const* part9, const float* bias, int relu, __nv_bfloat16* out, int B, int To, int Tq,
-                        int N, int ld_p, int ld_out, int n_planes, cudaStream_t stream) {
+int launch_ffa2_combine(float* const* part9, const float* bias, int relu, __nv_bfloat16* out, uint32_t* mask_out, int B,
+                        int To, int Tq, int N, int ld_p, int ld_out, int n_planes, cudaStream_t stream) {
   ST_CHECK_ARG(ld_out % 8 == 0 && n_planes >= 1 && n_planes <= 2, "launch_ffa2_combine: bad arguments");
   Ptr9c pp;
   for (int l = 0; l < 9; ++l) pp.p[l] = part9[l];
   const int blocks = ew_blocks((int64_t)B * Tq * (ld_out / 8));
-  if (n_planes == 2) ffa2_combine_kernel<2><<<blocks, 256, 0, stream>>>(pp, bias, relu, out, B, To, Tq, N, ld_p, ld_out);
-  else ffa2_combine_kernel<1><<<blocks, 256, 0, stream>>>(pp, bias, relu, out, B, To, Tq, N, ld_p, ld_out);
+  if (n_planes == 2) ffa2_combine_kernel<2><<<blocks, 256, 0, stream>>>(pp, bias, relu, out, mask_out, B, To, Tq, N, ld_p, ld_out);
+  else ffa2_combine_kernel<1><<<blocks, 256, 0, stream>>>(pp, bias, relu, out, mask_out, B, To, Tq, N, ld_p, ld_out);
   ST_CUDA_LAUNCH_CHECK("ffa2_combine_kernel");
   return ST_OK;
 }
@@ -2138,7 +2253,7 @@ int launch_ffa2_dz_prep(const __nv_bfloat16* dy, __nv_bfloat16* const* out9, int
   return ST_OK;
 }
 
-int launch_ffa2_dx_combine(float* const* g9, const __nv_bfloat16* mask, __nv_bfloat16* out, float* db, int B, int T,
+int launch_ffa2_dx_combine(float* const* g9, const uint32_t* mask, __nv_bfloat16* out, float* db, int B, int T,
                            int Tqx, int N, int ldp, int ld, int n_planes, cudaStream_t stream) {
   ST_CHECK_ARG(ld % 8 == 0 && ld <= 256 && ldp % 4 == 0 && ldp >= ld && n_planes >= 1 && n_planes <= 2,
                "launch_ffa2_dx_combine: bad arguments");
@@ -2168,8 +2283,9 @@ int launch_ffa2_dw_combine(float* dW, float* const* c9, int J, int64_t tap_elems
 
 // Does a filter-gradient launch of `num_tiles` tiles cut its last wave into K slices (which ACCUMULATE into dW, so the
 // outputs must be zero on entry)?  Mirrors the wave-aligned split of tc_wgrad_kernel.
-int wgrad_best_split(int num_tiles, int total_iters) {
-  const int G = st_num_sms();
+int wgrad_best_split(int num_tiles, int total_iters, bool pair) {
+  int G = st_num_sms();
+  if (pair) { G /= 2; num_tiles /= 2; }          // scheduling units: tile pairs on clusters
   if (num_tiles >= G) return 1;
   int best = 1;
   int64_t best_cost = (int64_t)((num_tiles + G - 1) / G) * total_iters;
@@ -2181,8 +2297,9 @@ int wgrad_best_split(int num_tiles, int total_iters) {
   return best;
 }
 
-bool wgrad_accumulates(int num_tiles, int total_iters) {
-  const int G = st_num_sms();
+bool wgrad_accumulates(int num_tiles, int total_iters, bool pair) {
+  int G = st_num_sms();
+  if (pair) { G /= 2; num_tiles /= 2; }
   const int tail_tiles = num_tiles % G;
   if (tail_tiles == 0) return false;
   const int cap = total_iters / 4 > 0 ? total_iters / 4 : 1;
@@ -2224,6 +2341,20 @@ int launch_pack_ffa2(const float* w, __nv_bfloat16* const* fwd9, __nv_bfloat16* 
     pack_ffa2_kernel<1><<<blocks, dim3(32, 8), smem, stream>>>(w, f, b, m, J, Cin, Cout, cin_p, ld_co);
   }
   ST_CUDA_LAUNCH_CHECK("pack_ffa2_kernel");
+  return ST_OK;
+}
+
+int launch_pack_bwd(const float* w, __nv_bfloat16* const* bwd, const int* masks, int n_leaves, int group, int J, int Cin,
+                    int Cout, int ld_co, int n_planes, cudaStream_t stream) {
+  ST_CHECK_ARG(n_leaves >= 1 && n_leaves <= 9 && group >= 1 && group <= 4 && Cout % 8 == 0 && ld_co % 8 == 0 &&
+               ld_co >= Cout && n_planes >= 1 && n_planes <= 2, "launch_pack_bwd: bad arguments");
+  Ptr9h b;
+  LeafMasks m;
+  for (int l = 0; l < 9; ++l) { b.p[l] = bwd[l < n_leaves ? l : 0]; m.m[l] = masks[l < n_leaves ? l : 0]; }
+  const int blocks = ew_blocks((int64_t)J * Cin * (ld_co / 8));
+  if (n_planes == 2) pack_bwd_kernel<2><<<blocks, 256, 0, stream>>>(w, b, m, n_leaves, group, J, Cin, Cout, ld_co);
+  else pack_bwd_kernel<1><<<blocks, 256, 0, stream>>>(w, b, m, n_leaves, group, J, Cin, Cout, ld_co);
+  ST_CUDA_LAUNCH_CHECK("pack_bwd_kernel");
   return ST_OK;
 }
 

@@ -26,8 +26,13 @@ struct ConvParams {
   int ld_out;
   float* out_f32;
   int ld_f32;
-  const __nv_bfloat16* mask_hi;  // same [B,To,ld_mask] indexing as the output; value > 0 passes
-  int ld_mask;
+  // ReLU masks as BIT words: word w of row r (r = b * To + t) holds "output channel 32 w + i was > 0" in bit i, stored
+  // column-major [word][rows] so that the 32 lanes (= 32 rows) of an epilogue warp touch one 128-byte line.
+  // mask_out (forward, layers with a ReLU): written beside the activation planes; mask_bits (data gradient): the words
+  // the forward pass of the layer below wrote.  64 MB of bf16 read back per 2000-channel layer become 4 MB.
+  uint32_t* mask_out;
+  const uint32_t* mask_bits;
+  int64_t mask_rows;             // rows of the mask arrays (B * To)
   float* col_sum;                // nullable: += column sums of the stored tile (bias gradient), [N] fp32
   int tma_store;                 // set by launch_conv: bf16 planes leave through the store tensor map tmOut
   long long* timeline;           // debug (st_debug_conv_timeline): [grid][8] %globaltimer stamps of the CTA's first tile
@@ -40,6 +45,9 @@ struct ConvParams {
   // CTA pairs (cta_group::2): 1 = launch as clusters of two CTAs sharing 256-row tiles.  The B tensor map must then
   // have boxes of block_n / 2 rows (each CTA loads half of the B tile).  Decide with want_pair().
   int pair;
+  // 1: the B operand is MN-major -- tmB maps the filter's BACKWARD layout [planes * K * Cin rows][ld_co] with boxes of
+  // {64 channels, 64 rows}; b_row_step = rows per tap (Cin), b_plane_rows = K * Cin.  256-wide tiles, <= 2 planes.
+  int b_mn;
   int n_problems;                // 0 / 1: single problem (the fields above); 2..kMaxProblems: use the arrays below
   int k_split;                   // 0 / 1: whole contraction per tile
   int pad_left_q[9];
@@ -70,7 +78,10 @@ struct WgradParams {
 };
 // slices per tile that balance `num_tiles` tiles of `total_iters` iterations over the SMs (1 = leave the wave-aligned
 // split in charge)
-int wgrad_best_split(int num_tiles, int total_iters);
+int wgrad_best_split(int num_tiles, int total_iters, bool pair);
+// does a filter-gradient launch with these tile counts run on CTA pairs (two tiles that share their dZ tile per
+// cluster, tcgen05.mma.cta_group::2)?  The split helpers need to know: the scheduling unit is then a tile pair.
+bool wgrad_pair(int taps, int m_tiles, int block_n, int n_planes);
 
 int make_map_3d(CUtensorMap* map, const void* base, int C, int T, int Bn, int64_t ld, int64_t batch_stride,
                 int box_c, int box_t);
@@ -126,13 +137,13 @@ int launch_pair_sum_planes(const __nv_bfloat16* x, __nv_bfloat16* xs, int B, int
 // y[2u] = act(A00[u] + A11[u] + bias), y[2u+1] = act(S[u] - A11[u] - A00[u+1] + bias): fp32 [B][Tu][ld_p] partial
 // products -> bf16 planes [n][B][To][ld_out]
 int launch_ffa_combine(const float* a00, const float* a11, const float* sm, const float* bias, int relu,
-                       __nv_bfloat16* out, int B, int To, int Tu, int N, int ld_p, int ld_out, int n_planes,
-                       cudaStream_t stream);
+                       __nv_bfloat16* out, uint32_t* mask_out, int B, int To, int Tu, int N, int ld_p, int ld_out,
+                       int n_planes, cudaStream_t stream);
 // backward of the same form: dy planes [n][B][To][ld] -> dA00 / dA11 / dS planes [n][B][Tu][ld]
 int launch_ffa_dz_prep(const __nv_bfloat16* dy, __nv_bfloat16* d00, __nv_bfloat16* d11, __nv_bfloat16* ds, int B,
                        int To, int Tu, int ld, int n_planes, cudaStream_t stream);
 // fp32 partials d_odd / d_even / d_xs [B][Tx][ldp] -> masked dx planes [n][B][T][ld] + column sums into db
-int launch_ffa_dx_combine(const float* d_odd, const float* d_even, const float* d_xs, const __nv_bfloat16* mask,
+int launch_ffa_dx_combine(const float* d_odd, const float* d_even, const float* d_xs, const uint32_t* mask_bits,
                           __nv_bfloat16* out, float* db, int B, int T, int Tx, int N, int ldp, int ld, int n_planes,
                           cudaStream_t stream);
 // dW[2j] += cs[j], dW[2j+1] += cs[j] for j < J; tap_elems = Cin*Cout
@@ -142,21 +153,25 @@ int launch_ffa_dw_combine(float* dW, const float* cs, int J, int64_t tap_elems, 
 int launch_ffa2_inputs(const __nv_bfloat16* x, __nv_bfloat16* const* s5, int B, int T, int Tq, int ld, int n_planes,
                        cudaStream_t stream);
 // nine fp32 partial products [B][Tq][ld_p] -> act(y + bias) planes [n][B][To][ld_out]
-int launch_ffa2_combine(float* const* part9, const float* bias, int relu, __nv_bfloat16* out, int B, int To, int Tq,
-                        int N, int ld_p, int ld_out, int n_planes, cudaStream_t stream);
+int launch_ffa2_combine(float* const* part9, const float* bias, int relu, __nv_bfloat16* out, uint32_t* mask_out, int B,
+                        int To, int Tq, int N, int ld_p, int ld_out, int n_planes, cudaStream_t stream);
 // dy planes [n][B][To][ld] -> gradients of the nine leaf products, planes [n][B][Tq][ld]
 int launch_ffa2_dz_prep(const __nv_bfloat16* dy, __nv_bfloat16* const* out9, int B, int To, int Tq, int ld, int n_planes,
                         cudaStream_t stream);
 // nine fp32 input-gradient partials [B][Tqx][ldp] -> masked dx planes [n][B][T][ld] + column sums into db
-int launch_ffa2_dx_combine(float* const* g9, const __nv_bfloat16* mask, __nv_bfloat16* out, float* db, int B, int T,
+int launch_ffa2_dx_combine(float* const* g9, const uint32_t* mask_bits, __nv_bfloat16* out, float* db, int B, int T,
                            int Tqx, int N, int ldp, int ld, int n_planes, cudaStream_t stream);
 // nine fp32 leaf correlations [J][tap_elems] -> dW [4J][tap_elems]
 int launch_ffa2_dw_combine(float* dW, float* const* c9, int J, int64_t tap_elems, cudaStream_t stream);
 // the nine leaf filters (tap sums selected by masks9[l] over w[4i + c]) in both operand layouts, one pass over w
 int launch_pack_ffa2(const float* w, __nv_bfloat16* const* fwd9, __nv_bfloat16* const* bwd9, const int* masks9, int J,
                      int Cin, int Cout, int cin_p, int ld_co, int n_planes, cudaStream_t stream);
+// backward-layout planes only (layers whose forward reads the filter MN-major): leaf l = sum over the bits c of
+// masks[l] of the source taps group * k + c, k < J; bwd[l] planes [n][J * Cin][ld_co]; Cout % 8 == 0
+int launch_pack_bwd(const float* w, __nv_bfloat16* const* bwd, const int* masks, int n_leaves, int group, int J, int Cin,
+                    int Cout, int ld_co, int n_planes, cudaStream_t stream);
 // true when a filter-gradient launch of num_tiles tiles accumulates into its outputs (they must then be zeroed)
-bool wgrad_accumulates(int num_tiles, int total_iters);
+bool wgrad_accumulates(int num_tiles, int total_iters, bool pair);
 // db[n] = sum over rows and planes of dz planes [n_planes][rows][ld]
 int launch_bias_grad(const __nv_bfloat16* dz, int64_t rows, int N, int ld, int n_planes, float* db,
                      cudaStream_t stream);

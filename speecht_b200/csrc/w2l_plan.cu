@@ -21,6 +21,7 @@ struct Layer {
   int ld_co;                  // Cout rounded up (backward filter layout)
   size_t off_wfwd, off_wbwd;  // arena offsets (bytes)
   size_t off_out;             // arena offset of this layer's OUTPUT activation planes (layers 0..9)
+  size_t off_mask;            // ... and of its ReLU-mask bit words [ceil(ld_out / 32)][B * To] (tc::ConvParams::mask_out)
   int64_t w_off, b_off;       // float offsets into the flat parameter / gradient buffers
   CUtensorMap tm_fwd_a, tm_fwd_b;     // forward
   CUtensorMap tm_dg_a[2], tm_dg_b;    // data gradient (A = dz ping or pong)
@@ -72,6 +73,10 @@ struct st_plan {
   // problems, 56 % of the MMAs (tools/ffa2_study.py).  `ffa` is the level in use: SPEECHT_B200_FFA=1 keeps one level,
   // =0 restores the direct 32-tap kernels; bf16x6 (three planes) always uses the direct kernels.
   int ffa;
+  // Forward launches of the two widest layers (the nine fast-FIR leaves of layer 8, layer 9) read their filters
+  // MN-major from the BACKWARD layout (tc::ConvParams::b_mn): no forward layout is packed for them, and their packing
+  // is a pure streaming pass (tc::launch_pack_bwd).  SPEECHT_B200_BMN=0 restores the K-major forward layouts.
+  bool bmn;
   int ffa2_Tq, ffa2_Tqi;                         // rows of the leaf products / of the quarter-rate input sequences
   size_t off_ffa2_s[5], off_ffa2_w[9], off_ffa2_wb[9], off_ffa2_p[9], off_ffa2_dxp[9], off_ffa2_c[9];
   bool ffa2_pair_fwd, ffa2_pair_dg;
@@ -114,6 +119,8 @@ __nv_bfloat16* bf(st_plan* p, size_t off) { return reinterpret_cast<__nv_bfloat1
 
 const __nv_bfloat16* act_in(st_plan* p, int l) { return l == 0 ? bf(p, p->off_in) : bf(p, p->layers[l - 1].off_out); }
 
+uint32_t* mask_of(st_plan* p, int l) { return reinterpret_cast<uint32_t*>(p->arena + p->layers[l].off_mask); }
+
 }  // namespace
 
 ST_API int st_plan_create(st_plan** out, int B, int T, int input_size, int num_classes, int n_planes) {
@@ -134,6 +141,8 @@ ST_API int st_plan_create(st_plan** out, int B, int T, int input_size, int num_c
     p->merge_wgrad = !(e && e[0] == '0') && n_planes <= 2;
     e = getenv("SPEECHT_B200_FFA");
     p->ffa = n_planes > 2 ? 0 : (e && e[0] >= '0' && e[0] <= '2' ? e[0] - '0' : 2);
+    e = getenv("SPEECHT_B200_BMN");
+    p->bmn = !(e && e[0] == '0') && n_planes <= 2;
   }
   const int ffa_requested = p->ffa;
   // reference speech_model.py:275-292
@@ -194,6 +203,7 @@ ST_API int st_plan_create(st_plan** out, int B, int T, int input_size, int num_c
   for (int l = 0; l < 10; ++l) {
     Layer& L = p->layers[l];
     L.off_out = take((size_t)n_planes * B * L.To * L.ld_out * 2);
+    L.off_mask = take((size_t)((L.ld_out + 31) / 32) * B * L.To * sizeof(uint32_t));
   }
   p->off_logits = take((size_t)B * p->To * 32 * sizeof(float));
   p->off_dlogits = take((size_t)n_planes * B * p->To * 64 * 2);
@@ -297,8 +307,12 @@ int bind_ffa2(st_plan* p) {
       }
       if (rc) return rc;
     }
-    rc = tc::make_map_2d(&p->tm_ffa2_b[l], bf(p, p->off_ffa2_w[l]), J * L8.cin_p, npl * L8.Cout, (int64_t)J * L8.cin_p,
-                         64, p->ffa2_pair_fwd ? wide_n(p) / 2 : wide_n(p));
+    if (p->bmn) {
+      rc = tc::make_map_2d(&p->tm_ffa2_b[l], bf(p, p->off_ffa2_wb[l]), L8.Cout, npl * J * L8.Cin, L8.ld_co, 64, 64);
+    } else {
+      rc = tc::make_map_2d(&p->tm_ffa2_b[l], bf(p, p->off_ffa2_w[l]), J * L8.cin_p, npl * L8.Cout,
+                           (int64_t)J * L8.cin_p, 64, p->ffa2_pair_fwd ? wide_n(p) / 2 : wide_n(p));
+    }
     if (rc) return rc;
     // backward: the gradient of the leaf product as planes [npl*B][Tq][Cout]
     const __nv_bfloat16* dA = bf(p, p->off_ffa2_p[l]);
@@ -343,8 +357,12 @@ ST_API int st_plan_bind(st_plan* p, void* arena, size_t arena_bytes, float* para
     if (rc) return rc;
     L.pair_fwd = tc::want_pair(B * ((L.To + tc::kTileM - 1) / tc::kTileM), (L.Cout + block_n - 1) / block_n, block_n,
                                npl, false, L.K * (L.cin_p / 64));
-    rc = tc::make_map_2d(&L.tm_fwd_b, bf(p, L.off_wfwd), L.K * L.cin_p, npl * L.Cout, (int64_t)L.K * L.cin_p, 64,
-                         L.pair_fwd ? block_n / 2 : block_n);
+    if (l == 9 && p->bmn) {
+      rc = tc::make_map_2d(&L.tm_fwd_b, bf(p, L.off_wbwd), L.Cout, npl * L.K * L.Cin, L.ld_co, 64, 64);
+    } else {
+      rc = tc::make_map_2d(&L.tm_fwd_b, bf(p, L.off_wfwd), L.K * L.cin_p, npl * L.Cout, (int64_t)L.K * L.cin_p, 64,
+                           L.pair_fwd ? block_n / 2 : block_n);
+    }
     if (rc) return rc;
     // ---- filter gradient: X = input activation planes (boxes of 64 rows), dZ = gradient wrt this layer's output
     if (L.stride == 1) {
@@ -469,8 +487,18 @@ int pack_layers(st_plan* p, cudaStream_t s) {
         b9[i] = bf(p, p->off_ffa2_wb[i]);
         m9[i] = kLeaves[i].tap_mask;
       }
-      const int rc2 = tc::launch_pack_ffa2(p->params + L8.w_off, f9, b9, m9, L8.K / 4, L8.Cin, L8.Cout, L8.cin_p,
-                                           L8.ld_co, p->npl, s);
+      const int rc2 = p->bmn ? tc::launch_pack_bwd(p->params + L8.w_off, b9, m9, 9, 4, L8.K / 4, L8.Cin, L8.Cout, L8.ld_co,
+                                                   p->npl, s)
+                             : tc::launch_pack_ffa2(p->params + L8.w_off, f9, b9, m9, L8.K / 4, L8.Cin, L8.Cout, L8.cin_p,
+                                                    L8.ld_co, p->npl, s);
+      if (rc2) return rc2;
+      p->launches++;
+      continue;
+    }
+    if (l == 9 && p->bmn) {
+      __nv_bfloat16* b1[1] = {bf(p, L.off_wbwd)};
+      const int one = 1;
+      const int rc2 = tc::launch_pack_bwd(p->params + L.w_off, b1, &one, 1, 1, L.K, L.Cin, L.Cout, L.ld_co, p->npl, s);
       if (rc2) return rc2;
       p->launches++;
       continue;
@@ -542,8 +570,8 @@ int forward_layer8_ffa(st_plan* p, cudaStream_t s) {
   if (rc) return rc;
   timed_end(p, ti, 0, 8, 2.0 * L.K * L.Cin * L.Cout * (double)L.To * p->B, s);
   p->launches++;
-  rc = tc::launch_ffa_combine(part[0], part[1], part[2], p->params + L.b_off, L.relu, bf(p, L.off_out), p->B, L.To,
-                              p->ffa_Tu, L.Cout, L.Cout, L.ld_out, p->npl, s);
+  rc = tc::launch_ffa_combine(part[0], part[1], part[2], p->params + L.b_off, L.relu, bf(p, L.off_out), mask_of(p, 8),
+                              p->B, L.To, p->ffa_Tu, L.Cout, L.Cout, L.ld_out, p->npl, s);
   if (rc) return rc;
   p->launches++;
   return ST_OK;
@@ -618,7 +646,7 @@ int backward_layer8_ffa(st_plan* p, const __nv_bfloat16* dz, __nv_bfloat16* dz_o
   if (rc) return rc;
   timed_end(p, ti, 1, 8, 2.0 * L.K * L.Cin * L.Cout * (double)L.To * p->B, s);
   p->launches++;
-  rc = tc::launch_ffa_dx_combine(dxp[0], dxp[1], dxp[2], bf(p, Lb.off_out), dz_out, p->grads + Lb.b_off, p->B, L.Ti,
+  rc = tc::launch_ffa_dx_combine(dxp[0], dxp[1], dxp[2], mask_of(p, 7), dz_out, p->grads + Lb.b_off, p->B, L.Ti,
                                  p->ffa_Tx, L.Cin, 256, Lb.ld_out, p->npl, s);
   if (rc) return rc;
   p->launches++;
@@ -653,6 +681,12 @@ int forward_layer8_ffa2(st_plan* p, cudaStream_t s) {
   c.n_problems = 9;
   c.k_split = 1;
   c.pair = p->ffa2_pair_fwd;
+  if (p->bmn) {
+    c.b_mn = 1;
+    c.b_row_step = L.Cin;
+    c.b_col_step = 0;
+    c.b_plane_rows = (L.K / 4) * L.Cin;
+  }
   for (int i = 0; i < 9; ++i) {
     part[i] = reinterpret_cast<float*>(p->arena + p->off_ffa2_p[i]);
     c.pad_left_q[i] = kLeaves[i].pad;
@@ -663,8 +697,8 @@ int forward_layer8_ffa2(st_plan* p, cudaStream_t s) {
   if (rc) return rc;
   timed_end(p, ti, 0, 8, 2.0 * L.K * L.Cin * L.Cout * (double)L.To * p->B, s);
   p->launches++;
-  rc = tc::launch_ffa2_combine(part, p->params + L.b_off, L.relu, bf(p, L.off_out), p->B, L.To, p->ffa2_Tq, L.Cout,
-                               L.Cout, L.ld_out, p->npl, s);
+  rc = tc::launch_ffa2_combine(part, p->params + L.b_off, L.relu, bf(p, L.off_out), mask_of(p, 8), p->B, L.To,
+                               p->ffa2_Tq, L.Cout, L.Cout, L.ld_out, p->npl, s);
   if (rc) return rc;
   p->launches++;
   return ST_OK;
@@ -695,7 +729,8 @@ int backward_layer8_ffa2(st_plan* p, const __nv_bfloat16* dz, __nv_bfloat16* dz_
   w.trim = p->trim;
   w.n_problems = 9;
   for (int i = 0; i < 9; ++i) { w.pad_left_q[i] = kLeaves[i].pad; w.dW_q[i] = cw[i]; w.tap_stride_q[i] = 1; }
-  if (tc::wgrad_accumulates(9 * J * w.m_tiles * w.n_tiles, p->B * w.t_chunks)) {
+  if (tc::wgrad_accumulates(9 * J * w.m_tiles * w.n_tiles, p->B * w.t_chunks,
+                            tc::wgrad_pair(J, w.m_tiles, wide_n(p), p->npl))) {
     const size_t bytes = (size_t)J * L.Cin * L.Cout * sizeof(float);
     for (int i = 0; i < 9; ++i) ST_CUDA_CALL(cudaMemsetAsync(cw[i], 0, bytes, s));
   }
@@ -733,7 +768,7 @@ int backward_layer8_ffa2(st_plan* p, const __nv_bfloat16* dz, __nv_bfloat16* dz_
   if (rc) return rc;
   timed_end(p, ti, 1, 8, 2.0 * L.K * L.Cin * L.Cout * (double)L.To * p->B, s);
   p->launches++;
-  rc = tc::launch_ffa2_dx_combine(dxp, bf(p, Lb.off_out), dz_out, p->grads + Lb.b_off, p->B, L.Ti, p->ffa2_Tqi, L.Cin,
+  rc = tc::launch_ffa2_dx_combine(dxp, mask_of(p, 7), dz_out, p->grads + Lb.b_off, p->B, L.Ti, p->ffa2_Tqi, L.Cin,
                                   256, Lb.ld_out, p->npl, s);
   if (rc) return rc;
   p->launches++;
@@ -776,6 +811,8 @@ ST_API int st_plan_forward(st_plan* p, const float* inputs, st_stream_t stream) 
       c.out_planes = bf(p, L.off_out);
       c.out_plane_stride = (int64_t)p->B * L.To * L.ld_out;
       c.ld_out = L.ld_out;
+      c.mask_out = L.relu ? mask_of(p, l) : nullptr;
+      c.mask_rows = (int64_t)p->B * L.To;
     } else {
       c.out_f32 = reinterpret_cast<float*>(p->arena + p->off_logits);
       c.ld_f32 = 32;
@@ -784,6 +821,12 @@ ST_API int st_plan_forward(st_plan* p, const float* inputs, st_stream_t stream) 
     c.k_cols = L.Cin;
     c.trim = p->trim;
     c.pair = L.pair_fwd;
+    if (l == 9 && p->bmn) {
+      c.b_mn = 1;
+      c.b_row_step = L.Cin;
+      c.b_col_step = 0;
+      c.b_plane_rows = L.K * L.Cin;
+    }
     const int ti = timed_begin(p, s);
     rc = tc::launch_conv(L.tm_fwd_a, L.tm_fwd_b, l < 10 ? &L.tm_fwd_out : nullptr, c, block_n, p->npl, s);
     if (rc) return rc;
@@ -872,8 +915,8 @@ ST_API int st_plan_backward_range(st_plan* p, int hi, int lo, st_stream_t stream
       c.out_planes = l - 1 <= 7 ? bf(p, p->off_dzs[l - 1]) : bf(p, p->off_dz[nxt]);
       c.out_plane_stride = (int64_t)p->B * Lb.To * Lb.ld_out;
       c.ld_out = Lb.ld_out;
-      c.mask_hi = bf(p, Lb.off_out);
-      c.ld_mask = Lb.ld_out;
+      c.mask_bits = mask_of(p, l - 1);
+      c.mask_rows = (int64_t)p->B * Lb.To;
       c.col_sum = p->grads + Lb.b_off;
       c.tma_store = p->tma_store;
       c.k_cols = L.Cout;
@@ -920,7 +963,8 @@ ST_API int st_plan_backward_range(st_plan* p, int hi, int lo, st_stream_t stream
       w.n_problems = 0;
       rc = tc::launch_wgrad(tx[0], tz[0], w, wide_n(p), p->npl, s);
     } else {
-      w.force_split = tc::wgrad_best_split(n_deferred * w.taps * w.m_tiles * w.n_tiles, p->B * w.t_chunks);
+      w.force_split = tc::wgrad_best_split(n_deferred * w.taps * w.m_tiles * w.n_tiles, p->B * w.t_chunks,
+                                           tc::wgrad_pair(w.taps, w.m_tiles, wide_n(p), p->npl));
       rc = tc::launch_wgrad_multi(tx, tz, w, wide_n(p), p->npl, s);
     }
     if (rc) return rc;

@@ -24,6 +24,8 @@ CAPTURES = {
   'l1_7_wgrad': ('l1_7_wgrad_bf16x3', None, 'filter gradients of the seven 250-channel layers, one launch, forced K slices'),
   'ctc_alpha_beta': ('ctc_alpha_beta', None, 'CTC alpha/beta recursion'),
   'pack': ('pack_ffa2', None, 'one-pass packing of the nine leaf filters of layer 8'),
+  'ffa2_combine': ('ffa2_combine', None, 'forward combine of the nine leaf products (bias + ReLU + plane split)'),
+  'ffa2_dz_prep': ('ffa2_dz_prep', None, 'backward prepare: the nine leaf gradients from dy'),
   'l8_fwd_cfg3': ('l8_fwd_bf16_cfg3', 'bf16/B64/T1001', 'layer-8 forward at config 3 (plain bf16, batch 64)'),
 }
 
@@ -46,7 +48,9 @@ def main():
       open(os.path.join(prof, 'r02_gpu_tests_final.txt'), 'w').write(''.join(keep))
   traffic = {}
   for cap, (tag, key, what) in CAPTURES.items():
-    rep = os.path.join(src, 'ncu_%s.ncu-rep' % cap)
+    rep = os.path.join(src, 'ncu_%s.raw.csv' % cap)
+    if not os.path.exists(rep):
+      rep = os.path.join(src, 'ncu_%s.ncu-rep' % cap)
     if not os.path.exists(rep):
       continue
     launches = ncu_summary.read(rep)

@@ -53,7 +53,10 @@ full() {  # name, kernel regex, skip, extra bench args
   name=$1; rx=$2; skip=$3; shift 3
   timeout 900 ncu --set full --clock-control none --import-source on -k regex:$rx --launch-skip $skip --launch-count 1 \
     -o $O/ncu_$name -f $B "$@" > $O/ncu_$name.log 2>&1
-  stamp "ncu full $name rc=$?"
+  rc=$?
+  # gpurun brings back at most 64 MiB: keep the raw metric page (what tools/collect_round2.py reads), drop the report
+  ncu -i $O/ncu_$name.ncu-rep --page raw --csv > $O/ncu_$name.raw.csv 2>/dev/null && rm -f $O/ncu_$name.ncu-rep
+  stamp "ncu full $name rc=$rc"
 }
 # tc_conv launches: 11 (loss-delta forward) + 21 (warm-up step) + 21 (first timed step), then forward L0..L10, data
 # gradients L10, L9, L8, L7..L1; tc_wgrad launches: 5 per step in the order L10, L9, L8 (nine leaves), L0, L1-7 (merged)
@@ -65,5 +68,7 @@ full l8_wgrad tc_wgrad_kernel 12
 full l1_7_wgrad tc_wgrad_kernel 14
 full ctc_alpha_beta ctc_alpha_beta 3
 full pack pack_ffa2 3
+full ffa2_combine ffa2_combine 3
+full ffa2_dz_prep ffa2_dz_prep 3
 full l8_fwd_cfg3 tc_conv_kernel 61 --config 3
 cat $S

@@ -25,7 +25,10 @@ UNIT = {'byte': 1, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9, 'Tbyte': 1e12}
 
 
 def read(rep):
-  out = subprocess.run(['ncu', '-i', rep, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
+  if rep.endswith('.csv'):          # raw page exported on the GPU box (tools/gpu_round2.sh)
+    out = open(rep).read()
+  else:
+    out = subprocess.run(['ncu', '-i', rep, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
   rows = list(csv.reader(io.StringIO(out)))
   hdr, units = rows[0], rows[1]
   res = []

@@ -61,7 +61,12 @@ struct ConvCfg {
   static constexpr int STAGE_BYTES = NPL * (A_BYTES + B_BYTES);
   // epilogue staging tiles for the TMA stores (one [2 planes][32][32] bf16 tile per epilogue warp); the three-plane
   // mode has no shared memory left for them and keeps the direct stores
-  static constexpr int STAGING_BYTES = NPL <= 2 ? kEpilogueWarps * kStageTileBytes : 0;
+  // Epilogue warps.  128-wide one- / two-plane tiles are used by ONE launch, the layer-10 data gradient (29-deep contraction,
+  // 2000 outputs: all epilogue, ~590 instructions per 32-column chunk and warp at 0.3 IPC): it needs 110 registers, so
+  // SIXTEEN epilogue warps fit the register file (576 threads x 112) and every warp owns one chunk of a tile.
+  static constexpr int EPW = (BLOCK_N == 128 && NPL <= 2 && !PAIR) ? 16 : kEpilogueWarps;
+  static constexpr int THREADS = 64 + 32 * EPW;
+  static constexpr int STAGING_BYTES = NPL <= 2 ? EPW * kStageTileBytes : 0;
   static constexpr int STAGES_RAW = (kSmemBudget - 1024 - kBarrierBytes - STAGING_BYTES) / STAGE_BYTES;
   static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
   // [<= 1023 alignment slack][STAGES x stage][barriers, 1 KB][staging tiles]
@@ -267,7 +272,7 @@ template <> struct Products<3> {
 // contiguous, boxes of 64 rows x 64 channels like the filter-gradient operands), so a forward launch needs no packed
 // layout of its own (ConvParams::b_row_step = rows per tap; K rows past Cin meet zero channels of A).
 template <int BLOCK_N, int NPL, bool EARLY, int NPROB, bool PAIR, bool BMN = false>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__((ConvCfg<BLOCK_N, NPL, PAIR>::THREADS), 1)
 tc_conv_kernel(const __grid_constant__ std::conditional_t<NPROB == 1, TmSet1, TmSetN> tmAs,
                const __grid_constant__ std::conditional_t<NPROB == 1, TmSet1, TmSetN> tmBs,
                const __grid_constant__ CUtensorMap tmOut, const ConvParams p) {
@@ -326,7 +331,7 @@ tc_conv_kernel(const __grid_constant__ std::conditional_t<NPROB == 1, TmSet1, Tm
     for (int a = 0; a < 2; ++a) {
       mbar_init(tmem_full + a, 1);
       // PAIR: the leader's MMA thread waits for the epilogue warps of BOTH CTAs (the peer's arrive remotely)
-      mbar_init(tmem_empty + a, kEpilogueWarps * (PAIR ? 2 : 1));
+      mbar_init(tmem_empty + a, Cfg::EPW * (PAIR ? 2 : 1));
     }
     fence_barrier_init();
   }
@@ -532,10 +537,10 @@ tc_conv_kernel(const __grid_constant__ std::conditional_t<NPROB == 1, TmSet1, Tm
     }
     __syncwarp();
   } else {
-    // ===================================================== epilogue warps 2..9
+    // ===================================================== epilogue warps 2 .. 2 + EPW - 1
     const int quarter = warp & 3;                         // TMEM lane quarter this warp may read
-    const int chunk0 = (warp - 2) >> 2;                   // warps w and w+4 share a quarter: even / odd chunks
-    constexpr int kChunkStep = kEpilogueWarps / 4;
+    const int chunk0 = (warp - 2) >> 2;                   // warps w, w+4, ... share a quarter and split its chunks
+    constexpr int kChunkStep = Cfg::EPW / 4;
     constexpr int kChunks = BLOCK_N / 32;
     const int row = quarter * 32 + lane;
     uint8_t* stage = smem + STAGES * Cfg::STAGE_BYTES + kBarrierBytes + (warp - 2) * kStageTileBytes;
@@ -1617,46 +1622,75 @@ ffa2_combine_kernel(const Ptr9c part, const float* __restrict__ bias, int relu, 
 // Backward prepare: gradients of the nine leaf products from dy (planes [NPL][B][To][ld]), planes [NPL][B][Tq][ld]:
 // level 1: GX[u] = dy[2u] - dy[2u-1], GY[u] = dy[2u] - dy[2u+1], GZ[u] = dy[2u+1]; level 2 of each G:
 // d?X[q] = G[2q] - G[2q-1], d?Y[q] = G[2q] - G[2q+1], d?Z[q] = G[2q+1]  (dy = 0 outside [0, To)).
+// One thread per FOUR channels of one q: 8-byte loads / stores keep a warp on 256 contiguous bytes, and at ~60
+// registers four blocks are resident per SM (eight channels per thread: 98 registers, two blocks, 46 % of HBM peak).
 template <int NPL>
-__global__ void __launch_bounds__(256)
+__device__ __forceinline__ void store_planes4(__nv_bfloat16* dst, int64_t plane_stride, const float* v) {
+  float rem[4] = {v[0], v[1], v[2], v[3]};
+#pragma unroll
+  for (int p = 0; p < NPL; ++p) {
+    uint32_t w[2];
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const __nv_bfloat162 h = __floats2bfloat162_rn(rem[2 * i], rem[2 * i + 1]);
+      w[i] = *reinterpret_cast<const uint32_t*>(&h);
+      if (p + 1 < NPL) {
+        rem[2 * i] -= __uint_as_float(w[i] << 16);
+        rem[2 * i + 1] -= __uint_as_float(w[i] & 0xffff0000u);
+      }
+    }
+    *reinterpret_cast<uint2*>(dst + p * plane_stride) = make_uint2(w[0], w[1]);
+  }
+}
+
+template <int NPL>
+__global__ void __launch_bounds__(256, 4)
 ffa2_dz_prep_kernel(const __nv_bfloat16* __restrict__ dy, const Ptr9h out, int B, int To, int Tq, int ld) {
-  const int cg = ld / 8;
+  const int cg = ld / 4;
   const int64_t groups = (int64_t)B * Tq * cg;
   const int64_t in_plane = (int64_t)B * To * ld, out_plane = (int64_t)B * Tq * ld;
   for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < groups; g += (int64_t)gridDim.x * blockDim.x) {
-    const int c8 = (int)(g % cg);
+    const int c4 = (int)(g % cg);
     const int64_t bq = g / cg;
     const int q = (int)(bq % Tq);
     const int b = (int)(bq / Tq);
-    float d[7][8];                                   // dy rows 4q-3 .. 4q+3
+    float d[7][4];                                   // dy rows 4q-3 .. 4q+3
 #pragma unroll
     for (int h = 0; h < 7; ++h) {
       const int t = 4 * q - 3 + h;
-      if (t >= 0 && t < To) load_merged8(dy + ((int64_t)b * To + t) * ld + c8 * 8, in_plane, NPL, d[h]);
-      else {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) d[h][i] = 0.f;
+      for (int i = 0; i < 4; ++i) d[h][i] = 0.f;
+      if (t >= 0 && t < To) {
+        const __nv_bfloat16* src = dy + ((int64_t)b * To + t) * ld + c4 * 4;
+#pragma unroll
+        for (int pl = NPL - 1; pl >= 0; --pl) {
+          const uint2 w = *reinterpret_cast<const uint2*>(src + pl * in_plane);
+          d[h][0] += __uint_as_float(w.x << 16);
+          d[h][1] += __uint_as_float(w.x & 0xffff0000u);
+          d[h][2] += __uint_as_float(w.y << 16);
+          d[h][3] += __uint_as_float(w.y & 0xffff0000u);
+        }
       }
     }
-    const int64_t off = ((int64_t)b * Tq + q) * ld + c8 * 8;
-    float o[8];
+    const int64_t off = ((int64_t)b * Tq + q) * ld + c4 * 4;
+    float o[4];
     // G(2q-1), G(2q), G(2q+1) of the three level-1 gradients, from rows d[k+3] = dy[4q+k]
 #pragma unroll
     for (int lvl = 0; lvl < 3; ++lvl) {
-      float gm[8], g0[8], gp[8];
+      float gm[4], g0[4], gp[4];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
+      for (int i = 0; i < 4; ++i) {
         if (lvl == 0) { gm[i] = d[1][i] - d[0][i]; g0[i] = d[3][i] - d[2][i]; gp[i] = d[5][i] - d[4][i]; }
         else if (lvl == 1) { gm[i] = d[1][i] - d[2][i]; g0[i] = d[3][i] - d[4][i]; gp[i] = d[5][i] - d[6][i]; }
         else { gm[i] = d[2][i]; g0[i] = d[4][i]; gp[i] = d[6][i]; }
       }
 #pragma unroll
-      for (int i = 0; i < 8; ++i) o[i] = g0[i] - gm[i];
-      store_planes8<NPL>(out.p[3 * lvl + 0] + off, out_plane, o);
+      for (int i = 0; i < 4; ++i) o[i] = g0[i] - gm[i];
+      store_planes4<NPL>(out.p[3 * lvl + 0] + off, out_plane, o);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) o[i] = g0[i] - gp[i];
-      store_planes8<NPL>(out.p[3 * lvl + 1] + off, out_plane, o);
-      store_planes8<NPL>(out.p[3 * lvl + 2] + off, out_plane, gp);
+      for (int i = 0; i < 4; ++i) o[i] = g0[i] - gp[i];
+      store_planes4<NPL>(out.p[3 * lvl + 1] + off, out_plane, o);
+      store_planes4<NPL>(out.p[3 * lvl + 2] + off, out_plane, gp);
     }
   }
 }
@@ -1785,10 +1819,11 @@ int grid_for(int work_items) {
 // Launch with the programmatic-stream-serialization attribute (PDL): the kernel may begin while the previous kernel
 // of the stream drains; it synchronises with `griddepcontrol.wait` before touching global memory.
 template <class Kernel, class... Args>
-cudaError_t launch_pdl_cluster(Kernel kernel, int grid, int cluster, int smem, cudaStream_t stream, const Args&... args) {
+cudaError_t launch_pdl_cluster_t(Kernel kernel, int grid, int threads, int cluster, int smem, cudaStream_t stream,
+                                 const Args&... args) {
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(grid);
-  cfg.blockDim = dim3(kThreads);
+  cfg.blockDim = dim3(threads);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = stream;
   static const bool pdl = []() { const char* e = getenv("SPEECHT_B200_PDL"); return !(e && e[0] == '0'); }();
@@ -1805,6 +1840,11 @@ cudaError_t launch_pdl_cluster(Kernel kernel, int grid, int cluster, int smem, c
     cfg.numAttrs = 2;
   }
   return cudaLaunchKernelEx(&cfg, kernel, args...);
+}
+
+template <class Kernel, class... Args>
+cudaError_t launch_pdl_cluster(Kernel kernel, int grid, int cluster, int smem, cudaStream_t stream, const Args&... args) {
+  return launch_pdl_cluster_t(kernel, grid, kThreads, cluster, smem, stream, args...);
 }
 
 template <class Kernel, class... Args>
@@ -1847,8 +1887,8 @@ int launch_conv_e(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensor
     ST_CUDA_CALL(launch_pdl_cluster(tc_conv_kernel<BLOCK_N, NPL, EARLY, 1, true, BMN>,
                                     pair_grid(((m_tiles + 1) / 2) * p.n_tiles), 2, Cfg::SMEM_BYTES, stream, a, b, tmOut, p));
   } else {
-    ST_CUDA_CALL(launch_pdl(tc_conv_kernel<BLOCK_N, NPL, EARLY, 1, false, BMN>, grid_for(m_tiles * p.n_tiles),
-                            Cfg::SMEM_BYTES, stream, a, b, tmOut, p));
+    ST_CUDA_CALL(launch_pdl_cluster_t(tc_conv_kernel<BLOCK_N, NPL, EARLY, 1, false, BMN>, grid_for(m_tiles * p.n_tiles),
+                                      Cfg::THREADS, 1, Cfg::SMEM_BYTES, stream, a, b, tmOut, p));
   }
   return ST_OK;
 }
@@ -2079,6 +2119,7 @@ int launch_conv(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMa
   if (block_n == 32 && n_planes == 1) return launch_conv_t<32, 1>(tmA, tmB, tmOut, p, stream);
   if (block_n == 128 && n_planes == 3) return launch_conv_t<128, 3>(tmA, tmB, tmOut, p, stream);
   if (block_n == 128 && n_planes == 2) return launch_conv_t<128, 2>(tmA, tmB, tmOut, p, stream);
+  if (block_n == 128 && n_planes == 1) return launch_conv_t<128, 1>(tmA, tmB, tmOut, p, stream);
   if (block_n == 32 && n_planes == 3) return launch_conv_t<32, 3>(tmA, tmB, tmOut, p, stream);
   st_set_error("launch_conv: unsupported (block_n=%d, n_planes=%d)", block_n, n_planes);
   return ST_ERR_UNSUPPORTED;
@@ -2246,7 +2287,7 @@ int launch_ffa2_dz_prep(const __nv_bfloat16* dy, __nv_bfloat16* const* out9, int
   ST_CHECK_ARG(ld % 8 == 0 && n_planes >= 1 && n_planes <= 2, "launch_ffa2_dz_prep: bad arguments");
   Ptr9h pp;
   for (int l = 0; l < 9; ++l) pp.p[l] = out9[l];
-  const int blocks = ew_blocks((int64_t)B * Tq * (ld / 8));
+  const int blocks = ew_blocks((int64_t)B * Tq * (ld / 4));
   if (n_planes == 2) ffa2_dz_prep_kernel<2><<<blocks, 256, 0, stream>>>(dy, pp, B, To, Tq, ld);
   else ffa2_dz_prep_kernel<1><<<blocks, 256, 0, stream>>>(dy, pp, B, To, Tq, ld);
   ST_CUDA_LAUNCH_CHECK("ffa2_dz_prep_kernel");

@@ -53,7 +53,9 @@ struct SF { float p; int e; };
 constexpr int kZeroExp = -(1 << 28);
 
 __device__ __forceinline__ float sf_scaled(float p, int de) {          // p * 2^max(de, -126), de <= 0
-  return p * __int_as_float((max(de, -126) + 127) << 23);
+  // p is in [1,2) (biased exponent 127), so the scaling is an integer add on the exponent field: the result stays a
+  // normal number (127 + de >= 1) and is bit-identical to the multiplication by the exact power of two
+  return __int_as_float(__float_as_int(p) + (int)((unsigned)max(de, -126) << 23));
 }
 __device__ __forceinline__ SF sf_norm(float x, int ebase) {            // x normal and positive
   const int bits = __float_as_int(x);

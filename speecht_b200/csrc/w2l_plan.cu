@@ -64,7 +64,8 @@ struct st_plan {
   bool trim;                   // MMAs over channel / time padding are not issued (SPEECHT_B200_TRIM=0 disables)
   // Layer-10 data gradient (dz9 = dlogits . W10^T, 29-deep contraction, 2000 outputs): an HBM / epilogue kernel, not a
   // GEMM.  128-wide tiles leave room for TWO accumulator stages in the split modes (2 x 2 x 128 TMEM columns), so the
-  // epilogue of one tile runs under the loads + MMAs of the next (SPEECHT_B200_L10_N128=0 restores 256-wide tiles).
+  // epilogue of one tile runs under the loads + MMAs of the next, and their kernel instantiation needs few enough
+  // registers for SIXTEEN epilogue warps (ConvCfg::EPW) (SPEECHT_B200_L10_N128=0 restores 256-wide tiles).
   bool l10_n128;
   // Fast-FIR split of the 32-tap layer 8 (65 % of the FLOPs): forward, data gradient and filter gradient each run
   // THREE half-rate 16-tap problems (75 % of the MMAs) in one persistent launch, plus elementwise prepare / combine
@@ -75,7 +76,9 @@ struct st_plan {
   int ffa;
   // Forward launches of the two widest layers (the nine fast-FIR leaves of layer 8, layer 9) read their filters
   // MN-major from the BACKWARD layout (tc::ConvParams::b_mn): no forward layout is packed for them, and their packing
-  // is a pure streaming pass (tc::launch_pack_bwd).  SPEECHT_B200_BMN=0 restores the K-major forward layouts.
+  // is a pure streaming pass (tc::launch_pack_bwd): packing 165 -> 81 us per step under ncu.  The MN-major operand costs
+  // the forward kernels 2-4 % in bf16x3 and 10 % in plain bf16 (profiles/r02_bmn_ab_session19.txt), so it is the default
+  // for two planes only (step -0.5 .. -1 %); SPEECHT_B200_BMN=0 / 1 forces the K-major forward layouts / MN-major.
   bool bmn;
   int ffa2_Tq, ffa2_Tqi;                         // rows of the leaf products / of the quarter-rate input sequences
   size_t off_ffa2_s[5], off_ffa2_w[9], off_ffa2_wb[9], off_ffa2_p[9], off_ffa2_dxp[9], off_ffa2_c[9];
@@ -136,13 +139,13 @@ ST_API int st_plan_create(st_plan** out, int B, int T, int input_size, int num_c
     const char* e = getenv("SPEECHT_B200_TRIM");
     p->trim = !(e && e[0] == '0');
     e = getenv("SPEECHT_B200_L10_N128");
-    p->l10_n128 = !(e && e[0] == '0') && n_planes == 2;
+    p->l10_n128 = !(e && e[0] == '0') && n_planes <= 2;
     e = getenv("SPEECHT_B200_MERGE_WGRAD");
     p->merge_wgrad = !(e && e[0] == '0') && n_planes <= 2;
     e = getenv("SPEECHT_B200_FFA");
     p->ffa = n_planes > 2 ? 0 : (e && e[0] >= '0' && e[0] <= '2' ? e[0] - '0' : 2);
     e = getenv("SPEECHT_B200_BMN");
-    p->bmn = !(e && e[0] == '0') && n_planes <= 2;
+    p->bmn = n_planes <= 2 && ((e && (e[0] == '0' || e[0] == '1')) ? e[0] == '1' : n_planes == 2);
   }
   const int ffa_requested = p->ffa;
   // reference speech_model.py:275-292

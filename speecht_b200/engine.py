@@ -365,8 +365,10 @@ class W2LEngine:
     return [g for g in np.array_split(order, max(1, min(int(buckets), len(order)))) if len(g)]
 
   @_on_engine_device
-  def evaluate_step(self, inputs, sequence_lengths, labels=None, decode=True, buckets=1):
+  def evaluate_step(self, inputs, sequence_lengths, labels=None, decode=True, buckets=1, defer_decode=False):
     """model.step(update=False, decode=True): returns dict(loss [B] tensor|None, avg_loss, decoded, logits).
+    defer_decode: 'decoded' is an ops.PendingDecode (kernel enqueued, nothing read back yet); pass the dict to
+    finish_evaluate() once the host has nothing better to do than to wait.
 
     buckets > 1 (optional; the reference always pads the whole batch to its longest utterance, speech_input.py:38-43):
     the batch is evaluated as that many length-sorted groups, each padded to its own maximum.  Results come back in
@@ -384,8 +386,18 @@ class W2LEngine:
       out['loss'] = loss
       out['avg_loss'] = BatchMean(loss)
     if decode:
-      out['decoded'], out['neg_sum_logits'] = ops.ctc_greedy_decoder(logits, ctc_len)
+      if defer_decode:
+        out['decoded'] = ops.PendingDecode(logits, ctc_len)
+      else:
+        out['decoded'], out['neg_sum_logits'] = ops.ctc_greedy_decoder(logits, ctc_len)
       self.launches += 1
+    return out
+
+  @staticmethod
+  def finish_evaluate(out):
+    """Completes an evaluate_step(defer_decode=True) result in place (the blocking device -> host read)."""
+    if isinstance(out.get('decoded'), ops.PendingDecode):
+      out['decoded'], out['neg_sum_logits'] = out['decoded'].finish()
     return out
 
   def _evaluate_bucketed(self, inputs, sequence_lengths, labels, decode, buckets):

@@ -238,6 +238,25 @@ def ctc_greedy_decoder(logits, sequence_length, merge_repeated=True):
   return [sparse_from_rows(values, counts)], neg.cpu().numpy().reshape(B, 1)
 
 
+class PendingDecode:
+  """A greedy decode whose kernel is enqueued and whose results are still on the device: finish() performs the
+  (blocking) read-back and builds what ctc_greedy_decoder returns.  Lets the caller put host work -- fetching and
+  uploading the next batch -- between the launch and the read (speech_model.SpeechModel.step, evaluate path)."""
+
+  def __init__(self, logits, sequence_length, merge_repeated=True):
+    _require_cuda(logits)
+    dev = logits.device
+    if torch.is_tensor(sequence_length):
+      d_seq = sequence_length.to(device=dev, dtype=torch.int32)
+    else:
+      d_seq = torch.from_numpy(np.ascontiguousarray(np.asarray(sequence_length, dtype=np.int32))).to(dev)
+    self.B = logits.shape[1]
+    self.values, self.counts, self.neg = ctc_greedy_decode_device(logits, d_seq, merge_repeated)
+
+  def finish(self):
+    return [sparse_from_rows(self.values, self.counts)], self.neg.cpu().numpy().reshape(self.B, 1)
+
+
 def sparse_from_rows(values, counts):
   """[B,T] int32 rows + counts -> the SparseTensor triple TF returns (row-major order).  Only the counts and the
   first max(count) columns of the rows cross to the host."""

@@ -314,12 +314,14 @@ class SpeechModel:
       if feed_dict is None:
         self._prefetch_next()                   # next batch's H2D overlaps this step's kernels
     else:
-      # an evaluate step ends with a blocking read of the decoded labels: the next batch's upload must be under way
-      # BEFORE it, or it would start only once this step has finished
+      # an evaluate step ends with a blocking read of the decoded labels.  Its kernels are enqueued FIRST; fetching
+      # the next batch and starting its upload (host work: a ragged batch is 256 small copies) then runs underneath
+      # them, and only after that does the host block on the results
+      res = self.engine.evaluate_step(d_inputs, lengths, labels if loss else None, decode=decode,
+                                      buckets=getattr(self, 'eval_buckets', 1), defer_decode=True)
       if feed_dict is None:
         self._prefetch_next()
-      res = self.engine.evaluate_step(d_inputs, lengths, labels if loss else None, decode=decode,
-                                      buckets=getattr(self, 'eval_buckets', 1))
+      self.engine.finish_evaluate(res)
     self.last_result = res
     output = []
     if loss:

@@ -23,7 +23,8 @@ CAPTURES = {
   'l8_wgrad': ('l8_wgrad_bf16x3', None, 'layer-8 filter gradient (nine-problem launch)'),
   'l1_7_wgrad': ('l1_7_wgrad_bf16x3', None, 'filter gradients of the seven 250-channel layers, one launch, forced K slices'),
   'ctc_alpha_beta': ('ctc_alpha_beta', None, 'CTC alpha/beta recursion'),
-  'pack': ('pack_ffa2', None, 'one-pass packing of the nine leaf filters of layer 8'),
+  'pack': ('pack_bwd', None, 'streaming pack of the nine leaf filters of layer 8 (backward layout only; the forward kernel reads it MN-major)'),
+  'l10_dgrad': ('l10_dgrad_bf16x3', None, 'layer-10 data gradient: 128-wide tiles, sixteen epilogue warps'),
   'ffa2_combine': ('ffa2_combine', None, 'forward combine of the nine leaf products (bias + ReLU + plane split)'),
   'ffa2_dz_prep': ('ffa2_dz_prep', None, 'backward prepare: the nine leaf gradients from dy'),
   'l8_fwd_cfg3': ('l8_fwd_bf16_cfg3', 'bf16/B64/T1001', 'layer-8 forward at config 3 (plain bf16, batch 64)'),

@@ -67,7 +67,8 @@ full l1_fwd tc_conv_kernel 54
 full l8_wgrad tc_wgrad_kernel 12
 full l1_7_wgrad tc_wgrad_kernel 14
 full ctc_alpha_beta ctc_alpha_beta 3
-full pack pack_ffa2 3
+full pack pack_bwd 2
+full l10_dgrad tc_conv_kernel 64
 full ffa2_combine ffa2_combine 3
 full ffa2_dz_prep ffa2_dz_prep 3
 full l8_fwd_cfg3 tc_conv_kernel 61 --config 3

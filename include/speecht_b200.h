@@ -126,6 +126,9 @@ int st_plan_pack_weights(st_plan* plan, st_stream_t stream);
 int st_plan_forward(st_plan* plan, const float* inputs, st_stream_t stream);
 int st_plan_backward(st_plan* plan, st_stream_t stream);
 int st_plan_backward_range(st_plan* plan, int layer_hi, int layer_lo, st_stream_t stream);  /* 10 first, downwards */
+/* Data parallelism (no reference counterpart: the reference is single-process).  Tensor-core grids launched after the
+ * call leave n_sms SMs free for a concurrent collective (the NCCL allreduce overlapped with backward); 0 = all SMs. */
+int st_plan_reserve_sms(st_plan* plan, int n_sms);
 float* st_plan_logits(st_plan* plan);
 void* st_plan_dlogits_planes(st_plan* plan);
 int st_plan_get_activation(st_plan* plan, int layer, float* dst, st_stream_t stream);

@@ -1811,8 +1811,17 @@ int current_device() {
   return (dev >= 0 && dev < kMaxDevices) ? dev : 0;
 }
 
+// SMs the persistent tensor-core grids may occupy: all of them, minus the ones a caller has set aside for a collective
+// that runs concurrently (set_reserved_sms; data-parallel training reserves room for the NCCL allreduce kernel, whose
+// CTAs cannot share an SM with a 227 KB tensor-core CTA and would otherwise start only when a wave drains)
+int g_reserved_sms = 0;
+int tc_sms() {
+  const int n = st_num_sms() - g_reserved_sms;
+  return n < 8 ? 8 : n;
+}
+
 int grid_for(int work_items) {
-  const int sms = st_num_sms();
+  const int sms = tc_sms();
   return work_items < sms ? work_items : sms;
 }
 
@@ -1860,7 +1869,7 @@ bool pair_enabled() {                        // read when a plan is bound (want_
 
 // grid of a CTA-pair launch: one cluster of two CTAs per work item, at most one cluster per TPC
 int pair_grid(int pair_work) {
-  const int clusters = st_num_sms() / 2;
+  const int clusters = tc_sms() / 2;
   return 2 * (pair_work < clusters ? pair_work : clusters);
 }
 
@@ -1952,7 +1961,7 @@ int launch_conv_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensor
   constexpr bool kCanPair = BLOCK_N == 256 && NPL <= 2;
   const bool pair = kCanPair && p.pair;
   const int work = pair ? ((m_tiles + 1) / 2) * p.n_tiles : m_tiles * p.n_tiles;
-  const int ctas = pair ? st_num_sms() / 2 : st_num_sms();
+  const int ctas = pair ? tc_sms() / 2 : tc_sms();
   const bool early = ConvCfg<BLOCK_N, NPL>::ACC_STAGES == 1 && work > ctas && p.taps * p.chunks_per_tap >= 16;
   if constexpr (kCanPair) {
     if (pair) {
@@ -1980,10 +1989,10 @@ int launch_wgrad_k(const Tm& x, const Tm& dz, const WgradParams& p, cudaStream_t
     configured[dev] = true;
   }
   if constexpr (PAIR) {
-    ST_CUDA_CALL(launch_pdl_cluster(tc_wgrad_kernel<BLOCK_N, NPL, NPROB, true>, 2 * (st_num_sms() / 2), 2, Cfg::SMEM_BYTES,
+    ST_CUDA_CALL(launch_pdl_cluster(tc_wgrad_kernel<BLOCK_N, NPL, NPROB, true>, 2 * (tc_sms() / 2), 2, Cfg::SMEM_BYTES,
                                     stream, x, dz, p));
   } else {
-    ST_CUDA_CALL(launch_pdl(tc_wgrad_kernel<BLOCK_N, NPL, NPROB, false>, st_num_sms(), Cfg::SMEM_BYTES, stream, x, dz, p));
+    ST_CUDA_CALL(launch_pdl(tc_wgrad_kernel<BLOCK_N, NPL, NPROB, false>, tc_sms(), Cfg::SMEM_BYTES, stream, x, dz, p));
   }
   return ST_OK;
 }
@@ -2038,6 +2047,8 @@ bool wgrad_pair(int taps, int m_tiles, int block_n, int n_planes) {
   if (e && (e[0] == '0' || e[0] == '1')) return e[0] == '1';
   return n_planes == 1 || taps == 1;
 }
+
+void set_reserved_sms(int n) { g_reserved_sms = n < 0 ? 0 : n; }
 
 void set_conv_timeline(long long* buf, int launch_index) {
   g_timeline_buf = buf;
@@ -2325,7 +2336,7 @@ int launch_ffa2_dw_combine(float* dW, float* const* c9, int J, int64_t tap_elems
 // Does a filter-gradient launch of `num_tiles` tiles cut its last wave into K slices (which ACCUMULATE into dW, so the
 // outputs must be zero on entry)?  Mirrors the wave-aligned split of tc_wgrad_kernel.
 int wgrad_best_split(int num_tiles, int total_iters, bool pair) {
-  int G = st_num_sms();
+  int G = tc_sms();
   if (pair) { G /= 2; num_tiles /= 2; }          // scheduling units: tile pairs on clusters
   if (num_tiles >= G) return 1;
   int best = 1;
@@ -2339,7 +2350,7 @@ int wgrad_best_split(int num_tiles, int total_iters, bool pair) {
 }
 
 bool wgrad_accumulates(int num_tiles, int total_iters, bool pair) {
-  int G = st_num_sms();
+  int G = tc_sms();
   if (pair) { G /= 2; num_tiles /= 2; }
   const int tail_tiles = num_tiles % G;
   if (tail_tiles == 0) return false;

@@ -89,6 +89,8 @@ int make_map_2d(CUtensorMap* map, const void* base, int cols, int rows, int64_t 
 // store map over output planes [Bn][T][C] (C = padded channel count ld), box {32, 32, 1}
 int make_map_3d_store(CUtensorMap* map, const void* base, int C, int T, int Bn, int64_t ld, int64_t batch_stride);
 
+// SMs left free by the tensor-core grids launched from now on (0 = use every SM): room for a concurrent collective.
+void set_reserved_sms(int n);
 // Debug hook: the conv launch number `launch_index` (counted from the call) writes its per-CTA timeline into buf.
 void set_conv_timeline(long long* buf, int launch_index);
 

@@ -979,6 +979,17 @@ ST_API int st_plan_backward_range(st_plan* p, int hi, int lo, st_stream_t stream
 
 ST_API int st_plan_backward(st_plan* p, st_stream_t stream) { return st_plan_backward_range(p, 10, 0, stream); }
 
+// Data-parallel training: the tensor-core grids launched after this call leave `n_sms` SMs free (0 restores the full
+// machine).  The NCCL allreduce of the layer-8..10 gradients runs underneath the backward pass of layers 7..0; its
+// CTAs cannot share an SM with a tensor-core CTA (227 KB of shared memory, 54 K registers), and the persistent
+// filter-gradient grids assign their work statically to 148 CTAs -- without free SMs the collective starts late and
+// then delays whole CTAs of those grids.  Process-wide setting (one engine per process in DP runs).
+ST_API int st_plan_reserve_sms(st_plan* p, int n_sms) {
+  ST_CHECK_ARG(p && n_sms >= 0 && n_sms <= 64, "st_plan_reserve_sms: 0 <= n_sms <= 64");
+  tc::set_reserved_sms(n_sms);
+  return ST_OK;
+}
+
 // Debug / test access: activation planes of layer `layer` output (0..9) merged to fp32 [B][To][Cout];
 // layer = -1 gives the split input [B][Tpad][F].
 ST_API int st_plan_get_activation(st_plan* p, int layer, float* dst, st_stream_t stream) {

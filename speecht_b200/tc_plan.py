@@ -6,6 +6,7 @@ parameter / gradient buffers.  The sequence per train step is
   ->  plan.backward  ->  [NCCL allreduce]  ->  clip_by_global_norm + Adam on the flat fp32 buffers.
 """
 import ctypes
+import os
 
 import numpy as np
 import torch
@@ -14,6 +15,10 @@ from . import ops
 from ._lib import check, lib, ptr, stream_ptr
 
 N_PLANES = {'bf16': 1, 'bf16x3': 2, 'bf16x6': 3}
+# SMs the backward pass of layers 7..0 leaves to the concurrent NCCL allreduce in data-parallel runs.  Measured on two
+# GPUs (profiles/r02_dp_reserve_ab_2gpu.txt): NCCL finds its SMs anyway (the 250-channel layers occupy 128 of 148), and
+# reserving 8 / 16 costs 1.5 % per step -- so the default is 0; the switch stays for boxes where NCCL needs more CTAs.
+DP_RESERVE_SMS = int(os.environ.get('SPEECHT_B200_DP_RESERVE_SMS', '0'))
 MAX_CACHED_SHAPES = 64
 
 
@@ -171,7 +176,13 @@ class TCPlan:
         split = eng.layout.w_off[8]
         check(lib().st_plan_backward_range(sh.handle, 10, 8, stream_ptr()))
         handles = eng.allreduce_gradients(async_ranges=[(split, eng.grads.numel())])
-        check(lib().st_plan_backward_range(sh.handle, 7, 0, stream_ptr()))
+        if DP_RESERVE_SMS > 0:       # optionally leave room for the allreduce kernel's CTAs (st_plan_reserve_sms)
+          check(lib().st_plan_reserve_sms(sh.handle, DP_RESERVE_SMS))
+        try:
+          check(lib().st_plan_backward_range(sh.handle, 7, 0, stream_ptr()))
+        finally:
+          if DP_RESERVE_SMS > 0:
+            check(lib().st_plan_reserve_sms(sh.handle, 0))
         handles += eng.allreduce_gradients(async_ranges=[(0, split)])
         for h in handles:
           h.wait()

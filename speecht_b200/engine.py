@@ -365,10 +365,12 @@ class W2LEngine:
     return [g for g in np.array_split(order, max(1, min(int(buckets), len(order)))) if len(g)]
 
   @_on_engine_device
-  def evaluate_step(self, inputs, sequence_lengths, labels=None, decode=True, buckets=1, defer_decode=False):
+  def evaluate_step(self, inputs, sequence_lengths, labels=None, decode=True, buckets=1, defer_decode=False,
+                    fresh_decode=False):
     """model.step(update=False, decode=True): returns dict(loss [B] tensor|None, avg_loss, decoded, logits).
     defer_decode: 'decoded' is an ops.PendingDecode (kernel enqueued, nothing read back yet); pass the dict to
-    finish_evaluate() once the host has nothing better to do than to wait.
+    finish_evaluate() once the host has nothing better to do than to wait (fresh_decode: the decoded rows get their own
+    buffers, so that a second step may be enqueued before this one is read).
 
     buckets > 1 (optional; the reference always pads the whole batch to its longest utterance, speech_input.py:38-43):
     the batch is evaluated as that many length-sorted groups, each padded to its own maximum.  Results come back in
@@ -380,16 +382,20 @@ class W2LEngine:
     logits = self.forward(inputs, keep_activations=False)
     ctc_len = np.asarray(sequence_lengths, dtype=np.int32) // 2      # speech_model.py:74,114
     out = {'logits': logits, 'loss': None, 'avg_loss': None, 'decoded': None}
+    d_seq = ctc_len
     if labels is not None:
-      loss, _ = ops.ctc_loss(labels, logits, ctc_len, want_grad=False)
+      batch = labels if isinstance(labels, ops.CTCBatch) else ops.CTCBatch(labels, ctc_len, logits.shape[0],
+                                                                           self.num_classes, self.device)
+      loss, _ = ops.ctc_loss(batch, logits, want_grad=False)
+      d_seq = batch.seq_len                                     # already on the device (pinned, asynchronous upload)
       self.launches += 2
       out['loss'] = loss
-      out['avg_loss'] = BatchMean(loss)
+      out['avg_loss'] = BatchMean(loss, early=defer_decode)     # deferred: the [B] losses start their trip to the host now
     if decode:
       if defer_decode:
-        out['decoded'] = ops.PendingDecode(logits, ctc_len)
+        out['decoded'] = ops.PendingDecode(logits, d_seq, fresh=fresh_decode)
       else:
-        out['decoded'], out['neg_sum_logits'] = ops.ctc_greedy_decoder(logits, ctc_len)
+        out['decoded'], out['neg_sum_logits'] = ops.ctc_greedy_decoder(logits, d_seq)
       self.launches += 1
     return out
 
@@ -412,7 +418,7 @@ class W2LEngine:
     # every group's kernels are enqueued first (the next group's forward reuses the arena, which stream order makes
     # safe); results cross to the host once, at the end
     for group in self.length_buckets(lengths, buckets):
-      idx = torch.from_numpy(group.astype(np.int64)).to(self.device)
+      idx = ops.upload_int32_async(group, self.device).long()       # pinned + asynchronous: no stream synchronisation
       t_max = max(int(lengths[group].max()), 2)
       x = inputs.index_select(0, idx)[:, :t_max].contiguous()
       logits = self.forward(x, keep_activations=False)

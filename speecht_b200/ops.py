@@ -130,6 +130,22 @@ class _PinnedPool:
 _pinned_pool = _PinnedPool()
 
 
+def upload_int32_async(values, device):
+  """Small int32 host array -> device tensor through the pinned pool, WITHOUT blocking the host: a plain
+  torch.from_numpy(x).to(device) of pageable memory synchronises the stream, i.e. waits for every kernel enqueued
+  before it (a whole forward pass when it sits between the forward and the decode kernel)."""
+  arr = np.ascontiguousarray(np.asarray(values, dtype=np.int32)).reshape(-1)
+  n = max(int(arr.size), 1)
+  item = _pinned_pool.acquire(n)
+  host = item[0][:n]
+  host.numpy()[:arr.size] = arr
+  dev = host.to(device, non_blocking=True)
+  ev = torch.cuda.Event()
+  ev.record()
+  item[1] = ev
+  return dev[:arr.size]
+
+
 class CTCBatch:
   """Device-side label / length tensors of one batch, uploaded asynchronously from pinned memory so that no host
   synchronisation sits between the forward pass and the loss kernels."""
@@ -233,28 +249,69 @@ def ctc_greedy_decoder(logits, sequence_length, merge_repeated=True):
   if torch.is_tensor(sequence_length):
     d_seq = sequence_length.to(device=dev, dtype=torch.int32)
   else:
-    d_seq = torch.from_numpy(np.ascontiguousarray(np.asarray(sequence_length, dtype=np.int32))).to(dev)
+    d_seq = upload_int32_async(sequence_length, dev)
   values, counts, neg = ctc_greedy_decode_device(logits, d_seq, merge_repeated)
   return [sparse_from_rows(values, counts)], neg.cpu().numpy().reshape(B, 1)
 
 
 class PendingDecode:
-  """A greedy decode whose kernel is enqueued and whose results are still on the device: finish() performs the
-  (blocking) read-back and builds what ctc_greedy_decoder returns.  Lets the caller put host work -- fetching and
-  uploading the next batch -- between the launch and the read (speech_model.SpeechModel.step, evaluate path)."""
+  """A greedy decode whose kernel is enqueued and whose results are on their way to pinned host memory: finish() waits
+  for THAT copy (an event recorded right behind it, not the whole stream) and builds what ctc_greedy_decoder returns.
+  Lets the caller put host work -- fetching and uploading the next batch, even enqueueing the next step's kernels --
+  between the launch and the read (speech_model.SpeechModel.step, evaluate path)."""
 
-  def __init__(self, logits, sequence_length, merge_repeated=True):
+  _free = []                                        # pinned int32 staging buffers not owned by a live PendingDecode
+
+  def __init__(self, logits, sequence_length, merge_repeated=True, fresh=False):
     _require_cuda(logits)
     dev = logits.device
     if torch.is_tensor(sequence_length):
       d_seq = sequence_length.to(device=dev, dtype=torch.int32)
     else:
-      d_seq = torch.from_numpy(np.ascontiguousarray(np.asarray(sequence_length, dtype=np.int32))).to(dev)
-    self.B = logits.shape[1]
-    self.values, self.counts, self.neg = ctc_greedy_decode_device(logits, d_seq, merge_repeated)
+      d_seq = upload_int32_async(sequence_length, dev)
+    self.B = B = logits.shape[1]
+    values, counts, neg = ctc_greedy_decode_device(logits, d_seq, merge_repeated, fresh=fresh)
+    self.width = W = values.shape[1]
+    n = B * W + 2 * B                               # [label rows | counts | neg_sum_logits bits]
+    self._host = None
+    for i, buf in enumerate(PendingDecode._free):
+      if buf.numel() >= n:
+        self._host = PendingDecode._free.pop(i)
+        break
+    if self._host is None:
+      self._host = torch.empty((n,), dtype=torch.int32).pin_memory()
+    h = self._host
+    h[:B * W].view(B, W).copy_(values, non_blocking=True)
+    h[B * W:B * W + B].copy_(counts, non_blocking=True)
+    h[B * W + B:n].view(torch.float32).copy_(neg, non_blocking=True)
+    self._event = torch.cuda.Event()
+    self._event.record()
+    self._keep = (values, counts, neg)              # alive until the copies have run
 
   def finish(self):
-    return [sparse_from_rows(self.values, self.counts)], self.neg.cpu().numpy().reshape(self.B, 1)
+    self._event.synchronize()
+    B, W = self.B, self.width
+    h = self._host.numpy()
+    out = [sparse_from_host_rows(h[:B * W].reshape(B, W), h[B * W:B * W + B])], \
+        h[B * W + B:B * W + 2 * B].view(np.float32).reshape(B, 1).copy()
+    if len(PendingDecode._free) < 8:
+      PendingDecode._free.append(self._host)
+    self._host = self._keep = None
+    return out
+
+
+def sparse_from_host_rows(values_h, counts_h):
+  """Host-side half of sparse_from_rows: [B,T] int32 rows + counts (numpy) -> SparseTensorValue (row-major order)."""
+  counts_h = counts_h.astype(np.int64)
+  B = counts_h.shape[0]
+  width = int(counts_h.max()) if B else 0
+  n = int(counts_h.sum())
+  rows = np.repeat(np.arange(B, dtype=np.int64), counts_h)
+  starts = np.cumsum(counts_h) - counts_h
+  cols = np.arange(n, dtype=np.int64) - np.repeat(starts, counts_h)
+  indices = np.stack([rows, cols], axis=1).reshape(n, 2)
+  vals = values_h[rows, cols].astype(np.int64) if n else np.zeros((0,), dtype=np.int64)
+  return SparseTensorValue(indices, vals, np.array([B, width], dtype=np.int64))
 
 
 def sparse_from_rows(values, counts):

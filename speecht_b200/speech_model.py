@@ -12,6 +12,8 @@ import abc
 import glob
 import os
 import re
+import sys
+import time
 
 import numpy as np
 import torch
@@ -20,6 +22,9 @@ from . import vocabulary
 from .engine import W2LEngine
 from .errors import OutOfRangeError  # noqa: F401  (re-exported for callers)
 from .speech_input import BaseInputLoader
+
+
+_STEP_TRACE = os.environ.get('SPEECHT_B200_STEP_TRACE') == '1'      # host-side phase timing of evaluate steps -> stderr
 
 
 class Session:
@@ -193,6 +198,10 @@ class SpeechModel:
     self.max_gradient_norm = 5.0
     self._prefetched = None                      # next batch, already on its way to the device
     self._copy_stream = None
+    # evaluate steps are software-pipelined: the kernels of the NEXT batch are enqueued before the host blocks on the
+    # results of this one (SPEECHT_B200_EVAL_PIPELINE=0 disables it)
+    self._speculated = None
+    self._pipeline_eval = os.environ.get('SPEECHT_B200_EVAL_PIPELINE', '1') != '0'
 
   def add_training_ops(self, learning_rate: float = 1e-3, learning_rate_decay_factor: float = 0,
                        max_gradient_norm: float = 5.0, momentum: float = 0.9):
@@ -293,8 +302,32 @@ class SpeechModel:
     except OutOfRangeError as e:
       self._prefetched = e
 
+  def _speculate(self, flags, buckets):
+    """Software pipelining of evaluate steps: takes the prefetched next batch and enqueues its forward / loss / decode
+    kernels now, so that the GPU works on it while the host reads back and post-processes the current results (the
+    decoded rows and losses of a step live in their own buffers; only `logits` of the previous step is overwritten).
+    The result is handed out by the next step() if it asks for the same outputs; a training step just takes the batch."""
+    item = self._prefetched
+    if not self._pipeline_eval or buckets > 1 or item is None or isinstance(item, Exception):
+      return
+    self._prefetched = None
+    dev, lengths, labels, ev = item
+    if ev is not None:
+      torch.cuda.current_stream().wait_event(ev)
+      dev.record_stream(torch.cuda.current_stream())
+    res = None
+    try:
+      if not flags[0] or labels is not None:
+        res = self.engine.evaluate_step(dev, lengths, labels if flags[0] else None, decode=flags[1], buckets=1,
+                                        defer_decode=True, fresh_decode=True)
+    except Exception:
+      res = None                                # e.g. a label that does not fit: raised by the step that owns the batch
+    self._speculated = {'batch': (dev, lengths, labels), 'flags': flags, 'res': res}
+
   def input_exhausted(self):
     """True when the NEXT step would find no batch (the prefetch already hit the end, or the loader says so)."""
+    if self._speculated is not None:
+      return False
     if self._prefetched is not None:
       return isinstance(self._prefetched, Exception)
     at_end = getattr(self.input_loader, 'at_end', None)
@@ -303,7 +336,13 @@ class SpeechModel:
   def step(self, sess, loss=True, update=True, decode=False, return_label=False, summary=False, feed_dict=None):
     """speech_model.py:197-235.  Returns: avg_loss (optional), decoded (optional), label (optional),
     update (optional, None), summary (optional, None) -- in that order."""
-    d_inputs, lengths, labels = self._next_batch(feed_dict)
+    spec = None
+    if feed_dict is None and self._speculated is not None:
+      # the batch an earlier evaluate step already took from the loader (and enqueued kernels for)
+      spec, self._speculated = self._speculated, None
+      d_inputs, lengths, labels = spec['batch']
+    else:
+      d_inputs, lengths, labels = self._next_batch(feed_dict)
     if (loss or update) and (labels is None or not self._training):
       raise ValueError('loss/update requested but the model has no labels / training ops')
     if decode and not self._decoding:
@@ -317,11 +356,30 @@ class SpeechModel:
       # an evaluate step ends with a blocking read of the decoded labels.  Its kernels are enqueued FIRST; fetching
       # the next batch and starting its upload (host work: a ragged batch is 256 small copies) then runs underneath
       # them, and only after that does the host block on the results
-      res = self.engine.evaluate_step(d_inputs, lengths, labels if loss else None, decode=decode,
-                                      buckets=getattr(self, 'eval_buckets', 1), defer_decode=True)
+      buckets = getattr(self, 'eval_buckets', 1)
+      flags = (bool(loss), bool(decode))
+      trace = [time.perf_counter()] if _STEP_TRACE else None
+      if spec is not None and spec['res'] is not None and spec['flags'] == flags:
+        res = spec['res']                       # enqueued during the previous step
+      else:
+        res = self.engine.evaluate_step(d_inputs, lengths, labels if loss else None, decode=decode, buckets=buckets,
+                                        defer_decode=True)
+      if trace: trace.append(time.perf_counter())
       if feed_dict is None:
         self._prefetch_next()
+        if trace: trace.append(time.perf_counter())
+        self._speculate(flags, buckets)         # the next batch's kernels go in BEFORE the blocking read below
+      if trace: trace.append(time.perf_counter())
       self.engine.finish_evaluate(res)
+      if trace:
+        trace.append(time.perf_counter())
+        if loss:
+          res['avg_loss'].item()
+        trace.append(time.perf_counter())
+        sys.stderr.write('evaluate step trace (ms): enqueue %.2f prefetch %.2f speculate %.2f finish %.2f loss %.2f | since last %.2f\n'
+                         % tuple([1e3 * (b - a) for a, b in zip(trace[:-1], trace[1:])] +
+                                 [1e3 * (trace[0] - getattr(self, '_trace_last', trace[0]))]))
+        self._trace_last = trace[-1]
     self.last_result = res
     output = []
     if loss:

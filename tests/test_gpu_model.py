@@ -307,14 +307,30 @@ def test_training_reduces_the_loss_on_a_fixed_batch(precision):
   assert np.mean(losses[-10:]) < np.mean(losses[:10])
 
 
-@pytest.mark.parametrize('level,pair', [(0, '1'), (1, '1'), (2, '1'), (2, '0')])
-def test_fast_fir_levels_and_cta_pairs_give_the_same_step(level, pair, monkeypatch):
-  """Layer 8 as the direct 32-tap kernels (level 0), one fast-FIR level (three half-rate problems) or two (nine
-  quarter-rate problems, the default), on CTA pairs or single CTAs: activations of every layer against the float64
-  oracle (1e-4 gate) and the gradients of one train step "same-mask" against the oracle backward (3e-4).  The
-  switches are read when a plan is created / the library first launches."""
-  monkeypatch.setenv('SPEECHT_B200_FFA', str(level))
-  monkeypatch.setenv('SPEECHT_B200_PAIR', pair)
+KERNEL_VARIANTS = [
+  {'SPEECHT_B200_FFA': '0'}, {'SPEECHT_B200_FFA': '1'}, {'SPEECHT_B200_FFA': '2'},
+  {'SPEECHT_B200_PAIR': '0'},                       # no CTA pairs in forward / data gradient
+  {'SPEECHT_B200_PAIR_SMALL': '1'},                 # pairs on the one-wave launches too
+  {'SPEECHT_B200_WGRAD_PAIR': '1'},                 # every eligible filter-gradient launch on CTA pairs
+  {'SPEECHT_B200_WGRAD_PAIR': '0'},
+  {'SPEECHT_B200_BMN': '0'},                        # K-major forward layouts for layers 8 / 9
+  {'SPEECHT_B200_BMN': '1', 'SPEECHT_B200_PAIR': '0'},
+  {'SPEECHT_B200_L10_N128': '0'},                   # 256-wide layer-10 data gradient (8 epilogue warps)
+  {'SPEECHT_B200_MERGE_WGRAD': '0'},                # one filter-gradient launch per 250-channel layer
+  {'SPEECHT_B200_TRIM': '0'},
+]
+
+
+@pytest.mark.parametrize('variant', KERNEL_VARIANTS, ids=lambda v: ','.join('%s=%s' % (k[13:], x) for k, x in v.items()))
+def test_fast_fir_levels_and_cta_pairs_give_the_same_step(variant, monkeypatch):
+  """Every kernel variant behind an environment switch -- layer 8 as the direct 32-tap kernels (FFA 0), one fast-FIR
+  level or two (the default), CTA pairs on / off in forward, data gradient and filter gradient, MN-major or K-major
+  forward filters, tile widths, merged filter gradients: activations of every layer against the float64 oracle
+  (1e-4 gate) and the gradients of one train step "same-mask" against the oracle backward (3e-4).  The switches are
+  read when a plan is created / bound / launched."""
+  level, pair = variant.get('SPEECHT_B200_FFA', '2'), variant.get('SPEECHT_B200_PAIR', '1')
+  for k, v in variant.items():
+    monkeypatch.setenv(k, v)
   inputs, lengths, labels = O.synthetic_batch(seed=4, batch=3, seconds=[3, 2, 3])
   weights = O.xavier_weights(np.random.default_rng(98), dtype=np.float32)
   w64 = [(w.astype(np.float64), b.astype(np.float64)) for w, b in weights]
@@ -324,7 +340,7 @@ def test_fast_fir_levels_and_cta_pairs_give_the_same_step(level, pair, monkeypat
   res = eng.train_step(torch.from_numpy(inputs).cuda(), lengths, labels, 1e-4)
   gpu_acts = _gpu_activations(eng)
   errs = [rel(a, acts[l + 1]) for l, a in enumerate(gpu_acts)]
-  print('fast-FIR level %d pair %s: per-layer rel err vs float64 oracle %s' % (level, pair, ' '.join('%.2e' % e for e in errs)))
+  print('fast-FIR level %s pair %s %s: per-layer rel err vs float64 oracle %s' % (level, pair, variant, ' '.join('%.2e' % e for e in errs)))
   assert max(errs) < 1e-4, errs
   assert rel(res['loss'].cpu().numpy(), loss) < 1e-4
   acts_h = [acts[0]] + [np.where(g > 0, np.maximum(acts[l + 1], 1e-30), 0.0) for l, g in enumerate(gpu_acts)]
@@ -403,3 +419,30 @@ def test_bucketed_evaluate_restores_order_and_equals_per_group_evaluation():
     np.testing.assert_array_equal(rows[u], full_rows[u])
   # shorter utterances see other padding than in the reference batch: close, not identical
   assert np.max(np.abs(loss - full_loss) / full_loss) < 0.05
+
+
+@pytest.mark.parametrize('variant', [{'SPEECHT_B200_WGRAD_PAIR': '0'}, {'SPEECHT_B200_BMN': '1'},
+                                     {'SPEECHT_B200_PAIR': '0'}, {'SPEECHT_B200_L10_N128': '0'}],
+                         ids=lambda v: ','.join('%s=%s' % (k[13:], x) for k, x in v.items()))
+def test_plain_bf16_kernel_variants_agree_with_the_default_build(variant, monkeypatch):
+  """Plain bf16 (BASELINE configs 3-4) cannot be gated against the float64 oracle at 1e-4, so its kernel variants are
+  checked against the default variant of the same precision: same operands, same products -- only the order of the
+  fp32 accumulation over K slices may differ (1e-5 of the tensor maximum)."""
+  inputs, lengths, labels = O.synthetic_batch(seed=9, batch=4, seconds=[3, 2, 3, 1])
+  weights = O.xavier_weights(np.random.default_rng(77), dtype=np.float32)
+  x = torch.from_numpy(inputs).cuda()
+
+  def run():
+    eng = _engine('bf16', weights)
+    res = eng.train_step(x, lengths, labels, 1e-4)
+    return (res['loss'].cpu().numpy(), res['logits'].detach().cpu().numpy().copy(),
+            [(dw.cpu().numpy().copy(), db.cpu().numpy().copy()) for dw, db in eng.weight_grads])
+
+  loss0, logits0, grads0 = run()
+  for k, v in variant.items():
+    monkeypatch.setenv(k, v)
+  loss1, logits1, grads1 = run()
+  assert rel(logits1, logits0) < 1e-5, rel(logits1, logits0)
+  assert rel(loss1, loss0) < 1e-5
+  for li, ((dw1, db1), (dw0, db0)) in enumerate(zip(grads1, grads0)):
+    assert rel(dw1, dw0) < 1e-5 and rel(db1, db0) < 1e-5, (li, rel(dw1, dw0), rel(db1, db0))

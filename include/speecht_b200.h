@@ -129,6 +129,10 @@ int st_plan_backward_range(st_plan* plan, int layer_hi, int layer_lo, st_stream_
 /* Data parallelism (no reference counterpart: the reference is single-process).  Tensor-core grids launched after the
  * call leave n_sms SMs free for a concurrent collective (the NCCL allreduce overlapped with backward); 0 = all SMs. */
 int st_plan_reserve_sms(st_plan* plan, int n_sms);
+/* Optional, before st_plan_forward of a train step: zeroes the flat gradient buffer on the plan's side stream underneath
+ * the forward pass (TF zero-initialises gradient accumulators per sess.run, speech_model.py:78); st_plan_backward then
+ * waits for it instead of zeroing in line. */
+int st_plan_prepare_backward(st_plan* plan, st_stream_t stream);
 float* st_plan_logits(st_plan* plan);
 void* st_plan_dlogits_planes(st_plan* plan);
 int st_plan_get_activation(st_plan* plan, int layer, float* dst, st_stream_t stream);

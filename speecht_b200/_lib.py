@@ -59,6 +59,7 @@ _SIGNATURES = {
   'st_plan_forward': (c_int, [P, P, P]),
   'st_plan_backward': (c_int, [P, P]),
   'st_plan_reserve_sms': (c_int, [P, c_int]),
+  'st_plan_prepare_backward': (c_int, [P, P]),
   'st_plan_backward_range': (c_int, [P, c_int, c_int, P]),
   'st_plan_logits': (c_void_p, [P]),
   'st_plan_dlogits_planes': (c_void_p, [P]),

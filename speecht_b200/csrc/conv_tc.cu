@@ -1200,50 +1200,69 @@ pack_ffa2_kernel(const float* __restrict__ w, const Ptr9h fwd, const Ptr9h bwd, 
 }
 
 // Backward-layout planes ONLY, for layers whose forward kernel reads the filter MN-major (ConvParams::b_mn): no
-// transposed copy, so this is a pure streaming pass -- one thread per 8 output channels of one (packed tap, ci) row,
-// 16-byte loads and stores.  Leaf l = sum of the source taps group * k + c over the set bits c of masks.m[l] (plain
-// layers: one leaf, group 1, mask 1; the two-level fast-FIR split of layer 8: nine leaves, group 4).
+// transposed copy, so this is a pure streaming pass -- one thread per 4 output channels of one (packed tap, ci) row.
+// Leaf l = sum of the source taps group * k + c over the set bits c of masks.m[l] (plain layers: one leaf, group 1,
+// mask 1; the two-level fast-FIR split of layer 8: nine leaves, group 4).
+// BACKGROUND kernels (this one, ffa2_dw_combine_kernel, zero_f32_kernel): no shared memory and at most 40 registers
+// (__launch_bounds__(256, 6)), so that ONE such block fits on an SM beside a resident tensor-core CTA (54 K registers,
+// 227 KB of shared memory).  The step plan launches them with one block per SM on a side stream underneath tensor-core
+// launches that leave the HBM idle (w2l_plan.cu, "overlap").
 template <int NPL>
-__global__ void __launch_bounds__(256)
+__device__ __forceinline__ void store_planes4(__nv_bfloat16* dst, int64_t plane_stride, const float* v) {
+  float rem[4] = {v[0], v[1], v[2], v[3]};
+#pragma unroll
+  for (int p = 0; p < NPL; ++p) {
+    uint32_t w[2];
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const __nv_bfloat162 h = __floats2bfloat162_rn(rem[2 * i], rem[2 * i + 1]);
+      w[i] = *reinterpret_cast<const uint32_t*>(&h);
+      if (p + 1 < NPL) {
+        rem[2 * i] -= __uint_as_float(w[i] << 16);
+        rem[2 * i + 1] -= __uint_as_float(w[i] & 0xffff0000u);
+      }
+    }
+    *reinterpret_cast<uint2*>(dst + p * plane_stride) = make_uint2(w[0], w[1]);
+  }
+}
+
+template <int NPL>
+__global__ void __launch_bounds__(256, 6)
 pack_bwd_kernel(const float* __restrict__ w, const Ptr9h bwd, const LeafMasks masks, int n_leaves, int group, int J,
                 int Cin, int Cout, int ld_co) {
-  const int cg = ld_co / 8;
+  const int cg = ld_co / 4;
   const int64_t rows = (int64_t)J * Cin;
   const int64_t groups = rows * cg;
   const int64_t tap = (int64_t)Cin * Cout;
   const int64_t plane = rows * ld_co;
   for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < groups; g += (int64_t)gridDim.x * blockDim.x) {
-    const int c8 = (int)(g % cg);
+    const int c4 = (int)(g % cg);
     const int64_t row = g / cg;
     const int ci = (int)(row % Cin);
     const int k = (int)(row / Cin);
-    float t[4][8];
+    float4 t[4];
 #pragma unroll
     for (int gg = 0; gg < 4; ++gg) {
-#pragma unroll
-      for (int i = 0; i < 8; ++i) t[gg][i] = 0.f;
-      if (gg < group && c8 * 8 < Cout) {
-        const float4* src = reinterpret_cast<const float4*>(w + (int64_t)(group * k + gg) * tap + (int64_t)ci * Cout + c8 * 8);
-        const float4 a = __ldg(src), b = __ldg(src + 1);
-        t[gg][0] = a.x; t[gg][1] = a.y; t[gg][2] = a.z; t[gg][3] = a.w;
-        t[gg][4] = b.x; t[gg][5] = b.y; t[gg][6] = b.z; t[gg][7] = b.w;
-      }
+      t[gg] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (gg < group && c4 * 4 < Cout)
+        t[gg] = __ldg(reinterpret_cast<const float4*>(w + (int64_t)(group * k + gg) * tap + (int64_t)ci * Cout + c4 * 4));
     }
 #pragma unroll 1
     for (int l = 0; l < n_leaves; ++l) {
       const int mask = masks.m[l];
-      float v[8];
+      float v[4] = {0.f, 0.f, 0.f, 0.f};           // same order of additions as pack_ffa2_kernel (taps ascending)
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        float acc = 0.f;                       // same order of additions as pack_ffa2_kernel (taps ascending)
-#pragma unroll
-        for (int gg = 0; gg < 4; ++gg)
-          if (mask & (1 << gg)) acc += t[gg][i];
-        v[i] = acc;
-      }
-      store_planes8<NPL>(bwd.p[l] + row * ld_co + c8 * 8, plane, v);
+      for (int gg = 0; gg < 4; ++gg)
+        if (mask & (1 << gg)) { v[0] += t[gg].x; v[1] += t[gg].y; v[2] += t[gg].z; v[3] += t[gg].w; }
+      store_planes4<NPL>(bwd.p[l] + row * ld_co + c4 * 4, plane, v);
     }
   }
+}
+
+__global__ void __launch_bounds__(256, 6)
+zero_f32_kernel(float4* __restrict__ dst, int64_t n4) {
+  const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) dst[i] = z;
 }
 
 // db[n] += sum_rows sum_planes dz[pl][row][n]; block (32 column octets, 8 row lanes): each thread streams 16-byte
@@ -1625,25 +1644,6 @@ ffa2_combine_kernel(const Ptr9c part, const float* __restrict__ bias, int relu, 
 // One thread per FOUR channels of one q: 8-byte loads / stores keep a warp on 256 contiguous bytes, and at ~60
 // registers four blocks are resident per SM (eight channels per thread: 98 registers, two blocks, 46 % of HBM peak).
 template <int NPL>
-__device__ __forceinline__ void store_planes4(__nv_bfloat16* dst, int64_t plane_stride, const float* v) {
-  float rem[4] = {v[0], v[1], v[2], v[3]};
-#pragma unroll
-  for (int p = 0; p < NPL; ++p) {
-    uint32_t w[2];
-#pragma unroll
-    for (int i = 0; i < 2; ++i) {
-      const __nv_bfloat162 h = __floats2bfloat162_rn(rem[2 * i], rem[2 * i + 1]);
-      w[i] = *reinterpret_cast<const uint32_t*>(&h);
-      if (p + 1 < NPL) {
-        rem[2 * i] -= __uint_as_float(w[i] << 16);
-        rem[2 * i + 1] -= __uint_as_float(w[i] & 0xffff0000u);
-      }
-    }
-    *reinterpret_cast<uint2*>(dst + p * plane_stride) = make_uint2(w[0], w[1]);
-  }
-}
-
-template <int NPL>
 __global__ void __launch_bounds__(256, 4)
 ffa2_dz_prep_kernel(const __nv_bfloat16* __restrict__ dy, const Ptr9h out, int B, int To, int Tq, int ld) {
   const int cg = ld / 4;
@@ -1766,23 +1766,22 @@ ffa2_dx_combine_kernel(const Ptr9c gp, const uint32_t* __restrict__ mask, __nv_b
 // Filter-gradient combine of the nine leaf correlations c[l] ([J][tap] fp32, J = taps / 4):
 //   dW[4i]   = cXX + cXZ + cZX + cZZ      dW[4i+1] = cYX + cYZ + cZX + cZZ
 //   dW[4i+2] = cXY + cXZ + cZY + cZZ      dW[4i+3] = cYY + cYZ + cZY + cZZ
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 6)      // a background kernel (see pack_bwd_kernel): <= 40 registers, no smem
 ffa2_dw_combine_kernel(float* __restrict__ dW, const Ptr9c c, int J, int64_t tap_elems4) {
   const int64_t total = (int64_t)J * tap_elems4;
   float4* w4 = reinterpret_cast<float4*>(dW);
+  auto ld = [&](int l, int64_t i) { return reinterpret_cast<const float4*>(c.p[l])[i]; };
+  auto add = [](float4 a, float4 b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); };
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t j = i / tap_elems4, e = i - j * tap_elems4;
-    float4 v[9];
-#pragma unroll
-    for (int l = 0; l < 9; ++l) v[l] = reinterpret_cast<const float4*>(c.p[l])[i];
-    auto add4 = [](float4 a, float4 b, float4 cc, float4 d) {
-      return make_float4((a.x + b.x) + (cc.x + d.x), (a.y + b.y) + (cc.y + d.y), (a.z + b.z) + (cc.z + d.z),
-                         (a.w + b.w) + (cc.w + d.w));
-    };
-    w4[(4 * j + 0) * tap_elems4 + e] = add4(v[0], v[2], v[6], v[8]);
-    w4[(4 * j + 1) * tap_elems4 + e] = add4(v[3], v[5], v[6], v[8]);
-    w4[(4 * j + 2) * tap_elems4 + e] = add4(v[1], v[2], v[7], v[8]);
-    w4[(4 * j + 3) * tap_elems4 + e] = add4(v[4], v[5], v[7], v[8]);
+    // every output is (a + b) + (c + d) with the pairs of the formulas above; few values are live at a time
+    const float4 v8 = ld(8, i);
+    const float4 s68 = add(ld(6, i), v8), s78 = add(ld(7, i), v8);
+    const float4 v2 = ld(2, i), v5 = ld(5, i);
+    w4[(4 * j + 0) * tap_elems4 + e] = add(add(ld(0, i), v2), s68);
+    w4[(4 * j + 1) * tap_elems4 + e] = add(add(ld(3, i), v5), s68);
+    w4[(4 * j + 2) * tap_elems4 + e] = add(add(ld(1, i), v2), s78);
+    w4[(4 * j + 3) * tap_elems4 + e] = add(add(ld(4, i), v5), s78);
   }
 }
 
@@ -2269,6 +2268,11 @@ int ew_blocks(int64_t groups) {
   const int cap = 16 * st_num_sms();
   return blocks > cap ? cap : (blocks < 1 ? 1 : blocks);
 }
+// grid of a background kernel: ONE block per SM when it is to run beside resident tensor-core CTAs
+int bg_blocks(int64_t groups, bool background) {
+  const int blocks = ew_blocks(groups);
+  return background && blocks > st_num_sms() ? st_num_sms() : blocks;
+}
 }  // namespace
 
 int launch_ffa2_inputs(const __nv_bfloat16* x, __nv_bfloat16* const* s5, int B, int T, int Tq, int ld, int n_planes,
@@ -2324,11 +2328,11 @@ int launch_ffa2_dx_combine(float* const* g9, const uint32_t* mask, __nv_bfloat16
   return ST_OK;
 }
 
-int launch_ffa2_dw_combine(float* dW, float* const* c9, int J, int64_t tap_elems, cudaStream_t stream) {
+int launch_ffa2_dw_combine(float* dW, float* const* c9, int J, int64_t tap_elems, cudaStream_t stream, bool background) {
   ST_CHECK_ARG(tap_elems % 4 == 0, "launch_ffa2_dw_combine: tap size must be a multiple of 4 floats");
   Ptr9c pp;
   for (int l = 0; l < 9; ++l) pp.p[l] = c9[l];
-  ffa2_dw_combine_kernel<<<ew_blocks((int64_t)J * (tap_elems / 4)), 256, 0, stream>>>(dW, pp, J, tap_elems / 4);
+  ffa2_dw_combine_kernel<<<bg_blocks((int64_t)J * (tap_elems / 4), background), 256, 0, stream>>>(dW, pp, J, tap_elems / 4);
   ST_CUDA_LAUNCH_CHECK("ffa2_dw_combine_kernel");
   return ST_OK;
 }
@@ -2396,14 +2400,21 @@ int launch_pack_ffa2(const float* w, __nv_bfloat16* const* fwd9, __nv_bfloat16* 
   return ST_OK;
 }
 
+int launch_zero_f32(float* dst, int64_t n, cudaStream_t stream, bool background) {
+  ST_CHECK_ARG((reinterpret_cast<uintptr_t>(dst) & 15) == 0 && n % 4 == 0, "launch_zero_f32: 16-byte granularity");
+  zero_f32_kernel<<<bg_blocks(n / 4, background), 256, 0, stream>>>(reinterpret_cast<float4*>(dst), n / 4);
+  ST_CUDA_LAUNCH_CHECK("zero_f32_kernel");
+  return ST_OK;
+}
+
 int launch_pack_bwd(const float* w, __nv_bfloat16* const* bwd, const int* masks, int n_leaves, int group, int J, int Cin,
-                    int Cout, int ld_co, int n_planes, cudaStream_t stream) {
+                    int Cout, int ld_co, int n_planes, cudaStream_t stream, bool background) {
   ST_CHECK_ARG(n_leaves >= 1 && n_leaves <= 9 && group >= 1 && group <= 4 && Cout % 8 == 0 && ld_co % 8 == 0 &&
                ld_co >= Cout && n_planes >= 1 && n_planes <= 2, "launch_pack_bwd: bad arguments");
   Ptr9h b;
   LeafMasks m;
   for (int l = 0; l < 9; ++l) { b.p[l] = bwd[l < n_leaves ? l : 0]; m.m[l] = masks[l < n_leaves ? l : 0]; }
-  const int blocks = ew_blocks((int64_t)J * Cin * (ld_co / 8));
+  const int blocks = bg_blocks((int64_t)J * Cin * (ld_co / 4), background);
   if (n_planes == 2) pack_bwd_kernel<2><<<blocks, 256, 0, stream>>>(w, b, m, n_leaves, group, J, Cin, Cout, ld_co);
   else pack_bwd_kernel<1><<<blocks, 256, 0, stream>>>(w, b, m, n_leaves, group, J, Cin, Cout, ld_co);
   ST_CUDA_LAUNCH_CHECK("pack_bwd_kernel");

@@ -164,14 +164,18 @@ int launch_ffa2_dz_prep(const __nv_bfloat16* dy, __nv_bfloat16* const* out9, int
 int launch_ffa2_dx_combine(float* const* g9, const uint32_t* mask_bits, __nv_bfloat16* out, float* db, int B, int T,
                            int Tqx, int N, int ldp, int ld, int n_planes, cudaStream_t stream);
 // nine fp32 leaf correlations [J][tap_elems] -> dW [4J][tap_elems]
-int launch_ffa2_dw_combine(float* dW, float* const* c9, int J, int64_t tap_elems, cudaStream_t stream);
+// background = true (here and below): one block per SM, for launches on a side stream beside tensor-core CTAs
+int launch_ffa2_dw_combine(float* dW, float* const* c9, int J, int64_t tap_elems, cudaStream_t stream,
+                           bool background = false);
+// dst[0..n) = 0 (n a multiple of 4, 16-byte aligned)
+int launch_zero_f32(float* dst, int64_t n, cudaStream_t stream, bool background = false);
 // the nine leaf filters (tap sums selected by masks9[l] over w[4i + c]) in both operand layouts, one pass over w
 int launch_pack_ffa2(const float* w, __nv_bfloat16* const* fwd9, __nv_bfloat16* const* bwd9, const int* masks9, int J,
                      int Cin, int Cout, int cin_p, int ld_co, int n_planes, cudaStream_t stream);
 // backward-layout planes only (layers whose forward reads the filter MN-major): leaf l = sum over the bits c of
 // masks[l] of the source taps group * k + c, k < J; bwd[l] planes [n][J * Cin][ld_co]; Cout % 8 == 0
 int launch_pack_bwd(const float* w, __nv_bfloat16* const* bwd, const int* masks, int n_leaves, int group, int J, int Cin,
-                    int Cout, int ld_co, int n_planes, cudaStream_t stream);
+                    int Cout, int ld_co, int n_planes, cudaStream_t stream, bool background = false);
 // true when a filter-gradient launch of num_tiles tiles accumulates into its outputs (they must then be zeroed)
 bool wgrad_accumulates(int num_tiles, int total_iters, bool pair);
 // db[n] = sum over rows and planes of dz planes [n_planes][rows][ld]

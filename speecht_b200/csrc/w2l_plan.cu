@@ -45,6 +45,7 @@ struct st_plan {
   // ping / pong pair): the filter gradients of the seven 250-channel layers are deferred to ONE multi-problem launch
   // at the end of the backward pass and need all of them alive (SPEECHT_B200_MERGE_WGRAD=0: one launch per layer)
   size_t off_dzs[8];
+  int range_lo;                // lowest layer of the backward range being enqueued (st_plan_backward_range)
   bool merge_wgrad;
   size_t filter_bytes;         // leading arena region holding the packed filters (shape independent)
   size_t dz_elems;             // elements per plane of a dz buffer
@@ -80,6 +81,18 @@ struct st_plan {
   // the forward kernels 2-4 % in bf16x3 and 10 % in plain bf16 (profiles/r02_bmn_ab_session19.txt), so it is the default
   // for two planes only (step -0.5 .. -1 %); SPEECHT_B200_BMN=0 / 1 forces the K-major forward layouts / MN-major.
   bool bmn;
+  // Overlap of HBM-bound passes with tensor-core launches that leave the HBM idle (SPEECHT_B200_OVERLAP=0 disables it).
+  // On a plan-owned side stream, as BACKGROUND kernels (one block per SM, <= 40 registers, no shared memory: they fit on
+  // an SM beside a resident tensor-core CTA and never keep one from starting):
+  //   * packing of layers 8-9 (94 % of the filter bytes) underneath the forward pass of layers 0-7,
+  //   * zeroing of the flat gradient buffer underneath the forward pass,
+  //   * the filter-gradient combine of layer 8 underneath the backward pass of layers 8 (data gradient) .. 1.
+  // Every hand-over is an event pair: the side stream starts behind what the main stream has enqueued so far (the
+  // previous step's backward and Adam), the main stream waits for the side stream's event before the first consumer.
+  bool overlap;
+  cudaStream_t side;
+  cudaEvent_t ev_fork, ev_pack, ev_zero, ev_dw;
+  bool pack_pending, zero_pending, dw_pending;
   int ffa2_Tq, ffa2_Tqi;                         // rows of the leaf products / of the quarter-rate input sequences
   size_t off_ffa2_s[5], off_ffa2_w[9], off_ffa2_wb[9], off_ffa2_p[9], off_ffa2_dxp[9], off_ffa2_c[9];
   bool ffa2_pair_fwd, ffa2_pair_dg;
@@ -124,6 +137,26 @@ const __nv_bfloat16* act_in(st_plan* p, int l) { return l == 0 ? bf(p, p->off_in
 
 uint32_t* mask_of(st_plan* p, int l) { return reinterpret_cast<uint32_t*>(p->arena + p->layers[l].off_mask); }
 
+// Side stream of the plan (created on first use) positioned behind everything enqueued on `s` so far.
+int side_fork(st_plan* p, cudaStream_t s) {
+  if (!p->side) {
+    ST_CUDA_CALL(cudaStreamCreateWithFlags(&p->side, cudaStreamNonBlocking));
+    for (cudaEvent_t* e : {&p->ev_fork, &p->ev_pack, &p->ev_zero, &p->ev_dw})
+      ST_CUDA_CALL(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+  }
+  ST_CUDA_CALL(cudaEventRecord(p->ev_fork, s));
+  ST_CUDA_CALL(cudaStreamWaitEvent(p->side, p->ev_fork, 0));
+  return ST_OK;
+}
+// The main stream waits for a side-stream hand-over (if one is outstanding).
+int side_join(st_plan* p, bool* pending, cudaEvent_t ev, cudaStream_t s) {
+  if (*pending) {
+    ST_CUDA_CALL(cudaStreamWaitEvent(s, ev, 0));
+    *pending = false;
+  }
+  return ST_OK;
+}
+
 }  // namespace
 
 ST_API int st_plan_create(st_plan** out, int B, int T, int input_size, int num_classes, int n_planes) {
@@ -144,6 +177,11 @@ ST_API int st_plan_create(st_plan** out, int B, int T, int input_size, int num_c
     p->merge_wgrad = !(e && e[0] == '0') && n_planes <= 2;
     e = getenv("SPEECHT_B200_FFA");
     p->ffa = n_planes > 2 ? 0 : (e && e[0] >= '0' && e[0] <= '2' ? e[0] - '0' : 2);
+    e = getenv("SPEECHT_B200_OVERLAP");
+    p->overlap = !(e && e[0] == '0') && n_planes <= 2;
+    p->side = nullptr;
+    p->ev_fork = p->ev_pack = p->ev_zero = p->ev_dw = nullptr;
+    p->pack_pending = p->zero_pending = p->dw_pending = false;
     e = getenv("SPEECHT_B200_BMN");
     p->bmn = n_planes <= 2 && ((e && (e[0] == '0' || e[0] == '1')) ? e[0] == '1' : n_planes == 2);
   }
@@ -257,6 +295,12 @@ ST_API int st_plan_create(st_plan** out, int B, int T, int input_size, int num_c
 ST_API int st_plan_destroy(st_plan* p) {
   if (p) {
     for (cudaEvent_t e : p->ev_pool) cudaEventDestroy(e);
+    if (p->side) {
+      cudaStreamSynchronize(p->side);
+      for (cudaEvent_t e : {p->ev_fork, p->ev_pack, p->ev_zero, p->ev_dw})
+        if (e) cudaEventDestroy(e);
+      cudaStreamDestroy(p->side);
+    }
   }
   delete p;
   return ST_OK;
@@ -478,6 +522,18 @@ namespace {
 int pack_layers(st_plan* p, cudaStream_t s) {
   tc::PackTable tab{};
   Layer& L8 = p->layers[8];
+  // layers 8-9 as background kernels on the side stream (MN-major forward filters: their packing is its own launches)
+  const bool bg = p->overlap && p->bmn;
+  cudaStream_t sb = s;
+  if (bg) {
+    // a previous hand-over nobody consumed (packing twice without a forward in between) must not be lost
+    int rcj = side_join(p, &p->pack_pending, p->ev_pack, s);
+    if (rcj) return rcj;
+    rcj = side_fork(p, s);
+    if (rcj) return rcj;
+    sb = p->side;
+  }
+  bool side_used = false;
   for (int l = 0; l < 11; ++l) {
     Layer& L = p->layers[l];
     if (l == 8 && p->ffa == 2) {
@@ -491,18 +547,20 @@ int pack_layers(st_plan* p, cudaStream_t s) {
         m9[i] = kLeaves[i].tap_mask;
       }
       const int rc2 = p->bmn ? tc::launch_pack_bwd(p->params + L8.w_off, b9, m9, 9, 4, L8.K / 4, L8.Cin, L8.Cout, L8.ld_co,
-                                                   p->npl, s)
+                                                   p->npl, sb, bg)
                              : tc::launch_pack_ffa2(p->params + L8.w_off, f9, b9, m9, L8.K / 4, L8.Cin, L8.Cout, L8.cin_p,
                                                     L8.ld_co, p->npl, s);
       if (rc2) return rc2;
+      side_used = side_used || (bg && p->bmn);
       p->launches++;
       continue;
     }
     if (l == 9 && p->bmn) {
       __nv_bfloat16* b1[1] = {bf(p, L.off_wbwd)};
       const int one = 1;
-      const int rc2 = tc::launch_pack_bwd(p->params + L.w_off, b1, &one, 1, 1, L.K, L.Cin, L.Cout, L.ld_co, p->npl, s);
+      const int rc2 = tc::launch_pack_bwd(p->params + L.w_off, b1, &one, 1, 1, L.K, L.Cin, L.Cout, L.ld_co, p->npl, sb, bg);
       if (rc2) return rc2;
+      side_used = side_used || bg;
       p->launches++;
       continue;
     }
@@ -516,6 +574,10 @@ int pack_layers(st_plan* p, cudaStream_t s) {
     }
     tab.e[tab.n++] = tc::PackEntry{p->params + L.w_off, bf(p, L.off_wfwd), l > 0 ? bf(p, L.off_wbwd) : nullptr,
                                    L.K, L.Cin, L.Cout, L.cin_p, L.ld_co, 0, 1, 1};
+  }
+  if (side_used) {
+    ST_CUDA_CALL(cudaEventRecord(p->ev_pack, p->side));
+    p->pack_pending = true;                       // st_plan_forward waits for it in front of layer 8
   }
   int n = 0;
   const int rc = tc::launch_pack_filters(tab, p->npl, s, &n);
@@ -742,8 +804,20 @@ int backward_layer8_ffa2(st_plan* p, const __nv_bfloat16* dz, __nv_bfloat16* dz_
   if (rc) return rc;
   timed_end(p, ti, 2, 8, 2.0 * L.K * L.Cin * L.Cout * (double)L.To * p->B, s);
   p->launches++;
-  rc = tc::launch_ffa2_dw_combine(p->grads + L.w_off, cw, J, (int64_t)L.Cin * L.Cout, s);
-  if (rc) return rc;
+  if (p->overlap && p->range_lo == 0) {
+    // the combine (HBM-bound, 0.2 GB) runs on the side stream underneath the data gradients of layers 8 .. 1; its
+    // result is first needed behind the backward pass (st_plan_backward_range joins at its end).  Ranges that stop
+    // above layer 0 (data parallel: the allreduce of layers 8-10 is launched right after them) keep it in line.
+    rc = side_fork(p, s);
+    if (rc) return rc;
+    rc = tc::launch_ffa2_dw_combine(p->grads + L.w_off, cw, J, (int64_t)L.Cin * L.Cout, p->side, true);
+    if (rc) return rc;
+    ST_CUDA_CALL(cudaEventRecord(p->ev_dw, p->side));
+    p->dw_pending = true;
+  } else {
+    rc = tc::launch_ffa2_dw_combine(p->grads + L.w_off, cw, J, (int64_t)L.Cin * L.Cout, s);
+    if (rc) return rc;
+  }
   p->launches++;
   // ---- data gradient: nine transposed 8-tap correlations -> fp32 [B][Tqi][256], whole contraction per tile
   tc::ConvParams c{};
@@ -789,6 +863,10 @@ ST_API int st_plan_forward(st_plan* p, const float* inputs, st_stream_t stream) 
   for (int l = 0; l < 11; ++l) {
     Layer& L = p->layers[l];
     const int block_n = l == 10 ? 32 : wide_n(p);
+    if (l == 8) {                                 // the filters of layers 8-9 may still be on their way (side stream)
+      rc = side_join(p, &p->pack_pending, p->ev_pack, s);
+      if (rc) return rc;
+    }
     if (l == 8 && p->ffa) {
       rc = p->ffa == 2 ? forward_layer8_ffa2(p, s) : forward_layer8_ffa(p, s);
       if (rc) return rc;
@@ -848,9 +926,16 @@ ST_API int st_plan_backward_range(st_plan* p, int hi, int lo, st_stream_t stream
   cudaStream_t s = st_cu(stream);
   if (hi == 10) {
     p->cur_dz = 0;
-    // filter gradients of K-sliced tiles accumulate with atomics: zero the whole flat buffer once per backward
-    ST_CUDA_CALL(cudaMemsetAsync(p->grads, 0, (size_t)st_plan_param_floats(p) * sizeof(float), s));
+    // filter gradients of K-sliced tiles accumulate with atomics: the whole flat buffer is zeroed once per backward --
+    // already done underneath the forward pass when the caller announced the backward (st_plan_prepare_backward)
+    if (p->zero_pending) {
+      const int rcz = side_join(p, &p->zero_pending, p->ev_zero, s);
+      if (rcz) return rcz;
+    } else {
+      ST_CUDA_CALL(cudaMemsetAsync(p->grads, 0, (size_t)st_plan_param_floats(p) * sizeof(float), s));
+    }
   }
+  p->range_lo = lo;
   int cur = p->cur_dz;                          // ping / pong buffer holding the gradient wrt layer 8's / 9's output
   int deferred[8], n_deferred = 0;              // 250-channel layers whose filter gradient waits for the merged launch
   for (int l = hi; l >= lo; --l) {
@@ -974,10 +1059,29 @@ ST_API int st_plan_backward_range(st_plan* p, int hi, int lo, st_stream_t stream
     timed_end(p, ti, 2, deferred[n_deferred - 1], flops, s);
     p->launches++;
   }
-  return ST_OK;
+  return side_join(p, &p->dw_pending, p->ev_dw, s);
 }
 
 ST_API int st_plan_backward(st_plan* p, st_stream_t stream) { return st_plan_backward_range(p, 10, 0, stream); }
+
+// Announces a backward pass: the flat gradient buffer is zeroed NOW on the plan's side stream (behind everything
+// enqueued on `stream` so far -- the previous step's Adam), underneath the forward pass that the caller enqueues next;
+// st_plan_backward[_range] then waits for it instead of zeroing in line.  Optional: without it the backward zeroes.
+ST_API int st_plan_prepare_backward(st_plan* p, st_stream_t stream) {
+  ST_CHECK_ARG(p && p->bound, "st_plan_prepare_backward: plan is not bound");
+  if (!p->overlap) return ST_OK;
+  cudaStream_t s = st_cu(stream);
+  int rc = side_join(p, &p->zero_pending, p->ev_zero, s);     // an announced backward that never came
+  if (rc) return rc;
+  rc = side_fork(p, s);
+  if (rc) return rc;
+  rc = tc::launch_zero_f32(p->grads, st_plan_param_floats(p), p->side, true);
+  if (rc) return rc;
+  ST_CUDA_CALL(cudaEventRecord(p->ev_zero, p->side));
+  p->zero_pending = true;
+  p->launches++;
+  return ST_OK;
+}
 
 // Data-parallel training: the tensor-core grids launched after this call leave `n_sms` SMs free (0 restores the full
 // machine).  The NCCL allreduce of the layer-8..10 gradients runs underneath the backward pass of layers 7..0; its

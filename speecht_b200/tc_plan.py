@@ -158,6 +158,8 @@ class TCPlan:
     ctc_len = np.asarray(sequence_lengths, dtype=np.int32) // 2
     # the forward kernels are enqueued FIRST: flattening / validating the labels and their (pinned, asynchronous)
     # upload are host work that then runs underneath them instead of in front of the step
+    # the flat gradient buffer is zeroed on the plan's side stream underneath the forward pass
+    check(lib().st_plan_prepare_backward(self._shape(B, T).handle, stream_ptr()))
     logits = self.forward(inputs.contiguous(), keep_activations=True)
     batch = ops.CTCBatch(labels, ctc_len, -(-T // 2), eng.num_classes, eng.device)
     sh = self._last

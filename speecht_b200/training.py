@@ -47,6 +47,10 @@ class Training(DatasetExecutor):
       import torch.distributed as dist
       torch.cuda.set_device(self.local_rank)
       flags.process_group = dist.group.WORLD
+      # the per-step "has any rank run out of input?" word travels over a HOST (gloo) group: on the NCCL group it is
+      # ordered behind the previous step's gradient allreduce and Adam, and reading it would stall the host until that
+      # step has completely finished -- the GPU would then idle while the next step is enqueued
+      self.flag_group = dist.new_group(backend='gloo') if dist.get_backend() == 'nccl' else None
     super().__init__(flags)
 
   # ---- DatasetExecutor hooks ---------------------------------------------------------------------
@@ -95,6 +99,11 @@ class Training(DatasetExecutor):
     model.saver.save(sess, path, global_step=model.global_step)
     print('Model saved')
 
+  def _any_rank_exhausted(self, model):
+    if getattr(self, 'flag_group', None) is not None:
+      return parallel.any_rank_true(model.input_exhausted(), device='cpu', group=self.flag_group)
+    return parallel.any_rank_true(model.input_exhausted(), device=model.engine.device)
+
   # ---- the loop ----------------------------------------------------------------------------------
   def run(self, max_steps=None):
     per_checkpoint = self.flags.steps_per_checkpoint
@@ -110,7 +119,7 @@ class Training(DatasetExecutor):
         for step in itertools.count(1):
           if coord.should_stop() or (max_steps is not None and step > max_steps):
             break
-          if self.world > 1 and parallel.any_rank_true(model.input_exhausted(), device=model.engine.device):
+          if self.world > 1 and self._any_rank_exhausted(model):
             print('Done training -- a rank ran out of input')      # all ranks leave together: nobody waits in NCCL
             break
           at_checkpoint = step % per_checkpoint == 0

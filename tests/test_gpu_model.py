@@ -318,6 +318,7 @@ KERNEL_VARIANTS = [
   {'SPEECHT_B200_L10_N128': '0'},                   # 256-wide layer-10 data gradient (8 epilogue warps)
   {'SPEECHT_B200_MERGE_WGRAD': '0'},                # one filter-gradient launch per 250-channel layer
   {'SPEECHT_B200_TRIM': '0'},
+  {'SPEECHT_B200_OVERLAP': '0'},                    # no side stream: packing / zeroing / combine in line
 ]
 
 

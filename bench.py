@@ -491,6 +491,22 @@ def run_ours(args, rank, local_rank, world):
   for i in range(args.warmup):
     step_e2e(i)
   e2e_ms = timed(step_e2e, args.steps) / args.steps
+  # PCIe health beside the e2e number: pinned host -> device bandwidth of this box at this moment.  An e2e step needs
+  # h2d_bytes_per_step / ms_per_step (3.8 GB/s at config 2); two runs in 30 saw ~2 GB/s on a shared host (other tenants
+  # on the PCIe switch) and an e2e value bound by the upload, with `value` untouched (profiles/README.md).
+  h2d_probe = None
+  try:
+    probe_src, probe_dst = pinned[0].view(-1), torch.empty_like(pinned[0].view(-1), device=dev)
+    probe_dst.copy_(probe_src, non_blocking=True)
+    torch.cuda.synchronize(dev)
+    t_probe = time.perf_counter()
+    for _ in range(3):
+      probe_dst.copy_(probe_src, non_blocking=True)
+    torch.cuda.synchronize(dev)
+    h2d_probe = 3 * probe_src.numel() * 4 / 1e9 / (time.perf_counter() - t_probe)
+    del probe_dst
+  except Exception:
+    h2d_probe = None
   e2e_value = world * B / (e2e_ms * 1e-3)
   clocks = None
   if rank == 0:
@@ -523,7 +539,7 @@ def run_ours(args, rank, local_rank, world):
     'config': workload_config(args, world),
     'clocks': clocks,
     'e2e': {'value': e2e_value, 'unit': UNIT, 'ms_per_step': e2e_ms, 'h2d_bytes_per_step': h2d,
-            'd2h_bytes_per_step': int(d2h_bytes[0])},
+            'd2h_bytes_per_step': int(d2h_bytes[0]), 'h2d_probe_GB/s': h2d_probe},
     'gpu_launches': int(launches),
     'ctc_loss_delta': delta,
     'roofline': roofline,

@@ -348,10 +348,21 @@ class SpeechModel:
     if decode and not self._decoding:
       raise ValueError('decode requested but add_decoding_ops was not called')
     if update:
+      trace = [time.perf_counter()] if _STEP_TRACE else None
       res = self.engine.train_step(d_inputs, lengths, labels, self.learning_rate.value, self.max_gradient_norm,
                                    decode=decode)
+      if trace: trace.append(time.perf_counter())
       if feed_dict is None:
         self._prefetch_next()                   # next batch's H2D overlaps this step's kernels
+      if trace:
+        trace.append(time.perf_counter())
+        if loss:
+          res['avg_loss'].item()
+        trace.append(time.perf_counter())
+        sys.stderr.write('train step trace (ms): enqueue %.2f prefetch %.2f loss wait %.2f | since last %.2f\n'
+                         % tuple([1e3 * (b - a) for a, b in zip(trace[:-1], trace[1:])] +
+                                 [1e3 * (trace[0] - getattr(self, '_trace_last', trace[0]))]))
+        self._trace_last = trace[-1]
     else:
       # an evaluate step ends with a blocking read of the decoded labels.  Its kernels are enqueued FIRST; fetching
       # the next batch and starting its upload (host work: a ragged batch is 256 small copies) then runs underneath

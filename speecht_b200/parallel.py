@@ -21,11 +21,15 @@ def init_from_env(backend=None):
   world = int(os.environ.get('WORLD_SIZE', '1'))
   if world > 1 and not dist.is_initialized():
     if backend is None:
-      backend = 'nccl' if torch.cuda.is_available() else 'gloo'
+      # SPEECHT_B200_DIST_BACKEND=gloo: host-staged collectives, which also allow several ranks to share one GPU (a
+      # smoke run of the data-parallel loop on a single-GPU box; NCCL refuses two ranks on one device)
+      backend = os.environ.get('SPEECHT_B200_DIST_BACKEND') or ('nccl' if torch.cuda.is_available() else 'gloo')
     if backend == 'nccl':
       torch.cuda.set_device(local)
       dist.init_process_group(backend, device_id=torch.device('cuda', local))
     else:
+      if torch.cuda.is_available():
+        torch.cuda.set_device(local % torch.cuda.device_count())
       dist.init_process_group(backend)
   return rank, local, world
 

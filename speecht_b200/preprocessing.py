@@ -218,6 +218,13 @@ class SpeechCorpusReader:
     shuffle(files)
     files = files[:limit_count] if limit_count else files
     rank, world = shard if shard is not None else (0, 1)
+    if len(files) < world:
+      # fewer files than ranks (e.g. the single sample that determines the input size): a rank's every-world-th slice
+      # would be empty -- and with loop_infinitely the generator would spin forever without yielding; every rank reads
+      # the whole (tiny) list instead
+      rank, world = 0, 1
+    if not files:
+      return
     for epoch in itertools.count():
       if epoch and not loop_infinitely:
         return

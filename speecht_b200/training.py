@@ -45,7 +45,7 @@ class Training(DatasetExecutor):
     if self.world > 1:
       import torch
       import torch.distributed as dist
-      torch.cuda.set_device(self.local_rank)
+      torch.cuda.set_device(self.local_rank % torch.cuda.device_count())
       flags.process_group = dist.group.WORLD
       # the per-step "has any rank run out of input?" word travels over a HOST (gloo) group: on the NCCL group it is
       # ordered behind the previous step's gradient allreduce and Adam, and reading it would stall the host until that

@@ -172,6 +172,33 @@ def test_sharded_load_samples_partitions_one_commonly_shuffled_list(tmp_path):
   assert whole != sorted(whole)                                   # it IS shuffled
 
 
+def test_sharded_load_samples_never_starves_a_rank(tmp_path):
+  """Regression (2-rank CLI run hung at 'Determine input size from first sample'): DatasetExecutor peeks ONE sample
+  through the training generator -- limit_count=1, loop_infinitely=True, shard=(rank, world).  Rank 1's every-2nd
+  slice of a one-file list is empty, and the infinite generator then spun forever without yielding."""
+  import itertools
+  import random
+  from speecht_b200.preprocessing import SpeechCorpusReader
+  out = tmp_path / 'preprocessed-power' / 'train'
+  out.mkdir(parents=True)
+  for i in range(5):
+    np.savez(out / ('utt%02d' % i), audio_fragments=np.full((i + 1, 4), i, np.float32), transcript=np.array([i]))
+  reader = SpeechCorpusReader(str(tmp_path))
+  for rank in range(2):
+    gen = reader.load_samples('train', loop_infinitely=True, limit_count=1, feature_type='power', shard=(rank, 2),
+                              rng=random.Random(3))
+    first, _tr = next(iter(gen))                                  # must return (used to hang for rank 1)
+    assert first.shape[1] == 4
+  # ... and an infinite generator over an empty directory ends instead of spinning
+  empty = tmp_path / 'preprocessed-power' / 'dev'
+  empty.mkdir(parents=True)
+  assert list(itertools.islice(reader.load_samples('dev', loop_infinitely=True, feature_type='power'), 3)) == []
+  # the usual case is untouched: with at least `world` files the slices stay disjoint
+  parts = [[int(tr[0]) for _a, tr in reader.load_samples('train', feature_type='power', shard=(r, 2),
+                                                          rng=random.Random(3))] for r in range(2)]
+  assert sorted(parts[0] + parts[1]) == list(range(5)) and not set(parts[0]) & set(parts[1])
+
+
 def test_feeder_thread_failure_surfaces_and_full_queue_does_not_block_shutdown():
   from speecht_b200 import speech_input
 

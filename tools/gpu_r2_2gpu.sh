@@ -29,4 +29,14 @@ run bench_cfg4_n2 --config 4 --steps 10 --warmup 3 --no-sustained
 run bench_cfg5_n2 --config 5 --steps 5 --warmup 2 --no-sustained
 timeout 300 python bench.py --steps 20 --warmup 5 --no-cpu-baseline > $O/bench_cfg2_n1.json 2> $O/bench_cfg2_n1.err
 stamp "cfg2 N=1 same box rc=$?: $(python -c "import json;d=json.loads(open('$O/bench_cfg2_n1.json').read().strip().splitlines()[-1]);print(d['ms_per_step'], d['value'], d['e2e']['value'])" 2>&1 | tail -1)"
+# 2-rank CLI training smoke on a synthetic corpus (termination word over the gloo group, sharded file list)
+rm -rf /tmp/synth /tmp/synth_train /tmp/synth_log
+python tools/make_synth_data.py /tmp/synth 512 > /dev/null 2>&1
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29519 \
+  speecht-cli-b200 train --data-dir /tmp/synth --train-dir /tmp/synth_train --log-dir /tmp/synth_log --run-name dp2 \
+  --batch-size 32 --steps-per-checkpoint 50 --max-steps 200 > $O/cli_train_2gpu.log 2>&1
+stamp "2-rank CLI train rc=$?: $(grep 'global step' $O/cli_train_2gpu.log | tail -2 | cut -c1-90 | tr '\n' '|')"
+timeout 600 python speecht-cli-b200 train --data-dir /tmp/synth --train-dir /tmp/synth_train1 --log-dir /tmp/synth_log --run-name dp1 \
+  --batch-size 32 --steps-per-checkpoint 50 --max-steps 200 > $O/cli_train_1gpu.log 2>&1
+stamp "1-rank CLI train rc=$?: $(grep 'global step' $O/cli_train_1gpu.log | tail -2 | cut -c1-90 | tr '\n' '|')"
 cat $S

@@ -114,7 +114,12 @@ int st_melspec(const float* wav, int64_t wav_stride, const int32_t* n_samples, i
  *                          valid; view it time-major with stride_t=32, stride_b=T'*32, T' = st_plan_logit_frames)
  *   st_plan_backward     : consumes d(loss)/d(logits) from the bf16 planes [n_planes][B][T'][64] at
  *                          st_plan_dlogits_planes (st_ctc_loss writes them with c_pad=64) -> flat gradient buffer
- *   st_plan_get_activation: output of layer 0..9 merged back to fp32 [B,T',Cout] (parity tests); -1 = input planes */
+ *   st_plan_get_activation: output of layer 0..9 merged back to fp32 [B,T',Cout] (parity tests); -1 = input planes
+ * Stream semantics: every call only enqueues work; results are ordered on `stream`.  A plan may run HBM-bound passes
+ * (part of the packing, the zeroing of the gradient buffer, one combine pass of backward) on a side stream of its own
+ * underneath tensor-core launches -- it forks behind what `stream` holds at the call and the consumer (st_plan_forward in
+ * front of layer 8, st_plan_backward at its start / end) makes `stream` wait for it, so callers never see the side
+ * stream (SPEECHT_B200_OVERLAP=0 keeps everything on `stream`).  st_plan_destroy synchronises it. */
 typedef struct st_plan st_plan;
 int st_plan_create(st_plan** out, int B, int T, int input_size, int num_classes, int n_planes);
 int st_plan_destroy(st_plan* plan);

@@ -201,3 +201,9 @@ LIBROSA_MEL_FREQUENCIES_40 = np.array(
      7754.107, 8467.272, 9246.028, 10096.408, 11025.])
 LIBROSA_HZ_TO_MEL = ([60.0, 110.0, 220.0, 440.0], [0.9, 1.65, 3.3, 6.6])
 LIBROSA_MEL_TO_HZ = ([1.0, 2.0, 3.0, 4.0, 5.0], [66.667, 133.333, 200.0, 266.667, 333.333])
+# librosa.filters.mel docstring (0.5-0.10): `librosa.filters.mel(sr=22050, n_fft=2048)` prints
+# array([[ 0.   ,  0.016, ...,  0.   ,  0.   ], ...]) and, clipped to fmax=8000, array([[ 0.  ,  0.02, ...,  0.  ,  0.  ], ...]).
+# Two significant digits only -- but an un-normalised triangle would have 0.40 there, so they do pin the Slaney area
+# normalisation 2 / (f[i+2] - f[i]) that turns it into 0.016.
+LIBROSA_MEL_FILTER_0_1 = {'sr': 22050, 'n_fft': 2048, 'n_mels': 128, 'value': 0.016, 'decimals': 3}
+LIBROSA_MEL_FILTER_0_1_FMAX8000 = {'sr': 22050, 'n_fft': 2048, 'n_mels': 128, 'fmax': 8000.0, 'value': 0.02, 'decimals': 2}

@@ -318,3 +318,13 @@ def test_oracle_mel_scale_matches_librosa_published_docstring_values():
   np.testing.assert_allclose(O._mel_to_hz_slaney(np.array(mel)), hz, rtol=0, atol=5e-4)
   edges = O._mel_to_hz_slaney(np.linspace(O._hz_to_mel_slaney(0.0), O._hz_to_mel_slaney(11025.0), 40))
   np.testing.assert_allclose(edges, TFV.LIBROSA_MEL_FREQUENCIES_40, rtol=0, atol=5e-4)   # three printed decimals
+
+
+def test_oracle_mel_filter_normalisation_matches_librosa_docstring_values():
+  """The two filterbank entries librosa's own documentation prints (weak: two significant digits, but an
+  un-normalised triangle has 0.40 where the Slaney-normalised one has 0.016)."""
+  for case in (TFV.LIBROSA_MEL_FILTER_0_1, TFV.LIBROSA_MEL_FILTER_0_1_FMAX8000):
+    fb = O.mel_filterbank(case['sr'], case['n_fft'], case['n_mels'], fmax=case.get('fmax'))
+    assert fb.shape == (case['n_mels'], 1 + case['n_fft'] // 2)
+    assert round(float(fb[0, 1]), case['decimals']) == case['value'], fb[0, :3]
+    assert abs(float(fb[0, 0])) == 0.0 and fb[-1, -1] == 0.0

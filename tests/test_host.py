@@ -148,3 +148,36 @@ def test_native_plan_host_logic_without_a_gpu(monkeypatch):
     assert lib().st_plan_arena_bytes(h) < sizes[(32, 1001, 2)]
   finally:
     check(lib().st_plan_destroy(h))
+
+
+def test_sparse_from_host_rows_is_the_tf_sparse_triple():
+  """Host half of the greedy decoder's output (ops.PendingDecode.finish): padded label rows + counts -> the
+  SparseTensor triple tf.nn.ctc_greedy_decoder returns (row-major indices, dense_shape = [B, longest row]); compared
+  with the oracle's decoder output format on the same rows."""
+  from oracle import speecht_oracle as O
+  from speecht_b200.ops import sparse_from_host_rows
+  rows = np.array([[3, 1, 4, 0, 0], [0, 0, 0, 0, 0], [2, 7, 1, 8, 2]], dtype=np.int32)
+  counts = np.array([3, 0, 5], dtype=np.int32)
+  sp = sparse_from_host_rows(rows, counts)
+  np.testing.assert_array_equal(sp.indices, [[0, 0], [0, 1], [0, 2], [2, 0], [2, 1], [2, 2], [2, 3], [2, 4]])
+  np.testing.assert_array_equal(sp.values, [3, 1, 4, 2, 7, 1, 8, 2])
+  np.testing.assert_array_equal(sp.dense_shape, [3, 5])
+  assert sp.indices.dtype == np.int64 and sp.values.dtype == np.int64
+  # the same rows through the oracle's decoder: one-hot logits whose arg-max path is row r separated by blanks
+  C, blank = 10, 9
+  T = 2 * rows.shape[1]
+  logits = np.full((T, 3, C), -5.0)
+  seq = np.zeros(3, dtype=np.int64)
+  for b in range(3):
+    path = []
+    for v in rows[b, :counts[b]]:
+      path += [int(v), blank]
+    seq[b] = max(len(path), 1)
+    for t in range(T):
+      logits[t, b, path[t] if t < len(path) else blank] = 5.0
+  (ri, rv, rs), _neg = O.ctc_greedy_decoder(logits, seq)
+  np.testing.assert_array_equal(sp.indices, ri)
+  np.testing.assert_array_equal(sp.values, rv)
+  np.testing.assert_array_equal(sp.dense_shape, rs)
+  empty = sparse_from_host_rows(np.zeros((2, 1), np.int32), np.zeros(2, np.int32))
+  assert empty.indices.shape == (0, 2) and empty.values.shape == (0,) and list(empty.dense_shape) == [2, 0]

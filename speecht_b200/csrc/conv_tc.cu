@@ -18,11 +18,20 @@
 //   warp 1   : TMEM allocator + single-thread tcgen05.mma issuer (128 x BLOCK_N x 16 per instruction); hi*hi products
 //              go to the `main` accumulator, every product with a lo plane to the `side` accumulator
 //   warps 2-9: epilogue, two warps per TMEM lane quarter: tcgen05.ld 32 lanes x 32 columns of main (+ side),
-//              +bias, ReLU / ReLU-mask, split to planes, staged in a per-warp shared-memory tile and written with
-//              one TMA store per plane (ragged edges clipped by the tensor map), bias-gradient column sums
+//              +bias, ReLU (forward: the lane's 32 activity BITS are stored for the data gradient, which reads one
+//              word per chunk instead of 64 bytes of bf16 activations), split to planes, staged in a per-warp
+//              shared-memory tile and written with one TMA store per plane (ragged edges clipped by the tensor map),
+//              bias-gradient column sums.  The 128-wide instantiation (layer-10 data gradient, all epilogue) runs
+//              sixteen epilogue warps (ConvCfg::EPW).
+//   Variants: NPROB = 9 (several problems of one shape per launch: the fast-FIR leaves of layer 8), PAIR (clusters of
+//              two CTAs, tcgen05.mma.cta_group::2 with M = 256, each CTA holding half of the B tile), BMN (B read
+//              MN-major from the backward filter layout: no forward layout has to be packed for that layer).
 // tc_wgrad_kernel (filter gradient): same roles; both operands are MN-major (the contraction runs over time, the
-// slow axis), expressed through the MN-major SWIZZLE_128B shared-memory descriptors; wave-aligned split-K.
+// slow axis), expressed through the MN-major SWIZZLE_128B shared-memory descriptors; wave-aligned split-K; PAIR: two
+// tiles that share their dZ tile per cluster.
 // Both are launched with programmatic stream serialization (griddepcontrol.wait after the prologue).
+// The elementwise passes around them (packing, fast-FIR prepare / combine, zeroing) are at the end of the kernel
+// section; three of them are "background kernels" sized to run beside resident tensor-core CTAs (pack_bwd_kernel).
 //
 // Roofline: tensor-pipe bound (in practice: bound by the clock the power cap allows while the pipe is 95 % busy).
 // Algorithmic FLOPs per launch = 2*K*Cin*Cout*T'*B (unpadded); the tensor pipe executes 3x (bf16x3) / 6x (bf16x6) /

@@ -295,6 +295,13 @@ class SpeechModel:
   def _prefetch_next(self):
     if getattr(self.input_loader, 'queue', None) is None and not getattr(self.input_loader, 'prefetchable', False):
       return
+    if torch.device(self.engine.device).type != 'cuda':
+      # host-only use (the control flow is tested on the CPU with a stub engine): nothing to overlap, fetch in line
+      try:
+        self._prefetched = self._fetch(None, None)
+      except OutOfRangeError as e:
+        self._prefetched = e
+      return
     if self._copy_stream is None:
       self._copy_stream = torch.cuda.Stream(device=self.engine.device)
     try:

@@ -1147,7 +1147,6 @@ pack_ffa2_kernel(const float* __restrict__ w, const Ptr9h fwd, const Ptr9h bwd, 
   const int ci0 = (lb % ci_tiles) * 64;
   const int k = lb / ci_tiles;
   const int tx = threadIdx.x, ty = threadIdx.y;
-  const int64_t tap = (int64_t)Cin * Cout;
 #pragma unroll
   for (int g = 0; g < 4; ++g) {
 #pragma unroll

@@ -28,8 +28,8 @@ def main():
   ms = r['layers_ms_per_step']
   passes = int(r.get('mma_passes', 1))
   cfg = line['config']
-  B = int(cfg.get('batch_per_gpu', cfg.get('batch', 32)))
-  T = int(cfg.get('frames', 1001))
+  B = int(cfg['global_batch']) // max(1, int(line.get('n_gpus', 1)))
+  T = int(round(float(cfg['mean_frames'])))
   rows = []
   t = T
   print('# %s' % sys.argv[1])

@@ -181,3 +181,36 @@ def test_sparse_from_host_rows_is_the_tf_sparse_triple():
   np.testing.assert_array_equal(sp.dense_shape, rs)
   empty = sparse_from_host_rows(np.zeros((2, 1), np.int32), np.zeros(2, np.int32))
   assert empty.indices.shape == (0, 2) and empty.values.shape == (0,) and list(empty.dense_shape) == [2, 0]
+
+
+def test_kernel_resource_invariants_of_the_built_library():
+  """Resource facts the design relies on, read from the built library with cuobjdump (skipped without the toolkit):
+  * background kernels (run on a side stream beside resident tensor-core CTAs): at most 40
+    registers and no static shared memory, so that 256 threads x 40 + 320 x 168 registers and 1 KB + 227 KB of shared
+    memory fit one SM;
+  * tensor-core kernels: 10 warps x 168 registers (or 18 warps x 112 for the sixteen-epilogue-warp instantiations)
+    must fit the 64 K register file -- a build that needs more fails to LAUNCH, not to compile."""
+  import re
+  import shutil
+  import subprocess
+  from speecht_b200 import _lib
+  tool = shutil.which('cuobjdump') or '/usr/local/cuda/bin/cuobjdump'
+  if not os.path.exists(tool) or not os.path.exists(_lib.LIB_PATH):
+    pytest.skip('cuobjdump or the built library is not available')
+  out = subprocess.run([tool, '-res-usage', _lib.LIB_PATH], capture_output=True, text=True).stdout
+  usage = {}
+  for name, reg, shared in re.findall(r'Function (\S+):\s*\n\s*REG:(\d+) STACK:\d+ SHARED:(\d+)', out):
+    usage[name] = (int(reg), int(shared))
+  assert len(usage) > 50, 'no resource records parsed'
+  background = [n for n in usage if re.search(r'pack_bwd_kernel|zero_f32_kernel|ffa2_dw_combine_kernel', n)]
+  assert len(background) >= 4
+  for n in background:
+    reg, shared = usage[n]
+    assert reg <= 40 and shared <= 1024, (n, reg, shared)        # 1024 = the per-block reservation, no static smem
+  tensor = [n for n in usage if re.search(r'tc_conv_kernel|tc_wgrad_kernel', n)]
+  assert len(tensor) >= 30
+  for n in tensor:
+    reg, shared = usage[n]
+    wide_epilogue = re.search(r'tc_conv_kernelILi128ELi[12]E', n) is not None      # ConvCfg::EPW == 16: 576 threads
+    assert reg <= (112 if wide_epilogue else 168), (n, reg)
+    assert shared <= 1024, (n, shared)                                             # pipeline stages are dynamic smem

@@ -56,10 +56,16 @@ def _worker(rank, world, port, out_dir):
   else:
     sp = SparseTensorValue(np.array([[1, 0]], np.int64), np.array([5], np.int64), np.array([2, 1], np.int64))
   g = parallel.gather_decoded_sparse(sp)
+  # the per-step termination word of the training loop travels over a SEPARATE host (gloo) group (training.py):
+  # a subgroup created next to the default one, CPU tensor, logical OR over ranks
+  flag_group = dist.new_group(backend='gloo')
+  any_true = [parallel.any_rank_true(rank == 1, device='cpu', group=flag_group),
+              parallel.any_rank_true(False, device='cpu', group=flag_group)]
   same = parallel.identical_across_ranks(flat)                       # the reduced gradient is identical everywhere
   differs = parallel.identical_across_ranks(torch.full((5,), float(rank)))
   np.savez(os.path.join(out_dir, 'rank%d.npz' % rank), flat=flat.numpy(), avg=avg.numpy(), rows=np.array(rows), t=t,
-           g_idx=g.indices, g_val=g.values, g_shape=g.dense_shape, same=same, differs=differs)
+           g_idx=g.indices, g_val=g.values, g_shape=g.dense_shape, same=same, differs=differs,
+           any_true=np.array(any_true))
   dist.destroy_process_group()
 
 
@@ -99,3 +105,4 @@ def test_two_rank_gradient_allreduce_matches_single_process(tmp_path):
     assert r['g_idx'].tolist() == [[0, 0], [0, 1], [2, 0], [4, 0]]
     assert r['g_val'].tolist() == [7, 8, 9, 5] and r['g_shape'].tolist() == [5, 2]
     assert bool(r['same']) and not bool(r['differs'])
+    assert r['any_true'].tolist() == [True, False]                  # one rank out of input -> every rank stops

@@ -50,7 +50,12 @@ class Training(DatasetExecutor):
       # the per-step "has any rank run out of input?" word travels over a HOST (gloo) group: on the NCCL group it is
       # ordered behind the previous step's gradient allreduce and Adam, and reading it would stall the host until that
       # step has completely finished -- the GPU would then idle while the next step is enqueued
-      self.flag_group = dist.new_group(backend='gloo') if dist.get_backend() == 'nccl' else None
+      self.flag_group = None
+      if dist.get_backend() == 'nccl':
+        try:
+          self.flag_group = dist.new_group(backend='gloo')
+        except Exception as e:            # no gloo in this build: fall back to the (stalling) word on the NCCL group
+          print('speecht_b200: no host group for the termination word (%s); using the NCCL group' % e)
     super().__init__(flags)
 
   # ---- DatasetExecutor hooks ---------------------------------------------------------------------
